@@ -1,0 +1,130 @@
+/*
+ * slice3d_b200 -- C ABI of the B200-native slice-to-3D hot path.
+ *
+ * The reference (yizhiwang96/Slice3D, reg_slices/) has NO native boundary on this
+ * path: everything is PyTorch library calls made from Slices3DRegModel.forward
+ * (reg_slices/src/models.py:48-94) and Generator3D.eval_points
+ * (reg_slices/reconstruct.py:74-102).  The entry points below are what a
+ * maintainer would bind (ctypes) to replace those calls:
+ *
+ *   s3d_model_create      <- Slices3DRegModel.load_state_dict + .cuda().eval()
+ *                            (reconstruct.py:343-345): takes the tensors of the
+ *                            244-key state_dict by name, keeps folded/packed copies.
+ *   s3d_encoder_fwd       <- self.slices_generator(img_input)          (models.py:65,
+ *                            unet_custom.py:40-69) + the fc_s projection hoisted onto
+ *                            the planes (models.py:80; exact, bilinear sampling is linear).
+ *   s3d_decoder_fwd       <- query flip / rotation (models.py:53-60), project_coord
+ *                            (:28-36,69), sample_from_planes x5 (:38-46,71-78),
+ *                            fc_p/fc_s (:79-80), att_decoder (:82-83), fc_out (:84),
+ *                            and the negation done by eval_points (reconstruct.py:97).
+ *   s3d_decoder_grid_fwd  <- the same over a make_3d_grid slab without materialising
+ *                            the (nx*ny*nz,3) point tensor (src_convonet/common.py:145-164,
+ *                            reconstruct.py:137-146).
+ *
+ * Conventions
+ *   - plain C types only; every pointer named *_dev is a CUDA device pointer on the
+ *     device the model was created on; all work is enqueued on `stream`
+ *     (a cudaStream_t passed as void*), no implicit synchronisation.
+ *   - the caller owns every buffer (inputs, outputs, workspaces); the library owns
+ *     only the packed weight copies inside s3d_model, freed by s3d_model_destroy.
+ *   - return value: 0 on success, negative S3D_ERR_* otherwise; s3d_last_error()
+ *     returns a thread-local message.  Nothing throws across the ABI.
+ *   - one s3d_model per device; calls on one model must be externally serialised
+ *     (the Python host holds the GIL).
+ */
+#ifndef SLICE3D_B200_H
+#define SLICE3D_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define S3D_ABI_VERSION 1
+
+#define S3D_OK 0
+#define S3D_ERR_BAD_ARG (-1)
+#define S3D_ERR_MISSING_TENSOR (-2)
+#define S3D_ERR_CUDA (-3)
+#define S3D_ERR_WORKSPACE (-4)
+#define S3D_ERR_UNSUPPORTED (-5)
+
+/* Decoder arithmetic.  All modes accumulate in fp32. */
+#define S3D_PREC_FP32 0   /* CUDA-core fp32 (validation grade, slow)                     */
+#define S3D_PREC_BF16X3 1 /* tcgen05, operands split into bf16 hi+lo, 3 MMA passes (<=1e-4) */
+#define S3D_PREC_BF16 2   /* tcgen05, single bf16 pass (fast, ~5e-3)                      */
+
+typedef struct s3d_model s3d_model;
+
+/* One tensor of the checkpoint: state_dict key, device pointer, element count.
+ * dtype is float32 for every key the library reads (int64 num_batches_tracked is ignored). */
+typedef struct {
+  const char* name;
+  const void* data_dev;
+  int64_t numel;
+} s3d_tensor;
+
+/* Query grid descriptor: point (ix,iy,iz) = (px[ix], py[iy], pz[iz]), flat index
+ * (ix*ny+iy)*nz+iz (x slowest, z fastest, as make_3d_grid).  px/py/pz are device
+ * arrays holding the per-axis torch.linspace values times box_size. */
+typedef struct {
+  int32_t nx, ny, nz;
+  const float* px_dev;
+  const float* py_dev;
+  const float* pz_dev;
+} s3d_grid;
+
+int s3d_abi_version(void);
+const char* s3d_last_error(void);
+
+/* Create / destroy.  `tensors` must contain every key under slices_generator.*,
+ * att_decoder.*, fc_p.*, fc_s.*, fc_out.* (att_layer.*, vggptlossfunc.* and
+ * num_batches_tracked are not read).  n_slices = K (12 in the reference). */
+int s3d_model_create(s3d_model** out, const s3d_tensor* tensors, int32_t n_tensors, int32_t n_slices,
+                     int32_t device, void* stream);
+void s3d_model_destroy(s3d_model* m);
+int s3d_model_n_slices(const s3d_model* m);
+
+/* Encoder.  img_dev: (B,3,S,S) fp32 NCHW, S a multiple of 16.
+ *   planes_dev      out, s3d_planes_bytes(B,K,S) bytes: per image, per scale s=0..4,
+ *                   (K, S/16*2^s, S/16*2^s, 128) fp32 channels-last = fc_s_s . plane_s.
+ *   feats_nchw_dev  optional (may be NULL, entries may be NULL): the five raw feature
+ *                   planes (B*K, C_s, H_s, W_s) fp32 NCHW, C = 512,256,128,64,32.
+ *   slices_rec_dev  optional: (B*K,3,S,S) fp32 NCHW, tanh output.
+ */
+size_t s3d_planes_bytes(int32_t B, int32_t K, int32_t S);
+size_t s3d_encoder_workspace_bytes(int32_t B, int32_t K, int32_t S);
+int s3d_encoder_fwd(const s3d_model* m, const float* img_dev, int32_t B, int32_t S, void* planes_dev,
+                    float* const* feats_nchw_dev, float* slices_rec_dev, void* workspace_dev,
+                    size_t workspace_bytes, void* stream);
+
+/* Decoder over explicit points.  For image `b` of the encoder batch pass
+ * planes_dev + b * s3d_planes_bytes(1,K,S).
+ *   qry_dev    (n,3) fp32 query points (qry_norot).
+ *   T_dev      (4,3) fp32 trans_mat_wo_rot_tp.
+ *   rot_dev    (3,3) fp32 obj_rot_mat or NULL.  NULL => test mode: y,z are negated
+ *              (models.py:55); with flip_in_place != 0 the negated values are also
+ *              written back to qry_dev, reproducing the reference's in-place side effect.
+ *   out_dev    (n) fp32 = out_scale * sdf_pred  (out_scale = -1 gives eval_points' values).
+ */
+size_t s3d_decoder_workspace_bytes(int64_t n, int32_t precision);
+int s3d_decoder_fwd(const s3d_model* m, const void* planes_dev, int32_t S, float* qry_dev, int64_t n,
+                    const float* T_dev, const float* rot_dev, int32_t flip_in_place, float out_scale,
+                    float* out_dev, int32_t precision, void* workspace_dev, size_t workspace_bytes,
+                    void* stream);
+
+/* Decoder over grid points [first, first+count) of `grid` (test-mode y,z flip applied
+ * on the fly).  out_dev receives `count` values. */
+int s3d_decoder_grid_fwd(const s3d_model* m, const void* planes_dev, int32_t S, const s3d_grid* grid,
+                         int64_t first, int64_t count, const float* T_dev, float out_scale, float* out_dev,
+                         int32_t precision, void* workspace_dev, size_t workspace_bytes, void* stream);
+
+/* Instrumentation: number of kernels this library has launched since load (all models). */
+int64_t s3d_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SLICE3D_B200_H */
