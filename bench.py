@@ -1,0 +1,330 @@
+#!/usr/bin/env python
+"""Benchmark of the slice-to-3D hot path (BASELINE.json metric: occupancy queries/sec for a
+dense grid, 12 slices, 256x256 input).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--grid 256] [--precision P]
+    python bench.py --impl reference ...      # the reference algorithm on the host cores
+
+One "step" = the whole path for one input view: plane encoder + decoder over the dense
+nx^3 query grid (+ the slab all-gather when N > 1; the grid is split into axis-0 slabs, so
+the total work is fixed: strong scaling).  `value` is measured with the inputs resident in
+HBM; `e2e` goes through ``Generator3D.generate_grid`` with HOST (pinned) inputs and a host
+output volume, so it contains the H2D and D2H copies.  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FLOP_PER_QUERY = 32.82e6  # minimal exact algorithm (contract figure)
+METRIC = "occupancy_queries_per_sec"
+UNIT = "queries/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--grid", type=int, default=256)
+    ap.add_argument("--img", type=int, default=256)
+    ap.add_argument("--precision", default=None, help="fp32 | bf16x3 | bf16 (default: best <=1e-4 mode built)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample", type=int, default=6000, help="queries in the bounded CPU sample")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("bf16_tflops_sustained", 1414.1), d.get("bf16_tflops", 1688.5), "measured"
+    return 1400.0, 1590.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.path = index, None, None
+
+    def start(self):
+        try:
+            f = tempfile.NamedTemporaryFile("w", suffix=".csv", delete=False)
+            self.path = f.name
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=f,
+                                         stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        for line in open(self.path):
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1])); mx.append(float(c[2])); pw.append(float(c[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.path)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "power_w_max": max(pw), "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------ CPU arms
+def cpu_reference_setup(S, K=12, seed=0):
+    import torch
+    from slice3d_b200 import Slices3DRegModel, synth
+    torch.manual_seed(0)
+    sd = synth.synthetic_state_dict(Slices3DRegModel(S, K, "test").state_dict(), seed)
+    feed = synth.synthetic_inputs(S, K, seed)
+    return sd, feed
+
+
+def cpu_sample_points(nx, n, seed=0):
+    """A bounded, contiguous run of the dense grid starting mid-volume (so the sample projects
+    inside the image like the bulk of the workload)."""
+    import torch
+    from slice3d_b200 import synth
+    ax = torch.linspace(-0.5, 0.5, nx)
+    first = (nx // 2) * nx * nx + (nx // 3) * nx
+    idx = torch.arange(first, first + n)
+    iz, iy, ix = idx % nx, (idx // nx) % nx, idx // (nx * nx)
+    return torch.stack([ax[ix], ax[iy], ax[iz]], -1)
+
+
+def cpu_baseline(S, nx, n_sample, as_written_chunks=1):
+    """Oracle port (the reference algorithm restated in torch CPU ops, oracle/oracle.py) timed on
+    this host's cores: (a) decoder only with the planes computed once; (b) as the reference's
+    Generator3D.eval_points runs it: U-Net + VGG19 loss + decoder for every 3000-point chunk."""
+    import torch
+    from oracle import oracle
+    from oracle.timing_port import TimingPort
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd, feed = cpu_reference_setup(S)
+    port = TimingPort(sd)
+    pts = cpu_sample_points(nx, n_sample)
+    with torch.no_grad():
+        t0 = time.perf_counter()
+        feats, _ = oracle.unet_forward(sd, feed["img_input"], 12)
+        t_enc = time.perf_counter() - t0
+        q = oracle.prepare_queries(pts.unsqueeze(0), None, "test")
+        port.decode(feats, q[:, :512], feed["trans_mat_wo_rot_tp"])  # warm
+        t0 = time.perf_counter()
+        for s in range(0, n_sample, 3000):
+            port.decode(feats, q[:, s:s + 3000], feed["trans_mat_wo_rot_tp"])
+        t_dec = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        for c in range(as_written_chunks):
+            f = dict(feed)
+            f["qry_norot"] = pts[3000 * c:3000 * (c + 1)].clone().unsqueeze(0)
+            port.forward_as_written(f)
+        t_aw = time.perf_counter() - t0
+    return {"value": 3000 * as_written_chunks / t_aw, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{as_written_chunks} chunk(s) of 3000 grid points as Generator3D.eval_points runs them "
+                      f"(U-Net + VGG19 loss + decoder per chunk), S={S}, fp32, torch CPU",
+            "decoder_only_qps": n_sample / t_dec, "decoder_only_sample": f"{n_sample} grid points, planes precomputed",
+            "encoder_s": t_enc}
+
+
+def run_reference(args):
+    """--impl reference: the reference's algorithm (oracle port; the reference is a Python package that
+    cannot travel to the GPU box) on the host cores.  A step = one 3000-point chunk of the
+    dense grid through the whole model, exactly what Generator3D.eval_points does per chunk."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    from oracle.timing_port import TimingPort
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    S, nx = args.img, args.grid
+    sd, feed = cpu_reference_setup(S)
+    port = TimingPort(sd)
+    pts = cpu_sample_points(nx, 3000 * (args.steps + args.warmup))
+    times = []
+    with torch.no_grad():
+        for i in range(args.steps + args.warmup):
+            f = dict(feed)
+            f["qry_norot"] = pts[3000 * i:3000 * (i + 1)].clone().unsqueeze(0)
+            t0 = time.perf_counter()
+            port.forward_as_written(f)
+            times.append(time.perf_counter() - t0)
+    t = sum(times[args.warmup:])
+    v = 3000 * args.steps / t
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"12 slices {S}x{S} -> {nx}^3 dense occupancy grid", "grid": nx, "img_size": S,
+                       "n_slices": 12},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": "each step = one 3000-point chunk of the grid through U-Net + VGG19 loss + "
+                                       "decoder, as Generator3D.eval_points (reconstruct.py:74-102) runs it"},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------ native arm
+def run_native(args):
+    import torch
+    import torch.distributed as dist
+    from slice3d_b200 import Generator3D, Slices3DRegModel, _native, synth
+    from slice3d_b200 import dist as s3d_dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    S, nx, K = args.img, args.grid, 12
+    prec = args.precision or [p for p in ("bf16x3", "fp32") if p in _native.available_precisions()][0]
+
+    torch.manual_seed(0)
+    model = Slices3DRegModel(S, K, "test", precision=prec)
+    model.load_state_dict(synth.synthetic_state_dict(model.state_dict(), 0))
+    model = model.to(dev).eval()
+    feed = synth.synthetic_inputs(S, K, 0)
+    gen = Generator3D(model, upsampling_steps=0, resolution0=nx, pred_type="sdf")
+    nat = model.native()
+    img_d = feed["img_input"].to(dev)
+    T_d = feed["trans_mat_wo_rot_tp"].to(dev)
+    ax = gen.grid_axes(nx, dev)
+    lo, hi = s3d_dist.slab_range(nx, rank, world)
+    first, count = lo * nx * nx, (hi - lo) * nx * nx
+    vol = torch.empty(nx ** 3, dtype=torch.float32, device=dev)
+    dec_ev = []
+
+    def step(timed):
+        planes = nat.encode(img_d, want_slices_rec=True)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        nat.decode_grid(planes, 0, (ax, ax, ax), first, count, T_d[0], out_scale=-1.0, precision=prec,
+                        out=vol[first:first + count])
+        e1.record()
+        if timed:
+            dec_ev.append((e0, e1))
+        if world > 1:
+            s3d_dist.all_gather_slabs(vol, nx)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    with torch.no_grad():
+        for _ in range(args.warmup):
+            step(False)
+        barrier()
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+        l0 = _native.launch_count()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for _ in range(args.steps):
+            step(True)
+        s1.record()
+        barrier()
+        launches = _native.launch_count() - l0
+        ms = max_over_ranks(s0.elapsed_time(s1))
+        dec_ms = sum(a.elapsed_time(b) for a, b in dec_ev) / len(dec_ev)
+        clocks = sampler.stop() if rank == 0 else None
+
+        # ---- end to end through the public API with host buffers
+        host_feed = {"img_input": feed["img_input"].pin_memory(),
+                     "trans_mat_wo_rot_tp": feed["trans_mat_wo_rot_tp"].pin_memory()}
+        out_host = torch.empty(nx, nx, nx, dtype=torch.float32, pin_memory=True)
+
+        def e2e_step():
+            model._enc_cache = None  # a new view every step: nothing cached across steps
+            gen.generate_grid(host_feed, resolution=nx, precision=prec, out_host=out_host)
+
+        for _ in range(max(1, min(args.warmup, 2))):
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            e2e_step()
+        barrier()
+        e2e_ms = max_over_ranks(1e3 * (time.perf_counter() - t0))
+
+    value = nx ** 3 * args.steps / (ms / 1e3)
+    sustained, burst, how = peaks()
+    dec_tflops = FLOP_PER_QUERY * count / (dec_ms / 1e3) / 1e12
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": {"fp32": "f32", "bf16x3": "bf16x3 (bf16 hi/lo split operands, 3 tcgen05 passes, fp32 accumulate)",
+                  "bf16": "bf16"}[prec],
+        "data": "synthetic",
+        "config": {"workload": f"12 slices {S}x{S} -> {nx}^3 dense occupancy grid (encoder + decoder"
+                               + (" + slab all-gather" if world > 1 else "") + ")",
+                   "grid": nx, "img_size": S, "n_slices": K, "precision": prec,
+                   "parallelism": f"axis-0 slabs x{world}" if world > 1 else "single GPU",
+                   "l2": "inputs larger than L2 (projected planes %.0f MB)" % (nat_planes_mb(K, S))},
+        "e2e": {"value": nx ** 3 * args.steps / (e2e_ms / 1e3), "unit": UNIT,
+                "h2d_bytes_per_step": int(feed["img_input"].numel() * 4 + feed["trans_mat_wo_rot_tp"].numel() * 4),
+                "d2h_bytes_per_step": int(nx ** 3 * 4), "ms_per_step": e2e_ms / args.steps},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "tensor", "achieved": dec_tflops, "peak": sustained, "unit": "TFLOP/s",
+                     "frac": dec_tflops / sustained, "traffic": None,
+                     "kernel": "decoder (all launches of one decode_grid call)", "kernel_ms": dec_ms,
+                     "flop_per_query": FLOP_PER_QUERY, "queries_per_launch": count, "peak_source": how + " sustained bf16"},
+        "clocks": clocks,
+    }
+    if rank == 0:
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(S, nx, args.cpu_sample)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def nat_planes_mb(K, S):
+    px = sum(((S // 16) << s) ** 2 for s in range(5))
+    return K * px * 128 * 4 / 1e6
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_native(a)

@@ -121,6 +121,14 @@ int s3d_decoder_grid_fwd(const s3d_model* m, const void* planes_dev, int32_t S, 
                          int64_t first, int64_t count, const float* T_dev, float out_scale, float* out_dev,
                          int32_t precision, void* workspace_dev, size_t workspace_bytes, void* stream);
 
+/* Validation aid (fp32 path only): like s3d_decoder_fwd with out_scale = 1 and no in-place
+ * flip, and additionally writes the token matrices (K+1 rows of 128 per query) after the
+ * token build and after each of the three attention layers to tokens_dev, laid out
+ * [4][n][K+1][128] fp32.  Workspace as for S3D_PREC_FP32. */
+int s3d_decoder_debug_tokens(const s3d_model* m, const void* planes_dev, int32_t S, const float* qry_dev,
+                             int64_t n, const float* T_dev, const float* rot_dev, float* out_dev,
+                             float* tokens_dev, void* workspace_dev, size_t workspace_bytes, void* stream);
+
 /* Instrumentation: number of kernels this library has launched since load (all models). */
 int64_t s3d_launch_count(void);
 

@@ -147,12 +147,14 @@ def transformer_layer(sd, p, x, nhead=4):
     return F.layer_norm(x + h, (D,), sd[p + ".norm2.weight"], sd[p + ".norm2.bias"], EPS_LN)
 
 
-def decode(sd, feats, qry, T, n_slices=12, chunk=8192):
+def decode(sd, feats, qry, T, n_slices=12, chunk=8192, return_tokens=False):
     """src/models.py:69-84 given the planes and the (already flipped/rotated) queries.
-    feats: 5 planes (B*K,C,H,W); qry (B,M,3); T (B,4,3).  Returns sdf_pred (B,M)."""
+    feats: 5 planes (B*K,C,H,W); qry (B,M,3); T (B,4,3).  Returns sdf_pred (B,M)
+    (and, with return_tokens, the token matrices (4, B*M, K+1, 128): after the token
+    build and after each attention layer -- used to localise a failing stage)."""
     B, M, _ = qry.shape
     K = n_slices
-    outs = []
+    outs, toks = [], []
     for s in range(0, M, chunk):
         q = qry[:, s:s + chunk]
         m = q.shape[1]
@@ -164,10 +166,16 @@ def decode(sd, feats, qry, T, n_slices=12, chunk=8192):
         tok_s = sampled @ sd["fc_s.weight"].t() + sd["fc_s.bias"]
         tok_q = (q @ sd["fc_p.weight"].t() + sd["fc_p.bias"]).view(B * m, 1, 128)
         x = torch.cat([tok_q, tok_s], 1)
+        stages = [x]
         for l in range(3):
             x = transformer_layer(sd, f"att_decoder.layers.{l}", x)
+            stages.append(x)
+        if return_tokens:
+            toks.append(torch.stack(stages, 0))
         t0 = x.view(B, m, K + 1, 128)[:, :, 0, :]
         outs.append((t0 @ sd["fc_out.0.weight"].t() + sd["fc_out.0.bias"]).squeeze(-1))
+    if return_tokens:
+        return torch.cat(outs, 1), torch.cat(toks, 1)
     return torch.cat(outs, 1)
 
 
@@ -183,7 +191,10 @@ def prepare_queries(qry_norot, obj_rot_mat, mode):
 
 
 def vgg_perceptual(sd, a, b):
-    """src/vgg_perceptual_loss.py:51-71 restated; taps are pre-ReLU conv outputs."""
+    """src/vgg_perceptual_loss.py:51-71 restated.  Taps 1-4 are POST-ReLU and tap 5 is
+    pre-ReLU: each slice ends on a conv, but the next slice starts with torchvision's
+    ``ReLU(inplace=True)``, which overwrites the tensor already stored in the output list
+    (vgg_perceptual_loss.py:33-38); only conv5_2 has no successor."""
     p = "vggptlossfunc."
     mean, std = sd[p + "mean"], sd[p + "std"]
     cfg = [64, 64, "M", 128, 128, "M", 256, 256, 256, 256, "M", 512, 512, 512, 512, "M", 512, 512, 512, 512, "M"]
@@ -203,7 +214,7 @@ def vgg_perceptual(sd, a, b):
                     x = F.relu(x)
                 else:
                     x = F.max_pool2d(x, 2, 2)
-            out.append(x)
+            out.append(F.relu(x) if n < 5 else x)
         return out
 
     w = [1.0 / 2.6, 1.0 / 4.8, 1.0 / 3.7, 1.0 / 5.6, 10.0 / 1.5]

@@ -1,0 +1,11 @@
+"""slice3d_b200 -- B200-native implementation of Slice3D's slice-to-3D hot path.
+
+Public surface mirrors the reference (reg_slices/src/models.py, reg_slices/reconstruct.py):
+``Slices3DRegModel`` and ``Generator3D``; the arithmetic lives in the CUDA library behind the
+C ABI declared in ``include/slice3d_b200.h``.
+"""
+from .models import Slices3DRegModel  # noqa: F401
+from .generator import Generator3D  # noqa: F401
+from .synth import make_3d_grid  # noqa: F401
+
+__all__ = ["Slices3DRegModel", "Generator3D", "make_3d_grid"]

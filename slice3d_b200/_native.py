@@ -1,0 +1,238 @@
+"""ctypes binding of the C ABI in include/slice3d_b200.h.
+
+PyTorch supplies device memory and streams only; every pointer handed to the
+library is a raw ``data_ptr()``.  There is no CPU path: loading fails loudly if the
+shared library has not been built, and ``NativeModel`` refuses non-CUDA tensors.
+"""
+import ctypes as C
+import os
+
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "_lib", "libslice3d_b200.so")
+
+PREC_FP32, PREC_BF16X3, PREC_BF16 = 0, 1, 2
+PRECISIONS = {"fp32": PREC_FP32, "bf16x3": PREC_BF16X3, "bf16": PREC_BF16}
+ABI_VERSION = 1
+
+# every symbol include/slice3d_b200.h declares (tests check the library exports all of them)
+SYMBOLS = [
+    "s3d_abi_version", "s3d_last_error", "s3d_model_create", "s3d_model_destroy", "s3d_model_n_slices",
+    "s3d_planes_bytes", "s3d_encoder_workspace_bytes", "s3d_encoder_fwd", "s3d_decoder_workspace_bytes",
+    "s3d_decoder_fwd", "s3d_decoder_grid_fwd", "s3d_decoder_debug_tokens", "s3d_launch_count",
+]
+
+
+class S3DTensor(C.Structure):
+    _fields_ = [("name", C.c_char_p), ("data_dev", C.c_void_p), ("numel", C.c_int64)]
+
+
+class S3DGrid(C.Structure):
+    _fields_ = [("nx", C.c_int32), ("ny", C.c_int32), ("nz", C.c_int32), ("px_dev", C.c_void_p),
+                ("py_dev", C.c_void_p), ("pz_dev", C.c_void_p)]
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib():
+    """Load (once) and type the shared library.  No fallback: a missing build is an error."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise NativeError(f"{LIB_PATH} not built; run `python -m slice3d_b200.build` "
+                          "(slice3d_b200 has no PyTorch/CPU fallback for the inference path)")
+    L = C.CDLL(LIB_PATH)
+    L.s3d_abi_version.restype = C.c_int
+    L.s3d_last_error.restype = C.c_char_p
+    L.s3d_launch_count.restype = C.c_int64
+    L.s3d_model_create.restype = C.c_int
+    L.s3d_model_create.argtypes = [C.POINTER(C.c_void_p), C.POINTER(S3DTensor), C.c_int32, C.c_int32, C.c_int32,
+                                   C.c_void_p]
+    L.s3d_model_destroy.restype = None
+    L.s3d_model_destroy.argtypes = [C.c_void_p]
+    L.s3d_model_n_slices.restype = C.c_int
+    L.s3d_model_n_slices.argtypes = [C.c_void_p]
+    L.s3d_planes_bytes.restype = C.c_size_t
+    L.s3d_planes_bytes.argtypes = [C.c_int32, C.c_int32, C.c_int32]
+    L.s3d_encoder_workspace_bytes.restype = C.c_size_t
+    L.s3d_encoder_workspace_bytes.argtypes = [C.c_int32, C.c_int32, C.c_int32]
+    L.s3d_encoder_fwd.restype = C.c_int
+    L.s3d_encoder_fwd.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.POINTER(C.c_void_p),
+                                  C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+    L.s3d_decoder_workspace_bytes.restype = C.c_size_t
+    L.s3d_decoder_workspace_bytes.argtypes = [C.c_int64, C.c_int32]
+    L.s3d_decoder_fwd.restype = C.c_int
+    L.s3d_decoder_fwd.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
+                                  C.c_int32, C.c_float, C.c_void_p, C.c_int32, C.c_void_p, C.c_size_t, C.c_void_p]
+    L.s3d_decoder_grid_fwd.restype = C.c_int
+    L.s3d_decoder_grid_fwd.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(S3DGrid), C.c_int64, C.c_int64,
+                                       C.c_void_p, C.c_float, C.c_void_p, C.c_int32, C.c_void_p, C.c_size_t,
+                                       C.c_void_p]
+    L.s3d_decoder_debug_tokens.restype = C.c_int
+    L.s3d_decoder_debug_tokens.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p,
+                                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+    if L.s3d_abi_version() != ABI_VERSION:
+        raise NativeError(f"ABI mismatch: library {L.s3d_abi_version()}, binding {ABI_VERSION}")
+    _lib = L
+    return L
+
+
+def _check(rc):
+    if rc != 0:
+        raise NativeError(f"slice3d_b200 error {rc}: {lib().s3d_last_error().decode()}")
+
+
+def available_precisions():
+    """Decoder arithmetic modes built into this revision of the library."""
+    return ("fp32",)
+
+
+def launch_count():
+    return int(lib().s3d_launch_count())
+
+
+def _stream(device):
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _f32c(t, what):
+    if not t.is_cuda:
+        raise NativeError(f"{what} must be a CUDA tensor (slice3d_b200 has no CPU path)")
+    if t.dtype != torch.float32:
+        raise NativeError(f"{what} must be float32")
+    return t if t.is_contiguous() else t.contiguous()
+
+
+class Planes:
+    """Device blob produced by the encoder for a batch of input views: per image and per
+    scale s a (K, R_s, R_s, 128) fp32 channels-last plane = fc_s_s applied to feature plane s."""
+
+    def __init__(self, blob, B, K, S, slices_rec):
+        self.blob, self.B, self.K, self.S, self.slices_rec = blob, B, K, S, slices_rec
+        self.bytes_per_image = blob.numel() * 4 // B
+
+    def image_ptr(self, b):
+        return self.blob.data_ptr() + b * self.bytes_per_image
+
+
+class NativeModel:
+    """Owns one s3d_model handle (packed/folded weights on one device)."""
+
+    def __init__(self, state_dict, n_slices, device):
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise NativeError("NativeModel needs a CUDA device (slice3d_b200 has no CPU path)")
+        self.device = device
+        self.K = n_slices
+        L = lib()
+        keep, arr = [], []
+        for name, t in state_dict.items():
+            if t.dtype != torch.float32 or name.startswith(("vggptlossfunc.", "att_layer.")):
+                continue
+            t = t.detach().to(device=device).contiguous()
+            keep.append(t)
+            arr.append(S3DTensor(name.encode(), t.data_ptr(), t.numel()))
+        tensors = (S3DTensor * len(arr))(*arr)
+        h = C.c_void_p()
+        with torch.cuda.device(device):
+            torch.cuda.current_stream(device).synchronize()
+            _check(L.s3d_model_create(C.byref(h), tensors, len(arr), n_slices, device.index or 0, _stream(device)))
+        self._h = h
+        self._ws = {}
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h and _lib is not None:
+            _lib.s3d_model_destroy(h)
+
+    def _workspace(self, key, nbytes):
+        ws = self._ws.get(key)
+        if ws is None or ws.numel() < nbytes:
+            ws = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=self.device)
+            self._ws[key] = ws
+        return ws
+
+    def release_workspaces(self):
+        self._ws.clear()
+
+    # ---- encoder ----------------------------------------------------------------
+    def encode(self, img, want_feats=False, want_slices_rec=True):
+        """img (B,3,S,S) -> Planes (+ the five raw NCHW feature planes when asked)."""
+        img = _f32c(img, "img_input")
+        B, c, S, S2 = img.shape
+        if c != 3 or S != S2:
+            raise NativeError("img_input must be (B,3,S,S)")
+        L, K = lib(), self.K
+        with torch.cuda.device(self.device):
+            blob = torch.empty(L.s3d_planes_bytes(B, K, S) // 4, dtype=torch.float32, device=self.device)
+            rec = torch.empty(B * K, 3, S, S, dtype=torch.float32, device=self.device) if want_slices_rec else None
+            feats, fptr = None, None
+            if want_feats:
+                chans = [512, 256, 128, 64, 32]
+                feats = [torch.empty(B * K, chans[s], (S // 16) << s, (S // 16) << s, dtype=torch.float32,
+                                     device=self.device) for s in range(5)]
+                fptr = (C.c_void_p * 5)(*[f.data_ptr() for f in feats])
+            nws = L.s3d_encoder_workspace_bytes(B, K, S)
+            ws = self._workspace("enc", nws)
+            _check(L.s3d_encoder_fwd(self._h, img.data_ptr(), B, S, blob.data_ptr(), fptr,
+                                     rec.data_ptr() if rec is not None else None, ws.data_ptr(), ws.numel(),
+                                     _stream(self.device)))
+        planes = Planes(blob, B, K, S, rec)
+        return (planes, feats) if want_feats else planes
+
+    # ---- decoder ----------------------------------------------------------------
+    def decode(self, planes, b, qry, T, rot=None, flip_in_place=False, out_scale=1.0, precision="bf16x3", out=None):
+        """qry (n,3) of image b -> (n,) = out_scale * sdf_pred.  rot None = test mode (y,z negated)."""
+        if not qry.is_cuda or qry.dtype != torch.float32 or not qry.is_contiguous():
+            raise NativeError("qry must be a contiguous float32 CUDA tensor")
+        T = _f32c(T, "trans_mat_wo_rot_tp")
+        rot = _f32c(rot, "obj_rot_mat") if rot is not None else None
+        n = qry.shape[0]
+        L, prec = lib(), PRECISIONS[precision]
+        with torch.cuda.device(self.device):
+            if out is None:
+                out = torch.empty(n, dtype=torch.float32, device=self.device)
+            ws = self._workspace("dec", L.s3d_decoder_workspace_bytes(n, prec))
+            _check(L.s3d_decoder_fwd(self._h, planes.image_ptr(b), planes.S, qry.data_ptr(), n, T.data_ptr(),
+                                     rot.data_ptr() if rot is not None else None, 1 if flip_in_place else 0,
+                                     out_scale, out.data_ptr(), prec, ws.data_ptr(), ws.numel(),
+                                     _stream(self.device)))
+        return out
+
+    def decode_grid(self, planes, b, axes, first, count, T, out_scale=1.0, precision="bf16x3", out=None):
+        """Grid points [first, first+count) of the (nx,ny,nz) grid given by the three per-axis
+        coordinate tensors ``axes`` (x slowest, z fastest), test-mode flip applied on the fly."""
+        px, py, pz = (_f32c(a, "grid axis") for a in axes)
+        T = _f32c(T, "trans_mat_wo_rot_tp")
+        L, prec = lib(), PRECISIONS[precision]
+        g = S3DGrid(px.numel(), py.numel(), pz.numel(), px.data_ptr(), py.data_ptr(), pz.data_ptr())
+        with torch.cuda.device(self.device):
+            if out is None:
+                out = torch.empty(count, dtype=torch.float32, device=self.device)
+            ws = self._workspace("dec", L.s3d_decoder_workspace_bytes(count, prec))
+            _check(L.s3d_decoder_grid_fwd(self._h, planes.image_ptr(b), planes.S, C.byref(g), first, count,
+                                          T.data_ptr(), out_scale, out.data_ptr(), prec, ws.data_ptr(), ws.numel(),
+                                          _stream(self.device)))
+        return out
+
+    def debug_tokens(self, planes, b, qry, T, rot=None):
+        """fp32 validation path: returns (sdf (n,), tokens (4,n,K+1,128))."""
+        qry, T = _f32c(qry, "qry"), _f32c(T, "T")
+        rot = _f32c(rot, "rot") if rot is not None else None
+        n, L = qry.shape[0], lib()
+        with torch.cuda.device(self.device):
+            out = torch.empty(n, dtype=torch.float32, device=self.device)
+            tok = torch.empty(4, n, self.K + 1, 128, dtype=torch.float32, device=self.device)
+            ws = self._workspace("dec", L.s3d_decoder_workspace_bytes(n, PREC_FP32))
+            _check(L.s3d_decoder_debug_tokens(self._h, planes.image_ptr(b), planes.S, qry.data_ptr(), n,
+                                              T.data_ptr(), rot.data_ptr() if rot is not None else None,
+                                              out.data_ptr(), tok.data_ptr(), ws.data_ptr(), ws.numel(),
+                                              _stream(self.device)))
+        return out, tok

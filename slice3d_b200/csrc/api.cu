@@ -1,0 +1,406 @@
+// C ABI of slice3d_b200 (include/slice3d_b200.h): model creation (weight folding / packing)
+// and the thin entry points over encoder.cu / decoder_simt.cu / decoder_tc.cu.
+#include <cmath>
+#include <cstring>
+#include <map>
+
+#include "common.cuh"
+
+namespace s3d {
+
+static thread_local std::string g_err;
+std::atomic<long long> g_launches{0};
+void set_error(const std::string& msg) { g_err = msg; }
+
+namespace {
+
+constexpr float kBnEps = 1e-5f;
+
+struct Packer {
+  s3d_model* m;
+  std::map<std::string, const s3d_tensor*> by_name;
+  cudaStream_t st;
+  std::string err;
+
+  bool fetch(const std::string& name, int64_t numel, std::vector<float>& out) {
+    auto it = by_name.find(name);
+    if (it == by_name.end()) {
+      err = "missing tensor: " + name;
+      return false;
+    }
+    if (it->second->numel != numel) {
+      err = "tensor " + name + ": numel " + std::to_string(it->second->numel) + ", expected " + std::to_string(numel);
+      return false;
+    }
+    out.resize((size_t)numel);
+    cudaError_t e = cudaMemcpyAsync(out.data(), it->second->data_dev, (size_t)numel * sizeof(float),
+                                    cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) {
+      err = "copy of " + name + " failed: " + cudaGetErrorString(e);
+      return false;
+    }
+    return true;
+  }
+
+  float* upload(const std::vector<float>& h) {
+    float* d = nullptr;
+    if (cudaMalloc(&d, h.size() * sizeof(float)) != cudaSuccess) {
+      err = "cudaMalloc failed";
+      return nullptr;
+    }
+    m->allocs.push_back(d);
+    if (cudaMemcpyAsync(d, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice, st) != cudaSuccess ||
+        cudaStreamSynchronize(st) != cudaSuccess) {
+      err = "upload failed";
+      return nullptr;
+    }
+    return d;
+  }
+
+  // eval-mode BatchNorm as y = x*scale + shift; `bias` (may be empty) is the preceding
+  // convolution's bias folded into shift.
+  bool bn_fold(const std::string& p, int C, const std::vector<float>& bias, std::vector<float>& scale,
+               std::vector<float>& shift) {
+    std::vector<float> g, b, mu, var;
+    if (!fetch(p + ".weight", C, g) || !fetch(p + ".bias", C, b) || !fetch(p + ".running_mean", C, mu) ||
+        !fetch(p + ".running_var", C, var))
+      return false;
+    scale.resize(C);
+    shift.resize(C);
+    for (int c = 0; c < C; ++c) {
+      double s = (double)g[c] / std::sqrt((double)var[c] + (double)kBnEps);
+      double cb = bias.empty() ? 0.0 : (double)bias[c];
+      scale[c] = (float)s;
+      shift[c] = (float)((cb - (double)mu[c]) * s + (double)b[c]);
+    }
+    return true;
+  }
+
+  // Conv2d weight (Cout, Cin, ks, ks) -> [(tap*CinP + ci)][Cout], CinP = Cin rounded up to 4.
+  bool pack_conv(const std::string& wname, int Cout, int Cin, int ks, ConvW& cw) {
+    std::vector<float> w;
+    if (!fetch(wname, (int64_t)Cout * Cin * ks * ks, w)) return false;
+    const int CinP = (Cin + 3) / 4 * 4, taps = ks * ks;
+    cw.cin = CinP;
+    cw.ncols = Cout;
+    cw.ks = ks;
+    cw.k = taps * CinP;
+    cw.kpad = (cw.k + 15) / 16 * 16;
+    std::vector<float> t((size_t)cw.kpad * Cout, 0.f);
+    for (int co = 0; co < Cout; ++co)
+      for (int ci = 0; ci < Cin; ++ci)
+        for (int tp = 0; tp < taps; ++tp)
+          t[((size_t)tp * CinP + ci) * Cout + co] = w[((size_t)co * Cin + ci) * taps + tp];
+    cw.w = upload(t);
+    return cw.w != nullptr;
+  }
+
+  // Linear weight (out, in) restricted to input columns [c0, c0+cin) -> [cin][out]
+  bool pack_linear(const std::string& wname, int out, int in, int c0, int cin, ConvW& cw) {
+    std::vector<float> w;
+    if (!fetch(wname, (int64_t)out * in, w)) return false;
+    cw.cin = cin;
+    cw.ncols = out;
+    cw.ks = 1;
+    cw.k = cin;
+    cw.kpad = (cin + 15) / 16 * 16;
+    std::vector<float> t((size_t)cw.kpad * out, 0.f);
+    for (int o = 0; o < out; ++o)
+      for (int i = 0; i < cin; ++i) t[(size_t)i * out + o] = w[(size_t)o * in + c0 + i];
+    cw.w = upload(t);
+    return cw.w != nullptr;
+  }
+
+  bool vec(const std::string& name, int n, float*& dst) {
+    std::vector<float> v;
+    if (!fetch(name, n, v)) return false;
+    dst = upload(v);
+    return dst != nullptr;
+  }
+
+  bool build() {
+    const std::string g = "slices_generator.";
+    // ---- VGG16-BN trunk (unet_custom.py:15-19; torchvision feature indices)
+    struct VC {
+      const char* blk;
+      int idx, cin, cout, bn;  // bn = index of the BatchNorm that follows inside the block, -1 for the tap conv
+    };
+    const VC vc[13] = {{"down1", 0, 3, 64, 1},     {"down1", 3, 64, 64, -1},   {"down2", 7, 64, 128, 8},
+                       {"down2", 10, 128, 128, -1}, {"down3", 14, 128, 256, 15}, {"down3", 17, 256, 256, 18},
+                       {"down3", 20, 256, 256, -1}, {"down4", 24, 256, 512, 25}, {"down4", 27, 512, 512, 28},
+                       {"down4", 30, 512, 512, -1}, {"down5", 34, 512, 512, 35}, {"down5", 37, 512, 512, 38},
+                       {"down5", 40, 512, 512, -1}};
+    for (int i = 0; i < 13; ++i) {
+      std::string p = g + vc[i].blk + "." + std::to_string(vc[i].idx);
+      if (!pack_conv(p + ".weight", vc[i].cout, vc[i].cin, 3, m->vgg[i])) return false;
+      std::vector<float> bias;
+      if (!fetch(p + ".bias", vc[i].cout, bias)) return false;
+      if (vc[i].bn >= 0) {
+        std::vector<float> sc, sh;
+        if (!bn_fold(g + vc[i].blk + "." + std::to_string(vc[i].bn), vc[i].cout, bias, sc, sh)) return false;
+        if (!(m->vgg[i].scale = upload(sc)) || !(m->vgg[i].shift = upload(sh))) return false;
+      } else {
+        if (!(m->vgg[i].shift = upload(bias))) return false;
+      }
+    }
+    const char* lead[4] = {"down2.4", "down3.11", "down4.21", "down5.31"};
+    const int leadc[4] = {64, 128, 256, 512};
+    for (int i = 0; i < 4; ++i) {
+      std::vector<float> sc, sh;
+      if (!bn_fold(g + lead[i], leadc[i], {}, sc, sh)) return false;
+      if (!(m->bn_scale[i] = upload(sc)) || !(m->bn_shift[i] = upload(sh))) return false;
+    }
+    // ---- trans_c: 1x1 conv over cat[x5 (512), slice embedding (128)] (unet_custom.py:52-57)
+    {
+      const int K = m->K;
+      std::vector<float> w, b, emb;
+      if (!fetch(g + "trans_c.weight", 512 * 640, w) || !fetch(g + "trans_c.bias", 512, b) ||
+          !fetch(g + "emds.weight", (int64_t)K * 128, emb))
+        return false;
+      ConvW& cw = m->trans_c;
+      cw.cin = 512; cw.ncols = 512; cw.ks = 1; cw.k = 512; cw.kpad = 512;
+      std::vector<float> t((size_t)512 * 512);
+      for (int co = 0; co < 512; ++co)
+        for (int ci = 0; ci < 512; ++ci) t[(size_t)ci * 512 + co] = w[(size_t)co * 640 + ci];
+      if (!(cw.w = upload(t))) return false;
+      std::vector<float> e((size_t)K * 512);
+      for (int k = 0; k < K; ++k)
+        for (int co = 0; co < 512; ++co) {
+          float s = 0.f;  // fp32 like the reference's convolution
+          for (int j = 0; j < 128; ++j) s = fmaf(w[(size_t)co * 640 + 512 + j], emb[(size_t)k * 128 + j], s);
+          e[(size_t)k * 512 + co] = s + b[co];
+        }
+      if (!(m->trans_c_e = upload(e))) return false;
+    }
+    // ---- Up stages
+    for (int n = 1; n <= 4; ++n) {
+      const int Cin = kPlaneC[n - 1], C = kPlaneC[n];
+      std::string up = g + "up" + std::to_string(n);
+      {  // ConvTranspose2d weight (Cin, C, 2, 2) -> [ci][(dy*2+dx)*C + co]
+        std::vector<float> w, b;
+        if (!fetch(up + ".up.weight", (int64_t)Cin * C * 4, w) || !fetch(up + ".up.bias", C, b)) return false;
+        ConvW& cw = m->up_t[n - 1];
+        cw.cin = Cin; cw.ncols = 4 * C; cw.ks = 1; cw.k = Cin; cw.kpad = Cin;
+        std::vector<float> t((size_t)Cin * 4 * C);
+        for (int ci = 0; ci < Cin; ++ci)
+          for (int co = 0; co < C; ++co)
+            for (int q = 0; q < 4; ++q) t[(size_t)ci * 4 * C + (size_t)q * C + co] = w[((size_t)ci * C + co) * 4 + q];
+        if (!(cw.w = upload(t)) || !(cw.shift = upload(b))) return false;
+      }
+      const std::string dc = up + ".conv.double_conv";
+      if (!pack_conv(dc + ".0.weight", C, 2 * C, 3, m->dc1[n - 1])) return false;
+      if (!pack_conv(dc + ".3.weight", C, C, 3, m->dc2[n - 1])) return false;
+      std::vector<float> sc, sh;
+      if (!bn_fold(dc + ".1", C, {}, sc, sh)) return false;
+      if (!(m->dc1[n - 1].scale = upload(sc)) || !(m->dc1[n - 1].shift = upload(sh))) return false;
+      if (!bn_fold(dc + ".4", C, {}, sc, sh)) return false;
+      if (!(m->dc2[n - 1].scale = upload(sc)) || !(m->dc2[n - 1].shift = upload(sh))) return false;
+      // 1x1 skip adapter trans_up{n}: 2C -> C
+      std::string tu = g + "trans_up" + std::to_string(n);
+      if (!pack_conv(tu + ".weight", C, 2 * C, 1, m->trans_up[n - 1])) return false;
+      if (!vec(tu + ".bias", C, m->trans_up[n - 1].shift)) return false;
+    }
+    if (!vec(g + "outc.conv.weight", 96, m->outc_w) || !vec(g + "outc.conv.bias", 3, m->outc_b)) return false;
+    // ---- fc_s hoisted per scale (models.py:80; input channel order = scale order 512,256,128,64,32)
+    {
+      int c0 = 0;
+      for (int s = 0; s < 5; ++s) {
+        if (!pack_linear("fc_s.weight", 128, 992, c0, kPlaneC[s], m->fcs[s])) return false;
+        c0 += kPlaneC[s];
+      }
+    }
+    // ---- decoder
+    DecF32& d = m->dec32;
+    {
+      std::vector<float> w;
+      if (!fetch("fc_p.weight", 128 * 3, w)) return false;
+      std::vector<float> t(3 * 128);
+      for (int c = 0; c < 128; ++c)
+        for (int j = 0; j < 3; ++j) t[j * 128 + c] = w[c * 3 + j];
+      if (!(d.fcp_wt = upload(t))) return false;
+    }
+    if (!vec("fc_p.bias", 128, d.fcp_b) || !vec("fc_s.bias", 128, d.fcs_b) || !vec("fc_out.0.weight", 128, d.fco_w) ||
+        !vec("fc_out.0.bias", 1, d.fco_b))
+      return false;
+    for (int l = 0; l < 3; ++l) {
+      std::string p = "att_decoder.layers." + std::to_string(l);
+      DecLayerF32& L = d.L[l];
+      if (!pack_linear(p + ".self_attn.in_proj_weight", 384, 128, 0, 128, L.in_proj) ||
+          !vec(p + ".self_attn.in_proj_bias", 384, L.in_proj.shift) ||
+          !pack_linear(p + ".self_attn.out_proj.weight", 128, 128, 0, 128, L.out_proj) ||
+          !vec(p + ".self_attn.out_proj.bias", 128, L.out_proj.shift) ||
+          !pack_linear(p + ".linear1.weight", 2048, 128, 0, 128, L.lin1) || !vec(p + ".linear1.bias", 2048, L.lin1.shift) ||
+          !pack_linear(p + ".linear2.weight", 128, 2048, 0, 2048, L.lin2) || !vec(p + ".linear2.bias", 128, L.lin2.shift) ||
+          !vec(p + ".norm1.weight", 128, L.n1_w) || !vec(p + ".norm1.bias", 128, L.n1_b) ||
+          !vec(p + ".norm2.weight", 128, L.n2_w) || !vec(p + ".norm2.bias", 128, L.n2_b))
+        return false;
+    }
+    return true;
+  }
+};
+
+__global__ void k_flip_yz(float* q, long long n) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  q[3 * i + 1] = -q[3 * i + 1];
+  q[3 * i + 2] = -q[3 * i + 2];
+}
+
+int run_decoder(const s3d_model* m, const void* planes, int S, const QueryCtx& q, int64_t n, float out_scale,
+                float* out, int precision, float* debug_tokens, void* ws, size_t ws_bytes, cudaStream_t st) {
+  if (!m || !planes || !out || !q.T || n < 0 || S < 32 || S % 16) {
+    set_error("decoder: bad argument");
+    return S3D_ERR_BAD_ARG;
+  }
+  if (precision == S3D_PREC_FP32)
+    return decoder_simt(m, static_cast<const float*>(planes), S, q, n, out_scale, out, debug_tokens, ws, ws_bytes, st);
+  if (precision == S3D_PREC_BF16X3 || precision == S3D_PREC_BF16) {
+    if (debug_tokens) {
+      set_error("decoder: token dump is only available with S3D_PREC_FP32");
+      return S3D_ERR_UNSUPPORTED;
+    }
+    return decoder_tc(m, static_cast<const float*>(planes), S, q, n, out_scale, out, precision, ws, ws_bytes, st);
+  }
+  set_error("decoder: unknown precision mode");
+  return S3D_ERR_BAD_ARG;
+}
+
+}  // namespace
+}  // namespace s3d
+
+using namespace s3d;
+
+extern "C" {
+
+int s3d_abi_version(void) { return S3D_ABI_VERSION; }
+const char* s3d_last_error(void) { return g_err.c_str(); }
+int64_t s3d_launch_count(void) { return g_launches.load(); }
+
+int s3d_model_create(s3d_model** out, const s3d_tensor* tensors, int32_t n_tensors, int32_t n_slices, int32_t device,
+                     void* stream) {
+  if (!out || !tensors || n_tensors <= 0 || n_slices < 1 || n_slices > 12) {
+    set_error("model_create: bad argument (n_slices must be 1..12)");
+    return S3D_ERR_BAD_ARG;
+  }
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    set_error("model_create: no CUDA device; slice3d_b200 has no CPU path");
+    return S3D_ERR_CUDA;
+  }
+  S3D_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  S3D_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) {
+    set_error("model_create: this library is built for sm_100a (B200) only");
+    return S3D_ERR_UNSUPPORTED;
+  }
+  s3d_model* m = new s3d_model();
+  m->device = device;
+  m->K = n_slices;
+  Packer pk{m, {}, static_cast<cudaStream_t>(stream), ""};
+  for (int i = 0; i < n_tensors; ++i)
+    if (tensors[i].name) pk.by_name[tensors[i].name] = &tensors[i];
+  if (!pk.build()) {
+    set_error("model_create: " + pk.err);
+    bool missing = pk.err.rfind("missing", 0) == 0;
+    s3d_model_destroy(m);
+    return missing ? S3D_ERR_MISSING_TENSOR : S3D_ERR_BAD_ARG;
+  }
+  int r = dectc_pack(m, static_cast<cudaStream_t>(stream));
+  if (r != S3D_OK) {
+    s3d_model_destroy(m);
+    return r;
+  }
+  *out = m;
+  return S3D_OK;
+}
+
+void s3d_model_destroy(s3d_model* m) {
+  if (!m) return;
+  for (void* p : m->allocs) cudaFree(p);
+  delete m;
+}
+
+int s3d_model_n_slices(const s3d_model* m) { return m ? m->K : 0; }
+
+size_t s3d_planes_bytes(int32_t B, int32_t K, int32_t S) {
+  if (B <= 0 || K <= 0 || S <= 0) return 0;
+  return (size_t)B * plane_offset_floats(K, S, 5) * sizeof(float);
+}
+
+size_t s3d_encoder_workspace_bytes(int32_t B, int32_t K, int32_t S) {
+  if (B <= 0 || K <= 0 || S <= 0) return 0;
+  return encoder_workspace_bytes(B, K, S);
+}
+
+int s3d_encoder_fwd(const s3d_model* m, const float* img_dev, int32_t B, int32_t S, void* planes_dev,
+                    float* const* feats_nchw_dev, float* slices_rec_dev, void* workspace_dev, size_t workspace_bytes,
+                    void* stream) {
+  if (!m || !img_dev) {
+    set_error("encoder: null model or image");
+    return S3D_ERR_BAD_ARG;
+  }
+  return encoder_fwd(m, img_dev, B, S, planes_dev, feats_nchw_dev, slices_rec_dev, workspace_dev, workspace_bytes,
+                     static_cast<cudaStream_t>(stream));
+}
+
+size_t s3d_decoder_workspace_bytes(int64_t n, int32_t precision) {
+  if (precision == S3D_PREC_FP32) return decoder_simt_workspace_bytes(n);
+  return decoder_tc_workspace_bytes(n);
+}
+
+int s3d_decoder_fwd(const s3d_model* m, const void* planes_dev, int32_t S, float* qry_dev, int64_t n,
+                    const float* T_dev, const float* rot_dev, int32_t flip_in_place, float out_scale, float* out_dev,
+                    int32_t precision, void* workspace_dev, size_t workspace_bytes, void* stream) {
+  if (!qry_dev) {
+    set_error("decoder: null query pointer");
+    return S3D_ERR_BAD_ARG;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  QueryCtx q{};
+  q.qry = qry_dev;
+  q.T = T_dev;
+  q.rot = rot_dev;
+  if (!rot_dev && flip_in_place && n > 0) {
+    k_flip_yz<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(qry_dev, n);
+    S3D_LAUNCH_CHECK();
+    q.preflipped = 1;
+  }
+  return run_decoder(m, planes_dev, S, q, n, out_scale, out_dev, precision, nullptr, workspace_dev, workspace_bytes, st);
+}
+
+int s3d_decoder_grid_fwd(const s3d_model* m, const void* planes_dev, int32_t S, const s3d_grid* grid, int64_t first,
+                         int64_t count, const float* T_dev, float out_scale, float* out_dev, int32_t precision,
+                         void* workspace_dev, size_t workspace_bytes, void* stream) {
+  if (!grid || !grid->px_dev || !grid->py_dev || !grid->pz_dev || grid->nx <= 0 || grid->ny <= 0 || grid->nz <= 0 ||
+      first < 0 || count < 0 || first + count > (int64_t)grid->nx * grid->ny * grid->nz) {
+    set_error("decoder_grid: bad grid descriptor or range");
+    return S3D_ERR_BAD_ARG;
+  }
+  QueryCtx q{};
+  q.nx = grid->nx; q.ny = grid->ny; q.nz = grid->nz;
+  q.px = grid->px_dev; q.py = grid->py_dev; q.pz = grid->pz_dev;
+  q.first = first;
+  q.T = T_dev;
+  return run_decoder(m, planes_dev, S, q, count, out_scale, out_dev, precision, nullptr, workspace_dev,
+                     workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+
+int s3d_decoder_debug_tokens(const s3d_model* m, const void* planes_dev, int32_t S, const float* qry_dev, int64_t n,
+                             const float* T_dev, const float* rot_dev, float* out_dev, float* tokens_dev,
+                             void* workspace_dev, size_t workspace_bytes, void* stream) {
+  if (!qry_dev || !tokens_dev) {
+    set_error("decoder_debug: null pointer");
+    return S3D_ERR_BAD_ARG;
+  }
+  QueryCtx q{};
+  q.qry = qry_dev;
+  q.T = T_dev;
+  q.rot = rot_dev;
+  return run_decoder(m, planes_dev, S, q, n, 1.f, out_dev, S3D_PREC_FP32, tokens_dev, workspace_dev, workspace_bytes,
+                     static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

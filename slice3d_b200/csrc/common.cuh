@@ -4,9 +4,9 @@
 #include <cuda_bf16.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <atomic>
 #include <string>
 #include <vector>
-#include <atomic>
 
 #include "../../include/slice3d_b200.h"
 
@@ -35,38 +35,49 @@ extern std::atomic<long long> g_launches;
     }                                                                                   \
   } while (0)
 
+#define S3D_TRY(expr)                                                                   \
+  do {                                                                                  \
+    int _r = (expr);                                                                    \
+    if (_r != S3D_OK) return _r;                                                        \
+  } while (0)
+
 // ---- model ------------------------------------------------------------------
-// A convolution lowered to an implicit GEMM: w is [ks*ks*cin][ncols] fp32 (ncols
-// contiguous); epilogue v = acc*scale[col] + shift[col] (scale may be null = 1).
+// A convolution / linear layer lowered to an implicit GEMM: w is [kpad][ncols] fp32
+// (ncols contiguous, rows >= k zero); epilogue v = acc*scale[col] + shift[col]
+// (scale null = 1, shift null = 0).
 struct ConvW {
   float* w = nullptr;
   float* scale = nullptr;
   float* shift = nullptr;
-  int cin = 0, ncols = 0, ks = 1;
+  int cin = 0;    // input channels as stored in the NHWC activation (after padding to 4)
+  int ncols = 0;  // GEMM N
+  int ks = 1;     // 1 or 3
+  int k = 0, kpad = 0;
 };
 
 struct DecLayerF32 {
-  const float *in_wt, *in_b;    // [128][384], [384]
-  const float *out_wt, *out_b;  // [128][128], [128]
-  const float *l1_wt, *l1_b;    // [128][2048], [2048]
-  const float *l2_wt, *l2_b;    // [2048][128], [128]
-  const float *n1_w, *n1_b, *n2_w, *n2_b;
+  ConvW in_proj;   // 128 -> 384, shift = in_proj_bias
+  ConvW out_proj;  // 128 -> 128
+  ConvW lin1;      // 128 -> 2048
+  ConvW lin2;      // 2048 -> 128
+  float *n1_w = nullptr, *n1_b = nullptr, *n2_w = nullptr, *n2_b = nullptr;
 };
 
 struct DecF32 {
-  const float* fcp_wt;  // [3][128]
-  const float* fcp_b;   // [128]
-  const float* fcs_b;   // [128]
+  float* fcp_wt = nullptr;  // [3][128]
+  float* fcp_b = nullptr;   // [128]
+  float* fcs_b = nullptr;   // [128]
   DecLayerF32 L[3];
-  const float* fco_w;   // [128]
-  const float* fco_b;   // [1]
+  float* fco_w = nullptr;   // [128]
+  float* fco_b = nullptr;   // [1]
 };
 
-// tcgen05 decoder weights: bf16 hi/lo "shared-memory images" (128B-swizzled K-major
-// tiles, see decoder_tc.cu) plus fp32 bias / LayerNorm vectors.
+// tcgen05 decoder weights (decoder_tc.cu): bf16 hi/lo operand images in the canonical
+// K-major 128B-swizzled shared-memory layout, plus packed fp32 vectors.
 struct DecTC {
-  const __nv_bfloat16* wimg = nullptr;  // all tiles, hi then lo per tile
-  const float* vec = nullptr;           // packed fp32 vectors
+  __nv_bfloat16* wimg = nullptr;
+  float* vec = nullptr;
+  size_t wimg_elems = 0;
 };
 
 }  // namespace s3d
@@ -74,18 +85,18 @@ struct DecTC {
 struct s3d_model {
   int device = 0;
   int K = 12;
-  // encoder
-  s3d::ConvW vgg[13];
-  float* bn_scale[4] = {nullptr, nullptr, nullptr, nullptr};  // block-leading BNs (idx 4, 11, 21, 31)
-  float* bn_shift[4] = {nullptr, nullptr, nullptr, nullptr};
-  s3d::ConvW trans_c;        // 512 -> 512 part acting on x5
+  // encoder (all BatchNorms are eval-mode and folded)
+  s3d::ConvW vgg[13];          // conv idx 0,3 | 7,10 | 14,17,20 | 24,27,30 | 34,37,40
+  float* bn_scale[4] = {};     // block-leading BNs (features idx 4, 11, 21, 31) applied to the raw taps
+  float* bn_shift[4] = {};
+  s3d::ConvW trans_c;          // 512 -> 512 part acting on x5 (no bias)
   float* trans_c_e = nullptr;  // [K][512] = W[:,512:] . emb_k + bias
-  s3d::ConvW up_t[4];        // ConvTranspose2d as [cin][4*cout]
-  s3d::ConvW dc1[4], dc2[4];
-  s3d::ConvW trans_up[4];
-  float* outc_w = nullptr;   // [3][32]
-  float* outc_b = nullptr;
-  s3d::ConvW fcs[5];         // fc_s hoisted per scale: [C_s][128]
+  s3d::ConvW up_t[4];          // ConvTranspose2d as [cin][4*cout]; shift = bias[cout]
+  s3d::ConvW dc1[4], dc2[4];   // DoubleConv (BN folded, ReLU)
+  s3d::ConvW trans_up[4];      // 1x1 skip adapters
+  float* outc_w = nullptr;     // [3][32]
+  float* outc_b = nullptr;     // [3]
+  s3d::ConvW fcs[5];           // fc_s hoisted per scale: [C_s][128], no bias
   // decoder
   s3d::DecF32 dec32;
   s3d::DecTC dectc;
@@ -94,30 +105,27 @@ struct s3d_model {
 
 namespace s3d {
 
-static inline int plane_res(int S, int s) { return (S / 16) << s; }
+__host__ __device__ static inline int plane_res(int S, int s) { return (S / 16) << s; }
 static const int kPlaneC[5] = {512, 256, 128, 64, 32};
+
+// Offset (in floats) of scale s inside one image's projected-plane blob: per scale
+// (K, R_s, R_s, 128) fp32 channels-last.
+static inline size_t plane_offset_floats(int K, int S, int s) {
+  size_t o = 0;
+  for (int i = 0; i < s; ++i) o += (size_t)K * plane_res(S, i) * plane_res(S, i) * 128;
+  return o;
+}
 
 // encoder.cu
 int encoder_fwd(const s3d_model* m, const float* img, int B, int S, void* planes, float* const* feats_nchw,
                 float* slices_rec, void* ws, size_t ws_bytes, cudaStream_t st);
 size_t encoder_workspace_bytes(int B, int K, int S);
 
-// decoder_simt.cu
-int decoder_simt(const s3d_model* m, const float* planes, int S, float* qry, const s3d_grid* grid, int64_t first,
-                 int64_t n, const float* T, const float* rot, int flip_in_place, float out_scale, float* out,
-                 cudaStream_t st);
-
-// decoder_tc.cu
-int dectc_pack(s3d_model* m, const DecF32& src, cudaStream_t st);
-size_t dectc_workspace_bytes(int64_t n);
-int decoder_tc(const s3d_model* m, const float* planes, int S, float* qry, const s3d_grid* grid, int64_t first,
-               int64_t n, const float* T, const float* rot, int flip_in_place, float out_scale, float* out,
-               int precision, void* ws, size_t ws_bytes, cudaStream_t st);
-
-// ---- device helpers shared by the decoders ---------------------------------------
+// ---- queries ----------------------------------------------------------------------
 struct QueryCtx {
   const float* qry;     // explicit points (n,3) or null
-  float* qry_rw;        // same pointer when flip_in_place, else null
+  int preflipped;       // 1: explicit points already carry the test-mode y,z flip (api.cu flips the
+                        // caller's tensor in place first, reproducing models.py:55's side effect)
   int nx, ny, nz;       // grid (when qry == null)
   const float *px, *py, *pz;
   long long first;
@@ -125,9 +133,20 @@ struct QueryCtx {
   const float* rot;     // (3,3) or null
 };
 
+// decoder_simt.cu
+size_t decoder_simt_workspace_bytes(int64_t n);
+int decoder_simt(const s3d_model* m, const float* planes, int S, const QueryCtx& q, int64_t n, float out_scale,
+                 float* out, float* debug_tokens, void* ws, size_t ws_bytes, cudaStream_t st);
+
+// decoder_tc.cu
+int dectc_pack(s3d_model* m, cudaStream_t st);
+size_t decoder_tc_workspace_bytes(int64_t n);
+int decoder_tc(const s3d_model* m, const float* planes, int S, const QueryCtx& q, int64_t n, float out_scale,
+               float* out, int precision, void* ws, size_t ws_bytes, cudaStream_t st);
+
 #ifdef __CUDACC__
 // Query i -> model-space point (after the test-mode y,z flip or the train-mode rotation)
-// and the clamped grid_sample coordinates (models.py:53-60, 28-36).
+// and the clamped grid_sample coordinates (reference models.py:53-60, 28-36).
 __device__ __forceinline__ void load_query(const QueryCtx& c, long long i, float& x, float& y, float& z, float& gu,
                                            float& gv) {
   if (c.qry) {
@@ -145,12 +164,12 @@ __device__ __forceinline__ void load_query(const QueryCtx& c, long long i, float
     z = c.pz[iz];
   }
   if (c.rot) {
-    const float* R = c.rot;
-    float rx = x * R[0] + y * R[3] + z * R[6];
-    float ry = x * R[1] + y * R[4] + z * R[7];
-    float rz = x * R[2] + y * R[5] + z * R[8];
+    const float* R = c.rot;  // qry_rot = qry (1x3) . R (3x3)
+    float rx = __fmaf_rn(z, R[6], __fmaf_rn(y, R[3], __fmul_rn(x, R[0])));
+    float ry = __fmaf_rn(z, R[7], __fmaf_rn(y, R[4], __fmul_rn(x, R[1])));
+    float rz = __fmaf_rn(z, R[8], __fmaf_rn(y, R[5], __fmul_rn(x, R[2])));
     x = rx; y = ry; z = rz;
-  } else {
+  } else if (!c.preflipped) {
     y = -y;
     z = -z;
   }
@@ -162,18 +181,20 @@ __device__ __forceinline__ void load_query(const QueryCtx& c, long long i, float
   gv = fminf(fmaxf(2.f * (pv / pw - 0.5f), -1.f), 1.f);
 }
 
-// grid_sample(bilinear, zeros, align_corners=True) tap set for one plane resolution R.
+// grid_sample(bilinear, zeros, align_corners=True) tap set for one plane resolution R
+// (reference models.py:45).  Coordinates are clamped to [-1,1] so every tap with a
+// non-zero weight is in bounds; out-of-range neighbours get weight 0 and a clamped offset.
 struct Taps {
-  int o00, o01, o10, o11;  // pixel offsets (y*R + x) of the four taps (clamped in-bounds)
+  int o00, o01, o10, o11;  // pixel offsets (y*R + x)
   float w00, w01, w10, w11;
 };
 __device__ __forceinline__ Taps make_taps(float gu, float gv, int R) {
-  float ix = ((gu + 1.f) / 2.f) * (float)(R - 1);
-  float iy = ((gv + 1.f) / 2.f) * (float)(R - 1);
+  float ix = ((gu + 1.f) * 0.5f) * (float)(R - 1);
+  float iy = ((gv + 1.f) * 0.5f) * (float)(R - 1);
   float fx = floorf(ix), fy = floorf(iy);
   int x0 = (int)fx, y0 = (int)fy;
   float ax = ix - fx, ay = iy - fy;  // weight of the +1 neighbours
-  float bx = (fx + 1.f) - ix, by = (fy + 1.f) - iy;
+  float bx = (fx + 1.f) - ix, by = (fy + 1.f) - iy;  // ATen: (ix_se - ix), (iy_se - iy)
   Taps t;
   bool x0ok = (x0 >= 0) && (x0 < R), x1ok = (x0 + 1 >= 0) && (x0 + 1 < R);
   bool y0ok = (y0 >= 0) && (y0 < R), y1ok = (y0 + 1 >= 0) && (y0 + 1 < R);

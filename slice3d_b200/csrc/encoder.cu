@@ -1,0 +1,275 @@
+// Plane encoder: the reference's slice generator (reg_slices/src/unet_custom.py:40-69,
+// reg_slices/src/unet_parts.py) in eval mode, NHWC fp32, every convolution an implicit GEMM
+// (gemm_simt.cuh), BatchNorm folded into the GEMM epilogue, plus the hoisted fc_s projection
+// (reg_slices/src/models.py:80) that turns the five feature planes into five 128-channel
+// channels-last planes the decoder samples directly.
+//
+// Work the reference repeats 12x (the 1x1 skip adapters trans_up1..4 and the trans_c
+// contribution of x5 run on the slice-tiled batch, unet_custom.py:57-66) is done once per
+// input view here; the results are identical because those operands do not depend on the slice.
+#include "gemm_simt.cuh"
+
+namespace s3d {
+
+namespace {
+
+__global__ void k_nchw3_to_nhwc4(const float* __restrict__ in, float* __restrict__ out, int B, int HW) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)B * HW) return;
+  int b = (int)(i / HW), p = (int)(i % HW);
+  const float* s = in + (size_t)b * 3 * HW + p;
+  *reinterpret_cast<float4*>(out + i * 4) = make_float4(s[0], s[HW], s[2 * HW], 0.f);
+}
+
+// y = maxpool2x2(relu(x*scale + shift)) on NHWC; C % 4 == 0.
+__global__ void k_bn_relu_pool(const float* __restrict__ in, float* __restrict__ out, const float* __restrict__ scale,
+                               const float* __restrict__ shift, int B, int H, int W, int C) {
+  const int Ho = H / 2, Wo = W / 2, C4 = C / 4;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long total = (long long)B * Ho * Wo * C4;
+  if (i >= total) return;
+  int c = (int)(i % C4) * 4;
+  long long t = i / C4;
+  int xo = (int)(t % Wo);
+  t /= Wo;
+  int yo = (int)(t % Ho);
+  int b = (int)(t / Ho);
+  float4 sc = *reinterpret_cast<const float4*>(scale + c);
+  float4 sh = *reinterpret_cast<const float4*>(shift + c);
+  float4 m = make_float4(0.f, 0.f, 0.f, 0.f);  // relu output >= 0
+#pragma unroll
+  for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+    for (int dx = 0; dx < 2; ++dx) {
+      float4 v = *reinterpret_cast<const float4*>(in + (((size_t)b * H + 2 * yo + dy) * W + 2 * xo + dx) * C + c);
+      m.x = fmaxf(m.x, fmaf(v.x, sc.x, sh.x));
+      m.y = fmaxf(m.y, fmaf(v.y, sc.y, sh.y));
+      m.z = fmaxf(m.z, fmaf(v.z, sc.z, sh.z));
+      m.w = fmaxf(m.w, fmaf(v.w, sc.w, sh.w));
+    }
+  *reinterpret_cast<float4*>(out + (((size_t)b * Ho + yo) * Wo + xo) * C + c) = m;
+}
+
+// latent[b,k,p,:] = base[b,p,:] + e[k,:]   (trans_c split into its x5 part and its slice-embedding part)
+__global__ void k_add_slice_bias(const float* __restrict__ base, const float* __restrict__ e, float* __restrict__ out,
+                                 int B, int K, int HW, int C) {
+  const int C4 = C / 4;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long total = (long long)B * K * HW * C4;
+  if (i >= total) return;
+  int c = (int)(i % C4) * 4;
+  long long t = i / C4;
+  int p = (int)(t % HW);
+  t /= HW;
+  int k = (int)(t % K);
+  int b = (int)(t / K);
+  float4 a = *reinterpret_cast<const float4*>(base + ((size_t)b * HW + p) * C + c);
+  float4 v = *reinterpret_cast<const float4*>(e + (size_t)k * C + c);
+  *reinterpret_cast<float4*>(out + i * 4) = make_float4(a.x + v.x, a.y + v.y, a.z + v.z, a.w + v.w);
+}
+
+// slices_rec = tanh(conv1x1 32->3) written NCHW (unet_parts.py:78-84).
+__global__ void k_outc_tanh(const float* __restrict__ f, const float* __restrict__ w, const float* __restrict__ b,
+                            float* __restrict__ out, long long NI, int HW) {
+  __shared__ float sw[3 * 32 + 3];
+  if (threadIdx.x < 99) sw[threadIdx.x] = threadIdx.x < 96 ? w[threadIdx.x] : b[threadIdx.x - 96];
+  __syncthreads();
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= NI * HW) return;
+  long long img = i / HW;
+  int p = (int)(i % HW);
+  const float4* src = reinterpret_cast<const float4*>(f + i * 32);
+  float a0 = sw[96], a1 = sw[97], a2 = sw[98];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    float4 v = __ldg(src + q);
+    const float* w0 = sw + q * 4;
+    a0 += v.x * w0[0] + v.y * w0[1] + v.z * w0[2] + v.w * w0[3];
+    a1 += v.x * w0[32] + v.y * w0[33] + v.z * w0[34] + v.w * w0[35];
+    a2 += v.x * w0[64] + v.y * w0[65] + v.z * w0[66] + v.w * w0[67];
+  }
+  float* o = out + (size_t)img * 3 * HW + p;
+  o[0] = tanhf(a0);
+  o[HW] = tanhf(a1);
+  o[2 * HW] = tanhf(a2);
+}
+
+// NHWC -> NCHW export of a feature plane (parity tests / callers that want the raw planes).
+__global__ void k_nhwc_to_nchw(const float* __restrict__ in, float* __restrict__ out, int HW, int C) {
+  __shared__ float tile[32][33];
+  int img = blockIdx.z;
+  int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const float* src = in + (size_t)img * HW * C;
+  float* dst = out + (size_t)img * HW * C;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    int p = p0 + j, c = c0 + threadIdx.x;
+    if (p < HW && c < C) tile[j][threadIdx.x] = src[(size_t)p * C + c];
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    int c = c0 + j, p = p0 + threadIdx.x;
+    if (p < HW && c < C) dst[(size_t)c * HW + p] = tile[threadIdx.x][j];
+  }
+}
+
+struct Bump {
+  char* base;
+  size_t off = 0, cap;
+  float* take(size_t floats) {
+    size_t o = off;
+    off += ((floats * sizeof(float) + 255) / 256) * 256;
+    return base ? reinterpret_cast<float*>(base + o) : nullptr;
+  }
+};
+
+struct EncBufs {
+  float *x0, *ta, *tb, *x[6], *base5, *skip[5], *feat[5], *u, *d;
+};
+
+// The single place that lays out the encoder workspace; called with base == nullptr to size it.
+void carve(Bump& bp, EncBufs& e, int B, int K, int S) {
+  const size_t S2 = (size_t)S * S;
+  e.x0 = bp.take(B * S2 * 4);
+  e.ta = bp.take(B * S2 * 64);
+  e.tb = bp.take(B * S2 * 64);
+  const int xc[6] = {0, 64, 128, 256, 512, 512};
+  for (int i = 1; i <= 5; ++i) e.x[i] = bp.take(B * (S2 >> (2 * (i - 1))) * xc[i]);
+  const int R0 = S / 16;
+  e.base5 = bp.take((size_t)B * R0 * R0 * 512);
+  for (int n = 1; n <= 4; ++n) e.skip[n] = bp.take((size_t)B * plane_res(S, n) * plane_res(S, n) * kPlaneC[n]);
+  for (int s = 0; s < 5; ++s) e.feat[s] = bp.take((size_t)B * K * plane_res(S, s) * plane_res(S, s) * kPlaneC[s]);
+  e.u = bp.take((size_t)B * K * S2 * 32);
+  e.d = bp.take((size_t)B * K * S2 * 32);
+}
+
+int conv(const ConvW& w, const float* src0, int c0, int bcast0, const float* src1, int c1, int NI, int H, int W,
+         float* out, int relu, cudaStream_t st) {
+  LoadConv L{src0, src1, NI * H * W, w.k, H, W, c0, c1, bcast0, w.ks};
+  EpiAffine E{out, w.scale, w.shift, w.ncols, relu};
+  return launch_gemm(L, w.w, w.ncols, w.kpad, E, st);
+}
+
+int dense(const ConvW& w, const float* a, long long M, float* out, int relu, cudaStream_t st) {
+  LoadPlain L{a, (int)M, w.k, w.k};
+  EpiAffine E{out, w.scale, w.shift, w.ncols, relu};
+  return launch_gemm(L, w.w, w.ncols, w.kpad, E, st);
+}
+
+inline unsigned blocks_for(long long n, int t) { return (unsigned)((n + t - 1) / t); }
+
+}  // namespace
+
+size_t encoder_workspace_bytes(int B, int K, int S) {
+  Bump bp{nullptr, 0, 0};
+  EncBufs e;
+  carve(bp, e, B, K, S);
+  return bp.off;
+}
+
+int encoder_fwd(const s3d_model* m, const float* img, int B, int S, void* planes, float* const* feats_nchw,
+                float* slices_rec, void* ws, size_t ws_bytes, cudaStream_t st) {
+  const int K = m->K;
+  if (B <= 0 || S < 32 || (S % 16) != 0) {
+    set_error("encoder: S must be a multiple of 16 (>= 32) and B positive");
+    return S3D_ERR_BAD_ARG;
+  }
+  if ((long long)B * K * S * S >= (1ll << 31) / 4) {
+    set_error("encoder: B*K*S*S too large for 32-bit row indexing");
+    return S3D_ERR_UNSUPPORTED;
+  }
+  if (ws == nullptr || ws_bytes < encoder_workspace_bytes(B, K, S)) {
+    set_error("encoder: workspace too small");
+    return S3D_ERR_WORKSPACE;
+  }
+  Bump bp{static_cast<char*>(ws), 0, ws_bytes};
+  EncBufs e;
+  carve(bp, e, B, K, S);
+
+  // ---- VGG16-BN trunk on the input view (unet_custom.py:42-48); taps x1..x5 are the
+  //      pre-BN outputs of the last convolution of each block (unet_custom.py:15-19).
+  k_nchw3_to_nhwc4<<<blocks_for((long long)B * S * S, 256), 256, 0, st>>>(img, e.x0, B, S * S);
+  S3D_LAUNCH_CHECK();
+  int H = S;
+  // down1
+  S3D_TRY(conv(m->vgg[0], e.x0, 4, 1, nullptr, 0, B, H, H, e.ta, 1, st));
+  S3D_TRY(conv(m->vgg[1], e.ta, 64, 1, nullptr, 0, B, H, H, e.x[1], 0, st));
+  // down2..down5: BN+ReLU+pool on the previous tap, then 2 or 3 convolutions
+  const int first_conv[4] = {2, 4, 7, 10};
+  const int n_conv[4] = {2, 3, 3, 3};
+  const int cprev[4] = {64, 128, 256, 512};
+  for (int b = 0; b < 4; ++b) {
+    long long tot = (long long)B * (H / 2) * (H / 2) * (cprev[b] / 4);
+    k_bn_relu_pool<<<blocks_for(tot, 256), 256, 0, st>>>(e.x[b + 1], e.ta, m->bn_scale[b], m->bn_shift[b], B, H, H,
+                                                         cprev[b]);
+    S3D_LAUNCH_CHECK();
+    H /= 2;
+    float* cur = e.ta;
+    float* nxt = e.tb;
+    int cin = cprev[b];
+    for (int j = 0; j < n_conv[b]; ++j) {
+      const ConvW& w = m->vgg[first_conv[b] + j];
+      bool last = (j == n_conv[b] - 1);
+      float* dst = last ? e.x[b + 2] : nxt;
+      S3D_TRY(conv(w, cur, cin, 1, nullptr, 0, B, H, H, dst, last ? 0 : 1, st));
+      cin = w.ncols;
+      if (!last) {
+        float* t = cur;
+        cur = nxt;
+        nxt = t;
+      }
+    }
+  }
+  // ---- latent = trans_c(cat[x5 tiled, slice embedding]) (unet_custom.py:52-57) -> feat[0]
+  const int R0 = S / 16;
+  S3D_TRY(dense(m->trans_c, e.x[5], (long long)B * R0 * R0, e.base5, 0, st));
+  {
+    long long tot = (long long)B * K * R0 * R0 * (512 / 4);
+    k_add_slice_bias<<<blocks_for(tot, 256), 256, 0, st>>>(e.base5, m->trans_c_e, e.feat[0], B, K, R0 * R0, 512);
+    S3D_LAUNCH_CHECK();
+  }
+  // ---- four Up stages (unet_custom.py:60-66, unet_parts.py:57-75)
+  for (int n = 1; n <= 4; ++n) {
+    const int Rp = plane_res(S, n - 1), R = plane_res(S, n), C = kPlaneC[n];
+    // skip adapter on the un-tiled tap x_{5-n}
+    S3D_TRY(dense(m->trans_up[n - 1], e.x[5 - n], (long long)B * R * R, e.skip[n], 0, st));
+    // ConvTranspose2d 2x2 s2: GEMM with N = 4*C + pixel shuffle
+    {
+      const ConvW& w = m->up_t[n - 1];
+      LoadPlain L{e.feat[n - 1], B * K * Rp * Rp, w.k, w.k};
+      EpiShuffle2x E{e.u, w.shift, Rp, Rp, C};
+      S3D_TRY(launch_gemm(L, w.w, w.ncols, w.kpad, E, st));
+    }
+    // DoubleConv on cat([skip, up]) (skip first: unet_parts.py:73)
+    S3D_TRY(conv(m->dc1[n - 1], e.skip[n], C, K, e.u, C, B * K, R, R, e.d, 1, st));
+    S3D_TRY(conv(m->dc2[n - 1], e.d, C, 1, nullptr, 0, B * K, R, R, e.feat[n], 1, st));
+  }
+  // ---- outputs
+  if (slices_rec) {
+    long long tot = (long long)B * K * S * S;
+    k_outc_tanh<<<blocks_for(tot, 256), 256, 0, st>>>(e.feat[4], m->outc_w, m->outc_b, slices_rec, (long long)B * K,
+                                                      S * S);
+    S3D_LAUNCH_CHECK();
+  }
+  if (planes) {
+    float* pl = static_cast<float*>(planes);
+    const size_t per_img = s3d_planes_bytes(1, K, S) / sizeof(float);
+    for (int b = 0; b < B; ++b)
+      for (int s = 0; s < 5; ++s) {
+        const int R = plane_res(S, s);
+        const float* src = e.feat[s] + (size_t)b * K * R * R * kPlaneC[s];
+        S3D_TRY(dense(m->fcs[s], src, (long long)K * R * R, pl + b * per_img + plane_offset_floats(K, S, s), 0, st));
+      }
+  }
+  if (feats_nchw) {
+    for (int s = 0; s < 5; ++s) {
+      if (!feats_nchw[s]) continue;
+      const int R = plane_res(S, s), C = kPlaneC[s];
+      dim3 grid((R * R + 31) / 32, (C + 31) / 32, B * K), blk(32, 8);
+      k_nhwc_to_nchw<<<grid, blk, 0, st>>>(e.feat[s], feats_nchw[s], R * R, C);
+      S3D_LAUNCH_CHECK();
+    }
+  }
+  return S3D_OK;
+}
+
+}  // namespace s3d

@@ -1,0 +1,52 @@
+"""Multi-GPU sharding of the dense query grid (one process per GPU).
+
+Queries are independent given the planes, so the (nx,ny,nz) value volume is split into
+contiguous slabs along axis 0 -- the slowest axis of ``make_3d_grid`` (reference:
+reg_slices/src_convonet/common.py:159-162) -- which makes every rank's result one contiguous
+range of the flat volume.  Each rank runs the (cheap) encoder redundantly; the only exchange
+is one all-gather of the slabs (NCCL on GPUs, gloo in the CPU tests).
+"""
+import torch
+import torch.distributed as dist
+
+
+def rank_world(group=None):
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(group), dist.get_world_size(group)
+    return 0, 1
+
+
+def slab_bounds(nx, world):
+    """Axis-0 boundaries [b_0=0, ..., b_world=nx]; the first nx % world ranks get one extra plane."""
+    base, rem = divmod(nx, world)
+    b = [0]
+    for r in range(world):
+        b.append(b[-1] + base + (1 if r < rem else 0))
+    return b
+
+
+def slab_range(nx, rank, world):
+    b = slab_bounds(nx, world)
+    return b[rank], b[rank + 1]
+
+
+def all_gather_slabs(vol_flat, nx, group=None):
+    """In place: every rank has filled its own slab of ``vol_flat`` (nx^3 values, flat);
+    afterwards every rank holds the whole volume."""
+    rank, world = rank_world(group)
+    if world == 1:
+        return vol_flat
+    plane = vol_flat.numel() // nx
+    b = slab_bounds(nx, world)
+    if nx % world == 0:
+        lo, hi = b[rank], b[rank + 1]
+        # equal slabs: a single in-place all-gather straight into the volume
+        dist.all_gather_into_tensor(vol_flat, vol_flat[lo * plane:hi * plane].clone(), group=group)
+    else:
+        outs = [vol_flat[b[r] * plane:b[r + 1] * plane] for r in range(world)]
+        if hasattr(dist, "all_gather") and all(o.numel() == outs[0].numel() for o in outs):
+            dist.all_gather(outs, outs[rank].clone(), group=group)
+        else:
+            for r in range(world):  # ragged slabs: one broadcast per owner
+                dist.broadcast(outs[r], src=dist.get_global_rank(group, r) if group is not None else r, group=group)
+    return vol_flat

@@ -1,0 +1,132 @@
+"""``Generator3D`` -- the dense-grid query driver of the reference's ``reconstruct.py``
+(reference: reg_slices/reconstruct.py:19-173), B200-native.
+
+* ``eval_points(data)`` keeps the reference semantics (chunk the queries, call
+  ``model(data_chunk)``, negate ``sdf_pred``, concatenate; reconstruct.py:74-102).  The model
+  caches the encoder output per input view, so the chunk loop no longer re-runs the U-Net.
+* ``generate_grid(data)`` is the ``upsampling_steps == 0`` branch of ``generate_from_latent``
+  (reconstruct.py:135-146): a dense ``make_3d_grid`` evaluated without ever materialising the
+  (nx^3, 3) point tensor -- the CUDA decoder derives each point from its flat index and the
+  three per-axis ``torch.linspace`` vectors, which reproduces ``make_3d_grid`` bit for bit.
+  With ``torch.distributed`` initialised the grid is split into contiguous axis-0 slabs, one
+  per rank, and reassembled with a single all-gather (``slice3d_b200.dist``).
+
+Mesh extraction (marching cubes, reconstruct.py:175-243) and the MISE octree branch
+(reconstruct.py:147-167) are outside the hot path.
+"""
+import math
+
+import numpy as np
+import torch
+
+from . import dist as s3d_dist
+from .synth import make_3d_grid  # noqa: F401  (re-exported: reference src_convonet/common.py:145)
+
+
+class Generator3D(object):
+    def __init__(self, model, points_batch_size=100000, threshold=0.5, refinement_step=0, device=None,
+                 resolution0=64, upsampling_steps=2, chunk_size=3000, with_normals=False, padding=0.0, sample=False,
+                 input_type=None, vol_info=None, vol_bound=None, simplify_nfaces=None, pred_type="occ"):
+        self.model = model
+        self.points_batch_size = points_batch_size
+        self.refinement_step = refinement_step
+        self.threshold = threshold
+        self.device = device
+        self.resolution0 = resolution0
+        self.upsampling_steps = upsampling_steps
+        self.with_normals = with_normals
+        self.input_type = input_type
+        self.padding = padding
+        self.sample = sample
+        self.simplify_nfaces = simplify_nfaces
+        self.chunk_size = chunk_size
+        self.pred_type = pred_type
+        self.vol_bound = vol_bound
+        if vol_info is not None:
+            self.input_vol, _, _ = vol_info
+
+    # ------------------------------------------------------------------ reference-shaped API
+    def eval_points(self, data):
+        """reconstruct.py:74-102.  ``data['qry_norot']`` is (1, n_qry, 3); returns (n_qry,)."""
+        n_qry = data["qry_norot"].shape[1]
+        chunk_size = self.chunk_size
+        n_chunk = math.ceil(n_qry / chunk_size)
+        ret = []
+        for idx in range(n_chunk):
+            data_chunk = {}
+            for key in data:
+                if key == "qry_norot":
+                    data_chunk[key] = data[key][:, chunk_size * idx:min(chunk_size * (idx + 1), n_qry), ...]
+                else:
+                    data_chunk[key] = data[key]
+            ret_dict = self.model(data_chunk)
+            if self.pred_type == "occ":
+                # the reference reads a key its model never returns
+                ret.append(ret_dict["occ_pred"])
+            else:
+                ret.append(-ret_dict["sdf_pred"])
+        return torch.cat(ret, -1).squeeze(0)
+
+    def generate_mesh(self, data, return_stats=True):
+        stats_dict = {}
+        mesh = self.generate_from_latent(data, stats_dict=stats_dict)
+        return (mesh, stats_dict) if return_stats else mesh
+
+    def generate_from_latent(self, c=None, stats_dict=None):
+        if self.upsampling_steps != 0:
+            raise NotImplementedError("MISE refinement (reconstruct.py:147-167) is outside the hot path; "
+                                      "use upsampling_steps=0 (dense grid)")
+        value_grid = self.generate_grid(c)
+        return self.extract_mesh(value_grid, c, stats_dict=stats_dict if stats_dict is not None else {})
+
+    def extract_mesh(self, occ_hat, c=None, stats_dict=None):
+        raise NotImplementedError("marching cubes / mesh export (reconstruct.py:175-243) is outside the hot path "
+                                  "(SURVEY.md section 8f-2); generate_grid() returns the value volume")
+
+    # ------------------------------------------------------------------ dense hot path
+    def grid_axes(self, nx, device):
+        box_size = 1 + self.padding
+        # box_size * linspace, exactly as reconstruct.py:137-139 scales make_3d_grid's output
+        ax = box_size * torch.linspace(-0.5, 0.5, nx)
+        return ax.to(device)
+
+    def generate_grid(self, data, resolution=None, precision=None, group=None, as_numpy=True, out_host=None):
+        """Dense ``-sdf_pred`` volume (nx,nx,nx) for one input view.
+
+        ``data`` holds ``img_input`` (1,3,S,S) and ``trans_mat_wo_rot_tp`` (1,4,3) on the host or
+        on the device.  Host tensors are copied to the model's device here and the volume is
+        copied back (into ``out_host`` when given), so timing this call measures the end-to-end
+        path.  Under torch.distributed each rank evaluates one axis-0 slab.
+        """
+        model = self.model
+        nx = int(resolution or self.resolution0)
+        dev = next(model.parameters()).device
+        precision = precision or model.precision
+        img = data["img_input"].to(dev, non_blocking=True)
+        T = data["trans_mat_wo_rot_tp"].to(dev, non_blocking=True)
+        if self.pred_type == "occ":
+            raise KeyError("occ_pred")  # same failure as the reference (reconstruct.py:95)
+        nat = model.native()
+        planes = model.encode(img)
+        ax = self.grid_axes(nx, dev)
+        rank, world = s3d_dist.rank_world(group)
+        lo, hi = s3d_dist.slab_range(nx, rank, world)
+        vol = torch.empty(nx * nx * nx, dtype=torch.float32, device=dev)
+        if hi > lo:
+            first, count = lo * nx * nx, (hi - lo) * nx * nx
+            nat.decode_grid(planes, 0, (ax, ax, ax), first, count, T[0], out_scale=-1.0, precision=precision,
+                            out=vol[first:first + count])
+        if world > 1:
+            s3d_dist.all_gather_slabs(vol, nx, group)
+        vol = vol.view(nx, nx, nx)
+        if not as_numpy and out_host is None:
+            return vol
+        if out_host is None:
+            out_host = torch.empty(nx, nx, nx, dtype=torch.float32, pin_memory=True)
+        out_host.copy_(vol, non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+        return out_host.numpy() if as_numpy else out_host
+
+    def threshold_logit(self):
+        """reconstruct.py:128."""
+        return np.log(self.threshold) - np.log(1.0 - self.threshold)

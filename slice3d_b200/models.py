@@ -1,0 +1,155 @@
+"""``Slices3DRegModel`` -- drop-in for the reference module of the same name
+(reference: reg_slices/src/models.py:12-94).
+
+Same constructor, same ``forward(feed_dict) -> ret_dict`` contract, same 244-key
+``state_dict`` (so ``train.py`` / ``reconstruct.py`` checkpoints load with ``strict=True``).
+
+Two arithmetic paths:
+
+* **inference** (``model.eval()`` under ``torch.no_grad()``, what ``reconstruct.py`` and
+  ``train.py:val_step`` do): the hand-written CUDA library behind the C ABI
+  (``slice3d_b200._native``).  The U-Net runs once per input view and its planes are cached,
+  instead of once per 3000-point chunk as ``Generator3D.eval_points`` makes the reference do
+  (reference: reg_slices/reconstruct.py:82-93); the values are identical.  There is no CPU or
+  PyTorch fallback for this path: without a CUDA device or the built library it raises.
+* **training** (``model.train()`` or grad enabled): autograd arithmetic written with torch ops
+  (batch-statistics BatchNorm, dropout), used by ``train_step`` (reference: reg_slices/train.py:41-53).
+"""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import _native
+from .perceptual import VGGPerceptualLoss
+from .unet import UNet
+
+DEFAULT_PRECISION = "fp32"
+
+
+class Slices3DRegModel(nn.Module):
+    def __init__(self, img_size=128, n_slices=12, mode="train", precision=None):
+        super().__init__()
+        self.mode = mode
+        self.slices_generator = UNet(n_channels=3, n_slices=n_slices)
+        self.img_size = img_size
+        # registered-but-unused original layer, exactly like the reference (nn.TransformerEncoder
+        # deep-copies it); keeps the 12 ``att_layer.*`` checkpoint keys (models.py:18-19)
+        self.att_layer = nn.TransformerEncoderLayer(d_model=128, nhead=4, batch_first=True)
+        self.att_decoder = nn.TransformerEncoder(self.att_layer, num_layers=3)
+        self.fc_p = nn.Linear(3, 128)
+        self.fc_s = nn.Linear(992, 128)
+        self.fc_out = nn.Sequential(nn.Linear(128, 1))
+        self.vggptlossfunc = VGGPerceptualLoss()
+        self.n_slices = n_slices
+        # --- not part of the reference API ---
+        self.precision = precision or DEFAULT_PRECISION  # decoder arithmetic: fp32 | bf16x3 | bf16
+        self.test_time_vgg_loss = True  # the reference evaluates (and discards) it at test time too
+        self._native_model = None
+        self._native_key = None
+        self._enc_cache = None
+
+    # ------------------------------------------------------------------ native plumbing
+    def _weights_key(self):
+        return tuple((t.data_ptr(), t._version) for t in self.state_dict(keep_vars=True).values())
+
+    def native(self):
+        """The C-ABI model handle for the current weights (rebuilt when any tensor changed)."""
+        dev = self.fc_p.weight.device
+        key = (dev, self._weights_key())
+        if self._native_model is None or self._native_key != key:
+            self._native_model = _native.NativeModel(self.state_dict(), self.n_slices, dev)
+            self._native_key = key
+            self._enc_cache = None
+        return self._native_model
+
+    def encode(self, img_input):
+        """Run the plane encoder once for ``img_input`` (B,3,S,S); cached per tensor object/version."""
+        nat = self.native()
+        c = self._enc_cache
+        if c is not None and c["img"] is img_input and c["ver"] == img_input._version:
+            return c["planes"]
+        planes = nat.encode(img_input)
+        # the cache keeps a reference to the tensor, so its storage cannot be recycled for
+        # another image while the entry is alive
+        self._enc_cache = {"img": img_input, "ver": img_input._version, "planes": planes, "vgg": None}
+        return planes
+
+    def _cached_vgg_loss(self, planes, img_slices):
+        c = self._enc_cache
+        key = (img_slices.data_ptr(), img_slices._version)
+        if c["vgg"] is None or c["vgg"][0] != key:
+            B, K, S = planes.B, planes.K, planes.S
+            tgt = img_slices.view(B, K, 3, S, S).view(B * K, 3, S, S)
+            c["vgg"] = (key, self.vggptlossfunc(planes.slices_rec, tgt)["pt_c_loss"] * 0.001, img_slices)
+        return c["vgg"][1]
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, feed_dict):
+        if self.training or torch.is_grad_enabled():
+            return self._forward_autograd(feed_dict)
+        return self._forward_native(feed_dict)
+
+    def _forward_native(self, feed_dict):
+        img_input = feed_dict["img_input"]
+        if not img_input.is_cuda:
+            raise _native.NativeError("inference needs CUDA tensors: slice3d_b200 has no CPU/PyTorch fallback")
+        n_bs, _, S, _ = img_input.shape
+        K = self.n_slices
+        nat = self.native()
+        planes = self.encode(img_input)
+        qry = feed_dict["qry_norot"]
+        n_qry = qry.shape[1]
+        T = feed_dict["trans_mat_wo_rot_tp"]
+        sdf = torch.empty(n_bs, n_qry, dtype=torch.float32, device=img_input.device)
+        for b in range(n_bs):
+            qb = qry[b]
+            if self.mode == "test":
+                # y,z of the caller's tensor are negated in place, like models.py:55
+                if qb.is_contiguous() and qb.dtype == torch.float32:
+                    nat.decode(planes, b, qb, T[b], None, True, 1.0, self.precision, out=sdf[b])
+                else:
+                    tmp = qb.float().contiguous()
+                    nat.decode(planes, b, tmp, T[b], None, True, 1.0, self.precision, out=sdf[b])
+                    qb.copy_(tmp)
+            else:
+                nat.decode(planes, b, qb.float().contiguous(), T[b], feed_dict["obj_rot_mat"][b], False, 1.0,
+                           self.precision, out=sdf[b])
+        ret = {"sdf_pred": sdf, "slices_rec": planes.slices_rec.view(n_bs, K * 3, S, S)}
+        if self.test_time_vgg_loss and "img_slices" in feed_dict:
+            ret["vgg_loss"] = self._cached_vgg_loss(planes, feed_dict["img_slices"])
+        else:
+            ret["vgg_loss"] = torch.zeros((), dtype=torch.float32, device=img_input.device)
+        return ret
+
+    # ---- training arithmetic (autograd) -------------------------------------------
+    @staticmethod
+    def project_coord(coordinates, trans_mat_wo_rot_tp):
+        """models.py:28-36 (device-agnostic: the reference hard-codes .cuda())."""
+        ones = torch.ones(coordinates.shape[0], coordinates.shape[1], 1, dtype=coordinates.dtype,
+                          device=coordinates.device)
+        pc = torch.bmm(torch.cat((coordinates, ones), dim=-1), trans_mat_wo_rot_tp)
+        uv = pc[:, :, :2] / pc[:, :, 2:]
+        return torch.clamp(2 * (uv - 0.5), min=-1, max=1)
+
+    def _forward_autograd(self, feed_dict):
+        img_input = feed_dict["img_input"]
+        n_bs, _, S, _ = img_input.shape
+        K = self.n_slices
+        qry = feed_dict["qry_norot"]
+        if self.mode == "test":
+            qry[:, :, 1:] *= -1
+        else:
+            qry = torch.bmm(qry, feed_dict["obj_rot_mat"])
+        n_qry = qry.shape[1]
+        feats, slices_rec = self.slices_generator.forward_train(img_input)
+        uv = self.project_coord(qry, feed_dict["trans_mat_wo_rot_tp"])
+        grid = uv.view(n_bs, 1, 1, n_qry, 2).expand(-1, K, -1, -1, -1).reshape(n_bs * K, 1, n_qry, 2)
+        sampled = [F.grid_sample(f, grid, mode="bilinear", padding_mode="zeros", align_corners=True)
+                   .permute(0, 3, 2, 1).reshape(n_bs * K, n_qry, f.shape[1]) for f in feats]
+        agg = torch.cat(sampled, dim=2).view(n_bs, K, n_qry, 992).permute(0, 2, 1, 3).reshape(n_bs * n_qry, K, 992)
+        tok = torch.cat([self.fc_p(qry).view(n_bs * n_qry, 1, 128), self.fc_s(agg)], 1)
+        att = self.att_decoder(tok).view(n_bs, n_qry, K + 1, 128)[:, :, 0, :]
+        ret = {"sdf_pred": self.fc_out(att).squeeze(-1), "slices_rec": slices_rec.view(n_bs, K * 3, S, S)}
+        tgt = feed_dict["img_slices"].view(n_bs, K, 3, S, S).view(n_bs * K, 3, S, S)
+        ret["vgg_loss"] = self.vggptlossfunc(slices_rec, tgt)["pt_c_loss"] * 0.001
+        return ret

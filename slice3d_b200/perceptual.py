@@ -3,8 +3,12 @@
 State-dict layout follows the reference ``VGGPerceptualLoss`` / ``VGG19Feats``
 (reference: reg_slices/src/vgg_perceptual_loss.py:6-71): buffers ``mean``/``std``
 and 28 frozen tensors ``vgg.slice{1..5}.<torchvision idx>.{weight,bias}``.
-The five taps are the *pre-ReLU* outputs of conv1_2, conv2_2, conv3_2, conv4_2,
-conv5_2 (features[0:3], [3:8], [8:13], [13:22], [22:31]).
+The five taps are the outputs of conv1_2, conv2_2, conv3_2, conv4_2, conv5_2
+(features[0:3], [3:8], [8:13], [13:22], [22:31]).  Because torchvision's VGG uses
+``ReLU(inplace=True)`` and every slice but the last is followed by one, taps 1-4 are
+rectified in place by the next slice before the loss reads them (so they are effectively
+post-ReLU) while conv5_2 stays pre-ReLU; the in-place ReLUs are kept here so the
+arithmetic -- and its gradient -- is the reference's.
 
 Not on the inference hot path: the reference evaluates and discards it on every
 test-time chunk (models.py:90-92); here it is evaluated in test mode only when
@@ -25,7 +29,7 @@ def _vgg19_feature_list():
         if v == "M":
             layers.append(nn.MaxPool2d(2, 2))
         else:
-            layers += [nn.Conv2d(cin, v, 3, padding=1), nn.ReLU(inplace=False)]
+            layers += [nn.Conv2d(cin, v, 3, padding=1), nn.ReLU(inplace=True)]
             cin = v
     return layers
 

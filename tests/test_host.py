@@ -1,0 +1,129 @@
+"""CPU-side checks: checkpoint layout, C-ABI exports, autograd (training) arithmetic against
+the reference golden, grid/slab logic, and the world_size-2 gloo path of the slab all-gather."""
+import ctypes
+import json
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+import torch
+
+from slice3d_b200 import Slices3DRegModel, _native, dist as s3d_dist, synth
+from slice3d_b200.generator import Generator3D
+from tests import helpers
+
+ROOT = helpers.ROOT
+
+
+def test_state_dict_layout_matches_reference_manifest():
+    """244 keys, same order/shape/dtype as the reference module (manifest generated from
+    the reference in the build container: SURVEY.md section 8b)."""
+    manifest = json.load(open(os.path.join(helpers.GOLDEN, "state_dict_manifest.json")))
+    sd = Slices3DRegModel(128, 12, "test").state_dict()
+    assert list(sd.keys()) == list(manifest.keys())
+    assert len(sd) == 244
+    for k, (shape, dtype) in manifest.items():
+        assert list(sd[k].shape) == shape and str(sd[k].dtype) == dtype, k
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "slice3d_b200.h")).read()
+    declared = set(re.findall(r"\b(s3d_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(_native.SYMBOLS)
+    lib = ctypes.CDLL(_native.LIB_PATH)
+    for s in declared:
+        assert hasattr(lib, s), s
+    lib.s3d_abi_version.restype = ctypes.c_int
+    assert lib.s3d_abi_version() == _native.ABI_VERSION
+
+
+def test_inference_without_cuda_fails_loudly():
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    m = Slices3DRegModel(128, 12, "test").eval()
+    feed = synth.synthetic_inputs(128)
+    feed["qry_norot"] = torch.zeros(1, 8, 3)
+    with torch.no_grad(), pytest.raises(_native.NativeError):
+        m(feed)
+
+
+def test_autograd_path_matches_reference_val_golden():
+    """Training arithmetic (torch ops) in eval mode == reference forward (rotation branch)."""
+    case = helpers.load_case("k12_s128_val_rot")
+    m, sd = helpers.case_weights(case)
+    m.load_state_dict(sd, strict=True)
+    m.eval()
+    feed = helpers.case_feed(case, batch=2)
+    feed["qry_norot"] = torch.from_numpy(case["qry"]).clone()
+    feed["obj_rot_mat"] = torch.from_numpy(case["obj_rot_mat"])
+    with torch.no_grad():
+        ret = m._forward_autograd(feed)
+    assert helpers.maxabs(ret["sdf_pred"], case["sdf"]) < 2e-5
+    assert helpers.maxabs(ret["vgg_loss"], case["vgg_loss"]) < 1e-6
+    assert helpers.maxabs(ret["slices_rec"][:, :, ::8, ::8], case["slices_rec_sub_b"]) < 2e-5
+
+
+def test_train_step_runs_and_unused_params_get_no_grad():
+    """reg_slices/train.py:41-53 semantics on a tiny batch: loss = L1(sdf)+L1(img)+vgg."""
+    torch.manual_seed(0)
+    m = Slices3DRegModel(32, 12, "train").train()
+    feed = synth.synthetic_inputs(32, batch=2)
+    feed["qry_norot"] = torch.rand(2, 16, 3) - 0.5
+    feed["sdf"] = torch.randn(2, 16) * 0.1
+    opt = torch.optim.Adam(m.parameters(), lr=3e-4)
+    x = m(feed)
+    loss = (torch.nn.functional.l1_loss(x["sdf_pred"], feed["sdf"]) +
+            torch.nn.functional.l1_loss(x["slices_rec"], feed["img_slices"]) + x["vgg_loss"])
+    loss.backward()
+    opt.step()
+    assert torch.isfinite(loss)
+    no_grad = [n for n, p in m.named_parameters() if p.requires_grad and p.grad is None]
+    # att_layer.* (12 tensors) and down5_.41.{weight,bias} never get a gradient
+    assert len(no_grad) == 14 and all(n.startswith(("att_layer.", "slices_generator.down5_.")) for n in no_grad)
+
+
+def test_make_3d_grid_order_and_axes():
+    g = synth.make_3d_grid((-0.5,) * 3, (0.5,) * 3, (3, 4, 5))
+    assert g.shape == (60, 3)
+    ax = torch.linspace(-0.5, 0.5, 5)
+    assert torch.equal(g[:5, 2], ax) and torch.all(g[:5, 0] == -0.5)  # z fastest
+    gen = Generator3D(model=None, upsampling_steps=0, resolution0=5)
+    assert torch.equal(gen.grid_axes(5, "cpu"), ax)
+
+
+@pytest.mark.parametrize("nx,world", [(256, 8), (128, 2), (65, 4), (7, 8), (1, 2)])
+def test_slab_bounds_partition(nx, world):
+    b = s3d_dist.slab_bounds(nx, world)
+    assert b[0] == 0 and b[-1] == nx and len(b) == world + 1
+    sizes = [b[i + 1] - b[i] for i in range(world)]
+    assert all(s >= 0 for s in sizes) and max(sizes) - min(sizes) <= 1
+    assert [s3d_dist.slab_range(nx, r, world) for r in range(world)] == [(b[r], b[r + 1]) for r in range(world)]
+
+
+_WORKER = r"""
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from slice3d_b200 import dist as sd
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%s" % sys.argv[2], rank=int(sys.argv[3]), world_size=2)
+ok = True
+for nx in (8, 7):
+    full = torch.arange(nx * 3 * 2, dtype=torch.float32)
+    lo, hi = sd.slab_range(nx, dist.get_rank(), 2)
+    vol = torch.full_like(full, -1.0)
+    vol[lo * 6:hi * 6] = full[lo * 6:hi * 6]
+    sd.all_gather_slabs(vol, nx)
+    ok = ok and torch.equal(vol, full)
+dist.destroy_process_group()
+sys.exit(0 if ok else 3)
+"""
+
+
+def test_slab_all_gather_world2_gloo(tmp_path):
+    script = tmp_path / "w.py"
+    script.write_text(_WORKER)
+    port = str(29500 + os.getpid() % 2000)
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT, port, str(r)]) for r in range(2)]
+    codes = [p.wait(timeout=120) for p in procs]
+    assert codes == [0, 0]
