@@ -354,6 +354,7 @@ size_t s3d_decoder_workspace_bytes(int64_t n, int32_t precision) {
 int s3d_decoder_fwd(const s3d_model* m, const void* planes_dev, int32_t S, float* qry_dev, int64_t n,
                     const float* T_dev, const float* rot_dev, int32_t flip_in_place, float out_scale, float* out_dev,
                     int32_t precision, void* workspace_dev, size_t workspace_bytes, void* stream) {
+  if (n == 0) return S3D_OK;  /* empty query set (a zero-element tensor has a null data pointer) */
   if (!qry_dev) {
     set_error("decoder: null query pointer");
     return S3D_ERR_BAD_ARG;
