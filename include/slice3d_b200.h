@@ -129,6 +129,14 @@ int s3d_decoder_debug_tokens(const s3d_model* m, const void* planes_dev, int32_t
                              int64_t n, const float* T_dev, const float* rot_dev, float* out_dev,
                              float* tokens_dev, void* workspace_dev, size_t workspace_bytes, void* stream);
 
+/* Hardware self-test of the tensor-core plumbing the decoder relies on (UMMA shared-memory and
+ * instruction descriptors, 128-byte-swizzled operand tiles, bulk async copy, TMEM load): one
+ * 128-row tile against one weight unit, passes = 1 (bf16) or 3 (bf16 hi/lo split).
+ *   mode 0: d[128][64]  = a[128][128] . w[64][128]^T      mode 1: d[128][128] = a[128][64] . w[128][64]^T
+ * a_dev, w_dev, d_dev are fp32 row-major device arrays.  Synchronises the stream. */
+int s3d_selftest_umma(int32_t mode, int32_t passes, const float* a_dev, const float* w_dev, float* d_dev,
+                      void* stream);
+
 /* Instrumentation: number of kernels this library has launched since load (all models). */
 int64_t s3d_launch_count(void);
 

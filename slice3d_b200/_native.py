@@ -20,7 +20,7 @@ ABI_VERSION = 1
 SYMBOLS = [
     "s3d_abi_version", "s3d_last_error", "s3d_model_create", "s3d_model_destroy", "s3d_model_n_slices",
     "s3d_planes_bytes", "s3d_encoder_workspace_bytes", "s3d_encoder_fwd", "s3d_decoder_workspace_bytes",
-    "s3d_decoder_fwd", "s3d_decoder_grid_fwd", "s3d_decoder_debug_tokens", "s3d_launch_count",
+    "s3d_decoder_fwd", "s3d_decoder_grid_fwd", "s3d_decoder_debug_tokens", "s3d_selftest_umma", "s3d_launch_count",
 ]
 
 
@@ -78,6 +78,8 @@ def lib():
     L.s3d_decoder_debug_tokens.restype = C.c_int
     L.s3d_decoder_debug_tokens.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p,
                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+    L.s3d_selftest_umma.restype = C.c_int
+    L.s3d_selftest_umma.argtypes = [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     if L.s3d_abi_version() != ABI_VERSION:
         raise NativeError(f"ABI mismatch: library {L.s3d_abi_version()}, binding {ABI_VERSION}")
     _lib = L
@@ -91,7 +93,17 @@ def _check(rc):
 
 def available_precisions():
     """Decoder arithmetic modes built into this revision of the library."""
-    return ("fp32",)
+    return ("fp32", "bf16x3", "bf16")
+
+
+def selftest_umma(mode, passes, a, w):
+    """d = a . w^T on one tcgen05 tile (see include/slice3d_b200.h); a, w fp32 CUDA tensors."""
+    a, w = _f32c(a, "a"), _f32c(w, "w")
+    n = 64 if mode == 0 else 128
+    d = torch.empty(128, n, dtype=torch.float32, device=a.device)
+    with torch.cuda.device(a.device):
+        _check(lib().s3d_selftest_umma(mode, passes, a.data_ptr(), w.data_ptr(), d.data_ptr(), _stream(a.device)))
+    return d
 
 
 def launch_count():

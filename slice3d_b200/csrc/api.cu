@@ -389,6 +389,11 @@ int s3d_decoder_grid_fwd(const s3d_model* m, const void* planes_dev, int32_t S, 
                      workspace_bytes, static_cast<cudaStream_t>(stream));
 }
 
+int s3d_selftest_umma(int32_t mode, int32_t passes, const float* a_dev, const float* w_dev, float* d_dev,
+                      void* stream) {
+  return umma_selftest(mode, passes, a_dev, w_dev, d_dev, static_cast<cudaStream_t>(stream));
+}
+
 int s3d_decoder_debug_tokens(const s3d_model* m, const void* planes_dev, int32_t S, const float* qry_dev, int64_t n,
                              const float* T_dev, const float* rot_dev, float* out_dev, float* tokens_dev,
                              void* workspace_dev, size_t workspace_bytes, void* stream) {

@@ -170,3 +170,60 @@ def test_empty_and_ragged_queries():
         assert torch.equal(part, full[:n])
     with pytest.raises(_native.NativeError):
         nat.decode(planes, 0, pts.cpu(), T, precision="fp32")
+
+
+# ------------------------------------------------------------------ tcgen05 decoder
+@pytest.mark.parametrize("mode,passes", [(0, 3), (1, 3), (0, 1), (1, 1)])
+def test_umma_selftest(mode, passes):
+    """One UMMA tile vs fp64: validates descriptors / swizzle / bulk copy / TMEM load."""
+    g = torch.Generator().manual_seed(11 + mode)
+    k, n = (128, 64) if mode == 0 else (64, 128)
+    a = torch.randn(128, k, generator=g)
+    w = torch.randn(n, k, generator=g) * 0.2
+    d = _native.selftest_umma(mode, passes, a.to(DEV), w.to(DEV)).cpu()
+    want = a.double() @ w.double().t()
+    err = float((d.double() - want).abs().max())
+    assert err < (2e-4 if passes == 3 else 0.15), err
+    if passes == 1:  # exactly the product of the bf16-rounded operands (fp32 accumulate)
+        ref = a.bfloat16().double() @ w.bfloat16().double().t()
+        assert float((d.double() - ref).abs().max()) < 1e-4
+
+
+@pytest.mark.parametrize("name", ["k12_s128_g128", "k12_s256_g128_g256"])
+def test_decoder_bf16x3_matches_reference(name):
+    case = helpers.load_case(name)
+    m, _ = _model(case)
+    feed = _feed(case)
+    nat = m.native()
+    planes = nat.encode(feed["img_input"])
+    for key in [k for k in case if k.startswith("pts_g")]:
+        nx = key[len("pts_g"):]
+        q = torch.from_numpy(case[key]).to(DEV)
+        sdf = nat.decode(planes, 0, q, feed["trans_mat_wo_rot_tp"][0], precision="bf16x3")
+        err = helpers.maxabs(sdf.cpu(), case[f"sdf_g{nx}"])
+        print(f"bf16x3 {name} g{nx}: max-abs {err:.3e}")
+        assert err < TOL
+
+
+def test_decoder_tc_equals_fp32_path_on_dense_grid():
+    """Dense-grid entry point, ragged last tile (33^3 is not a multiple of 9), both tensor-core modes
+    against the fp32 CUDA path on the same device."""
+    case = helpers.load_case("k12_s128_g128")
+    m, _ = _model(case)
+    feed = _feed(case)
+    nat = m.native()
+    planes = nat.encode(feed["img_input"])
+    ax = torch.linspace(-0.5, 0.5, 33).to(DEV)
+    T = feed["trans_mat_wo_rot_tp"][0]
+    n = 33 ** 3
+    ref = nat.decode_grid(planes, 0, (ax, ax, ax), 0, n, T, precision="fp32")
+    x3 = nat.decode_grid(planes, 0, (ax, ax, ax), 0, n, T, precision="bf16x3")
+    b1 = nat.decode_grid(planes, 0, (ax, ax, ax), 0, n, T, precision="bf16")
+    e3, e1 = helpers.maxabs(x3.cpu(), ref.cpu()), helpers.maxabs(b1.cpu(), ref.cpu())
+    flips = int(((b1 >= 0) != (ref >= 0)).sum())
+    print(f"dense 33^3: bf16x3 max-abs {e3:.3e}; bf16 max-abs {e1:.3e}, sign flips {flips}/{n}")
+    assert e3 < TOL
+    assert e1 < 5e-2
+    # a sub-range gives the same values as the full launch (tile boundaries do not matter)
+    part = nat.decode_grid(planes, 0, (ax, ax, ax), 1000, 5000, T, precision="bf16x3")
+    assert helpers.maxabs(part.cpu(), x3[1000:6000].cpu()) < 1e-6
