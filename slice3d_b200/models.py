@@ -23,7 +23,7 @@ from . import _native
 from .perceptual import VGGPerceptualLoss
 from .unet import UNet
 
-DEFAULT_PRECISION = "fp32"
+DEFAULT_PRECISION = "bf16x3"
 
 
 class Slices3DRegModel(nn.Module):
