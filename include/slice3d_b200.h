@@ -137,6 +137,10 @@ int s3d_decoder_debug_tokens(const s3d_model* m, const void* planes_dev, int32_t
 int s3d_selftest_umma(int32_t mode, int32_t passes, const float* a_dev, const float* w_dev, float* d_dev,
                       void* stream);
 
+/* Instrumentation of the tensor-core decoder: 32 cycle counters (clock64 deltas summed over CTAs since the
+ * last reset; index meaning in slice3d_b200/_native.py PROFILE_FIELDS).  Synchronises the device. */
+int s3d_debug_profile(int64_t* out32, int32_t reset);
+
 /* Instrumentation: number of kernels this library has launched since load (all models). */
 int64_t s3d_launch_count(void);
 

@@ -20,7 +20,7 @@ ABI_VERSION = 1
 SYMBOLS = [
     "s3d_abi_version", "s3d_last_error", "s3d_model_create", "s3d_model_destroy", "s3d_model_n_slices",
     "s3d_planes_bytes", "s3d_encoder_workspace_bytes", "s3d_encoder_fwd", "s3d_decoder_workspace_bytes",
-    "s3d_decoder_fwd", "s3d_decoder_grid_fwd", "s3d_decoder_debug_tokens", "s3d_selftest_umma", "s3d_launch_count",
+    "s3d_decoder_fwd", "s3d_decoder_grid_fwd", "s3d_decoder_debug_tokens", "s3d_selftest_umma", "s3d_debug_profile", "s3d_launch_count",
 ]
 
 
@@ -80,6 +80,8 @@ def lib():
                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
     L.s3d_selftest_umma.restype = C.c_int
     L.s3d_selftest_umma.argtypes = [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.s3d_debug_profile.restype = C.c_int
+    L.s3d_debug_profile.argtypes = [C.POINTER(C.c_int64), C.c_int32]
     if L.s3d_abi_version() != ABI_VERSION:
         raise NativeError(f"ABI mismatch: library {L.s3d_abi_version()}, binding {ABI_VERSION}")
     _lib = L
@@ -104,6 +106,19 @@ def selftest_umma(mode, passes, a, w):
     with torch.cuda.device(a.device):
         _check(lib().s3d_selftest_umma(mode, passes, a.data_ptr(), w.data_ptr(), d.data_ptr(), _stream(a.device)))
     return d
+
+
+PROFILE_FIELDS = ["token", "vec", "wait_qkv", "attn", "wait_out", "ln1", "ffn_wait_d1", "ffn_math", "ffn_wait_hfree",
+                  "ffn_store", "wait_ffn", "ln2", "mma_wait_a", "mma_wait_full", "mma_wait_h", "mma_wait_d1free",
+                  "mma_total", "prod_wait_empty", "prod_total", "tiles"]
+
+
+def debug_profile(reset=True):
+    """Per-phase cycle counters of the tensor-core decoder (summed over CTAs) as a dict."""
+    torch.cuda.synchronize()
+    buf = (C.c_int64 * 32)()
+    _check(lib().s3d_debug_profile(buf, 1 if reset else 0))
+    return {k: int(buf[i]) for i, k in enumerate(PROFILE_FIELDS)}
 
 
 def launch_count():

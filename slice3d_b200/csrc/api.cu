@@ -389,6 +389,8 @@ int s3d_decoder_grid_fwd(const s3d_model* m, const void* planes_dev, int32_t S, 
                      workspace_bytes, static_cast<cudaStream_t>(stream));
 }
 
+int s3d_debug_profile(int64_t* out32, int32_t reset) { return debug_profile(reinterpret_cast<long long*>(out32), reset); }
+
 int s3d_selftest_umma(int32_t mode, int32_t passes, const float* a_dev, const float* w_dev, float* d_dev,
                       void* stream) {
   return umma_selftest(mode, passes, a_dev, w_dev, d_dev, static_cast<cudaStream_t>(stream));

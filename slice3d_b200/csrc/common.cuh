@@ -144,6 +144,7 @@ size_t decoder_tc_workspace_bytes(int64_t n);
 int decoder_tc(const s3d_model* m, const float* planes, int S, const QueryCtx& q, int64_t n, float out_scale,
                float* out, int precision, void* ws, size_t ws_bytes, cudaStream_t st);
 
+int debug_profile(long long* out32, int reset);
 int umma_selftest(int mode, int passes, const float* a_dev, const float* w_dev, float* d_dev, cudaStream_t st);
 
 #ifdef __CUDACC__

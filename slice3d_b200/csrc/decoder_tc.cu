@@ -34,11 +34,18 @@ using namespace ptx;
 
 constexpr int TILE_Q = 9;    // queries per tile
 constexpr int NTOK = 13;     // tokens per query (K = 12 slices + the query token)
-constexpr int NSLOT = 3;     // weight ring depth
+constexpr int NSLOT_MAX = 6;  // weight ring depth: 3 x 32 KB (bf16x3) or 6 x 16 KB (bf16)
 constexpr int UNITS_PER_LAYER = 72;  // 6 (in_proj) + 2 (out_proj) + 32 (linear1) + 32 (linear2)
 constexpr int UNIT_PART_BYTES = 16384;  // one precision part (hi or lo) of a unit: 64x128 or 128x64 bf16
 constexpr int UNIT_STRIDE_BYTES = 2 * UNIT_PART_BYTES;  // hi then lo in global memory
 constexpr int NCHUNK = 32;   // FFN hidden chunks of 64
+constexpr int NCW = 16;      // compute warps: warp w owns TMEM lanes 32*(w&3).. and column quarter w>>2
+constexpr int NCT = NCW * 32;
+constexpr int NTHREADS = NCT + 64;  // + producer warp + MMA warp
+
+// per-layer fp32 vector block staged in shared memory (floats)
+constexpr int V_BIN = 0, V_BONEXT = 384, V_LN1W = 512, V_LN1B = 640, V_B1 = 768, V_B2 = 2816, V_LN2W = 2944,
+              V_LN2B = 3072, VEC_FLOATS = 3200;
 
 // shared memory map (bytes from the 1024-aligned base)
 constexpr uint32_t OFF_AX_HI = 0;                 // [2 k-blocks][128 rows][64] bf16 = 32 KB
@@ -46,67 +53,92 @@ constexpr uint32_t OFF_AX_LO = 32768;             // 32 KB
 constexpr uint32_t OFF_HKV = 65536;               // H chunk operand (hi 16 KB, lo 16 KB) | K/V staging | gather scratch
 constexpr uint32_t HKV_BYTES = 36864;             // 2 x [128][36] fp32
 constexpr uint32_t OFF_RING = OFF_HKV + HKV_BYTES;  // 102400, 1024-aligned
-constexpr uint32_t OFF_BAR = OFF_RING + NSLOT * UNIT_STRIDE_BYTES;  // 200704
+constexpr uint32_t OFF_VEC = OFF_RING + 3 * UNIT_STRIDE_BYTES;  // 200704
+constexpr uint32_t OFF_RED = OFF_VEC + VEC_FLOATS * 4;              // 2 x [128][4] fp32 LayerNorm partials
+constexpr uint32_t OFF_BAR = OFF_RED + 4096;
 constexpr uint32_t SMEM_BYTES = OFF_BAR + 256 + 1024;               // + alignment slack
 
 // barrier indices (8 bytes each at OFF_BAR)
-enum { B_AREADY = 0, B_DDONE, B_D1READY0, B_D1READY1, B_D1FREE0, B_D1FREE1, B_HREADY, B_HFREE, B_FULL0, B_FULL1, B_FULL2,
-       B_EMPTY0, B_EMPTY1, B_EMPTY2, B_COUNT };
+enum { B_AREADY = 0, B_DDONE, B_D1READY0, B_D1READY1, B_D1FREE0, B_D1FREE1, B_HREADY, B_HFREE, B_FULL0,
+       B_EMPTY0 = B_FULL0 + NSLOT_MAX, B_COUNT = B_EMPTY0 + NSLOT_MAX };
 constexpr uint32_t OFF_TMEMPTR = OFF_BAR + 8 * B_COUNT;
 
 // TMEM columns
 constexpr uint32_t TM_R = 0;      // residual / out-proj / FFN2 accumulator, 128 columns
 constexpr uint32_t TM_S = 128;    // QKV accumulators (384 columns) | FFN1 chunk accumulators (2 x 64)
 
+// Phase-cycle counters (clock64 deltas summed over CTAs), read through s3d_debug_profile().
+enum { PF_TOKEN = 0, PF_VEC, PF_WAIT_QKV, PF_ATTN, PF_WAIT_OUT, PF_LN1, PF_FFN_WAIT_D1, PF_FFN_MATH, PF_FFN_WAIT_HFREE,
+       PF_FFN_STORE, PF_WAIT_FFN, PF_LN2, PF_MMA_WAIT_A, PF_MMA_WAIT_FULL, PF_MMA_WAIT_H, PF_MMA_WAIT_D1FREE, PF_MMA_TOTAL,
+       PF_PROD_WAIT_EMPTY, PF_PROD_TOTAL, PF_TILES, PF_COUNT };
+__device__ unsigned long long g_prof[32];
+
 struct TcParams {
   const uint8_t* wimg;  // [3 layers][72 units][hi 16 KB | lo 16 KB]
+  const float* vecs;    // [3 layers][VEC_FLOATS]
   const float* planes;
   int S;
   QueryCtx q;
   long long n;
   float out_scale;
   float* out;
-  const float *fcp_wt, *fcp_b, *fcs_b, *fco_w, *fco_b;
-  const float *b_in[3], *b_o[3], *ln1w[3], *ln1b[3], *b1[3], *b2[3], *ln2w[3], *ln2b[3];
+  const float *fcp_wt, *fcp_b, *fcs_b, *fco_w, *fco_b, *b_o0;
   long long num_tiles;
 };
 
 // ---- operand writes ------------------------------------------------------------------------
 // 8 consecutive k values of row r -> one 16-byte chunk of the hi tile (and of the lo tile).
+// x = hi + lo + O(2^-17 |x|): hi = bf16_rn(x), lo = bf16_rn(x - hi), converted two at a time.
 template <int NPASS>
 __device__ __forceinline__ void store_chunk(uint8_t* tile_hi, uint8_t* tile_lo, int r, int kc, const float* v) {
-  __nv_bfloat16 h[8], l[8];
+  uint32_t h[4], l[4];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) split_bf16(v[i], h[i], l[i]);
+  for (int i = 0; i < 4; ++i) {
+    const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+    h[i] = *reinterpret_cast<const uint32_t*>(&h2);
+    if (NPASS == 3) {
+      const float h0 = __uint_as_float(h[i] << 16), h1 = __uint_as_float(h[i] & 0xffff0000u);
+      const __nv_bfloat162 l2 = __floats2bfloat162_rn(v[2 * i] - h0, v[2 * i + 1] - h1);
+      l[i] = *reinterpret_cast<const uint32_t*>(&l2);
+    }
+  }
   const uint32_t off = sw128_chunk_off(r, kc);
-  *reinterpret_cast<uint4*>(tile_hi + off) = make_uint4(pack2(h[0], h[1]), pack2(h[2], h[3]), pack2(h[4], h[5]), pack2(h[6], h[7]));
-  if (NPASS == 3)
-    *reinterpret_cast<uint4*>(tile_lo + off) = make_uint4(pack2(l[0], l[1]), pack2(l[2], l[3]), pack2(l[4], l[5]), pack2(l[6], l[7]));
+  *reinterpret_cast<uint4*>(tile_hi + off) = make_uint4(h[0], h[1], h[2], h[3]);
+  if (NPASS == 3) *reinterpret_cast<uint4*>(tile_lo + off) = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
 // ---- MMA issue -----------------------------------------------------------------------------
-// One weight unit against one activation operand: KS k-steps of 16, NPASS passes.
-//   a_hi/a_lo, b_hi/b_lo: shared addresses of the operand tiles; *_kb: byte stride between 64-wide k-blocks.
-template <int NPASS>
-__device__ __forceinline__ void issue_unit(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint32_t a_kb, uint32_t b_hi,
-                                           uint32_t b_lo, uint32_t b_kb, int KS, uint32_t idesc, bool fresh) {
-  uint32_t acc = fresh ? 0u : 1u;
-#pragma unroll 1
+// One weight unit against one activation operand: KS k-steps of 16, NPASS passes, fully unrolled
+// with compile-time descriptor increments (the issuing lane executes ~2 instructions per MMA).
+//   a_hi/a_lo, b_hi/b_lo: shared addresses of the operand tiles; *_KB: byte stride between 64-wide k-blocks.
+template <int NPASS, int KS, uint32_t A_KB, uint32_t B_KB, uint32_t IDESC>
+__device__ __forceinline__ void issue_unit(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo,
+                                           bool fresh) {
+  const uint64_t ah = make_desc_sw128(a_hi), al = make_desc_sw128(a_lo);
+  const uint64_t bh = make_desc_sw128(b_hi), bl = make_desc_sw128(b_lo);
+#pragma unroll
   for (int pass = 0; pass < NPASS; ++pass) {
-    const uint32_t a = (pass == 1) ? a_lo : a_hi;
-    const uint32_t b = (pass == 2) ? b_lo : b_hi;
-    const uint64_t ad = make_desc_sw128(a), bd = make_desc_sw128(b);
-#pragma unroll 1
+    const uint64_t ad = (pass == 1) ? al : ah;
+    const uint64_t bd = (pass == 2) ? bl : bh;
+#pragma unroll
     for (int ks = 0; ks < KS; ++ks) {
+      constexpr uint32_t dummy = 0;
+      (void)dummy;
       const uint32_t kb = ks >> 2, kin = (ks & 3) * 32;
-      umma_bf16(d_tmem, ad + ((kb * a_kb + kin) >> 4), bd + ((kb * b_kb + kin) >> 4), idesc, acc);
-      acc = 1u;
+      umma_bf16(d_tmem, ad + ((kb * A_KB + kin) >> 4), bd + ((kb * B_KB + kin) >> 4), IDESC,
+                (pass == 0 && ks == 0 && fresh) ? 0u : 1u);
     }
   }
 }
 
+// warp-level arrive: every lane has fenced its own writes; one lane arrives for the warp.
+__device__ __forceinline__ void warp_arrive(uint32_t bar, int lane) {
+  __syncwarp();
+  if (lane == 0) mbar_arrive(bar);
+}
+
 template <int NPASS>
-__global__ void __launch_bounds__(192, 1) decoder_tc_kernel(const TcParams p) {
+__global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t sbase = (raw + 1023u) & ~1023u;
@@ -115,15 +147,15 @@ __global__ void __launch_bounds__(192, 1) decoder_tc_kernel(const TcParams p) {
   auto bar = [&](int i) { return sbase + OFF_BAR + 8u * i; };
 
   if (threadIdx.x == 0) {
-    mbar_init(bar(B_AREADY), 128);
+    mbar_init(bar(B_AREADY), NCW);
     mbar_init(bar(B_DDONE), 1);
     mbar_init(bar(B_D1READY0), 1);
     mbar_init(bar(B_D1READY1), 1);
-    mbar_init(bar(B_D1FREE0), 128);
-    mbar_init(bar(B_D1FREE1), 128);
-    mbar_init(bar(B_HREADY), 128);
+    mbar_init(bar(B_D1FREE0), NCW);
+    mbar_init(bar(B_D1FREE1), NCW);
+    mbar_init(bar(B_HREADY), NCW);
     mbar_init(bar(B_HFREE), 1);
-    for (int s = 0; s < NSLOT; ++s) {
+    for (int s = 0; s < NSLOT_MAX; ++s) {
       mbar_init(bar(B_FULL0 + s), 1);
       mbar_init(bar(B_EMPTY0 + s), 1);
     }
@@ -136,84 +168,126 @@ __global__ void __launch_bounds__(192, 1) decoder_tc_kernel(const TcParams p) {
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(sgen + OFF_TMEMPTR);
 
   constexpr uint32_t COPY_BYTES = (NPASS == 3) ? UNIT_STRIDE_BYTES : UNIT_PART_BYTES;
+  constexpr int NSLOT = (NPASS == 3) ? 3 : 6;
+  constexpr uint32_t SLOT_BYTES = COPY_BYTES;
 
-  if (warp == 4) {
+  if (warp == NCW) {
     // ===================================================================== weight producer
-    if (lane == 0) {
-      uint32_t ph_empty[NSLOT];
-      for (int s = 0; s < NSLOT; ++s) ph_empty[s] = 1;
+    {
+      uint32_t ph_empty = 0xffffffffu;  // one parity bit per slot ("empty"-type: first wait passes)
       int slot = 0;
+      long long w_e = 0;
+      const long long t_start = clock64();
       for (long long tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
 #pragma unroll 1
         for (int g = 0; g < 3 * UNITS_PER_LAYER; ++g) {
-          mbar_wait(bar(B_EMPTY0 + slot), ph_empty[slot]);
-          ph_empty[slot] ^= 1;
-          mbar_arrive_expect_tx(bar(B_FULL0 + slot), COPY_BYTES);
-          bulk_g2s(sbase + OFF_RING + slot * UNIT_STRIDE_BYTES, p.wimg + (size_t)g * UNIT_STRIDE_BYTES, COPY_BYTES,
-                   bar(B_FULL0 + slot));
+          const long long t0 = clock64();
+          mbar_wait(bar(B_EMPTY0 + slot), (ph_empty >> slot) & 1u);
+          ph_empty ^= 1u << slot;
+          w_e += clock64() - t0;
+          if (elect_one()) {
+            mbar_arrive_expect_tx(bar(B_FULL0 + slot), COPY_BYTES);
+#pragma unroll
+            for (uint32_t part = 0; part < COPY_BYTES; part += 8192)
+              bulk_g2s(sbase + OFF_RING + slot * SLOT_BYTES + part, p.wimg + (size_t)g * UNIT_STRIDE_BYTES + part, 8192,
+                       bar(B_FULL0 + slot));
+          }
+          __syncwarp();
           slot = (slot + 1 == NSLOT) ? 0 : slot + 1;
         }
       }
+      if (lane == 0) {
+        atomicAdd(&g_prof[PF_PROD_WAIT_EMPTY], (unsigned long long)w_e);
+        atomicAdd(&g_prof[PF_PROD_TOTAL], (unsigned long long)(clock64() - t_start));
+      }
     }
-  } else if (warp == 5) {
+  } else if (warp == NCW + 1) {
     // ===================================================================== MMA issuer
-    if (lane == 0) {
-      uint32_t ph_a = 0, ph_full[NSLOT], ph_d1free[2] = {1, 1}, ph_hr = 0;
-      for (int s = 0; s < NSLOT; ++s) ph_full[s] = 0;
+    // the whole warp runs the control flow (waits are warp-uniform); one elected lane issues
+    {
+      uint32_t ph_a = 0, ph_full = 0, ph_d1free = 3u, ph_hr = 0;  // parity bits
       int slot = 0;
+      long long w_a = 0, w_full = 0, w_h = 0, w_d1 = 0;
+      const long long t_start = clock64();
       const uint32_t ax_hi = sbase + OFF_AX_HI, ax_lo = sbase + OFF_AX_LO;
       const uint32_t h_hi = sbase + OFF_HKV, h_lo = sbase + OFF_HKV + UNIT_PART_BYTES;
       constexpr uint32_t ID64 = make_idesc_bf16(64), ID128 = make_idesc_bf16(128);
       auto wait_full = [&]() -> uint32_t {
-        mbar_wait(bar(B_FULL0 + slot), ph_full[slot]);
-        ph_full[slot] ^= 1;
-        return sbase + OFF_RING + slot * UNIT_STRIDE_BYTES;
+        const long long t0 = clock64();
+        mbar_wait(bar(B_FULL0 + slot), (ph_full >> slot) & 1u);
+        ph_full ^= 1u << slot;
+        w_full += clock64() - t0;
+        return sbase + OFF_RING + slot * SLOT_BYTES;
+      };
+      auto commit = [&](int b) {
+        if (elect_one()) umma_commit(bar(b));
+        __syncwarp();
       };
       auto release = [&]() {
-        umma_commit(bar(B_EMPTY0 + slot));
+        commit(B_EMPTY0 + slot);
         slot = (slot + 1 == NSLOT) ? 0 : slot + 1;
       };
       // unit of 64 output columns over K = 128 (in_proj / out_proj / linear1), A = AX
       auto unit_n64 = [&](uint32_t d_col, bool fresh) {
         const uint32_t w = wait_full();
         tc_fence_after();
-        issue_unit<NPASS>(tmem + d_col, ax_hi, ax_lo, 16384u, w, w + UNIT_PART_BYTES, 8192u, 8, ID64, fresh);
+        if (elect_one())
+          issue_unit<NPASS, 8, 16384u, 8192u, ID64>(tmem + d_col, ax_hi, ax_lo, w, w + UNIT_PART_BYTES, fresh);
+        __syncwarp();
         release();
       };
       for (long long tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
 #pragma unroll 1
         for (int layer = 0; layer < 3; ++layer) {
           // ---- QKV projection: S[:, 0:384] = X . Win^T
-          mbar_wait(bar(B_AREADY), ph_a);
+          {
+            const long long t0 = clock64();
+            mbar_wait(bar(B_AREADY), ph_a);
+            w_a += clock64() - t0;
+          }
           ph_a ^= 1;
           tc_fence_after();
           for (int u = 0; u < 6; ++u) unit_n64(TM_S + 64 * u, true);
-          umma_commit(bar(B_DDONE));
+          commit(B_DDONE);
           // ---- out-proj: R += O . Wo^T   (R pre-loaded with x + b_o)
-          mbar_wait(bar(B_AREADY), ph_a);
+          {
+            const long long t0 = clock64();
+            mbar_wait(bar(B_AREADY), ph_a);
+            w_a += clock64() - t0;
+          }
           ph_a ^= 1;
           tc_fence_after();
           for (int u = 0; u < 2; ++u) unit_n64(TM_R + 64 * u, false);
-          umma_commit(bar(B_DDONE));
+          commit(B_DDONE);
           // ---- FFN: D1[c] = X' . W1_c^T (N=64) ; R += relu(D1[c] + b1) . W2_c^T (N=128, K=64)
-          mbar_wait(bar(B_AREADY), ph_a);
+          {
+            const long long t0 = clock64();
+            mbar_wait(bar(B_AREADY), ph_a);
+            w_a += clock64() - t0;
+          }
           ph_a ^= 1;
           tc_fence_after();
           auto issue1 = [&](int c) {
-            mbar_wait(bar(B_D1FREE0 + (c & 1)), ph_d1free[c & 1]);
-            ph_d1free[c & 1] ^= 1;
+            const long long t0 = clock64();
+            mbar_wait(bar(B_D1FREE0 + (c & 1)), (ph_d1free >> (c & 1)) & 1u);
+            ph_d1free ^= 1u << (c & 1);
+            w_d1 += clock64() - t0;
             tc_fence_after();
             unit_n64(TM_S + 64 * (c & 1), true);
-            umma_commit(bar(B_D1READY0 + (c & 1)));
+            commit(B_D1READY0 + (c & 1));
           };
           auto issue2 = [&](int c) {
             const uint32_t w = wait_full();
+            const long long t0 = clock64();
             mbar_wait(bar(B_HREADY), ph_hr);
             ph_hr ^= 1;
+            w_h += clock64() - t0;
             tc_fence_after();
-            issue_unit<NPASS>(tmem + TM_R, h_hi, h_lo, 0u, w, w + UNIT_PART_BYTES, 0u, 4, ID128, false);
+            if (elect_one())
+              issue_unit<NPASS, 4, 0u, 0u, ID128>(tmem + TM_R, h_hi, h_lo, w, w + UNIT_PART_BYTES, false);
+            __syncwarp();
             release();
-            umma_commit(bar(B_HFREE));
+            commit(B_HFREE);
           };
           issue1(0);
 #pragma unroll 1
@@ -221,297 +295,352 @@ __global__ void __launch_bounds__(192, 1) decoder_tc_kernel(const TcParams p) {
             if (c + 1 < NCHUNK) issue1(c + 1);
             issue2(c);
           }
-          umma_commit(bar(B_DDONE));
+          commit(B_DDONE);
         }
+      }
+      if (lane == 0) {
+        atomicAdd(&g_prof[PF_MMA_WAIT_A], (unsigned long long)w_a);
+        atomicAdd(&g_prof[PF_MMA_WAIT_FULL], (unsigned long long)w_full);
+        atomicAdd(&g_prof[PF_MMA_WAIT_H], (unsigned long long)w_h);
+        atomicAdd(&g_prof[PF_MMA_WAIT_D1FREE], (unsigned long long)w_d1);
+        atomicAdd(&g_prof[PF_MMA_TOTAL], (unsigned long long)(clock64() - t_start));
       }
     }
   } else {
-    // ===================================================================== epilogue / compute warps
-    const int r = threadIdx.x;  // tile row == TMEM lane
-    const uint32_t trow = tmem + (static_cast<uint32_t>(warp * 32) << 16);
+    // ===================================================================== compute warps
+    // thread = (tile row r = TMEM lane, column quarter g): 32 of the 128 model channels per thread
+    const int q4 = warp & 3, g = warp >> 2;
+    const int r = q4 * 32 + lane;
+    const int tid = threadIdx.x;
+    const uint32_t trow = tmem + (static_cast<uint32_t>(q4 * 32) << 16);
     uint8_t* ax_hi = sgen + OFF_AX_HI;
     uint8_t* ax_lo = sgen + OFF_AX_LO;
     uint8_t* h_hi = sgen + OFF_HKV;
     uint8_t* h_lo = sgen + OFF_HKV + UNIT_PART_BYTES;
-    uint32_t ph_d = 0, ph_d1r[2] = {0, 0}, ph_hf = 1;
+    const float* vec = reinterpret_cast<const float*>(sgen + OFF_VEC);
+    float* red0 = reinterpret_cast<float*>(sgen + OFF_RED);
+    float* red1 = red0 + 512;
+    uint32_t ph_d = 0, ph_d1r = 0, ph_hf = 1;
     const int qi = r / NTOK, tk = r - qi * NTOK;
     const unsigned FULL = 0xffffffffu;
+    long long pf[12];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) pf[i] = 0;
+    long long tprev = clock64();
+    auto lap = [&](int i) {
+      const long long t = clock64();
+      pf[i] += t - tprev;
+      tprev = t;
+    };
+
+    // LayerNorm over the 128 channels of row r, 32 of them in v[] (partials exchanged through smem)
+    auto layer_norm = [&](float* v, const float* w, const float* b) {
+      float s = 0.f;
+#pragma unroll
+      for (int c = 0; c < 32; ++c) s += v[c];
+      red0[r * 4 + g] = s;
+      named_bar_sync(1, NCT);
+      const float4 s4 = *reinterpret_cast<const float4*>(red0 + r * 4);
+      const float mean = (s4.x + s4.y + s4.z + s4.w) * (1.f / 128.f);
+      float d2 = 0.f;
+#pragma unroll
+      for (int c = 0; c < 32; ++c) {
+        v[c] -= mean;
+        d2 = fmaf(v[c], v[c], d2);
+      }
+      red1[r * 4 + g] = d2;
+      named_bar_sync(1, NCT);
+      const float4 d4 = *reinterpret_cast<const float4*>(red1 + r * 4);
+      const float rstd = rsqrtf((d4.x + d4.y + d4.z + d4.w) * (1.f / 128.f) + 1e-5f);
+#pragma unroll
+      for (int c = 0; c < 32; c += 4) {
+        const float4 w4 = *reinterpret_cast<const float4*>(w + 32 * g + c);
+        const float4 b4 = *reinterpret_cast<const float4*>(b + 32 * g + c);
+        v[c] = fmaf(v[c] * rstd, w4.x, b4.x);
+        v[c + 1] = fmaf(v[c + 1] * rstd, w4.y, b4.y);
+        v[c + 2] = fmaf(v[c + 2] * rstd, w4.z, b4.z);
+        v[c + 3] = fmaf(v[c + 3] * rstd, w4.w, b4.w);
+      }
+    };
+    // v[0..31] = channels 32g.. of row r -> operand A (k-block g/2, chunks 4*(g&1)..+3)
+    auto store_ax = [&](const float* v) {
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc)
+        store_chunk<NPASS>(ax_hi + (g >> 1) * 16384, ax_lo + (g >> 1) * 16384, r, (g & 1) * 4 + cc, v + 8 * cc);
+    };
+    // R[r][32g..] = v + bias ; publish operand A + R to the MMA issuer
+    auto publish = [&](float* v, const float* bias) {
+#pragma unroll
+      for (int c = 0; c < 32; c += 4) {
+        const float4 b4 = *reinterpret_cast<const float4*>(bias + 32 * g + c);
+        v[c] += b4.x; v[c + 1] += b4.y; v[c + 2] += b4.z; v[c + 3] += b4.w;
+      }
+      tmem_st32(trow + TM_R + 32 * g, v);
+      tmem_st_wait();
+      tc_fence_before();
+      fence_proxy_async_smem();
+      warp_arrive(bar(B_AREADY), lane);
+    };
 
     for (long long tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       const long long q_idx = tile * TILE_Q + qi;
       const bool valid = (qi < TILE_Q) && (q_idx < p.n);
       // ------------------------------------------------------------------ token build
-      float px = 0.f, py = 0.f, pz = 0.f, gu = 0.f, gv = 0.f;
-      if (valid) load_query(p.q, q_idx, px, py, pz, gu, gv);
       {
-        float* scr = reinterpret_cast<float*>(sgen + OFF_HKV) + warp * (32 * 68);
+        float px = 0.f, py = 0.f, pz = 0.f, gu = 0.f, gv = 0.f;
+        if (valid) load_query(p.q, q_idx, px, py, pz, gu, gv);
+        float v[32];
+        float* scr = reinterpret_cast<float*>(sgen + OFF_HKV) + warp * (4 * 36);
         const int qtr = lane >> 3, l8 = lane & 7;
-        const float* b_o0 = p.b_o[0];
+        const int ch = 32 * g + l8 * 4;
 #pragma unroll 1
-        for (int half = 0; half < 2; ++half) {
-#pragma unroll 1
-          for (int rg = 0; rg < 8; ++rg) {
-            const int rl = rg * 4 + qtr;  // row (within this warp) gathered by this quarter-warp
-            const float ru = __shfl_sync(FULL, gu, rl), rv = __shfl_sync(FULL, gv, rl);
-            const int rvalid = __shfl_sync(FULL, valid ? 1 : 0, rl);
-            const int rr = warp * 32 + rl;
-            const int rt = rr % NTOK;
-            float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
-            if (rvalid && rt > 0) {
-              const int ch = half * 64 + l8 * 4;
-              a0 = __ldg(reinterpret_cast<const float4*>(p.fcs_b + ch));
-              a1 = __ldg(reinterpret_cast<const float4*>(p.fcs_b + ch + 32));
-              size_t off = 0;
-#pragma unroll 1
-              for (int s = 0; s < 5; ++s) {
-                const int R = plane_res(p.S, s);
-                const Taps t = make_taps(ru, rv, R);
-                const float* P = p.planes + off + (size_t)(rt - 1) * R * R * 128 + ch;
-                const float4 c00 = __ldg(reinterpret_cast<const float4*>(P + (size_t)t.o00 * 128));
-                const float4 c01 = __ldg(reinterpret_cast<const float4*>(P + (size_t)t.o01 * 128));
-                const float4 c10 = __ldg(reinterpret_cast<const float4*>(P + (size_t)t.o10 * 128));
-                const float4 c11 = __ldg(reinterpret_cast<const float4*>(P + (size_t)t.o11 * 128));
-                const float4 d00 = __ldg(reinterpret_cast<const float4*>(P + (size_t)t.o00 * 128 + 32));
-                const float4 d01 = __ldg(reinterpret_cast<const float4*>(P + (size_t)t.o01 * 128 + 32));
-                const float4 d10 = __ldg(reinterpret_cast<const float4*>(P + (size_t)t.o10 * 128 + 32));
-                const float4 d11 = __ldg(reinterpret_cast<const float4*>(P + (size_t)t.o11 * 128 + 32));
-                a0.x += c00.x * t.w00 + c01.x * t.w01 + c10.x * t.w10 + c11.x * t.w11;
-                a0.y += c00.y * t.w00 + c01.y * t.w01 + c10.y * t.w10 + c11.y * t.w11;
-                a0.z += c00.z * t.w00 + c01.z * t.w01 + c10.z * t.w10 + c11.z * t.w11;
-                a0.w += c00.w * t.w00 + c01.w * t.w01 + c10.w * t.w10 + c11.w * t.w11;
-                a1.x += d00.x * t.w00 + d01.x * t.w01 + d10.x * t.w10 + d11.x * t.w11;
-                a1.y += d00.y * t.w00 + d01.y * t.w01 + d10.y * t.w10 + d11.y * t.w11;
-                a1.z += d00.z * t.w00 + d01.z * t.w01 + d10.z * t.w10 + d11.z * t.w11;
-                a1.w += d00.w * t.w00 + d01.w * t.w01 + d10.w * t.w10 + d11.w * t.w11;
-                off += (size_t)12 * R * R * 128;
-              }
+        for (int rg = 0; rg < 8; ++rg) {
+          const int rl = rg * 4 + qtr;  // row (within this quadrant) gathered by this quarter-warp
+          const float ru = __shfl_sync(FULL, gu, rl), rv = __shfl_sync(FULL, gv, rl);
+          const int rvalid = __shfl_sync(FULL, valid ? 1 : 0, rl);
+          const int rt = (q4 * 32 + rl) % NTOK;
+          float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (rvalid && rt > 0) {
+            a0 = __ldg(reinterpret_cast<const float4*>(p.fcs_b + ch));
+            size_t off = 0;
+#pragma unroll
+            for (int s = 0; s < 5; ++s) {
+              const int R = plane_res(p.S, s);
+              const Taps t = make_taps(ru, rv, R);
+              const float* P = p.planes + off + (size_t)(rt - 1) * R * R * 128 + ch;
+              const float4 c00 = __ldg(reinterpret_cast<const float4*>(P + (size_t)t.o00 * 128));
+              const float4 c01 = __ldg(reinterpret_cast<const float4*>(P + (size_t)t.o01 * 128));
+              const float4 c10 = __ldg(reinterpret_cast<const float4*>(P + (size_t)t.o10 * 128));
+              const float4 c11 = __ldg(reinterpret_cast<const float4*>(P + (size_t)t.o11 * 128));
+              a0.x += c00.x * t.w00 + c01.x * t.w01 + c10.x * t.w10 + c11.x * t.w11;
+              a0.y += c00.y * t.w00 + c01.y * t.w01 + c10.y * t.w10 + c11.y * t.w11;
+              a0.z += c00.z * t.w00 + c01.z * t.w01 + c10.z * t.w10 + c11.z * t.w11;
+              a0.w += c00.w * t.w00 + c01.w * t.w01 + c10.w * t.w10 + c11.w * t.w11;
+              off += (size_t)12 * R * R * 128;
             }
-            *reinterpret_cast<float4*>(scr + rl * 68 + l8 * 4) = a0;
-            *reinterpret_cast<float4*>(scr + rl * 68 + 32 + l8 * 4) = a1;
           }
+          *reinterpret_cast<float4*>(scr + qtr * 36 + l8 * 4) = a0;
           __syncwarp();
-          float v[64];
+          if ((lane >> 2) == rg) {  // the four lanes that own the rows gathered in this step
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float4 t4 = *reinterpret_cast<const float4*>(scr + lane * 68 + i * 4);
-            v[4 * i] = t4.x; v[4 * i + 1] = t4.y; v[4 * i + 2] = t4.z; v[4 * i + 3] = t4.w;
-          }
-          if (valid && tk == 0) {  // query token: fc_p(q) (models.py:79)
-#pragma unroll
-            for (int c = 0; c < 64; ++c) {
-              const int ch = half * 64 + c;
-              v[c] = __ldg(p.fcp_b + ch) + px * __ldg(p.fcp_wt + ch) + py * __ldg(p.fcp_wt + 128 + ch) +
-                     pz * __ldg(p.fcp_wt + 256 + ch);
+            for (int i = 0; i < 8; ++i) {
+              const float4 t4 = *reinterpret_cast<const float4*>(scr + (lane & 3) * 36 + i * 4);
+              v[4 * i] = t4.x; v[4 * i + 1] = t4.y; v[4 * i + 2] = t4.z; v[4 * i + 3] = t4.w;
             }
           }
-#pragma unroll
-          for (int kc = 0; kc < 8; ++kc)
-            store_chunk<NPASS>(ax_hi + half * 16384, ax_lo + half * 16384, r, kc, v + 8 * kc);
-#pragma unroll
-          for (int c = 0; c < 64; ++c) v[c] += __ldg(b_o0 + half * 64 + c);
-          tmem_st32(trow + TM_R + half * 64, v);
-          tmem_st32(trow + TM_R + half * 64 + 32, v + 32);
           __syncwarp();
         }
-        tmem_st_wait();
-        tc_fence_before();
-        fence_proxy_async_smem();
-        mbar_arrive(bar(B_AREADY));
+        if (valid && tk == 0) {  // query token: fc_p(q) (models.py:79)
+#pragma unroll
+          for (int c = 0; c < 32; ++c) {
+            const int cc = 32 * g + c;
+            v[c] = __ldg(p.fcp_b + cc) + px * __ldg(p.fcp_wt + cc) + py * __ldg(p.fcp_wt + 128 + cc) +
+                   pz * __ldg(p.fcp_wt + 256 + cc);
+          }
+        }
+        store_ax(v);
+        publish(v, p.b_o0);
       }
+      lap(PF_TOKEN);
 
 #pragma unroll 1
       for (int layer = 0; layer < 3; ++layer) {
-        // -------------------------------------------------------------- attention
+        // -------------------------------------------------------------- stage this layer's vectors
+        named_bar_sync(1, NCT);  // everyone is done with the previous layer's vectors
+        {
+          const float4* src = reinterpret_cast<const float4*>(p.vecs + (size_t)layer * VEC_FLOATS);
+          float4* dst = reinterpret_cast<float4*>(sgen + OFF_VEC);
+          for (int i = tid; i < VEC_FLOATS / 4; i += NCT) dst[i] = __ldg(src + i);
+        }
+        named_bar_sync(1, NCT);
+        lap(PF_VEC);
+        // -------------------------------------------------------------- attention (13x13 per query and head)
         mbar_wait(bar(B_DDONE), ph_d);
         ph_d ^= 1;
         tc_fence_after();
-        {
-          float* Ks = reinterpret_cast<float*>(sgen + OFF_HKV);
-          float* Vs = Ks + 128 * 36;
-          const float* b_in = p.b_in[layer];
+        lap(PF_WAIT_QKV);
+        if (g < 2) {  // column groups 0,1 take heads (0,1) then (2,3); K then V staged per head
+          float* st = reinterpret_cast<float*>(sgen + OFF_HKV) + g * (128 * 36);
+          const float* b_in = vec + V_BIN;
 #pragma unroll 1
-          for (int h = 0; h < 4; ++h) {
+          for (int rnd = 0; rnd < 2; ++rnd) {
+            const int h = 2 * rnd + g;
+            float sc[NTOK];
             {
-              float kk[32], vv[32];
+              float kk[32];
               tmem_ld32(trow + TM_S + 128 + 32 * h, kk);
+              tmem_ld_wait();
+#pragma unroll
+              for (int c = 0; c < 32; c += 4) {
+                const float4 b4 = *reinterpret_cast<const float4*>(b_in + 128 + 32 * h + c);
+                *reinterpret_cast<float4*>(st + r * 36 + c) =
+                    make_float4(kk[c] + b4.x, kk[c + 1] + b4.y, kk[c + 2] + b4.z, kk[c + 3] + b4.w);
+              }
+            }
+            named_bar_sync(2, 256);
+            {
+              float qq[32];
+              tmem_ld32(trow + TM_S + 32 * h, qq);
+              tmem_ld_wait();
+#pragma unroll
+              for (int c = 0; c < 32; c += 4) {
+                const float4 b4 = *reinterpret_cast<const float4*>(b_in + 32 * h + c);
+                qq[c] = (qq[c] + b4.x) * 0.17677669529663687f;
+                qq[c + 1] = (qq[c + 1] + b4.y) * 0.17677669529663687f;
+                qq[c + 2] = (qq[c + 2] + b4.z) * 0.17677669529663687f;
+                qq[c + 3] = (qq[c + 3] + b4.w) * 0.17677669529663687f;
+              }
+#pragma unroll
+              for (int j = 0; j < NTOK; ++j) sc[j] = 0.f;
+              if (valid) {
+                const float* kb = st + qi * NTOK * 36;
+                float mx = -3.0e38f;
+#pragma unroll
+                for (int j = 0; j < NTOK; ++j) {
+                  float s = 0.f;
+#pragma unroll
+                  for (int c = 0; c < 32; c += 4) {
+                    const float4 k4 = *reinterpret_cast<const float4*>(kb + j * 36 + c);
+                    s = fmaf(qq[c], k4.x, s);
+                    s = fmaf(qq[c + 1], k4.y, s);
+                    s = fmaf(qq[c + 2], k4.z, s);
+                    s = fmaf(qq[c + 3], k4.w, s);
+                  }
+                  sc[j] = s;
+                  mx = fmaxf(mx, s);
+                }
+                float sum = 0.f;
+#pragma unroll
+                for (int j = 0; j < NTOK; ++j) {
+                  sc[j] = __expf(sc[j] - mx);
+                  sum += sc[j];
+                }
+                const float inv = 1.f / sum;
+#pragma unroll
+                for (int j = 0; j < NTOK; ++j) sc[j] *= inv;
+              }
+            }
+            named_bar_sync(2, 256);  // everyone has read K
+            {
+              float vv[32];
               tmem_ld32(trow + TM_S + 256 + 32 * h, vv);
               tmem_ld_wait();
 #pragma unroll
               for (int c = 0; c < 32; c += 4) {
-                *reinterpret_cast<float4*>(Ks + r * 36 + c) =
-                    make_float4(kk[c] + __ldg(b_in + 128 + 32 * h + c), kk[c + 1] + __ldg(b_in + 129 + 32 * h + c),
-                                kk[c + 2] + __ldg(b_in + 130 + 32 * h + c), kk[c + 3] + __ldg(b_in + 131 + 32 * h + c));
-                *reinterpret_cast<float4*>(Vs + r * 36 + c) =
-                    make_float4(vv[c] + __ldg(b_in + 256 + 32 * h + c), vv[c + 1] + __ldg(b_in + 257 + 32 * h + c),
-                                vv[c + 2] + __ldg(b_in + 258 + 32 * h + c), vv[c + 3] + __ldg(b_in + 259 + 32 * h + c));
+                const float4 b4 = *reinterpret_cast<const float4*>(b_in + 256 + 32 * h + c);
+                *reinterpret_cast<float4*>(st + r * 36 + c) =
+                    make_float4(vv[c] + b4.x, vv[c + 1] + b4.y, vv[c + 2] + b4.z, vv[c + 3] + b4.w);
               }
             }
-            named_bar_sync(1, 128);
-            float qq[32], o[32];
-            tmem_ld32(trow + TM_S + 32 * h, qq);
-            tmem_ld_wait();
+            named_bar_sync(2, 256);
+            {
+              float o[32];
 #pragma unroll
-            for (int c = 0; c < 32; ++c) {
-              qq[c] = (qq[c] + __ldg(b_in + 32 * h + c)) * 0.17677669529663687f;
-              o[c] = 0.f;
-            }
-            if (valid) {
-              const float* kb = Ks + qi * NTOK * 36;
-              const float* vb = Vs + qi * NTOK * 36;
-              float sc[NTOK];
-              float mx = -3.0e38f;
+              for (int c = 0; c < 32; ++c) o[c] = 0.f;
+              if (valid) {
+                const float* vb = st + qi * NTOK * 36;
 #pragma unroll
-              for (int j = 0; j < NTOK; ++j) {
-                float s = 0.f;
+                for (int j = 0; j < NTOK; ++j) {
 #pragma unroll
-                for (int c = 0; c < 32; c += 4) {
-                  const float4 k4 = *reinterpret_cast<const float4*>(kb + j * 36 + c);
-                  s = fmaf(qq[c], k4.x, s);
-                  s = fmaf(qq[c + 1], k4.y, s);
-                  s = fmaf(qq[c + 2], k4.z, s);
-                  s = fmaf(qq[c + 3], k4.w, s);
-                }
-                sc[j] = s;
-                mx = fmaxf(mx, s);
-              }
-              float sum = 0.f;
-#pragma unroll
-              for (int j = 0; j < NTOK; ++j) {
-                sc[j] = __expf(sc[j] - mx);
-                sum += sc[j];
-              }
-              const float inv = 1.f / sum;
-#pragma unroll
-              for (int j = 0; j < NTOK; ++j) {
-                const float pj = sc[j] * inv;
-#pragma unroll
-                for (int c = 0; c < 32; c += 4) {
-                  const float4 v4 = *reinterpret_cast<const float4*>(vb + j * 36 + c);
-                  o[c] = fmaf(pj, v4.x, o[c]);
-                  o[c + 1] = fmaf(pj, v4.y, o[c + 1]);
-                  o[c + 2] = fmaf(pj, v4.z, o[c + 2]);
-                  o[c + 3] = fmaf(pj, v4.w, o[c + 3]);
+                  for (int c = 0; c < 32; c += 4) {
+                    const float4 v4 = *reinterpret_cast<const float4*>(vb + j * 36 + c);
+                    o[c] = fmaf(sc[j], v4.x, o[c]);
+                    o[c + 1] = fmaf(sc[j], v4.y, o[c + 1]);
+                    o[c + 2] = fmaf(sc[j], v4.z, o[c + 2]);
+                    o[c + 3] = fmaf(sc[j], v4.w, o[c + 3]);
+                  }
                 }
               }
-            }
-            // O[:, 32h:32h+32] -> operand A (k-block h/2, chunks 4*(h&1)..+3)
+              // O[:, 32h:32h+32] -> operand A (k-block h/2, chunks 4*(h&1)..+3)
 #pragma unroll
-            for (int cc = 0; cc < 4; ++cc)
-              store_chunk<NPASS>(ax_hi + (h >> 1) * 16384, ax_lo + (h >> 1) * 16384, r, (h & 1) * 4 + cc, o + 8 * cc);
-            named_bar_sync(1, 128);  // everyone done with Ks/Vs before the next head overwrites them
+              for (int cc = 0; cc < 4; ++cc)
+                store_chunk<NPASS>(ax_hi + (h >> 1) * 16384, ax_lo + (h >> 1) * 16384, r, (h & 1) * 4 + cc, o + 8 * cc);
+            }
+            named_bar_sync(2, 256);  // everyone has read V before the next round overwrites the staging
           }
           fence_proxy_async_smem();
-          mbar_arrive(bar(B_AREADY));
         }
+        warp_arrive(bar(B_AREADY), lane);
+        lap(PF_ATTN);
         // -------------------------------------------------------------- residual + LayerNorm 1 (in place in TMEM)
         mbar_wait(bar(B_DDONE), ph_d);
         ph_d ^= 1;
         tc_fence_after();
+        lap(PF_WAIT_OUT);
         {
-          float v[128];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) tmem_ld32(trow + TM_R + 32 * j, v + 32 * j);
+          float v[32];
+          tmem_ld32(trow + TM_R + 32 * g, v);
           tmem_ld_wait();
-          float s = 0.f;
-#pragma unroll
-          for (int c = 0; c < 128; ++c) s += v[c];
-          const float mean = s * (1.f / 128.f);
-          float d2 = 0.f;
-#pragma unroll
-          for (int c = 0; c < 128; ++c) {
-            v[c] -= mean;
-            d2 = fmaf(v[c], v[c], d2);
-          }
-          const float rstd = rsqrtf(d2 * (1.f / 128.f) + 1e-5f);
-          const float* w = p.ln1w[layer];
-          const float* b = p.ln1b[layer];
-#pragma unroll
-          for (int c = 0; c < 128; ++c) v[c] = fmaf(v[c] * rstd, __ldg(w + c), __ldg(b + c));
-#pragma unroll
-          for (int kc = 0; kc < 16; ++kc)
-            store_chunk<NPASS>(ax_hi + (kc >> 3) * 16384, ax_lo + (kc >> 3) * 16384, r, kc & 7, v + 8 * kc);
-          const float* b2 = p.b2[layer];
-#pragma unroll
-          for (int c = 0; c < 128; ++c) v[c] += __ldg(b2 + c);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) tmem_st32(trow + TM_R + 32 * j, v + 32 * j);
-          tmem_st_wait();
-          tc_fence_before();
-          fence_proxy_async_smem();
-          mbar_arrive(bar(B_AREADY));
+          layer_norm(v, vec + V_LN1W, vec + V_LN1B);
+          store_ax(v);
+          publish(v, vec + V_B2);
         }
-        // -------------------------------------------------------------- FFN hidden chunks
+        lap(PF_LN1);
+        // -------------------------------------------------------------- FFN hidden chunks (16 columns per thread)
         {
-          const float* b1 = p.b1[layer];
 #pragma unroll 1
           for (int c = 0; c < NCHUNK; ++c) {
             const int bsel = c & 1;
-            mbar_wait(bar(B_D1READY0 + bsel), ph_d1r[bsel]);
-            ph_d1r[bsel] ^= 1;
+            mbar_wait(bar(B_D1READY0 + bsel), (ph_d1r >> bsel) & 1u);
+            ph_d1r ^= 1u << bsel;
             tc_fence_after();
-            float d[64];
-            tmem_ld32(trow + TM_S + 64 * bsel, d);
-            tmem_ld32(trow + TM_S + 64 * bsel + 32, d + 32);
+            lap(PF_FFN_WAIT_D1);
+            float d[16];
+            tmem_ld16(trow + TM_S + 64 * bsel + 16 * g, d);
             tmem_ld_wait();
             tc_fence_before();
-            mbar_arrive(bar(B_D1FREE0 + bsel));
+            warp_arrive(bar(B_D1FREE0 + bsel), lane);
 #pragma unroll
-            for (int j = 0; j < 64; ++j) d[j] = fmaxf(d[j] + __ldg(b1 + c * 64 + j), 0.f);
+            for (int j = 0; j < 16; j += 4) {
+              const float4 b4 = *reinterpret_cast<const float4*>(vec + V_B1 + c * 64 + 16 * g + j);
+              d[j] = fmaxf(d[j] + b4.x, 0.f);
+              d[j + 1] = fmaxf(d[j + 1] + b4.y, 0.f);
+              d[j + 2] = fmaxf(d[j + 2] + b4.z, 0.f);
+              d[j + 3] = fmaxf(d[j + 3] + b4.w, 0.f);
+            }
+            lap(PF_FFN_MATH);
             mbar_wait(bar(B_HFREE), ph_hf);
             ph_hf ^= 1;
-#pragma unroll
-            for (int kc = 0; kc < 8; ++kc) store_chunk<NPASS>(h_hi, h_lo, r, kc, d + 8 * kc);
+            lap(PF_FFN_WAIT_HFREE);
+            store_chunk<NPASS>(h_hi, h_lo, r, 2 * g, d);
+            store_chunk<NPASS>(h_hi, h_lo, r, 2 * g + 1, d + 8);
             fence_proxy_async_smem();
-            mbar_arrive(bar(B_HREADY));
+            warp_arrive(bar(B_HREADY), lane);
+            lap(PF_FFN_STORE);
           }
         }
         // -------------------------------------------------------------- residual + LayerNorm 2
         mbar_wait(bar(B_DDONE), ph_d);
         ph_d ^= 1;
         tc_fence_after();
+        lap(PF_WAIT_FFN);
         {
-          float v[128];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) tmem_ld32(trow + TM_R + 32 * j, v + 32 * j);
+          float v[32];
+          tmem_ld32(trow + TM_R + 32 * g, v);
           tmem_ld_wait();
-          float s = 0.f;
-#pragma unroll
-          for (int c = 0; c < 128; ++c) s += v[c];
-          const float mean = s * (1.f / 128.f);
-          float d2 = 0.f;
-#pragma unroll
-          for (int c = 0; c < 128; ++c) {
-            v[c] -= mean;
-            d2 = fmaf(v[c], v[c], d2);
-          }
-          const float rstd = rsqrtf(d2 * (1.f / 128.f) + 1e-5f);
-          const float* w = p.ln2w[layer];
-          const float* b = p.ln2b[layer];
-#pragma unroll
-          for (int c = 0; c < 128; ++c) v[c] = fmaf(v[c] * rstd, __ldg(w + c), __ldg(b + c));
+          layer_norm(v, vec + V_LN2W, vec + V_LN2B);
           if (layer < 2) {
-#pragma unroll
-            for (int kc = 0; kc < 16; ++kc)
-              store_chunk<NPASS>(ax_hi + (kc >> 3) * 16384, ax_lo + (kc >> 3) * 16384, r, kc & 7, v + 8 * kc);
-            const float* bo = p.b_o[layer + 1];
-#pragma unroll
-            for (int c = 0; c < 128; ++c) v[c] += __ldg(bo + c);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) tmem_st32(trow + TM_R + 32 * j, v + 32 * j);
-            tmem_st_wait();
-            tc_fence_before();
-            fence_proxy_async_smem();
-            mbar_arrive(bar(B_AREADY));
-          } else if (valid && tk == 0) {  // fc_out on token 0 (models.py:83-84)
+            store_ax(v);
+            publish(v, vec + V_BONEXT);
+          } else {  // fc_out on token 0 (models.py:83-84)
             float acc = 0.f;
 #pragma unroll
-            for (int c = 0; c < 128; ++c) acc = fmaf(v[c], __ldg(p.fco_w + c), acc);
-            p.out[q_idx] = p.out_scale * (acc + __ldg(p.fco_b));
+            for (int c = 0; c < 32; ++c) acc = fmaf(v[c], __ldg(p.fco_w + 32 * g + c), acc);
+            red0[r * 4 + g] = acc;
+            named_bar_sync(1, NCT);
+            if (g == 0 && valid && tk == 0) {
+              const float4 a4 = *reinterpret_cast<const float4*>(red0 + r * 4);
+              p.out[q_idx] = p.out_scale * (a4.x + a4.y + a4.z + a4.w + __ldg(p.fco_b));
+            }
           }
         }
+        lap(PF_LN2);
       }
-      // all warps must be done with TMEM R / the scratch before the next tile's token build
-      named_bar_sync(1, 128);
+      if (tid == 0) atomicAdd(&g_prof[PF_TILES], 1ull);
+    }
+    if (tid == 0) {
+#pragma unroll
+      for (int i = 0; i < 12; ++i) atomicAdd(&g_prof[i], (unsigned long long)pf[i]);
     }
   }
   tc_fence_before();
@@ -559,11 +688,11 @@ __global__ void __launch_bounds__(128, 1) umma_selftest_kernel(const float* __re
     tc_fence_after();
     const uint32_t w = sbase + OFF_RING;
     if (mode == 0)
-      issue_unit<NPASS>(tmem, sbase + OFF_AX_HI, sbase + OFF_AX_LO, 16384u, w, w + UNIT_PART_BYTES, 8192u, 8,
-                        make_idesc_bf16(64), true);
+      issue_unit<NPASS, 8, 16384u, 8192u, make_idesc_bf16(64)>(tmem, sbase + OFF_AX_HI, sbase + OFF_AX_LO, w,
+                                                                 w + UNIT_PART_BYTES, true);
     else
-      issue_unit<NPASS>(tmem, sbase + OFF_AX_HI, sbase + OFF_AX_LO, 0u, w, w + UNIT_PART_BYTES, 0u, 4,
-                        make_idesc_bf16(128), true);
+      issue_unit<NPASS, 4, 0u, 0u, make_idesc_bf16(128)>(tmem, sbase + OFF_AX_HI, sbase + OFF_AX_LO, w,
+                                                           w + UNIT_PART_BYTES, true);
     umma_commit(done);
   }
   mbar_wait(done, 0);
@@ -655,6 +784,43 @@ int dectc_pack(s3d_model* m, cudaStream_t st) {
   S3D_CUDA(cudaStreamSynchronize(st));
   m->dectc.wimg = static_cast<__nv_bfloat16*>(d);
   m->dectc.wimg_elems = total / 2;
+  // per-layer fp32 vector blocks (biases, LayerNorm affines) in the order of the V_* offsets
+  std::vector<float> vecs((size_t)3 * VEC_FLOATS, 0.f);
+  auto get = [&](const float* src, int n, float* dst) -> int {
+    S3D_CUDA(cudaMemcpyAsync(dst, src, n * sizeof(float), cudaMemcpyDeviceToHost, st));
+    return S3D_OK;
+  };
+  for (int l = 0; l < 3; ++l) {
+    const DecLayerF32& L = m->dec32.L[l];
+    float* v = vecs.data() + (size_t)l * VEC_FLOATS;
+    S3D_TRY(get(L.in_proj.shift, 384, v + V_BIN));
+    if (l < 2) S3D_TRY(get(m->dec32.L[l + 1].out_proj.shift, 128, v + V_BONEXT));
+    S3D_TRY(get(L.n1_w, 128, v + V_LN1W));
+    S3D_TRY(get(L.n1_b, 128, v + V_LN1B));
+    S3D_TRY(get(L.lin1.shift, 2048, v + V_B1));
+    S3D_TRY(get(L.lin2.shift, 128, v + V_B2));
+    S3D_TRY(get(L.n2_w, 128, v + V_LN2W));
+    S3D_TRY(get(L.n2_b, 128, v + V_LN2B));
+  }
+  S3D_CUDA(cudaStreamSynchronize(st));
+  void* dv = nullptr;
+  S3D_CUDA(cudaMalloc(&dv, vecs.size() * sizeof(float)));
+  m->allocs.push_back(dv);
+  S3D_CUDA(cudaMemcpyAsync(dv, vecs.data(), vecs.size() * sizeof(float), cudaMemcpyHostToDevice, st));
+  S3D_CUDA(cudaStreamSynchronize(st));
+  m->dectc.vec = static_cast<float*>(dv);
+  return S3D_OK;
+}
+
+int debug_profile(long long* out32, int reset) {
+  unsigned long long h[32];
+  S3D_CUDA(cudaMemcpyFromSymbol(h, g_prof, sizeof(h)));
+  if (out32)
+    for (int i = 0; i < 32; ++i) out32[i] = (long long)h[i];
+  if (reset) {
+    std::memset(h, 0, sizeof(h));
+    S3D_CUDA(cudaMemcpyToSymbol(g_prof, h, sizeof(h)));
+  }
   return S3D_OK;
 }
 
@@ -669,6 +835,7 @@ int decoder_tc(const s3d_model* m, const float* planes, int S, const QueryCtx& q
   if (n <= 0) return S3D_OK;
   TcParams p{};
   p.wimg = reinterpret_cast<const uint8_t*>(m->dectc.wimg);
+  p.vecs = m->dectc.vec;
   p.planes = planes;
   p.S = S;
   p.q = q;
@@ -677,12 +844,7 @@ int decoder_tc(const s3d_model* m, const float* planes, int S, const QueryCtx& q
   p.out = out;
   const DecF32& d = m->dec32;
   p.fcp_wt = d.fcp_wt; p.fcp_b = d.fcp_b; p.fcs_b = d.fcs_b; p.fco_w = d.fco_w; p.fco_b = d.fco_b;
-  for (int l = 0; l < 3; ++l) {
-    p.b_in[l] = d.L[l].in_proj.shift; p.b_o[l] = d.L[l].out_proj.shift;
-    p.ln1w[l] = d.L[l].n1_w; p.ln1b[l] = d.L[l].n1_b;
-    p.b1[l] = d.L[l].lin1.shift; p.b2[l] = d.L[l].lin2.shift;
-    p.ln2w[l] = d.L[l].n2_w; p.ln2b[l] = d.L[l].n2_b;
-  }
+  p.b_o0 = d.L[0].out_proj.shift;
   p.num_tiles = (n + TILE_Q - 1) / TILE_Q;
   int dev = 0, sms = 148;
   S3D_CUDA(cudaGetDevice(&dev));
@@ -690,10 +852,10 @@ int decoder_tc(const s3d_model* m, const float* planes, int S, const QueryCtx& q
   const unsigned grid = (unsigned)(p.num_tiles < sms ? p.num_tiles : sms);
   if (precision == S3D_PREC_BF16X3) {
     S3D_CUDA(cudaFuncSetAttribute(decoder_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    decoder_tc_kernel<3><<<grid, 192, SMEM_BYTES, st>>>(p);
+    decoder_tc_kernel<3><<<grid, NTHREADS, SMEM_BYTES, st>>>(p);
   } else {
     S3D_CUDA(cudaFuncSetAttribute(decoder_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    decoder_tc_kernel<1><<<grid, 192, SMEM_BYTES, st>>>(p);
+    decoder_tc_kernel<1><<<grid, NTHREADS, SMEM_BYTES, st>>>(p);
   }
   S3D_LAUNCH_CHECK();
   return S3D_OK;
