@@ -34,7 +34,7 @@ using namespace ptx;
 
 constexpr int TILE_Q = 9;    // queries per tile
 constexpr int NTOK = 13;     // tokens per query (K = 12 slices + the query token)
-constexpr int NSLOT_MAX = 6;  // weight ring depth: 3 x 32 KB (bf16x3) or 6 x 16 KB (bf16)
+constexpr int NSLOT = 5;      // weight ring: 5 slots of one 16 KB part (a unit = hi part [+ lo part])
 constexpr int UNITS_PER_LAYER = 72;  // 6 (in_proj) + 2 (out_proj) + 32 (linear1) + 32 (linear2)
 constexpr int UNIT_PART_BYTES = 16384;  // one precision part (hi or lo) of a unit: 64x128 or 128x64 bf16
 constexpr int UNIT_STRIDE_BYTES = 2 * UNIT_PART_BYTES;  // hi then lo in global memory
@@ -44,23 +44,23 @@ constexpr int NCT = NCW * 32;
 constexpr int NTHREADS = NCT + 64;  // + producer warp + MMA warp
 
 // per-layer fp32 vector block staged in shared memory (floats)
-constexpr int V_BIN = 0, V_BONEXT = 384, V_LN1W = 512, V_LN1B = 640, V_B1 = 768, V_B2 = 2816, V_LN2W = 2944,
-              V_LN2B = 3072, VEC_FLOATS = 3200;
+constexpr int V_BIN = 0, V_BONEXT = 384, V_LN1W = 512, V_LN1B = 640, V_B2 = 768, V_LN2W = 896, V_LN2B = 1024,
+              V_SMEM_FLOATS = 1152, V_B1 = 1152, VEC_FLOATS = 3200;  // b1 (2048) stays in global memory
 
 // shared memory map (bytes from the 1024-aligned base)
 constexpr uint32_t OFF_AX_HI = 0;                 // [2 k-blocks][128 rows][64] bf16 = 32 KB
 constexpr uint32_t OFF_AX_LO = 32768;             // 32 KB
-constexpr uint32_t OFF_HKV = 65536;               // H chunk operand (hi 16 KB, lo 16 KB) | K/V staging | gather scratch
-constexpr uint32_t HKV_BYTES = 36864;             // 2 x [128][36] fp32
-constexpr uint32_t OFF_RING = OFF_HKV + HKV_BYTES;  // 102400, 1024-aligned
-constexpr uint32_t OFF_VEC = OFF_RING + 3 * UNIT_STRIDE_BYTES;  // 200704
-constexpr uint32_t OFF_RED = OFF_VEC + VEC_FLOATS * 4;              // 2 x [128][4] fp32 LayerNorm partials
+constexpr uint32_t OFF_H = 65536;                 // 2 x (H chunk hi 16 KB + lo 16 KB) | K/V staging [128][128] fp32 | gather scratch
+constexpr uint32_t H_BUF_BYTES = 32768;
+constexpr uint32_t OFF_RING = OFF_H + 2 * H_BUF_BYTES;  // 131072
+constexpr uint32_t OFF_VEC = OFF_RING + NSLOT * UNIT_PART_BYTES;  // 212992
+constexpr uint32_t OFF_RED = OFF_VEC + V_SMEM_FLOATS * 4;          // 2 x [128][4] fp32 LayerNorm partials
 constexpr uint32_t OFF_BAR = OFF_RED + 4096;
-constexpr uint32_t SMEM_BYTES = OFF_BAR + 256 + 1024;               // + alignment slack
+constexpr uint32_t SMEM_BYTES = OFF_BAR + 256 + 1024;              // + alignment slack
 
 // barrier indices (8 bytes each at OFF_BAR)
-enum { B_AREADY = 0, B_DDONE, B_D1READY0, B_D1READY1, B_D1FREE0, B_D1FREE1, B_HREADY, B_HFREE, B_FULL0,
-       B_EMPTY0 = B_FULL0 + NSLOT_MAX, B_COUNT = B_EMPTY0 + NSLOT_MAX };
+enum { B_AREADY = 0, B_DDONE, B_D1READY0, B_D1READY1, B_D1FREE0, B_D1FREE1, B_HREADY0, B_HREADY1, B_HFREE0, B_HFREE1,
+       B_FULL0, B_EMPTY0 = B_FULL0 + NSLOT, B_COUNT = B_EMPTY0 + NSLOT };
 constexpr uint32_t OFF_TMEMPTR = OFF_BAR + 8 * B_COUNT;
 
 // TMEM columns
@@ -76,6 +76,7 @@ __device__ unsigned long long g_prof[32];
 struct TcParams {
   const uint8_t* wimg;  // [3 layers][72 units][hi 16 KB | lo 16 KB]
   const float* vecs;    // [3 layers][VEC_FLOATS]
+  const uint32_t* order;  // part stream: [bf16x3: 432 part indices][bf16: 216 part indices]
   const float* planes;
   int S;
   QueryCtx q;
@@ -108,22 +109,17 @@ __device__ __forceinline__ void store_chunk(uint8_t* tile_hi, uint8_t* tile_lo, 
 }
 
 // ---- MMA issue -----------------------------------------------------------------------------
-// One weight unit against one activation operand: KS k-steps of 16, NPASS passes, fully unrolled
-// with compile-time descriptor increments (the issuing lane executes ~2 instructions per MMA).
-//   a_hi/a_lo, b_hi/b_lo: shared addresses of the operand tiles; *_KB: byte stride between 64-wide k-blocks.
-template <int NPASS, int KS, uint32_t A_KB, uint32_t B_KB, uint32_t IDESC>
-__device__ __forceinline__ void issue_unit(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo,
-                                           bool fresh) {
-  const uint64_t ah = make_desc_sw128(a_hi), al = make_desc_sw128(a_lo);
-  const uint64_t bh = make_desc_sw128(b_hi), bl = make_desc_sw128(b_lo);
+// One 16 KB weight part (B) against NA activation operands (a0 [, a1]): D += a0.B [+ a1.B], KS k-steps
+// of 16 each, fully unrolled with compile-time descriptor increments.
+//   *_KB: byte stride between 64-wide k-blocks of the A / B tiles.
+template <int NA, int KS, uint32_t A_KB, uint32_t B_KB, uint32_t IDESC>
+__device__ __forceinline__ void issue_part(uint32_t d_tmem, uint32_t a0, uint32_t a1, uint32_t b, bool fresh) {
+  const uint64_t ad0 = make_desc_sw128(a0), ad1 = make_desc_sw128(a1), bd = make_desc_sw128(b);
 #pragma unroll
-  for (int pass = 0; pass < NPASS; ++pass) {
-    const uint64_t ad = (pass == 1) ? al : ah;
-    const uint64_t bd = (pass == 2) ? bl : bh;
+  for (int pass = 0; pass < NA; ++pass) {
+    const uint64_t ad = (pass == 1) ? ad1 : ad0;
 #pragma unroll
     for (int ks = 0; ks < KS; ++ks) {
-      constexpr uint32_t dummy = 0;
-      (void)dummy;
       const uint32_t kb = ks >> 2, kin = (ks & 3) * 32;
       umma_bf16(d_tmem, ad + ((kb * A_KB + kin) >> 4), bd + ((kb * B_KB + kin) >> 4), IDESC,
                 (pass == 0 && ks == 0 && fresh) ? 0u : 1u);
@@ -153,9 +149,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
     mbar_init(bar(B_D1READY1), 1);
     mbar_init(bar(B_D1FREE0), NCW);
     mbar_init(bar(B_D1FREE1), NCW);
-    mbar_init(bar(B_HREADY), NCW);
-    mbar_init(bar(B_HFREE), 1);
-    for (int s = 0; s < NSLOT_MAX; ++s) {
+    mbar_init(bar(B_HREADY0), NCW);
+    mbar_init(bar(B_HREADY1), NCW);
+    mbar_init(bar(B_HFREE0), 1);
+    mbar_init(bar(B_HFREE1), 1);
+    for (int s = 0; s < NSLOT; ++s) {
       mbar_init(bar(B_FULL0 + s), 1);
       mbar_init(bar(B_EMPTY0 + s), 1);
     }
@@ -167,9 +165,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
   tc_fence_after();
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(sgen + OFF_TMEMPTR);
 
-  constexpr uint32_t COPY_BYTES = (NPASS == 3) ? UNIT_STRIDE_BYTES : UNIT_PART_BYTES;
-  constexpr int NSLOT = (NPASS == 3) ? 3 : 6;
-  constexpr uint32_t SLOT_BYTES = COPY_BYTES;
+  constexpr int NPART = (NPASS == 3) ? 2 : 1;  // ring parts per weight unit (hi [, lo])
 
   if (warp == NCW) {
     // ===================================================================== weight producer
@@ -180,17 +176,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
       const long long t_start = clock64();
       for (long long tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
 #pragma unroll 1
-        for (int g = 0; g < 3 * UNITS_PER_LAYER; ++g) {
+        for (int g = 0; g < 3 * UNITS_PER_LAYER * NPART; ++g) {
           const long long t0 = clock64();
           mbar_wait(bar(B_EMPTY0 + slot), (ph_empty >> slot) & 1u);
           ph_empty ^= 1u << slot;
           w_e += clock64() - t0;
           if (elect_one()) {
-            mbar_arrive_expect_tx(bar(B_FULL0 + slot), COPY_BYTES);
+            // part g of the stream (order built on the host to match the issuer, see dectc_pack)
+            const uint8_t* src = p.wimg + (size_t)__ldg(p.order + (NPASS == 3 ? 0 : 3 * UNITS_PER_LAYER * 2) + g) * UNIT_PART_BYTES;
+            mbar_arrive_expect_tx(bar(B_FULL0 + slot), UNIT_PART_BYTES);
 #pragma unroll
-            for (uint32_t part = 0; part < COPY_BYTES; part += 8192)
-              bulk_g2s(sbase + OFF_RING + slot * SLOT_BYTES + part, p.wimg + (size_t)g * UNIT_STRIDE_BYTES + part, 8192,
-                       bar(B_FULL0 + slot));
+            for (uint32_t part = 0; part < UNIT_PART_BYTES; part += 8192)
+              bulk_g2s(sbase + OFF_RING + slot * UNIT_PART_BYTES + part, src + part, 8192, bar(B_FULL0 + slot));
           }
           __syncwarp();
           slot = (slot + 1 == NSLOT) ? 0 : slot + 1;
@@ -205,19 +202,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
     // ===================================================================== MMA issuer
     // the whole warp runs the control flow (waits are warp-uniform); one elected lane issues
     {
-      uint32_t ph_a = 0, ph_full = 0, ph_d1free = 3u, ph_hr = 0;  // parity bits
+      uint32_t ph_a = 0, ph_full = 0, ph_d1free = 3u, ph_hr = 0;  // parity bits (one per barrier / slot)
       int slot = 0;
       long long w_a = 0, w_full = 0, w_h = 0, w_d1 = 0;
       const long long t_start = clock64();
       const uint32_t ax_hi = sbase + OFF_AX_HI, ax_lo = sbase + OFF_AX_LO;
-      const uint32_t h_hi = sbase + OFF_HKV, h_lo = sbase + OFF_HKV + UNIT_PART_BYTES;
+      const uint32_t h_base = sbase + OFF_H;
       constexpr uint32_t ID64 = make_idesc_bf16(64), ID128 = make_idesc_bf16(128);
       auto wait_full = [&]() -> uint32_t {
         const long long t0 = clock64();
         mbar_wait(bar(B_FULL0 + slot), (ph_full >> slot) & 1u);
         ph_full ^= 1u << slot;
         w_full += clock64() - t0;
-        return sbase + OFF_RING + slot * SLOT_BYTES;
+        return sbase + OFF_RING + slot * UNIT_PART_BYTES;
       };
       auto commit = [&](int b) {
         if (elect_one()) umma_commit(bar(b));
@@ -227,14 +224,24 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
         commit(B_EMPTY0 + slot);
         slot = (slot + 1 == NSLOT) ? 0 : slot + 1;
       };
+      // One weight unit = its hi part (passes A_hi.B_hi [, A_lo.B_hi]) then, for bf16x3, its lo part
+      // (pass A_hi.B_lo); each part is one ring slot, released as soon as its MMAs are issued.  (Splitting
+      // the accumulation into two interleaved chains was measured and did not help: the pipe already runs
+      // at ~86 % of its rate while the issuer is busy.)
       // unit of 64 output columns over K = 128 (in_proj / out_proj / linear1), A = AX
       auto unit_n64 = [&](uint32_t d_col, bool fresh) {
-        const uint32_t w = wait_full();
+        uint32_t w = wait_full();
         tc_fence_after();
-        if (elect_one())
-          issue_unit<NPASS, 8, 16384u, 8192u, ID64>(tmem + d_col, ax_hi, ax_lo, w, w + UNIT_PART_BYTES, fresh);
+        if (elect_one()) issue_part<(NPASS == 3 ? 2 : 1), 8, 16384u, 8192u, ID64>(tmem + d_col, ax_hi, ax_lo, w, fresh);
         __syncwarp();
         release();
+        if (NPASS == 3) {
+          w = wait_full();
+          tc_fence_after();
+          if (elect_one()) issue_part<1, 8, 16384u, 8192u, ID64>(tmem + d_col, ax_hi, ax_hi, w, false);
+          __syncwarp();
+          release();
+        }
       };
       for (long long tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
 #pragma unroll 1
@@ -277,17 +284,24 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
             commit(B_D1READY0 + (c & 1));
           };
           auto issue2 = [&](int c) {
-            const uint32_t w = wait_full();
+            const uint32_t h_hi = h_base + (c & 1) * H_BUF_BYTES, h_lo = h_hi + UNIT_PART_BYTES;
+            uint32_t w = wait_full();
             const long long t0 = clock64();
-            mbar_wait(bar(B_HREADY), ph_hr);
-            ph_hr ^= 1;
+            mbar_wait(bar(B_HREADY0 + (c & 1)), (ph_hr >> (c & 1)) & 1u);
+            ph_hr ^= 1u << (c & 1);
             w_h += clock64() - t0;
             tc_fence_after();
-            if (elect_one())
-              issue_unit<NPASS, 4, 0u, 0u, ID128>(tmem + TM_R, h_hi, h_lo, w, w + UNIT_PART_BYTES, false);
+            if (elect_one()) issue_part<(NPASS == 3 ? 2 : 1), 4, 0u, 0u, ID128>(tmem + TM_R, h_hi, h_lo, w, false);
             __syncwarp();
             release();
-            commit(B_HFREE);
+            if (NPASS == 3) {
+              w = wait_full();
+              tc_fence_after();
+              if (elect_one()) issue_part<1, 4, 0u, 0u, ID128>(tmem + TM_R, h_hi, h_hi, w, false);
+              __syncwarp();
+              release();
+            }
+            commit(B_HFREE0 + (c & 1));
           };
           issue1(0);
 #pragma unroll 1
@@ -315,23 +329,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
     const uint32_t trow = tmem + (static_cast<uint32_t>(q4 * 32) << 16);
     uint8_t* ax_hi = sgen + OFF_AX_HI;
     uint8_t* ax_lo = sgen + OFF_AX_LO;
-    uint8_t* h_hi = sgen + OFF_HKV;
-    uint8_t* h_lo = sgen + OFF_HKV + UNIT_PART_BYTES;
     const float* vec = reinterpret_cast<const float*>(sgen + OFF_VEC);
     float* red0 = reinterpret_cast<float*>(sgen + OFF_RED);
     float* red1 = red0 + 512;
-    uint32_t ph_d = 0, ph_d1r = 0, ph_hf = 1;
+    uint32_t ph_d = 0, ph_d1r = 0, ph_hf = 3u;
     const int qi = r / NTOK, tk = r - qi * NTOK;
     const unsigned FULL = 0xffffffffu;
-    long long pf[12];
+    uint32_t pf[12];
 #pragma unroll
     for (int i = 0; i < 12; ++i) pf[i] = 0;
-    long long tprev = clock64();
-    auto lap = [&](int i) {
-      const long long t = clock64();
-      pf[i] += t - tprev;
-      tprev = t;
-    };
+    uint32_t tprev = (uint32_t)clock();
+#define lap(i)                            \
+  {                                       \
+    const uint32_t t_ = (uint32_t)clock(); \
+    pf[i] += t_ - tprev;                  \
+    tprev = t_;                           \
+  }
 
     // LayerNorm over the 128 channels of row r, 32 of them in v[] (partials exchanged through smem)
     auto layer_norm = [&](float* v, const float* w, const float* b) {
@@ -390,7 +403,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
         float px = 0.f, py = 0.f, pz = 0.f, gu = 0.f, gv = 0.f;
         if (valid) load_query(p.q, q_idx, px, py, pz, gu, gv);
         float v[32];
-        float* scr = reinterpret_cast<float*>(sgen + OFF_HKV) + warp * (4 * 36);
+        float* scr = reinterpret_cast<float*>(sgen + OFF_H) + warp * (4 * 36);
         const int qtr = lane >> 3, l8 = lane & 7;
         const int ch = 32 * g + l8 * 4;
 #pragma unroll 1
@@ -441,7 +454,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
         store_ax(v);
         publish(v, p.b_o0);
       }
-      lap(PF_TOKEN);
+      lap(PF_TOKEN)
 
 #pragma unroll 1
       for (int layer = 0; layer < 3; ++layer) {
@@ -450,123 +463,127 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
         {
           const float4* src = reinterpret_cast<const float4*>(p.vecs + (size_t)layer * VEC_FLOATS);
           float4* dst = reinterpret_cast<float4*>(sgen + OFF_VEC);
-          for (int i = tid; i < VEC_FLOATS / 4; i += NCT) dst[i] = __ldg(src + i);
+          for (int i = tid; i < V_SMEM_FLOATS / 4; i += NCT) dst[i] = __ldg(src + i);
         }
         named_bar_sync(1, NCT);
-        lap(PF_VEC);
+        lap(PF_VEC)
         // -------------------------------------------------------------- attention (13x13 per query and head)
         mbar_wait(bar(B_DDONE), ph_d);
         ph_d ^= 1;
         tc_fence_after();
-        lap(PF_WAIT_QKV);
-        if (g < 2) {  // column groups 0,1 take heads (0,1) then (2,3); K then V staged per head
-          float* st = reinterpret_cast<float*>(sgen + OFF_HKV) + g * (128 * 36);
+        lap(PF_WAIT_QKV)
+        {
+          // column group g takes head g.  K (then V) of all heads is staged as one [128][128] fp32 matrix in
+          // the H region; 16-byte chunk c4 of row q is stored at chunk (c4 ^ (q & 7)) so that the four
+          // queries a warp touches at once hit distinct banks without padding.
+          float* st = reinterpret_cast<float*>(sgen + OFF_H);
           const float* b_in = vec + V_BIN;
-#pragma unroll 1
-          for (int rnd = 0; rnd < 2; ++rnd) {
-            const int h = 2 * rnd + g;
-            float sc[NTOK];
-            {
-              float kk[32];
-              tmem_ld32(trow + TM_S + 128 + 32 * h, kk);
-              tmem_ld_wait();
+          const int h = g;
+          float sc[NTOK];
+          {
+            float kk[32];
+            tmem_ld32(trow + TM_S + 128 + 32 * h, kk);
+            tmem_ld_wait();
 #pragma unroll
-              for (int c = 0; c < 32; c += 4) {
-                const float4 b4 = *reinterpret_cast<const float4*>(b_in + 128 + 32 * h + c);
-                *reinterpret_cast<float4*>(st + r * 36 + c) =
-                    make_float4(kk[c] + b4.x, kk[c + 1] + b4.y, kk[c + 2] + b4.z, kk[c + 3] + b4.w);
-              }
+            for (int c = 0; c < 32; c += 4) {
+              const float4 b4 = *reinterpret_cast<const float4*>(b_in + 128 + 32 * h + c);
+              *reinterpret_cast<float4*>(st + r * 128 + ((((32 * h + c) >> 2) ^ (r & 7)) << 2)) =
+                  make_float4(kk[c] + b4.x, kk[c + 1] + b4.y, kk[c + 2] + b4.z, kk[c + 3] + b4.w);
             }
-            named_bar_sync(2, 256);
-            {
-              float qq[32];
-              tmem_ld32(trow + TM_S + 32 * h, qq);
-              tmem_ld_wait();
-#pragma unroll
-              for (int c = 0; c < 32; c += 4) {
-                const float4 b4 = *reinterpret_cast<const float4*>(b_in + 32 * h + c);
-                qq[c] = (qq[c] + b4.x) * 0.17677669529663687f;
-                qq[c + 1] = (qq[c + 1] + b4.y) * 0.17677669529663687f;
-                qq[c + 2] = (qq[c + 2] + b4.z) * 0.17677669529663687f;
-                qq[c + 3] = (qq[c + 3] + b4.w) * 0.17677669529663687f;
-              }
-#pragma unroll
-              for (int j = 0; j < NTOK; ++j) sc[j] = 0.f;
-              if (valid) {
-                const float* kb = st + qi * NTOK * 36;
-                float mx = -3.0e38f;
-#pragma unroll
-                for (int j = 0; j < NTOK; ++j) {
-                  float s = 0.f;
-#pragma unroll
-                  for (int c = 0; c < 32; c += 4) {
-                    const float4 k4 = *reinterpret_cast<const float4*>(kb + j * 36 + c);
-                    s = fmaf(qq[c], k4.x, s);
-                    s = fmaf(qq[c + 1], k4.y, s);
-                    s = fmaf(qq[c + 2], k4.z, s);
-                    s = fmaf(qq[c + 3], k4.w, s);
-                  }
-                  sc[j] = s;
-                  mx = fmaxf(mx, s);
-                }
-                float sum = 0.f;
-#pragma unroll
-                for (int j = 0; j < NTOK; ++j) {
-                  sc[j] = __expf(sc[j] - mx);
-                  sum += sc[j];
-                }
-                const float inv = 1.f / sum;
-#pragma unroll
-                for (int j = 0; j < NTOK; ++j) sc[j] *= inv;
-              }
-            }
-            named_bar_sync(2, 256);  // everyone has read K
-            {
-              float vv[32];
-              tmem_ld32(trow + TM_S + 256 + 32 * h, vv);
-              tmem_ld_wait();
-#pragma unroll
-              for (int c = 0; c < 32; c += 4) {
-                const float4 b4 = *reinterpret_cast<const float4*>(b_in + 256 + 32 * h + c);
-                *reinterpret_cast<float4*>(st + r * 36 + c) =
-                    make_float4(vv[c] + b4.x, vv[c + 1] + b4.y, vv[c + 2] + b4.z, vv[c + 3] + b4.w);
-              }
-            }
-            named_bar_sync(2, 256);
-            {
-              float o[32];
-#pragma unroll
-              for (int c = 0; c < 32; ++c) o[c] = 0.f;
-              if (valid) {
-                const float* vb = st + qi * NTOK * 36;
-#pragma unroll
-                for (int j = 0; j < NTOK; ++j) {
-#pragma unroll
-                  for (int c = 0; c < 32; c += 4) {
-                    const float4 v4 = *reinterpret_cast<const float4*>(vb + j * 36 + c);
-                    o[c] = fmaf(sc[j], v4.x, o[c]);
-                    o[c + 1] = fmaf(sc[j], v4.y, o[c + 1]);
-                    o[c + 2] = fmaf(sc[j], v4.z, o[c + 2]);
-                    o[c + 3] = fmaf(sc[j], v4.w, o[c + 3]);
-                  }
-                }
-              }
-              // O[:, 32h:32h+32] -> operand A (k-block h/2, chunks 4*(h&1)..+3)
-#pragma unroll
-              for (int cc = 0; cc < 4; ++cc)
-                store_chunk<NPASS>(ax_hi + (h >> 1) * 16384, ax_lo + (h >> 1) * 16384, r, (h & 1) * 4 + cc, o + 8 * cc);
-            }
-            named_bar_sync(2, 256);  // everyone has read V before the next round overwrites the staging
           }
+          named_bar_sync(1, NCT);
+          {
+            float qq[32];
+            tmem_ld32(trow + TM_S + 32 * h, qq);
+            tmem_ld_wait();
+#pragma unroll
+            for (int c = 0; c < 32; c += 4) {
+              const float4 b4 = *reinterpret_cast<const float4*>(b_in + 32 * h + c);
+              qq[c] = (qq[c] + b4.x) * 0.17677669529663687f;
+              qq[c + 1] = (qq[c + 1] + b4.y) * 0.17677669529663687f;
+              qq[c + 2] = (qq[c + 2] + b4.z) * 0.17677669529663687f;
+              qq[c + 3] = (qq[c + 3] + b4.w) * 0.17677669529663687f;
+            }
+#pragma unroll
+            for (int j = 0; j < NTOK; ++j) sc[j] = 0.f;
+            if (valid) {
+              float mx = -3.0e38f;
+#pragma unroll
+              for (int j = 0; j < NTOK; ++j) {
+                const int row = qi * NTOK + j;
+                const float* kb = st + row * 128;
+                float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+                for (int c = 0; c < 32; c += 8) {
+                  const float4 k4 = *reinterpret_cast<const float4*>(kb + ((((32 * h + c) >> 2) ^ (row & 7)) << 2));
+                  const float4 k5 = *reinterpret_cast<const float4*>(kb + ((((32 * h + c + 4) >> 2) ^ (row & 7)) << 2));
+                  s0 = fmaf(qq[c], k4.x, s0);
+                  s1 = fmaf(qq[c + 4], k5.x, s1);
+                  s0 = fmaf(qq[c + 1], k4.y, s0);
+                  s1 = fmaf(qq[c + 5], k5.y, s1);
+                  s0 = fmaf(qq[c + 2], k4.z, s0);
+                  s1 = fmaf(qq[c + 6], k5.z, s1);
+                  s0 = fmaf(qq[c + 3], k4.w, s0);
+                  s1 = fmaf(qq[c + 7], k5.w, s1);
+                }
+                sc[j] = s0 + s1;
+                mx = fmaxf(mx, sc[j]);
+              }
+              float sum = 0.f;
+#pragma unroll
+              for (int j = 0; j < NTOK; ++j) {
+                sc[j] = __expf(sc[j] - mx);
+                sum += sc[j];
+              }
+              const float inv = 1.f / sum;
+#pragma unroll
+              for (int j = 0; j < NTOK; ++j) sc[j] *= inv;
+            }
+          }
+          named_bar_sync(1, NCT);  // everyone has read K
+          {
+            float vv[32];
+            tmem_ld32(trow + TM_S + 256 + 32 * h, vv);
+            tmem_ld_wait();
+#pragma unroll
+            for (int c = 0; c < 32; c += 4) {
+              const float4 b4 = *reinterpret_cast<const float4*>(b_in + 256 + 32 * h + c);
+              *reinterpret_cast<float4*>(st + r * 128 + ((((32 * h + c) >> 2) ^ (r & 7)) << 2)) =
+                  make_float4(vv[c] + b4.x, vv[c + 1] + b4.y, vv[c + 2] + b4.z, vv[c + 3] + b4.w);
+            }
+          }
+          named_bar_sync(1, NCT);
+          {
+            float o[32];
+#pragma unroll
+            for (int c = 0; c < 32; ++c) o[c] = 0.f;
+            if (valid) {
+#pragma unroll
+              for (int j = 0; j < NTOK; ++j) {
+                const int row = qi * NTOK + j;
+                const float* vb = st + row * 128;
+#pragma unroll
+                for (int c = 0; c < 32; c += 4) {
+                  const float4 v4 = *reinterpret_cast<const float4*>(vb + ((((32 * h + c) >> 2) ^ (row & 7)) << 2));
+                  o[c] = fmaf(sc[j], v4.x, o[c]);
+                  o[c + 1] = fmaf(sc[j], v4.y, o[c + 1]);
+                  o[c + 2] = fmaf(sc[j], v4.z, o[c + 2]);
+                  o[c + 3] = fmaf(sc[j], v4.w, o[c + 3]);
+                }
+              }
+            }
+            store_ax(o);  // O[:, 32h:32h+32] -> operand A (same columns as this thread's quarter)
+          }
+          // (the staging region is next written by the FFN epilogue, after LayerNorm 1's barriers)
           fence_proxy_async_smem();
         }
         warp_arrive(bar(B_AREADY), lane);
-        lap(PF_ATTN);
+        lap(PF_ATTN)
         // -------------------------------------------------------------- residual + LayerNorm 1 (in place in TMEM)
         mbar_wait(bar(B_DDONE), ph_d);
         ph_d ^= 1;
         tc_fence_after();
-        lap(PF_WAIT_OUT);
+        lap(PF_WAIT_OUT)
         {
           float v[32];
           tmem_ld32(trow + TM_R + 32 * g, v);
@@ -575,45 +592,57 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
           store_ax(v);
           publish(v, vec + V_B2);
         }
-        lap(PF_LN1);
+        lap(PF_LN1)
         // -------------------------------------------------------------- FFN hidden chunks (16 columns per thread)
         {
+          const float4* b1g = reinterpret_cast<const float4*>(p.vecs + (size_t)layer * VEC_FLOATS + V_B1 + 16 * g);
+          float4 bn[4];  // linear1 bias of the next chunk, prefetched (uniform address per warp)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) bn[j] = __ldg(b1g + j);
 #pragma unroll 1
           for (int c = 0; c < NCHUNK; ++c) {
             const int bsel = c & 1;
+            float4 bc[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) bc[j] = bn[j];
+            if (c + 1 < NCHUNK) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) bn[j] = __ldg(b1g + (c + 1) * 16 + j);
+            }
             mbar_wait(bar(B_D1READY0 + bsel), (ph_d1r >> bsel) & 1u);
             ph_d1r ^= 1u << bsel;
             tc_fence_after();
-            lap(PF_FFN_WAIT_D1);
+            lap(PF_FFN_WAIT_D1)
             float d[16];
             tmem_ld16(trow + TM_S + 64 * bsel + 16 * g, d);
             tmem_ld_wait();
             tc_fence_before();
             warp_arrive(bar(B_D1FREE0 + bsel), lane);
 #pragma unroll
-            for (int j = 0; j < 16; j += 4) {
-              const float4 b4 = *reinterpret_cast<const float4*>(vec + V_B1 + c * 64 + 16 * g + j);
-              d[j] = fmaxf(d[j] + b4.x, 0.f);
-              d[j + 1] = fmaxf(d[j + 1] + b4.y, 0.f);
-              d[j + 2] = fmaxf(d[j + 2] + b4.z, 0.f);
-              d[j + 3] = fmaxf(d[j + 3] + b4.w, 0.f);
+            for (int j = 0; j < 4; ++j) {
+              d[4 * j] = fmaxf(d[4 * j] + bc[j].x, 0.f);
+              d[4 * j + 1] = fmaxf(d[4 * j + 1] + bc[j].y, 0.f);
+              d[4 * j + 2] = fmaxf(d[4 * j + 2] + bc[j].z, 0.f);
+              d[4 * j + 3] = fmaxf(d[4 * j + 3] + bc[j].w, 0.f);
             }
-            lap(PF_FFN_MATH);
-            mbar_wait(bar(B_HFREE), ph_hf);
-            ph_hf ^= 1;
-            lap(PF_FFN_WAIT_HFREE);
+            lap(PF_FFN_MATH)
+            mbar_wait(bar(B_HFREE0 + bsel), (ph_hf >> bsel) & 1u);
+            ph_hf ^= 1u << bsel;
+            lap(PF_FFN_WAIT_HFREE)
+            uint8_t* h_hi = sgen + OFF_H + bsel * H_BUF_BYTES;
+            uint8_t* h_lo = h_hi + UNIT_PART_BYTES;
             store_chunk<NPASS>(h_hi, h_lo, r, 2 * g, d);
             store_chunk<NPASS>(h_hi, h_lo, r, 2 * g + 1, d + 8);
             fence_proxy_async_smem();
-            warp_arrive(bar(B_HREADY), lane);
-            lap(PF_FFN_STORE);
+            warp_arrive(bar(B_HREADY0 + bsel), lane);
+            lap(PF_FFN_STORE)
           }
         }
         // -------------------------------------------------------------- residual + LayerNorm 2
         mbar_wait(bar(B_DDONE), ph_d);
         ph_d ^= 1;
         tc_fence_after();
-        lap(PF_WAIT_FFN);
+        lap(PF_WAIT_FFN)
         {
           float v[32];
           tmem_ld32(trow + TM_R + 32 * g, v);
@@ -634,14 +663,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
             }
           }
         }
-        lap(PF_LN2);
+        lap(PF_LN2)
       }
-      if (tid == 0) atomicAdd(&g_prof[PF_TILES], 1ull);
-    }
-    if (tid == 0) {
+      if (tid == 0) {
+        atomicAdd(&g_prof[PF_TILES], 1ull);
 #pragma unroll
-      for (int i = 0; i < 12; ++i) atomicAdd(&g_prof[i], (unsigned long long)pf[i]);
+        for (int i = 0; i < 12; ++i) atomicAdd(&g_prof[i], (unsigned long long)pf[i]);
+      }
+#pragma unroll
+      for (int i = 0; i < 12; ++i) pf[i] = 0;
     }
+#undef lap
   }
   tc_fence_before();
   __syncthreads();
@@ -688,11 +720,17 @@ __global__ void __launch_bounds__(128, 1) umma_selftest_kernel(const float* __re
     tc_fence_after();
     const uint32_t w = sbase + OFF_RING;
     if (mode == 0)
-      issue_unit<NPASS, 8, 16384u, 8192u, make_idesc_bf16(64)>(tmem, sbase + OFF_AX_HI, sbase + OFF_AX_LO, w,
-                                                                 w + UNIT_PART_BYTES, true);
+    {
+      issue_part<(NPASS == 3 ? 2 : 1), 8, 16384u, 8192u, make_idesc_bf16(64)>(tmem, sbase + OFF_AX_HI, sbase + OFF_AX_LO, w, true);
+      if (NPASS == 3)
+        issue_part<1, 8, 16384u, 8192u, make_idesc_bf16(64)>(tmem, sbase + OFF_AX_HI, sbase + OFF_AX_HI, w + UNIT_PART_BYTES, false);
+    }
     else
-      issue_unit<NPASS, 4, 0u, 0u, make_idesc_bf16(128)>(tmem, sbase + OFF_AX_HI, sbase + OFF_AX_LO, w,
-                                                           w + UNIT_PART_BYTES, true);
+    {
+      issue_part<(NPASS == 3 ? 2 : 1), 4, 0u, 0u, make_idesc_bf16(128)>(tmem, sbase + OFF_AX_HI, sbase + OFF_AX_LO, w, true);
+      if (NPASS == 3)
+        issue_part<1, 4, 0u, 0u, make_idesc_bf16(128)>(tmem, sbase + OFF_AX_HI, sbase + OFF_AX_HI, w + UNIT_PART_BYTES, false);
+    }
     umma_commit(done);
   }
   mbar_wait(done, 0);
@@ -809,6 +847,20 @@ int dectc_pack(s3d_model* m, cudaStream_t st) {
   S3D_CUDA(cudaMemcpyAsync(dv, vecs.data(), vecs.size() * sizeof(float), cudaMemcpyHostToDevice, st));
   S3D_CUDA(cudaStreamSynchronize(st));
   m->dectc.vec = static_cast<float*>(dv);
+  // part stream in consumption order: unit by unit, hi part then (bf16x3 only) lo part; unit u of layer l
+  // is parts 2*(72 l + u) (hi) and +1 (lo) of the image.
+  std::vector<uint32_t> order;
+  for (int x3 = 1; x3 >= 0; --x3)
+    for (int u = 0; u < 3 * UNITS_PER_LAYER; ++u) {
+      order.push_back(2u * u);
+      if (x3) order.push_back(2u * u + 1);
+    }
+  void* dord = nullptr;
+  S3D_CUDA(cudaMalloc(&dord, order.size() * sizeof(uint32_t)));
+  m->allocs.push_back(dord);
+  S3D_CUDA(cudaMemcpyAsync(dord, order.data(), order.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+  S3D_CUDA(cudaStreamSynchronize(st));
+  m->dectc.order = static_cast<uint32_t*>(dord);
   return S3D_OK;
 }
 
@@ -836,6 +888,7 @@ int decoder_tc(const s3d_model* m, const float* planes, int S, const QueryCtx& q
   TcParams p{};
   p.wimg = reinterpret_cast<const uint8_t*>(m->dectc.wimg);
   p.vecs = m->dectc.vec;
+  p.order = m->dectc.order;
   p.planes = planes;
   p.S = S;
   p.q = q;
