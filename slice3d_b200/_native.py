@@ -110,7 +110,7 @@ def selftest_umma(mode, passes, a, w):
 
 PROFILE_FIELDS = ["token", "vec", "wait_qkv", "attn", "wait_out", "ln1", "ffn_wait_d1", "ffn_math", "ffn_wait_hfree",
                   "ffn_store", "wait_ffn", "ln2", "mma_wait_a", "mma_wait_full", "mma_wait_h", "mma_wait_d1free",
-                  "mma_total", "prod_wait_empty", "prod_total", "tiles"]
+                  "mma_total", "prod_wait_empty", "prod_total", "tiles", "att_kstage", "att_scores", "att_vstage", "att_pv"]
 
 
 def debug_profile(reset=True):

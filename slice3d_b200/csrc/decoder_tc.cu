@@ -39,6 +39,8 @@ constexpr int UNITS_PER_LAYER = 72;  // 6 (in_proj) + 2 (out_proj) + 32 (linear1
 constexpr int UNIT_PART_BYTES = 16384;  // one precision part (hi or lo) of a unit: 64x128 or 128x64 bf16
 constexpr int UNIT_STRIDE_BYTES = 2 * UNIT_PART_BYTES;  // hi then lo in global memory
 constexpr int NCHUNK = 32;   // FFN hidden chunks of 64
+constexpr int TAIL_SLOTS = 14;  // tiles whose token-0 rows are batched into one tail pass (14 x 9 = 126 rows)
+constexpr int TAIL_UNIT0 = 2 * UNITS_PER_LAYER + 6;  // first unit of the tail pass: layer 2 out_proj
 constexpr int NCW = 16;      // compute warps: warp w owns TMEM lanes 32*(w&3).. and column quarter w>>2
 constexpr int NCT = NCW * 32;
 constexpr int NTHREADS = NCT + 64;  // + producer warp + MMA warp
@@ -76,6 +78,7 @@ __device__ unsigned long long g_prof[32];
 struct TcParams {
   const uint8_t* wimg;  // [3 layers][72 units][hi 16 KB | lo 16 KB]
   const float* vecs;    // [3 layers][VEC_FLOATS]
+  float* scratch;         // [grid][TAIL_SLOTS*9 rows][256] fp32: attention output | x + b_o of token-0 rows
   const uint32_t* order;  // part stream: [bf16x3: 432 part indices][bf16: 216 part indices]
   const float* planes;
   int S;
@@ -174,15 +177,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
       int slot = 0;
       long long w_e = 0;
       const long long t_start = clock64();
-      for (long long tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      // parts [g0, g1) of the stream (order built on the host to match the issuer, see dectc_pack)
+      auto stream = [&](int g0, int g1) {
 #pragma unroll 1
-        for (int g = 0; g < 3 * UNITS_PER_LAYER * NPART; ++g) {
+        for (int g = g0; g < g1; ++g) {
           const long long t0 = clock64();
           mbar_wait(bar(B_EMPTY0 + slot), (ph_empty >> slot) & 1u);
           ph_empty ^= 1u << slot;
           w_e += clock64() - t0;
           if (elect_one()) {
-            // part g of the stream (order built on the host to match the issuer, see dectc_pack)
             const uint8_t* src = p.wimg + (size_t)__ldg(p.order + (NPASS == 3 ? 0 : 3 * UNITS_PER_LAYER * 2) + g) * UNIT_PART_BYTES;
             mbar_arrive_expect_tx(bar(B_FULL0 + slot), UNIT_PART_BYTES);
 #pragma unroll
@@ -191,6 +194,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
           }
           __syncwarp();
           slot = (slot + 1 == NSLOT) ? 0 : slot + 1;
+        }
+      };
+      int pending = 0;
+      for (long long tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        stream(0, TAIL_UNIT0 * NPART);  // layers 0,1 and the in_proj of layer 2
+        ++pending;
+        if (pending == TAIL_SLOTS || tile + gridDim.x >= p.num_tiles) {
+          stream(TAIL_UNIT0 * NPART, 3 * UNITS_PER_LAYER * NPART);  // tail pass: out_proj + FFN of layer 2
+          pending = 0;
         }
       }
       if (lane == 0) {
@@ -243,73 +255,74 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
           release();
         }
       };
-      for (long long tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-#pragma unroll 1
-        for (int layer = 0; layer < 3; ++layer) {
-          // ---- QKV projection: S[:, 0:384] = X . Win^T
-          {
-            const long long t0 = clock64();
-            mbar_wait(bar(B_AREADY), ph_a);
-            w_a += clock64() - t0;
-          }
-          ph_a ^= 1;
+      auto wait_a = [&]() {
+        const long long t0 = clock64();
+        mbar_wait(bar(B_AREADY), ph_a);
+        w_a += clock64() - t0;
+        ph_a ^= 1;
+        tc_fence_after();
+      };
+      // QKV projection: S[:, 0:384] = X . Win^T
+      auto mma_qkv = [&]() {
+        wait_a();
+        for (int u = 0; u < 6; ++u) unit_n64(TM_S + 64 * u, true);
+        commit(B_DDONE);
+      };
+      // out-proj: R += O . Wo^T (R pre-loaded with x + b_o), then the FFN:
+      // D1[c] = X' . W1_c^T (N=64) ; R += relu(D1[c] + b1) . W2_c^T (N=128, K=64)
+      auto mma_out_ffn = [&]() {
+        wait_a();
+        for (int u = 0; u < 2; ++u) unit_n64(TM_R + 64 * u, false);
+        commit(B_DDONE);
+        wait_a();
+        auto issue1 = [&](int c) {
+          const long long t0 = clock64();
+          mbar_wait(bar(B_D1FREE0 + (c & 1)), (ph_d1free >> (c & 1)) & 1u);
+          ph_d1free ^= 1u << (c & 1);
+          w_d1 += clock64() - t0;
           tc_fence_after();
-          for (int u = 0; u < 6; ++u) unit_n64(TM_S + 64 * u, true);
-          commit(B_DDONE);
-          // ---- out-proj: R += O . Wo^T   (R pre-loaded with x + b_o)
-          {
-            const long long t0 = clock64();
-            mbar_wait(bar(B_AREADY), ph_a);
-            w_a += clock64() - t0;
-          }
-          ph_a ^= 1;
+          unit_n64(TM_S + 64 * (c & 1), true);
+          commit(B_D1READY0 + (c & 1));
+        };
+        auto issue2 = [&](int c) {
+          const uint32_t h_hi = h_base + (c & 1) * H_BUF_BYTES, h_lo = h_hi + UNIT_PART_BYTES;
+          uint32_t w = wait_full();
+          const long long t0 = clock64();
+          mbar_wait(bar(B_HREADY0 + (c & 1)), (ph_hr >> (c & 1)) & 1u);
+          ph_hr ^= 1u << (c & 1);
+          w_h += clock64() - t0;
           tc_fence_after();
-          for (int u = 0; u < 2; ++u) unit_n64(TM_R + 64 * u, false);
-          commit(B_DDONE);
-          // ---- FFN: D1[c] = X' . W1_c^T (N=64) ; R += relu(D1[c] + b1) . W2_c^T (N=128, K=64)
-          {
-            const long long t0 = clock64();
-            mbar_wait(bar(B_AREADY), ph_a);
-            w_a += clock64() - t0;
-          }
-          ph_a ^= 1;
-          tc_fence_after();
-          auto issue1 = [&](int c) {
-            const long long t0 = clock64();
-            mbar_wait(bar(B_D1FREE0 + (c & 1)), (ph_d1free >> (c & 1)) & 1u);
-            ph_d1free ^= 1u << (c & 1);
-            w_d1 += clock64() - t0;
+          if (elect_one()) issue_part<(NPASS == 3 ? 2 : 1), 4, 0u, 0u, ID128>(tmem + TM_R, h_hi, h_lo, w, false);
+          __syncwarp();
+          release();
+          if (NPASS == 3) {
+            w = wait_full();
             tc_fence_after();
-            unit_n64(TM_S + 64 * (c & 1), true);
-            commit(B_D1READY0 + (c & 1));
-          };
-          auto issue2 = [&](int c) {
-            const uint32_t h_hi = h_base + (c & 1) * H_BUF_BYTES, h_lo = h_hi + UNIT_PART_BYTES;
-            uint32_t w = wait_full();
-            const long long t0 = clock64();
-            mbar_wait(bar(B_HREADY0 + (c & 1)), (ph_hr >> (c & 1)) & 1u);
-            ph_hr ^= 1u << (c & 1);
-            w_h += clock64() - t0;
-            tc_fence_after();
-            if (elect_one()) issue_part<(NPASS == 3 ? 2 : 1), 4, 0u, 0u, ID128>(tmem + TM_R, h_hi, h_lo, w, false);
+            if (elect_one()) issue_part<1, 4, 0u, 0u, ID128>(tmem + TM_R, h_hi, h_hi, w, false);
             __syncwarp();
             release();
-            if (NPASS == 3) {
-              w = wait_full();
-              tc_fence_after();
-              if (elect_one()) issue_part<1, 4, 0u, 0u, ID128>(tmem + TM_R, h_hi, h_hi, w, false);
-              __syncwarp();
-              release();
-            }
-            commit(B_HFREE0 + (c & 1));
-          };
-          issue1(0);
-#pragma unroll 1
-          for (int c = 0; c < NCHUNK; ++c) {
-            if (c + 1 < NCHUNK) issue1(c + 1);
-            issue2(c);
           }
-          commit(B_DDONE);
+          commit(B_HFREE0 + (c & 1));
+        };
+        issue1(0);
+#pragma unroll 1
+        for (int c = 0; c < NCHUNK; ++c) {
+          if (c + 1 < NCHUNK) issue1(c + 1);
+          issue2(c);
+        }
+        commit(B_DDONE);
+      };
+      int pending = 0;
+      for (long long tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        for (int layer = 0; layer < 2; ++layer) {
+          mma_qkv();
+          mma_out_ffn();
+        }
+        mma_qkv();  // last layer: only token 0 of every query is consumed downstream -> batched tail pass
+        ++pending;
+        if (pending == TAIL_SLOTS || tile + gridDim.x >= p.num_tiles) {
+          mma_out_ffn();
+          pending = 0;
         }
       }
       if (lane == 0) {
@@ -335,9 +348,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
     uint32_t ph_d = 0, ph_d1r = 0, ph_hf = 3u;
     const int qi = r / NTOK, tk = r - qi * NTOK;
     const unsigned FULL = 0xffffffffu;
-    uint32_t pf[12];
+    uint32_t pf[16];
 #pragma unroll
-    for (int i = 0; i < 12; ++i) pf[i] = 0;
+    for (int i = 0; i < 16; ++i) pf[i] = 0;
     uint32_t tprev = (uint32_t)clock();
 #define lap(i)                            \
   {                                       \
@@ -395,83 +408,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
       warp_arrive(bar(B_AREADY), lane);
     };
 
-    for (long long tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-      const long long q_idx = tile * TILE_Q + qi;
-      const bool valid = (qi < TILE_Q) && (q_idx < p.n);
-      // ------------------------------------------------------------------ token build
-      {
-        float px = 0.f, py = 0.f, pz = 0.f, gu = 0.f, gv = 0.f;
-        if (valid) load_query(p.q, q_idx, px, py, pz, gu, gv);
-        float v[32];
-        float* scr = reinterpret_cast<float*>(sgen + OFF_H) + warp * (4 * 36);
-        const int qtr = lane >> 3, l8 = lane & 7;
-        const int ch = 32 * g + l8 * 4;
-#pragma unroll 1
-        for (int rg = 0; rg < 8; ++rg) {
-          const int rl = rg * 4 + qtr;  // row (within this quadrant) gathered by this quarter-warp
-          const float ru = __shfl_sync(FULL, gu, rl), rv = __shfl_sync(FULL, gv, rl);
-          const int rvalid = __shfl_sync(FULL, valid ? 1 : 0, rl);
-          const int rt = (q4 * 32 + rl) % NTOK;
-          float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (rvalid && rt > 0) {
-            a0 = __ldg(reinterpret_cast<const float4*>(p.fcs_b + ch));
-            size_t off = 0;
-#pragma unroll
-            for (int s = 0; s < 5; ++s) {
-              const int R = plane_res(p.S, s);
-              const Taps t = make_taps(ru, rv, R);
-              const float* P = p.planes + off + (size_t)(rt - 1) * R * R * 128 + ch;
-              const float4 c00 = __ldg(reinterpret_cast<const float4*>(P + (size_t)t.o00 * 128));
-              const float4 c01 = __ldg(reinterpret_cast<const float4*>(P + (size_t)t.o01 * 128));
-              const float4 c10 = __ldg(reinterpret_cast<const float4*>(P + (size_t)t.o10 * 128));
-              const float4 c11 = __ldg(reinterpret_cast<const float4*>(P + (size_t)t.o11 * 128));
-              a0.x += c00.x * t.w00 + c01.x * t.w01 + c10.x * t.w10 + c11.x * t.w11;
-              a0.y += c00.y * t.w00 + c01.y * t.w01 + c10.y * t.w10 + c11.y * t.w11;
-              a0.z += c00.z * t.w00 + c01.z * t.w01 + c10.z * t.w10 + c11.z * t.w11;
-              a0.w += c00.w * t.w00 + c01.w * t.w01 + c10.w * t.w10 + c11.w * t.w11;
-              off += (size_t)12 * R * R * 128;
-            }
-          }
-          *reinterpret_cast<float4*>(scr + qtr * 36 + l8 * 4) = a0;
-          __syncwarp();
-          if ((lane >> 2) == rg) {  // the four lanes that own the rows gathered in this step
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float4 t4 = *reinterpret_cast<const float4*>(scr + (lane & 3) * 36 + i * 4);
-              v[4 * i] = t4.x; v[4 * i + 1] = t4.y; v[4 * i + 2] = t4.z; v[4 * i + 3] = t4.w;
-            }
-          }
-          __syncwarp();
-        }
-        if (valid && tk == 0) {  // query token: fc_p(q) (models.py:79)
-#pragma unroll
-          for (int c = 0; c < 32; ++c) {
-            const int cc = 32 * g + c;
-            v[c] = __ldg(p.fcp_b + cc) + px * __ldg(p.fcp_wt + cc) + py * __ldg(p.fcp_wt + 128 + cc) +
-                   pz * __ldg(p.fcp_wt + 256 + cc);
-          }
-        }
-        store_ax(v);
-        publish(v, p.b_o0);
-      }
-      lap(PF_TOKEN)
-
-#pragma unroll 1
-      for (int layer = 0; layer < 3; ++layer) {
-        // -------------------------------------------------------------- stage this layer's vectors
-        named_bar_sync(1, NCT);  // everyone is done with the previous layer's vectors
-        {
-          const float4* src = reinterpret_cast<const float4*>(p.vecs + (size_t)layer * VEC_FLOATS);
-          float4* dst = reinterpret_cast<float4*>(sgen + OFF_VEC);
-          for (int i = tid; i < V_SMEM_FLOATS / 4; i += NCT) dst[i] = __ldg(src + i);
-        }
-        named_bar_sync(1, NCT);
-        lap(PF_VEC)
-        // -------------------------------------------------------------- attention (13x13 per query and head)
-        mbar_wait(bar(B_DDONE), ph_d);
-        ph_d ^= 1;
-        tc_fence_after();
-        lap(PF_WAIT_QKV)
+    // Self-attention over the 13 tokens of each query, 4 heads (one per column group).  tok0_only: last
+    // layer -- only token 0 of a query is consumed downstream (models.py:83), so only those rows attend and
+    // their output (and residual) is parked in the CTA's global scratch row `slot*9 + qi` for the tail pass.
+    auto attention = [&](bool tok0_only, bool valid, int slot) {
+      const bool act = valid && (!tok0_only || tk == 0);
+      float* tail_row = p.scratch + ((size_t)blockIdx.x * (TAIL_SLOTS * TILE_Q) + (size_t)slot * TILE_Q + (qi < TILE_Q ? qi : 0)) * 256;
         {
           // column group g takes head g.  K (then V) of all heads is staged as one [128][128] fp32 matrix in
           // the H region; 16-byte chunk c4 of row q is stored at chunk (c4 ^ (q & 7)) so that the four
@@ -492,43 +434,54 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
             }
           }
           named_bar_sync(1, NCT);
+          lap(12)
           {
-            float qq[32];
-            tmem_ld32(trow + TM_S + 32 * h, qq);
-            tmem_ld_wait();
-#pragma unroll
-            for (int c = 0; c < 32; c += 4) {
-              const float4 b4 = *reinterpret_cast<const float4*>(b_in + 32 * h + c);
-              qq[c] = (qq[c] + b4.x) * 0.17677669529663687f;
-              qq[c + 1] = (qq[c + 1] + b4.y) * 0.17677669529663687f;
-              qq[c + 2] = (qq[c + 2] + b4.z) * 0.17677669529663687f;
-              qq[c + 3] = (qq[c + 3] + b4.w) * 0.17677669529663687f;
-            }
 #pragma unroll
             for (int j = 0; j < NTOK; ++j) sc[j] = 0.f;
-            if (valid) {
-              float mx = -3.0e38f;
+            // head dim in two halves of 16: small live state (q 16 + k 16) lets the compiler keep several
+            // K rows of loads in flight under the 96-register cap
 #pragma unroll
-              for (int j = 0; j < NTOK; ++j) {
-                const int row = qi * NTOK + j;
-                const float* kb = st + row * 128;
-                float s0 = 0.f, s1 = 0.f;
+            for (int hf = 0; hf < 2; ++hf) {
+              float qq[16];
+              tmem_ld16(trow + TM_S + 32 * h + 16 * hf, qq);
+              tmem_ld_wait();
 #pragma unroll
-                for (int c = 0; c < 32; c += 8) {
-                  const float4 k4 = *reinterpret_cast<const float4*>(kb + ((((32 * h + c) >> 2) ^ (row & 7)) << 2));
-                  const float4 k5 = *reinterpret_cast<const float4*>(kb + ((((32 * h + c + 4) >> 2) ^ (row & 7)) << 2));
-                  s0 = fmaf(qq[c], k4.x, s0);
-                  s1 = fmaf(qq[c + 4], k5.x, s1);
-                  s0 = fmaf(qq[c + 1], k4.y, s0);
-                  s1 = fmaf(qq[c + 5], k5.y, s1);
-                  s0 = fmaf(qq[c + 2], k4.z, s0);
-                  s1 = fmaf(qq[c + 6], k5.z, s1);
-                  s0 = fmaf(qq[c + 3], k4.w, s0);
-                  s1 = fmaf(qq[c + 7], k5.w, s1);
-                }
-                sc[j] = s0 + s1;
-                mx = fmaxf(mx, sc[j]);
+              for (int c = 0; c < 16; c += 4) {
+                const float4 b4 = *reinterpret_cast<const float4*>(b_in + 32 * h + 16 * hf + c);
+                qq[c] = (qq[c] + b4.x) * 0.17677669529663687f;
+                qq[c + 1] = (qq[c + 1] + b4.y) * 0.17677669529663687f;
+                qq[c + 2] = (qq[c + 2] + b4.z) * 0.17677669529663687f;
+                qq[c + 3] = (qq[c + 3] + b4.w) * 0.17677669529663687f;
               }
+              if (act) {
+#pragma unroll
+                for (int j = 0; j < NTOK; ++j) {
+                  const int row = qi * NTOK + j;
+                  const float* kb = st + row * 128;
+                  float4 k4[4];
+#pragma unroll
+                  for (int c = 0; c < 4; ++c)
+                    k4[c] = *reinterpret_cast<const float4*>(kb + (((8 * h + 4 * hf + c) ^ (row & 7)) << 2));
+                  float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+                  for (int c = 0; c < 4; c += 2) {
+                    s0 = fmaf(qq[4 * c], k4[c].x, s0);
+                    s1 = fmaf(qq[4 * c + 4], k4[c + 1].x, s1);
+                    s0 = fmaf(qq[4 * c + 1], k4[c].y, s0);
+                    s1 = fmaf(qq[4 * c + 5], k4[c + 1].y, s1);
+                    s0 = fmaf(qq[4 * c + 2], k4[c].z, s0);
+                    s1 = fmaf(qq[4 * c + 6], k4[c + 1].z, s1);
+                    s0 = fmaf(qq[4 * c + 3], k4[c].w, s0);
+                    s1 = fmaf(qq[4 * c + 7], k4[c + 1].w, s1);
+                  }
+                  sc[j] += s0 + s1;
+                }
+              }
+            }
+            if (act) {
+              float mx = sc[0];
+#pragma unroll
+              for (int j = 1; j < NTOK; ++j) mx = fmaxf(mx, sc[j]);
               float sum = 0.f;
 #pragma unroll
               for (int j = 0; j < NTOK; ++j) {
@@ -540,6 +493,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
               for (int j = 0; j < NTOK; ++j) sc[j] *= inv;
             }
           }
+          lap(13)
           named_bar_sync(1, NCT);  // everyone has read K
           {
             float vv[32];
@@ -553,32 +507,62 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
             }
           }
           named_bar_sync(1, NCT);
+          lap(14)
           {
-            float o[32];
+            // O[:, 32h:32h+32] in two halves of 16 -> operand A chunks (k-block h/2, chunks 4*(h&1) + 2*hf ..+1)
 #pragma unroll
-            for (int c = 0; c < 32; ++c) o[c] = 0.f;
-            if (valid) {
+            for (int hf = 0; hf < 2; ++hf) {
+              float o[16];
 #pragma unroll
-              for (int j = 0; j < NTOK; ++j) {
-                const int row = qi * NTOK + j;
-                const float* vb = st + row * 128;
+              for (int c = 0; c < 16; ++c) o[c] = 0.f;
+              if (act) {
 #pragma unroll
-                for (int c = 0; c < 32; c += 4) {
-                  const float4 v4 = *reinterpret_cast<const float4*>(vb + ((((32 * h + c) >> 2) ^ (row & 7)) << 2));
-                  o[c] = fmaf(sc[j], v4.x, o[c]);
-                  o[c + 1] = fmaf(sc[j], v4.y, o[c + 1]);
-                  o[c + 2] = fmaf(sc[j], v4.z, o[c + 2]);
-                  o[c + 3] = fmaf(sc[j], v4.w, o[c + 3]);
+                for (int j = 0; j < NTOK; ++j) {
+                  const int row = qi * NTOK + j;
+                  const float* vb = st + row * 128;
+                  float4 v4[4];
+#pragma unroll
+                  for (int c = 0; c < 4; ++c)
+                    v4[c] = *reinterpret_cast<const float4*>(vb + (((8 * h + 4 * hf + c) ^ (row & 7)) << 2));
+#pragma unroll
+                  for (int c = 0; c < 4; ++c) {
+                    o[4 * c] = fmaf(sc[j], v4[c].x, o[4 * c]);
+                    o[4 * c + 1] = fmaf(sc[j], v4[c].y, o[4 * c + 1]);
+                    o[4 * c + 2] = fmaf(sc[j], v4[c].z, o[4 * c + 2]);
+                    o[4 * c + 3] = fmaf(sc[j], v4[c].w, o[4 * c + 3]);
+                  }
                 }
               }
+              if (!tok0_only) {
+                store_chunk<NPASS>(ax_hi + (h >> 1) * 16384, ax_lo + (h >> 1) * 16384, r, (h & 1) * 4 + 2 * hf, o);
+                store_chunk<NPASS>(ax_hi + (h >> 1) * 16384, ax_lo + (h >> 1) * 16384, r, (h & 1) * 4 + 2 * hf + 1, o + 8);
+              } else if (act) {  // last layer: park the attention output of token 0 for the tail pass
+                float4* dst = reinterpret_cast<float4*>(tail_row + 32 * h + 16 * hf);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) dst[c] = make_float4(o[4 * c], o[4 * c + 1], o[4 * c + 2], o[4 * c + 3]);
+              }
             }
-            store_ax(o);  // O[:, 32h:32h+32] -> operand A (same columns as this thread's quarter)
           }
+          lap(15)
           // (the staging region is next written by the FFN epilogue, after LayerNorm 1's barriers)
           fence_proxy_async_smem();
         }
-        warp_arrive(bar(B_AREADY), lane);
+        if (tok0_only) {
+          float v[32];
+          tmem_ld32(trow + TM_R + 32 * g, v);  // x + b_o of this row (pre-loaded accumulator of out-proj)
+          tmem_ld_wait();
+          if (act) {
+            float4* dst = reinterpret_cast<float4*>(tail_row + 128 + 32 * g);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) dst[c] = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+          }
+        } else {
+          warp_arrive(bar(B_AREADY), lane);
+        }
         lap(PF_ATTN)
+    };
+    // out-proj result + residual -> LayerNorm 1 -> FFN -> LayerNorm 2 -> next layer's operand / fc_out head
+    auto post_attn = [&](int layer, bool head_valid, long long head_q) {
         // -------------------------------------------------------------- residual + LayerNorm 1 (in place in TMEM)
         mbar_wait(bar(B_DDONE), ph_d);
         ph_d ^= 1;
@@ -657,21 +641,141 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
             for (int c = 0; c < 32; ++c) acc = fmaf(v[c], __ldg(p.fco_w + 32 * g + c), acc);
             red0[r * 4 + g] = acc;
             named_bar_sync(1, NCT);
-            if (g == 0 && valid && tk == 0) {
+            if (head_valid) {
               const float4 a4 = *reinterpret_cast<const float4*>(red0 + r * 4);
-              p.out[q_idx] = p.out_scale * (a4.x + a4.y + a4.z + a4.w + __ldg(p.fco_b));
+              p.out[head_q] = p.out_scale * (a4.x + a4.y + a4.z + a4.w + __ldg(p.fco_b));
             }
           }
         }
         lap(PF_LN2)
+    };
+    int pending = 0;
+    long long batch_tile0 = 0;
+    for (long long tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const long long q_idx = tile * TILE_Q + qi;
+      const bool valid = (qi < TILE_Q) && (q_idx < p.n);
+      // ------------------------------------------------------------------ token build
+      {
+        float px = 0.f, py = 0.f, pz = 0.f, gu = 0.f, gv = 0.f;
+        if (valid) load_query(p.q, q_idx, px, py, pz, gu, gv);
+        float v[32];
+        float* scr = reinterpret_cast<float*>(sgen + OFF_H) + warp * (4 * 36);
+        const int qtr = lane >> 3, l8 = lane & 7;
+        const int ch = 32 * g + l8 * 4;
+#pragma unroll 1
+        for (int rg = 0; rg < 8; ++rg) {
+          const int rl = rg * 4 + qtr;  // row (within this quadrant) gathered by this quarter-warp
+          const float ru = __shfl_sync(FULL, gu, rl), rv = __shfl_sync(FULL, gv, rl);
+          const int rvalid = __shfl_sync(FULL, valid ? 1 : 0, rl);
+          const int rt = (q4 * 32 + rl) % NTOK;
+          float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (rvalid && rt > 0) {
+            a0 = __ldg(reinterpret_cast<const float4*>(p.fcs_b + ch));
+            size_t off = 0;
+#pragma unroll
+            for (int s = 0; s < 5; ++s) {
+              const int R = plane_res(p.S, s);
+              const Taps t = make_taps(ru, rv, R);
+              const float* P = p.planes + off + (size_t)(rt - 1) * R * R * 128 + ch;
+              const float4 c00 = __ldg(reinterpret_cast<const float4*>(P + (size_t)t.o00 * 128));
+              const float4 c01 = __ldg(reinterpret_cast<const float4*>(P + (size_t)t.o01 * 128));
+              const float4 c10 = __ldg(reinterpret_cast<const float4*>(P + (size_t)t.o10 * 128));
+              const float4 c11 = __ldg(reinterpret_cast<const float4*>(P + (size_t)t.o11 * 128));
+              a0.x += c00.x * t.w00 + c01.x * t.w01 + c10.x * t.w10 + c11.x * t.w11;
+              a0.y += c00.y * t.w00 + c01.y * t.w01 + c10.y * t.w10 + c11.y * t.w11;
+              a0.z += c00.z * t.w00 + c01.z * t.w01 + c10.z * t.w10 + c11.z * t.w11;
+              a0.w += c00.w * t.w00 + c01.w * t.w01 + c10.w * t.w10 + c11.w * t.w11;
+              off += (size_t)12 * R * R * 128;
+            }
+          }
+          *reinterpret_cast<float4*>(scr + qtr * 36 + l8 * 4) = a0;
+          __syncwarp();
+          if ((lane >> 2) == rg) {  // the four lanes that own the rows gathered in this step
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 t4 = *reinterpret_cast<const float4*>(scr + (lane & 3) * 36 + i * 4);
+              v[4 * i] = t4.x; v[4 * i + 1] = t4.y; v[4 * i + 2] = t4.z; v[4 * i + 3] = t4.w;
+            }
+          }
+          __syncwarp();
+        }
+        if (valid && tk == 0) {  // query token: fc_p(q) (models.py:79)
+#pragma unroll
+          for (int c = 0; c < 32; ++c) {
+            const int cc = 32 * g + c;
+            v[c] = __ldg(p.fcp_b + cc) + px * __ldg(p.fcp_wt + cc) + py * __ldg(p.fcp_wt + 128 + cc) +
+                   pz * __ldg(p.fcp_wt + 256 + cc);
+          }
+        }
+        store_ax(v);
+        publish(v, p.b_o0);
+      }
+      lap(PF_TOKEN)
+
+#pragma unroll 1
+      for (int layer = 0; layer < 3; ++layer) {
+        // -------------------------------------------------------------- stage this layer's vectors
+        named_bar_sync(1, NCT);  // everyone is done with the previous layer's vectors
+        {
+          const float4* src = reinterpret_cast<const float4*>(p.vecs + (size_t)layer * VEC_FLOATS);
+          float4* dst = reinterpret_cast<float4*>(sgen + OFF_VEC);
+          for (int i = tid; i < V_SMEM_FLOATS / 4; i += NCT) dst[i] = __ldg(src + i);
+        }
+        named_bar_sync(1, NCT);
+        lap(PF_VEC)
+        // -------------------------------------------------------------- attention (13x13 per query and head)
+        mbar_wait(bar(B_DDONE), ph_d);
+        ph_d ^= 1;
+        tc_fence_after();
+        lap(PF_WAIT_QKV)
+        if (layer < 2) {
+          attention(false, valid, 0);
+          post_attn(layer, false, 0);
+        } else {
+          attention(true, valid, pending);
+        }
+      }
+      if (pending == 0) batch_tile0 = tile;
+      ++pending;
+      if (pending == TAIL_SLOTS || tile + gridDim.x >= p.num_tiles) {
+        // ---------------------------------------------------------------- tail pass: token 0 of up to 126 queries
+        named_bar_sync(1, NCT);  // scratch rows written by other threads are visible after the CTA barrier
+        {
+          const int k = r / TILE_Q, qq = r - k * TILE_Q;
+          const long long tq = (batch_tile0 + (long long)k * gridDim.x) * TILE_Q + qq;
+          const bool tvalid = (r < pending * TILE_Q) && (tq < p.n);
+          const float* row = p.scratch + ((size_t)blockIdx.x * (TAIL_SLOTS * TILE_Q) + (r < TAIL_SLOTS * TILE_Q ? r : 0)) * 256;
+          float v[32];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            float4 t4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (tvalid) t4 = __ldcg(reinterpret_cast<const float4*>(row + 32 * g) + c);
+            v[4 * c] = t4.x; v[4 * c + 1] = t4.y; v[4 * c + 2] = t4.z; v[4 * c + 3] = t4.w;
+          }
+          store_ax(v);  // attention output -> operand A of out-proj
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            float4 t4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (tvalid) t4 = __ldcg(reinterpret_cast<const float4*>(row + 128 + 32 * g) + c);
+            v[4 * c] = t4.x; v[4 * c + 1] = t4.y; v[4 * c + 2] = t4.z; v[4 * c + 3] = t4.w;
+          }
+          tmem_st32(trow + TM_R + 32 * g, v);  // x + b_o -> accumulator of out-proj
+          tmem_st_wait();
+          tc_fence_before();
+          fence_proxy_async_smem();
+          warp_arrive(bar(B_AREADY), lane);
+          post_attn(2, g == 0 && tvalid, tq);
+        }
+        pending = 0;
       }
       if (tid == 0) {
         atomicAdd(&g_prof[PF_TILES], 1ull);
 #pragma unroll
         for (int i = 0; i < 12; ++i) atomicAdd(&g_prof[i], (unsigned long long)pf[i]);
+        for (int i = 12; i < 16; ++i) atomicAdd(&g_prof[i + 8], (unsigned long long)pf[i]);
       }
 #pragma unroll
-      for (int i = 0; i < 12; ++i) pf[i] = 0;
+      for (int i = 0; i < 16; ++i) pf[i] = 0;
     }
 #undef lap
   }
@@ -876,10 +980,12 @@ int debug_profile(long long* out32, int reset) {
   return S3D_OK;
 }
 
-size_t decoder_tc_workspace_bytes(int64_t) { return 256; }
+size_t decoder_tc_workspace_bytes(int64_t) {
+  return (size_t)256 * TAIL_SLOTS * TILE_Q * 256 * sizeof(float);  // tail scratch for up to 256 CTAs
+}
 
 int decoder_tc(const s3d_model* m, const float* planes, int S, const QueryCtx& q, int64_t n, float out_scale, float* out,
-               int precision, void*, size_t, cudaStream_t st) {
+               int precision, void* ws, size_t ws_bytes, cudaStream_t st) {
   if (m->K != 12 || m->dectc.wimg == nullptr) {
     set_error("decoder: tensor-core modes need n_slices == 12 (use S3D_PREC_FP32 otherwise)");
     return S3D_ERR_UNSUPPORTED;
@@ -902,7 +1008,13 @@ int decoder_tc(const s3d_model* m, const float* planes, int S, const QueryCtx& q
   int dev = 0, sms = 148;
   S3D_CUDA(cudaGetDevice(&dev));
   S3D_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  if (sms > 256) sms = 256;
   const unsigned grid = (unsigned)(p.num_tiles < sms ? p.num_tiles : sms);
+  if (ws == nullptr || ws_bytes < decoder_tc_workspace_bytes(n)) {
+    set_error("decoder: workspace too small");
+    return S3D_ERR_WORKSPACE;
+  }
+  p.scratch = static_cast<float*>(ws);
   if (precision == S3D_PREC_BF16X3) {
     S3D_CUDA(cudaFuncSetAttribute(decoder_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     decoder_tc_kernel<3><<<grid, NTHREADS, SMEM_BYTES, st>>>(p);
