@@ -10,17 +10,19 @@
 //   head          fc_out on token 0 (models.py:84), scaled by out_scale
 //
 // Every dense contraction runs on tcgen05.mma (M=128, bf16 operands, fp32 accumulators in TMEM).
-// Activations are written by the epilogue warps straight into the canonical K-major/128B-swizzled
+// Activations are written by the compute warps straight into the canonical K-major/128B-swizzled
 // shared-memory operand layout; weights are pre-swizzled "operand images" in global memory streamed
-// through a 3-slot ring with bulk async copies (TMA engine) completing on mbarriers.  The residual
-// stream never leaves TMEM: the accumulator of out-proj / FFN2 is pre-loaded with x + bias, so the
-// MMA result is already residual + bias + contraction and LayerNorm runs in place, one thread per row.
+// as 16 KB parts through a 5-slot ring with bulk async copies (TMA engine) completing on mbarriers.
+// The residual stream never leaves TMEM: the accumulator of out-proj / FFN2 is pre-loaded with
+// x + bias, so the MMA result is already residual + bias + contraction and LayerNorm runs in place.
+// Only token 0 of a query feeds fc_out, so in the last layer only those rows attend and the rest of
+// that layer (out-proj, FFN, LayerNorms, head) runs as one "tail pass" per 14 tiles over 126 queries.
 //
 // Precision: BF16X3 splits both operands into bf16 hi + lo and issues hi*hi + lo*hi + hi*lo
-// (3 passes, ~16 mantissa bits, max-abs error ~2e-5 on sdf_pred); BF16 issues hi*hi only.
+// (3 passes, ~16 mantissa bits, max-abs error 3-4e-5 on sdf_pred); BF16 issues hi*hi only.
 //
-// Warp roles (192 threads): warps 0-3 = epilogue/compute (thread r owns tile row r = TMEM lane r),
-// warp 4 lane 0 = weight producer, warp 5 lane 0 = MMA issuer.
+// Warp roles (576 threads): warps 0-15 = compute, thread = (tile row r = TMEM lane, column quarter g);
+// warp 16 = weight producer; warp 17 = MMA issuer (warp-uniform control flow, one elected lane issues).
 #include <cstring>
 
 #include "common.cuh"
