@@ -49,7 +49,7 @@ constexpr int NTHREADS = NCT + 64;  // + producer warp + MMA warp
 
 // per-layer fp32 vector block staged in shared memory (floats)
 constexpr int V_BIN = 0, V_BONEXT = 384, V_LN1W = 512, V_LN1B = 640, V_B2 = 768, V_LN2W = 896, V_LN2B = 1024,
-              V_SMEM_FLOATS = 1152, V_B1 = 1152, VEC_FLOATS = 3200;  // b1 (2048) stays in global memory
+              V_B1 = 1152, VEC_FLOATS = 3200, V_SMEM_FLOATS = VEC_FLOATS;
 
 // shared memory map (bytes from the 1024-aligned base)
 constexpr uint32_t OFF_AX_HI = 0;                 // [2 k-blocks][128 rows][64] bf16 = 32 KB
@@ -216,7 +216,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
     // ===================================================================== MMA issuer
     // the whole warp runs the control flow (waits are warp-uniform); one elected lane issues
     {
-      uint32_t ph_a = 0, ph_full = 0, ph_d1free = 3u, ph_hr = 0;  // parity bits (one per barrier / slot)
+      uint32_t ph_a = 0, ph_full = 0, ph_hr = 0;  // parity bits (one per barrier / slot)
       int slot = 0;
       long long w_a = 0, w_full = 0, w_h = 0, w_d1 = 0;
       const long long t_start = clock64();
@@ -278,11 +278,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
         commit(B_DDONE);
         wait_a();
         auto issue1 = [&](int c) {
-          const long long t0 = clock64();
-          mbar_wait(bar(B_D1FREE0 + (c & 1)), (ph_d1free >> (c & 1)) & 1u);
-          ph_d1free ^= 1u << (c & 1);
-          w_d1 += clock64() - t0;
-          tc_fence_after();
+          // D1[c&1] is free: the compute warps loaded chunk c-2 out of it before they arrived on h_ready(c-2),
+          // which this warp has already waited for (issue2(c-2) precedes issue1(c)).
           unit_n64(TM_S + 64 * (c & 1), true);
           commit(B_D1READY0 + (c & 1));
         };
@@ -304,7 +301,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
             __syncwarp();
             release();
           }
-          commit(B_HFREE0 + (c & 1));
+          // no "H free" signal: d1_ready(c+2) is committed after MMA1_{c+2}, i.e. after these MMAs, and
+          // tcgen05.commit covers every earlier MMA -- the compute warps wait for it before rewriting H[c&1].
         };
         issue1(0);
 #pragma unroll 1
@@ -347,9 +345,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
     const float* vec = reinterpret_cast<const float*>(sgen + OFF_VEC);
     float* red0 = reinterpret_cast<float*>(sgen + OFF_RED);
     float* red1 = red0 + 512;
-    uint32_t ph_d = 0, ph_d1r = 0, ph_hf = 3u;
+    uint32_t ph_d = 0, ph_d1r = 0;
     const int qi = r / NTOK, tk = r - qi * NTOK;
-    const unsigned FULL = 0xffffffffu;
     uint32_t pf[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) pf[i] = 0;
@@ -408,6 +405,74 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
       tc_fence_before();
       fence_proxy_async_smem();
       warp_arrive(bar(B_AREADY), lane);
+    };
+
+    // Token gather, decoupled from row ownership.  The 108 (slice, query, 32-channel block) tasks of a tile are
+    // dealt four to a warp-step (one per quarter-warp, 16 bytes per lane; the four quarter-warps of a step take
+    // the same slice and channel block of four consecutive queries, whose texels coincide or neighbour each
+    // other, so their requests coalesce), 7 steps per warp.  Each step issues the 12 tap loads of plane scales
+    // 0-2 together, then the 8 of scales 3-4 (two L2 round trips per step instead of five: with ~226 KB of shared
+    // memory in use there is no L1 to speak of and the gather is bound by L2 latency x loads in flight).  The
+    // 16-byte token pieces go to this CTA's global token scratch [128 rows][128] (L2-resident); the row owners
+    // pick them up after a CTA barrier.
+    float* tokbuf = p.scratch + (size_t)gridDim.x * (TAIL_SLOTS * TILE_Q) * 256 + (size_t)blockIdx.x * (128 * 128);
+    constexpr int GATHER_STEPS = 7;
+    auto gather_step = [&](long long gt, int step) {
+      const int qtr = lane >> 3, l8 = lane & 7;
+      int q, k, cb;
+      const int idx = step * NCW + warp;  // 0..111
+      if (idx < 96) {  // steps 0..5: queries 0..7, four per step
+        cb = idx & 3;
+        const int grp = idx >> 2;  // 0..23
+        k = grp >> 1;
+        q = 4 * (grp & 1) + qtr;
+      } else {  // step 6: the 48 tasks of query 8, four slices per step
+        const int t = (idx - 96) * 4 + qtr;  // 0..63, 48 real
+        cb = t & 3;
+        k = t >> 2;
+        q = 8;
+      }
+      const long long gq = gt * TILE_Q + q;
+      if (k >= 12 || gq >= p.n) return;
+      const int ch = 32 * cb + l8 * 4;
+      float x, y, z, gu, gv;
+      load_query(p.q, gq, x, y, z, gu, gv);
+      float4 acc = __ldg(reinterpret_cast<const float4*>(p.fcs_b + ch));
+      const int R0 = plane_res(p.S, 0);
+      const float* P = p.planes + (size_t)k * R0 * R0 * 128 + ch;
+      auto fold = [&](const float4* v, const Taps& t) {
+        acc.x += v[0].x * t.w00 + v[1].x * t.w01 + v[2].x * t.w10 + v[3].x * t.w11;
+        acc.y += v[0].y * t.w00 + v[1].y * t.w01 + v[2].y * t.w10 + v[3].y * t.w11;
+        acc.z += v[0].z * t.w00 + v[1].z * t.w01 + v[2].z * t.w10 + v[3].z * t.w11;
+        acc.w += v[0].w * t.w00 + v[1].w * t.w01 + v[2].w * t.w10 + v[3].w * t.w11;
+      };
+      auto issue = [&](float4* v, const Taps& t, const float* base) {
+        v[0] = __ldg(reinterpret_cast<const float4*>(base + (size_t)t.o00 * 128));
+        v[1] = __ldg(reinterpret_cast<const float4*>(base + (size_t)t.o01 * 128));
+        v[2] = __ldg(reinterpret_cast<const float4*>(base + (size_t)t.o10 * 128));
+        v[3] = __ldg(reinterpret_cast<const float4*>(base + (size_t)t.o11 * 128));
+      };
+      // plane of scale s for slice k starts at P + (12 * sum_{i<s} R_i^2 + k * (R_s^2 - R_0^2)) * 128
+      const size_t r2 = (size_t)R0 * R0;
+      {
+        float4 v0[4], v1[4], v2[4];
+        const Taps t0 = make_taps(gu, gv, R0), t1 = make_taps(gu, gv, 2 * R0), t2 = make_taps(gu, gv, 4 * R0);
+        issue(v0, t0, P);
+        issue(v1, t1, P + (12 * r2 + (size_t)k * 3 * r2) * 128);
+        issue(v2, t2, P + (12 * 5 * r2 + (size_t)k * 15 * r2) * 128);
+        fold(v0, t0);
+        fold(v1, t1);
+        fold(v2, t2);
+      }
+      {
+        float4 v3[4], v4[4];
+        const Taps t3 = make_taps(gu, gv, 8 * R0), t4 = make_taps(gu, gv, 16 * R0);
+        issue(v3, t3, P + (12 * 21 * r2 + (size_t)k * 63 * r2) * 128);
+        issue(v4, t4, P + (12 * 85 * r2 + (size_t)k * 255 * r2) * 128);
+        fold(v3, t3);
+        fold(v4, t4);
+      }
+      __stcg(reinterpret_cast<float4*>(tokbuf + (size_t)(NTOK * q + 1 + k) * 128 + ch), acc);
     };
 
     // Self-attention over the 13 tokens of each query, 4 heads (one per column group).  tok0_only: last
@@ -581,20 +646,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
         lap(PF_LN1)
         // -------------------------------------------------------------- FFN hidden chunks (16 columns per thread)
         {
-          const float4* b1g = reinterpret_cast<const float4*>(p.vecs + (size_t)layer * VEC_FLOATS + V_B1 + 16 * g);
-          float4 bn[4];  // linear1 bias of the next chunk, prefetched (uniform address per warp)
-#pragma unroll
-          for (int j = 0; j < 4; ++j) bn[j] = __ldg(b1g + j);
 #pragma unroll 1
           for (int c = 0; c < NCHUNK; ++c) {
             const int bsel = c & 1;
-            float4 bc[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) bc[j] = bn[j];
-            if (c + 1 < NCHUNK) {
-#pragma unroll
-              for (int j = 0; j < 4; ++j) bn[j] = __ldg(b1g + (c + 1) * 16 + j);
-            }
             mbar_wait(bar(B_D1READY0 + bsel), (ph_d1r >> bsel) & 1u);
             ph_d1r ^= 1u << bsel;
             tc_fence_after();
@@ -602,24 +656,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
             float d[16];
             tmem_ld16(trow + TM_S + 64 * bsel + 16 * g, d);
             tmem_ld_wait();
-            tc_fence_before();
-            warp_arrive(bar(B_D1FREE0 + bsel), lane);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              d[4 * j] = fmaxf(d[4 * j] + bc[j].x, 0.f);
-              d[4 * j + 1] = fmaxf(d[4 * j + 1] + bc[j].y, 0.f);
-              d[4 * j + 2] = fmaxf(d[4 * j + 2] + bc[j].z, 0.f);
-              d[4 * j + 3] = fmaxf(d[4 * j + 3] + bc[j].w, 0.f);
+              const float4 b4 = *reinterpret_cast<const float4*>(vec + V_B1 + c * 64 + 16 * g + 4 * j);
+              d[4 * j] = fmaxf(d[4 * j] + b4.x, 0.f);
+              d[4 * j + 1] = fmaxf(d[4 * j + 1] + b4.y, 0.f);
+              d[4 * j + 2] = fmaxf(d[4 * j + 2] + b4.z, 0.f);
+              d[4 * j + 3] = fmaxf(d[4 * j + 3] + b4.w, 0.f);
             }
             lap(PF_FFN_MATH)
-            mbar_wait(bar(B_HFREE0 + bsel), (ph_hf >> bsel) & 1u);
-            ph_hf ^= 1u << bsel;
-            lap(PF_FFN_WAIT_HFREE)
+
             uint8_t* h_hi = sgen + OFF_H + bsel * H_BUF_BYTES;
             uint8_t* h_lo = h_hi + UNIT_PART_BYTES;
             store_chunk<NPASS>(h_hi, h_lo, r, 2 * g, d);
             store_chunk<NPASS>(h_hi, h_lo, r, 2 * g + 1, d + 8);
             fence_proxy_async_smem();
+            tc_fence_before();  // orders this thread's D1 load before the MMAs that will overwrite D1[bsel]
             warp_arrive(bar(B_HREADY0 + bsel), lane);
             lap(PF_FFN_STORE)
           }
@@ -657,51 +709,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
       const long long q_idx = tile * TILE_Q + qi;
       const bool valid = (qi < TILE_Q) && (q_idx < p.n);
       // ------------------------------------------------------------------ token build
-      {
-        float px = 0.f, py = 0.f, pz = 0.f, gu = 0.f, gv = 0.f;
-        if (valid) load_query(p.q, q_idx, px, py, pz, gu, gv);
-        float v[32];
-        float* scr = reinterpret_cast<float*>(sgen + OFF_H) + warp * (4 * 36);
-        const int qtr = lane >> 3, l8 = lane & 7;
-        const int ch = 32 * g + l8 * 4;
 #pragma unroll 1
-        for (int rg = 0; rg < 8; ++rg) {
-          const int rl = rg * 4 + qtr;  // row (within this quadrant) gathered by this quarter-warp
-          const float ru = __shfl_sync(FULL, gu, rl), rv = __shfl_sync(FULL, gv, rl);
-          const int rvalid = __shfl_sync(FULL, valid ? 1 : 0, rl);
-          const int rt = (q4 * 32 + rl) % NTOK;
-          float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (rvalid && rt > 0) {
-            a0 = __ldg(reinterpret_cast<const float4*>(p.fcs_b + ch));
-            size_t off = 0;
+      for (int st = 0; st < GATHER_STEPS; ++st) gather_step(tile, st);
+      named_bar_sync(1, NCT);  // token scratch written by all warps
+      {
+        float v[32];
 #pragma unroll
-            for (int s = 0; s < 5; ++s) {
-              const int R = plane_res(p.S, s);
-              const Taps t = make_taps(ru, rv, R);
-              const float* P = p.planes + off + (size_t)(rt - 1) * R * R * 128 + ch;
-              const float4 c00 = __ldg(reinterpret_cast<const float4*>(P + (size_t)t.o00 * 128));
-              const float4 c01 = __ldg(reinterpret_cast<const float4*>(P + (size_t)t.o01 * 128));
-              const float4 c10 = __ldg(reinterpret_cast<const float4*>(P + (size_t)t.o10 * 128));
-              const float4 c11 = __ldg(reinterpret_cast<const float4*>(P + (size_t)t.o11 * 128));
-              a0.x += c00.x * t.w00 + c01.x * t.w01 + c10.x * t.w10 + c11.x * t.w11;
-              a0.y += c00.y * t.w00 + c01.y * t.w01 + c10.y * t.w10 + c11.y * t.w11;
-              a0.z += c00.z * t.w00 + c01.z * t.w01 + c10.z * t.w10 + c11.z * t.w11;
-              a0.w += c00.w * t.w00 + c01.w * t.w01 + c10.w * t.w10 + c11.w * t.w11;
-              off += (size_t)12 * R * R * 128;
-            }
-          }
-          *reinterpret_cast<float4*>(scr + qtr * 36 + l8 * 4) = a0;
-          __syncwarp();
-          if ((lane >> 2) == rg) {  // the four lanes that own the rows gathered in this step
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float4 t4 = *reinterpret_cast<const float4*>(scr + (lane & 3) * 36 + i * 4);
-              v[4 * i] = t4.x; v[4 * i + 1] = t4.y; v[4 * i + 2] = t4.z; v[4 * i + 3] = t4.w;
-            }
-          }
-          __syncwarp();
+        for (int c = 0; c < 8; ++c) {
+          float4 t4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (valid && tk > 0) t4 = __ldcg(reinterpret_cast<const float4*>(tokbuf + (size_t)r * 128 + 32 * g) + c);
+          v[4 * c] = t4.x; v[4 * c + 1] = t4.y; v[4 * c + 2] = t4.z; v[4 * c + 3] = t4.w;
         }
         if (valid && tk == 0) {  // query token: fc_p(q) (models.py:79)
+          float px, py, pz, gu, gv;
+          load_query(p.q, q_idx, px, py, pz, gu, gv);
 #pragma unroll
           for (int c = 0; c < 32; ++c) {
             const int cc = 32 * g + c;
@@ -983,7 +1004,8 @@ int debug_profile(long long* out32, int reset) {
 }
 
 size_t decoder_tc_workspace_bytes(int64_t) {
-  return (size_t)256 * TAIL_SLOTS * TILE_Q * 256 * sizeof(float);  // tail scratch for up to 256 CTAs
+  // per CTA (up to 256): tail scratch [126][256] + token scratch [128][128], fp32
+  return (size_t)256 * (TAIL_SLOTS * TILE_Q * 256 + 128 * 128) * sizeof(float);
 }
 
 int decoder_tc(const s3d_model* m, const float* planes, int S, const QueryCtx& q, int64_t n, float out_scale, float* out,
