@@ -69,7 +69,11 @@ constexpr uint32_t OFF_TMEMPTR = OFF_BAR + 8 * B_COUNT;
 
 // TMEM columns
 constexpr uint32_t TM_R = 0;      // residual / out-proj / FFN2 accumulator, 128 columns
-constexpr uint32_t TM_S = 128;    // QKV accumulators (384 columns) | FFN1 chunk accumulators (2 x 64)
+constexpr uint32_t TM_S = 128;    // QKV accumulators (384 columns), or during the FFN:
+                                  //   128..255  FFN1 chunk accumulators D1 (2 x 64)
+constexpr uint32_t TM_AXT_HI = 256;  // 256..319  X' (FFN input) as packed bf16 hi, K = 128 -> 64 columns  (A operand in TMEM)
+constexpr uint32_t TM_AXT_LO = 320;  // 320..383  ... lo
+constexpr uint32_t TM_HT = 384;      // 384..511  H chunk operand: 2 buffers x (hi 32 | lo 32 columns), K = 64
 
 // Phase-cycle counters (clock64 deltas summed over CTAs), read through s3d_debug_profile().
 enum { PF_TOKEN = 0, PF_VEC, PF_WAIT_QKV, PF_ATTN, PF_WAIT_OUT, PF_LN1, PF_FFN_WAIT_D1, PF_FFN_MATH, PF_FFN_WAIT_HFREE,
@@ -98,16 +102,7 @@ struct TcParams {
 template <int NPASS>
 __device__ __forceinline__ void store_chunk(uint8_t* tile_hi, uint8_t* tile_lo, int r, int kc, const float* v) {
   uint32_t h[4], l[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
-    h[i] = *reinterpret_cast<const uint32_t*>(&h2);
-    if (NPASS == 3) {
-      const float h0 = __uint_as_float(h[i] << 16), h1 = __uint_as_float(h[i] & 0xffff0000u);
-      const __nv_bfloat162 l2 = __floats2bfloat162_rn(v[2 * i] - h0, v[2 * i + 1] - h1);
-      l[i] = *reinterpret_cast<const uint32_t*>(&l2);
-    }
-  }
+  split8<NPASS == 3>(v, h, l);
   const uint32_t off = sw128_chunk_off(r, kc);
   *reinterpret_cast<uint4*>(tile_hi + off) = make_uint4(h[0], h[1], h[2], h[3]);
   if (NPASS == 3) *reinterpret_cast<uint4*>(tile_lo + off) = make_uint4(l[0], l[1], l[2], l[3]);
@@ -128,6 +123,21 @@ __device__ __forceinline__ void issue_part(uint32_t d_tmem, uint32_t a0, uint32_
       const uint32_t kb = ks >> 2, kin = (ks & 3) * 32;
       umma_bf16(d_tmem, ad + ((kb * A_KB + kin) >> 4), bd + ((kb * B_KB + kin) >> 4), IDESC,
                 (pass == 0 && ks == 0 && fresh) ? 0u : 1u);
+    }
+  }
+}
+
+// Same with the A operand(s) in tensor memory (8 columns per k-step).
+template <int NA, int KS, uint32_t B_KB, uint32_t IDESC>
+__device__ __forceinline__ void issue_part_ts(uint32_t d_tmem, uint32_t a0_tmem, uint32_t a1_tmem, uint32_t b, bool fresh) {
+  const uint64_t bd = make_desc_sw128(b);
+#pragma unroll
+  for (int pass = 0; pass < NA; ++pass) {
+    const uint32_t at = (pass == 1) ? a1_tmem : a0_tmem;
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+      const uint32_t kb = ks >> 2, kin = (ks & 3) * 32;
+      umma_bf16_ts(d_tmem, at + 8 * ks, bd + ((kb * B_KB + kin) >> 4), IDESC, (pass == 0 && ks == 0 && fresh) ? 0u : 1u);
     }
   }
 }
@@ -221,7 +231,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
       long long w_a = 0, w_full = 0, w_h = 0, w_d1 = 0;
       const long long t_start = clock64();
       const uint32_t ax_hi = sbase + OFF_AX_HI, ax_lo = sbase + OFF_AX_LO;
-      const uint32_t h_base = sbase + OFF_H;
       constexpr uint32_t ID64 = make_idesc_bf16(64), ID128 = make_idesc_bf16(128);
       auto wait_full = [&]() -> uint32_t {
         const long long t0 = clock64();
@@ -280,24 +289,40 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
         auto issue1 = [&](int c) {
           // D1[c&1] is free: the compute warps loaded chunk c-2 out of it before they arrived on h_ready(c-2),
           // which this warp has already waited for (issue2(c-2) precedes issue1(c)).
-          unit_n64(TM_S + 64 * (c & 1), true);
+          {  // linear1 chunk: A = X' in tensor memory
+            uint32_t w = wait_full();
+            tc_fence_after();
+            if (elect_one())
+              issue_part_ts<(NPASS == 3 ? 2 : 1), 8, 8192u, ID64>(tmem + TM_S + 64 * (c & 1), tmem + TM_AXT_HI,
+                                                                   tmem + TM_AXT_LO, w, true);
+            __syncwarp();
+            release();
+            if (NPASS == 3) {
+              w = wait_full();
+              tc_fence_after();
+              if (elect_one())
+                issue_part_ts<1, 8, 8192u, ID64>(tmem + TM_S + 64 * (c & 1), tmem + TM_AXT_HI, tmem + TM_AXT_HI, w, false);
+              __syncwarp();
+              release();
+            }
+          }
           commit(B_D1READY0 + (c & 1));
         };
         auto issue2 = [&](int c) {
-          const uint32_t h_hi = h_base + (c & 1) * H_BUF_BYTES, h_lo = h_hi + UNIT_PART_BYTES;
+          const uint32_t h_hi = tmem + TM_HT + 64 * (c & 1), h_lo = h_hi + 32;  // H chunk operand in tensor memory
           uint32_t w = wait_full();
           const long long t0 = clock64();
           mbar_wait(bar(B_HREADY0 + (c & 1)), (ph_hr >> (c & 1)) & 1u);
           ph_hr ^= 1u << (c & 1);
           w_h += clock64() - t0;
           tc_fence_after();
-          if (elect_one()) issue_part<(NPASS == 3 ? 2 : 1), 4, 0u, 0u, ID128>(tmem + TM_R, h_hi, h_lo, w, false);
+          if (elect_one()) issue_part_ts<(NPASS == 3 ? 2 : 1), 4, 0u, ID128>(tmem + TM_R, h_hi, h_lo, w, false);
           __syncwarp();
           release();
           if (NPASS == 3) {
             w = wait_full();
             tc_fence_after();
-            if (elect_one()) issue_part<1, 4, 0u, 0u, ID128>(tmem + TM_R, h_hi, h_hi, w, false);
+            if (elect_one()) issue_part_ts<1, 4, 0u, ID128>(tmem + TM_R, h_hi, h_hi, w, false);
             __syncwarp();
             release();
           }
@@ -640,7 +665,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
           tmem_ld32(trow + TM_R + 32 * g, v);
           tmem_ld_wait();
           layer_norm(v, vec + V_LN1W, vec + V_LN1B);
-          store_ax(v);
+          {  // X' -> A operand of linear1, kept in tensor memory (packed bf16 hi / lo, 16 columns per thread)
+            uint32_t xh[16], xl[16];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) split8<NPASS == 3>(v + 8 * c, xh + 4 * c, xl + 4 * c);
+            tmem_st16(trow + TM_AXT_HI + 16 * g, xh);
+            if (NPASS == 3) tmem_st16(trow + TM_AXT_LO + 16 * g, xl);
+          }
           publish(v, vec + V_B2);
         }
         lap(PF_LN1)
@@ -666,12 +697,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
             }
             lap(PF_FFN_MATH)
 
-            uint8_t* h_hi = sgen + OFF_H + bsel * H_BUF_BYTES;
-            uint8_t* h_lo = h_hi + UNIT_PART_BYTES;
-            store_chunk<NPASS>(h_hi, h_lo, r, 2 * g, d);
-            store_chunk<NPASS>(h_hi, h_lo, r, 2 * g + 1, d + 8);
-            fence_proxy_async_smem();
-            tc_fence_before();  // orders this thread's D1 load before the MMAs that will overwrite D1[bsel]
+            {  // H chunk -> A operand of linear2 in tensor memory (8 packed columns per thread, hi and lo)
+              uint32_t hh[8], hl[8];
+              split8<NPASS == 3>(d, hh, hl);
+              split8<NPASS == 3>(d + 8, hh + 4, hl + 4);
+              tmem_st8(trow + TM_HT + 64 * bsel + 8 * g, hh);
+              if (NPASS == 3) tmem_st8(trow + TM_HT + 64 * bsel + 32 + 8 * g, hl);
+              tmem_st_wait();
+            }
+            tc_fence_before();  // orders this thread's D1 load / H store before the MMAs that follow the arrive
             warp_arrive(bar(B_HREADY0 + bsel), lane);
             lap(PF_FFN_STORE)
           }
