@@ -45,7 +45,8 @@ constexpr int TAIL_SLOTS = 14;  // tiles whose token-0 rows are batched into one
 constexpr int TAIL_UNIT0 = 2 * UNITS_PER_LAYER + 6;  // first unit of the tail pass: layer 2 out_proj
 constexpr int NCW = 16;      // compute warps: warp w owns TMEM lanes 32*(w&3).. and column quarter w>>2
 constexpr int NCT = NCW * 32;
-constexpr int NTHREADS = NCT + 64;  // + producer warp + MMA warp
+constexpr int NGW = 2;       // gather warps (token build for the tile after next, fully asynchronous)
+constexpr int NTHREADS = NCT + 64 + NGW * 32;  // + producer warp + MMA warp + gather warps
 
 // per-layer fp32 vector block staged in shared memory (floats)
 constexpr int V_BIN = 0, V_BONEXT = 384, V_LN1W = 512, V_LN1B = 640, V_B2 = 768, V_LN2W = 896, V_LN2B = 1024,
@@ -64,7 +65,7 @@ constexpr uint32_t SMEM_BYTES = OFF_BAR + 256 + 1024;              // + alignmen
 
 // barrier indices (8 bytes each at OFF_BAR)
 enum { B_AREADY = 0, B_DDONE, B_D1READY0, B_D1READY1, B_D1FREE0, B_D1FREE1, B_HREADY0, B_HREADY1, B_HFREE0, B_HFREE1,
-       B_FULL0, B_EMPTY0 = B_FULL0 + NSLOT, B_COUNT = B_EMPTY0 + NSLOT };
+       B_TOKFULL0, B_TOKFULL1, B_TOKEMPTY0, B_TOKEMPTY1, B_FULL0, B_EMPTY0 = B_FULL0 + NSLOT, B_COUNT = B_EMPTY0 + NSLOT };
 constexpr uint32_t OFF_TMEMPTR = OFF_BAR + 8 * B_COUNT;
 
 // TMEM columns
@@ -168,6 +169,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
     mbar_init(bar(B_HREADY1), NCW);
     mbar_init(bar(B_HFREE0), 1);
     mbar_init(bar(B_HFREE1), 1);
+    mbar_init(bar(B_TOKFULL0), NGW);
+    mbar_init(bar(B_TOKFULL1), NGW);
+    mbar_init(bar(B_TOKEMPTY0), NCW);
+    mbar_init(bar(B_TOKEMPTY1), NCW);
     for (int s = 0; s < NSLOT; ++s) {
       mbar_init(bar(B_FULL0 + s), 1);
       mbar_init(bar(B_EMPTY0 + s), 1);
@@ -358,6 +363,92 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
         atomicAdd(&g_prof[PF_MMA_TOTAL], (unsigned long long)(clock64() - t_start));
       }
     }
+  } else if (warp >= NCW + 2) {
+    // ===================================================================== gather warps
+    // They run up to two tiles ahead of the compute warps (double-buffered token scratch), so the L2 latency
+    // of the bilinear taps is off the critical path.
+    // Token gather, decoupled from row ownership.  The 108 (slice, query, 32-channel block) tasks of a tile are
+    // dealt four to a warp-step (one per quarter-warp, 16 bytes per lane; the four quarter-warps of a step take
+    // the same slice and channel block of four consecutive queries, whose texels coincide or neighbour each
+    // other, so their requests coalesce), 56 steps for each of the two gather warps.  Each step issues the 12 tap loads of plane scales
+    // 0-2 together, then the 8 of scales 3-4 (two L2 round trips per step instead of five: with ~226 KB of shared
+    // memory in use there is no L1 to speak of and the gather is bound by L2 latency x loads in flight).  The
+    // 16-byte token pieces go to this CTA's global token scratch [128 rows][128] (L2-resident); the row owners
+    // pick them up after a CTA barrier.
+    constexpr int GATHER_STEPS = 112 / NGW;
+    auto gather_step = [&](long long gt, int step, float* tokbuf) {
+      const int qtr = lane >> 3, l8 = lane & 7;
+      int q, k, cb;
+      const int idx = step * NGW + (warp - NCW - 2);  // 0..111
+      if (idx < 96) {  // steps 0..5: queries 0..7, four per step
+        cb = idx & 3;
+        const int grp = idx >> 2;  // 0..23
+        k = grp >> 1;
+        q = 4 * (grp & 1) + qtr;
+      } else {  // step 6: the 48 tasks of query 8, four slices per step
+        const int t = (idx - 96) * 4 + qtr;  // 0..63, 48 real
+        cb = t & 3;
+        k = t >> 2;
+        q = 8;
+      }
+      const long long gq = gt * TILE_Q + q;
+      if (k >= 12 || gq >= p.n) return;
+      const int ch = 32 * cb + l8 * 4;
+      float x, y, z, gu, gv;
+      load_query(p.q, gq, x, y, z, gu, gv);
+      float4 acc = __ldg(reinterpret_cast<const float4*>(p.fcs_b + ch));
+      const int R0 = plane_res(p.S, 0);
+      const float* P = p.planes + (size_t)k * R0 * R0 * 128 + ch;
+      auto fold = [&](const float4* v, const Taps& t) {
+        acc.x += v[0].x * t.w00 + v[1].x * t.w01 + v[2].x * t.w10 + v[3].x * t.w11;
+        acc.y += v[0].y * t.w00 + v[1].y * t.w01 + v[2].y * t.w10 + v[3].y * t.w11;
+        acc.z += v[0].z * t.w00 + v[1].z * t.w01 + v[2].z * t.w10 + v[3].z * t.w11;
+        acc.w += v[0].w * t.w00 + v[1].w * t.w01 + v[2].w * t.w10 + v[3].w * t.w11;
+      };
+      auto issue = [&](float4* v, const Taps& t, const float* base) {
+        v[0] = __ldg(reinterpret_cast<const float4*>(base + (size_t)t.o00 * 128));
+        v[1] = __ldg(reinterpret_cast<const float4*>(base + (size_t)t.o01 * 128));
+        v[2] = __ldg(reinterpret_cast<const float4*>(base + (size_t)t.o10 * 128));
+        v[3] = __ldg(reinterpret_cast<const float4*>(base + (size_t)t.o11 * 128));
+      };
+      // plane of scale s for slice k starts at P + (12 * sum_{i<s} R_i^2 + k * (R_s^2 - R_0^2)) * 128
+      const size_t r2 = (size_t)R0 * R0;
+      {
+        float4 v0[4], v1[4], v2[4];
+        const Taps t0 = make_taps(gu, gv, R0), t1 = make_taps(gu, gv, 2 * R0), t2 = make_taps(gu, gv, 4 * R0);
+        issue(v0, t0, P);
+        issue(v1, t1, P + (12 * r2 + (size_t)k * 3 * r2) * 128);
+        issue(v2, t2, P + (12 * 5 * r2 + (size_t)k * 15 * r2) * 128);
+        fold(v0, t0);
+        fold(v1, t1);
+        fold(v2, t2);
+      }
+      {
+        float4 v3[4], v4[4];
+        const Taps t3 = make_taps(gu, gv, 8 * R0), t4 = make_taps(gu, gv, 16 * R0);
+        issue(v3, t3, P + (12 * 21 * r2 + (size_t)k * 63 * r2) * 128);
+        issue(v4, t4, P + (12 * 85 * r2 + (size_t)k * 255 * r2) * 128);
+        fold(v3, t3);
+        fold(v4, t4);
+      }
+      __stcg(reinterpret_cast<float4*>(tokbuf + (size_t)(NTOK * q + 1 + k) * 128 + ch), acc);
+    };
+
+    {
+      float* const tokbase = p.scratch + (size_t)gridDim.x * (TAIL_SLOTS * TILE_Q) * 256 + (size_t)blockIdx.x * (2 * 128 * 128);
+      uint32_t ph_te = 3u;  // "empty"-type: the first wait on each buffer passes
+      int it = 0;
+      for (long long tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+        const int buf = it & 1;
+        mbar_wait(bar(B_TOKEMPTY0 + buf), (ph_te >> buf) & 1u);
+        ph_te ^= 1u << buf;
+#pragma unroll 1
+        for (int st = 0; st < GATHER_STEPS; ++st) gather_step(tile, st, tokbase + (size_t)buf * (128 * 128));
+        __threadfence_block();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar(B_TOKFULL0 + buf));
+      }
+    }
   } else {
     // ===================================================================== compute warps
     // thread = (tile row r = TMEM lane, column quarter g): 32 of the 128 model channels per thread
@@ -432,74 +523,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
       warp_arrive(bar(B_AREADY), lane);
     };
 
-    // Token gather, decoupled from row ownership.  The 108 (slice, query, 32-channel block) tasks of a tile are
-    // dealt four to a warp-step (one per quarter-warp, 16 bytes per lane; the four quarter-warps of a step take
-    // the same slice and channel block of four consecutive queries, whose texels coincide or neighbour each
-    // other, so their requests coalesce), 7 steps per warp.  Each step issues the 12 tap loads of plane scales
-    // 0-2 together, then the 8 of scales 3-4 (two L2 round trips per step instead of five: with ~226 KB of shared
-    // memory in use there is no L1 to speak of and the gather is bound by L2 latency x loads in flight).  The
-    // 16-byte token pieces go to this CTA's global token scratch [128 rows][128] (L2-resident); the row owners
-    // pick them up after a CTA barrier.
-    float* tokbuf = p.scratch + (size_t)gridDim.x * (TAIL_SLOTS * TILE_Q) * 256 + (size_t)blockIdx.x * (128 * 128);
-    constexpr int GATHER_STEPS = 7;
-    auto gather_step = [&](long long gt, int step) {
-      const int qtr = lane >> 3, l8 = lane & 7;
-      int q, k, cb;
-      const int idx = step * NCW + warp;  // 0..111
-      if (idx < 96) {  // steps 0..5: queries 0..7, four per step
-        cb = idx & 3;
-        const int grp = idx >> 2;  // 0..23
-        k = grp >> 1;
-        q = 4 * (grp & 1) + qtr;
-      } else {  // step 6: the 48 tasks of query 8, four slices per step
-        const int t = (idx - 96) * 4 + qtr;  // 0..63, 48 real
-        cb = t & 3;
-        k = t >> 2;
-        q = 8;
-      }
-      const long long gq = gt * TILE_Q + q;
-      if (k >= 12 || gq >= p.n) return;
-      const int ch = 32 * cb + l8 * 4;
-      float x, y, z, gu, gv;
-      load_query(p.q, gq, x, y, z, gu, gv);
-      float4 acc = __ldg(reinterpret_cast<const float4*>(p.fcs_b + ch));
-      const int R0 = plane_res(p.S, 0);
-      const float* P = p.planes + (size_t)k * R0 * R0 * 128 + ch;
-      auto fold = [&](const float4* v, const Taps& t) {
-        acc.x += v[0].x * t.w00 + v[1].x * t.w01 + v[2].x * t.w10 + v[3].x * t.w11;
-        acc.y += v[0].y * t.w00 + v[1].y * t.w01 + v[2].y * t.w10 + v[3].y * t.w11;
-        acc.z += v[0].z * t.w00 + v[1].z * t.w01 + v[2].z * t.w10 + v[3].z * t.w11;
-        acc.w += v[0].w * t.w00 + v[1].w * t.w01 + v[2].w * t.w10 + v[3].w * t.w11;
-      };
-      auto issue = [&](float4* v, const Taps& t, const float* base) {
-        v[0] = __ldg(reinterpret_cast<const float4*>(base + (size_t)t.o00 * 128));
-        v[1] = __ldg(reinterpret_cast<const float4*>(base + (size_t)t.o01 * 128));
-        v[2] = __ldg(reinterpret_cast<const float4*>(base + (size_t)t.o10 * 128));
-        v[3] = __ldg(reinterpret_cast<const float4*>(base + (size_t)t.o11 * 128));
-      };
-      // plane of scale s for slice k starts at P + (12 * sum_{i<s} R_i^2 + k * (R_s^2 - R_0^2)) * 128
-      const size_t r2 = (size_t)R0 * R0;
-      {
-        float4 v0[4], v1[4], v2[4];
-        const Taps t0 = make_taps(gu, gv, R0), t1 = make_taps(gu, gv, 2 * R0), t2 = make_taps(gu, gv, 4 * R0);
-        issue(v0, t0, P);
-        issue(v1, t1, P + (12 * r2 + (size_t)k * 3 * r2) * 128);
-        issue(v2, t2, P + (12 * 5 * r2 + (size_t)k * 15 * r2) * 128);
-        fold(v0, t0);
-        fold(v1, t1);
-        fold(v2, t2);
-      }
-      {
-        float4 v3[4], v4[4];
-        const Taps t3 = make_taps(gu, gv, 8 * R0), t4 = make_taps(gu, gv, 16 * R0);
-        issue(v3, t3, P + (12 * 21 * r2 + (size_t)k * 63 * r2) * 128);
-        issue(v4, t4, P + (12 * 85 * r2 + (size_t)k * 255 * r2) * 128);
-        fold(v3, t3);
-        fold(v4, t4);
-      }
-      __stcg(reinterpret_cast<float4*>(tokbuf + (size_t)(NTOK * q + 1 + k) * 128 + ch), acc);
-    };
-
+    float* const tokbase = p.scratch + (size_t)gridDim.x * (TAIL_SLOTS * TILE_Q) * 256 + (size_t)blockIdx.x * (2 * 128 * 128);
     // Self-attention over the 13 tokens of each query, 4 heads (one per column group).  tok0_only: last
     // layer -- only token 0 of a query is consumed downstream (models.py:83), so only those rows attend and
     // their output (and residual) is parked in the CTA's global scratch row `slot*9 + qi` for the tail pass.
@@ -737,15 +761,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
         }
         lap(PF_LN2)
     };
-    int pending = 0;
+    int pending = 0, tile_it = 0;
+    uint32_t ph_tf = 0;
     long long batch_tile0 = 0;
     for (long long tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       const long long q_idx = tile * TILE_Q + qi;
       const bool valid = (qi < TILE_Q) && (q_idx < p.n);
       // ------------------------------------------------------------------ token build
-#pragma unroll 1
-      for (int st = 0; st < GATHER_STEPS; ++st) gather_step(tile, st);
-      named_bar_sync(1, NCT);  // token scratch written by all warps
+      const int tbuf = tile_it & 1;
+      const float* tokbuf = tokbase + (size_t)tbuf * (128 * 128);
+      mbar_wait(bar(B_TOKFULL0 + tbuf), (ph_tf >> tbuf) & 1u);  // slice tokens of this tile gathered
+      ph_tf ^= 1u << tbuf;
       {
         float v[32];
 #pragma unroll
@@ -764,9 +790,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
                    pz * __ldg(p.fcp_wt + 256 + cc);
           }
         }
+        warp_arrive(bar(B_TOKEMPTY0 + tbuf), lane);  // this warp has read its tokens: the buffer may be refilled
         store_ax(v);
         publish(v, p.b_o0);
       }
+      ++tile_it;
       lap(PF_TOKEN)
 
 #pragma unroll 1
@@ -1038,8 +1066,8 @@ int debug_profile(long long* out32, int reset) {
 }
 
 size_t decoder_tc_workspace_bytes(int64_t) {
-  // per CTA (up to 256): tail scratch [126][256] + token scratch [128][128], fp32
-  return (size_t)256 * (TAIL_SLOTS * TILE_Q * 256 + 128 * 128) * sizeof(float);
+  // per CTA (up to 256): tail scratch [126][256] + double-buffered token scratch 2 x [128][128], fp32
+  return (size_t)256 * (TAIL_SLOTS * TILE_Q * 256 + 2 * 128 * 128) * sizeof(float);
 }
 
 int decoder_tc(const s3d_model* m, const float* planes, int S, const QueryCtx& q, int64_t n, float out_scale, float* out,
