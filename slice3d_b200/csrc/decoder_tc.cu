@@ -23,6 +23,7 @@
 //
 // Warp roles (576 threads): warps 0-15 = compute, thread = (tile row r = TMEM lane, column quarter g);
 // warp 16 = weight producer; warp 17 = MMA issuer (warp-uniform control flow, one elected lane issues).
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -36,7 +37,9 @@ using namespace ptx;
 
 constexpr int TILE_Q = 9;    // queries per tile
 constexpr int NTOK = 13;     // tokens per query (K = 12 slices + the query token)
-constexpr int NSLOT = 5;      // weight ring: 5 slots of one 16 KB part (a unit = hi part [+ lo part])
+constexpr int NSLOT_MAX = 10;  // weight ring: 80 KB = 5 slots of one 16 KB part, or (CTA pair) 10 slots of this CTA's 8 KB half
+constexpr uint32_t RING_BYTES = 81920;
+constexpr uint32_t ORDER_W2 = 0x80000000u;  // order[] flag: the part belongs to a linear2 unit ([128 n][64 k])
 constexpr int UNITS_PER_LAYER = 72;  // 6 (in_proj) + 2 (out_proj) + 32 (linear1) + 32 (linear2)
 constexpr int UNIT_PART_BYTES = 16384;  // one precision part (hi or lo) of a unit: 64x128 or 128x64 bf16
 constexpr int UNIT_STRIDE_BYTES = 2 * UNIT_PART_BYTES;  // hi then lo in global memory
@@ -58,14 +61,17 @@ constexpr uint32_t OFF_AX_LO = 32768;             // 32 KB
 constexpr uint32_t OFF_H = 65536;                 // 2 x (H chunk hi 16 KB + lo 16 KB) | K/V staging [128][128] fp32 | gather scratch
 constexpr uint32_t H_BUF_BYTES = 32768;
 constexpr uint32_t OFF_RING = OFF_H + 2 * H_BUF_BYTES;  // 131072
-constexpr uint32_t OFF_VEC = OFF_RING + NSLOT * UNIT_PART_BYTES;  // 212992
+constexpr uint32_t OFF_VEC = OFF_RING + RING_BYTES;  // 212992
 constexpr uint32_t OFF_RED = OFF_VEC + V_SMEM_FLOATS * 4;          // 2 x [128][4] fp32 LayerNorm partials
 constexpr uint32_t OFF_BAR = OFF_RED + 4096;
-constexpr uint32_t SMEM_BYTES = OFF_BAR + 256 + 1024;              // + alignment slack
+constexpr uint32_t SMEM_BYTES = OFF_BAR + 512 + 1024;              // + alignment slack
 
 // barrier indices (8 bytes each at OFF_BAR)
 enum { B_AREADY = 0, B_DDONE, B_D1READY0, B_D1READY1, B_D1FREE0, B_D1FREE1, B_HREADY0, B_HREADY1, B_HFREE0, B_HFREE1,
-       B_TOKFULL0, B_TOKFULL1, B_TOKEMPTY0, B_TOKEMPTY1, B_FULL0, B_EMPTY0 = B_FULL0 + NSLOT, B_COUNT = B_EMPTY0 + NSLOT };
+       B_TOKFULL0, B_TOKFULL1, B_TOKEMPTY0, B_TOKEMPTY1, B_FULL0, B_EMPTY0 = B_FULL0 + NSLOT_MAX,
+       B_PFULL0 = B_EMPTY0 + NSLOT_MAX,  // leader CTA only: the peer's half of the slot has landed
+       B_COUNT = B_PFULL0 + NSLOT_MAX };
+static_assert(8 * B_COUNT + 8 <= 512, "barrier area");
 constexpr uint32_t OFF_TMEMPTR = OFF_BAR + 8 * B_COUNT;
 
 // TMEM columns
@@ -113,7 +119,7 @@ __device__ __forceinline__ void store_chunk(uint8_t* tile_hi, uint8_t* tile_lo, 
 // One 16 KB weight part (B) against NA activation operands (a0 [, a1]): D += a0.B [+ a1.B], KS k-steps
 // of 16 each, fully unrolled with compile-time descriptor increments.
 //   *_KB: byte stride between 64-wide k-blocks of the A / B tiles.
-template <int NA, int KS, uint32_t A_KB, uint32_t B_KB, uint32_t IDESC>
+template <int CG, int NA, int KS, uint32_t A_KB, uint32_t B_KB, uint32_t IDESC>
 __device__ __forceinline__ void issue_part(uint32_t d_tmem, uint32_t a0, uint32_t a1, uint32_t b, bool fresh) {
   const uint64_t ad0 = make_desc_sw128(a0), ad1 = make_desc_sw128(a1), bd = make_desc_sw128(b);
 #pragma unroll
@@ -122,14 +128,18 @@ __device__ __forceinline__ void issue_part(uint32_t d_tmem, uint32_t a0, uint32_
 #pragma unroll
     for (int ks = 0; ks < KS; ++ks) {
       const uint32_t kb = ks >> 2, kin = (ks & 3) * 32;
-      umma_bf16(d_tmem, ad + ((kb * A_KB + kin) >> 4), bd + ((kb * B_KB + kin) >> 4), IDESC,
-                (pass == 0 && ks == 0 && fresh) ? 0u : 1u);
+      if (CG == 2)
+        umma_bf16_pair(d_tmem, ad + ((kb * A_KB + kin) >> 4), bd + ((kb * B_KB + kin) >> 4), IDESC,
+                       (pass == 0 && ks == 0 && fresh) ? 0u : 1u);
+      else
+        umma_bf16(d_tmem, ad + ((kb * A_KB + kin) >> 4), bd + ((kb * B_KB + kin) >> 4), IDESC,
+                  (pass == 0 && ks == 0 && fresh) ? 0u : 1u);
     }
   }
 }
 
 // Same with the A operand(s) in tensor memory (8 columns per k-step).
-template <int NA, int KS, uint32_t B_KB, uint32_t IDESC>
+template <int CG, int NA, int KS, uint32_t B_KB, uint32_t IDESC>
 __device__ __forceinline__ void issue_part_ts(uint32_t d_tmem, uint32_t a0_tmem, uint32_t a1_tmem, uint32_t b, bool fresh) {
   const uint64_t bd = make_desc_sw128(b);
 #pragma unroll
@@ -138,7 +148,10 @@ __device__ __forceinline__ void issue_part_ts(uint32_t d_tmem, uint32_t a0_tmem,
 #pragma unroll
     for (int ks = 0; ks < KS; ++ks) {
       const uint32_t kb = ks >> 2, kin = (ks & 3) * 32;
-      umma_bf16_ts(d_tmem, at + 8 * ks, bd + ((kb * B_KB + kin) >> 4), IDESC, (pass == 0 && ks == 0 && fresh) ? 0u : 1u);
+      if (CG == 2)
+        umma_bf16_ts_pair(d_tmem, at + 8 * ks, bd + ((kb * B_KB + kin) >> 4), IDESC, (pass == 0 && ks == 0 && fresh) ? 0u : 1u);
+      else
+        umma_bf16_ts(d_tmem, at + 8 * ks, bd + ((kb * B_KB + kin) >> 4), IDESC, (pass == 0 && ks == 0 && fresh) ? 0u : 1u);
     }
   }
 }
@@ -149,24 +162,47 @@ __device__ __forceinline__ void warp_arrive(uint32_t bar, int lane) {
   if (lane == 0) mbar_arrive(bar);
 }
 
-template <int NPASS>
+// CG = 1: every CTA is on its own.  CG = 2: CTA pairs (cluster of 2 = one TPC): the leader's MMA warp issues
+// cta_group::2 MMAs (M = 256: 128 rows = one tile in each CTA) and every CTA streams only ITS HALF of each weight
+// part (N/2 rows of B), which halves the L2 -> shared-memory weight traffic and the shared-memory operand reads per SM
+// and doubles the MMA time one ring slot covers.  Everything outside the MMA / producer warps is per CTA.
+template <int NPASS, int CG>
 __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
-  const uint32_t sbase = (raw + 1023u) & ~1023u;
+  const uint32_t sbase = (raw + 1023u) & ~1023u;  // (the dynamic window starts at the same offset in both CTAs of a pair)
   uint8_t* sgen = smem_raw + (sbase - raw);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   auto bar = [&](int i) { return sbase + OFF_BAR + 8u * i; };
+  constexpr int NSLOT = 5 * CG;
+  constexpr uint32_t SLOT_BYTES = UNIT_PART_BYTES / CG;
+  const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;
+  const bool leader = rank == 0;
+  // tiles of this CTA: base + rank for base = CG * group, CG * (group + #groups), ...
+  const long long tile_first = blockIdx.x;  // = CG * (blockIdx.x / CG) + rank
+  const long long base_first = (long long)blockIdx.x - rank;
+  // arrive on barrier i of the leader CTA (the MMA issuer's barriers)
+  auto arrive_lead = [&](int i) {
+    __syncwarp();
+    if (lane == 0) {
+      if (CG == 2 && !leader) mbar_arrive_cluster(mapa_u32(bar(i), 0));
+      else mbar_arrive(bar(i));
+    }
+  };
+  auto wait_lead = [&](int i, uint32_t parity) {  // leader-side wait on a barrier the peer arrives on too
+    if (CG == 2) mbar_wait_cluster(bar(i), parity);
+    else mbar_wait(bar(i), parity);
+  };
 
   if (threadIdx.x == 0) {
-    mbar_init(bar(B_AREADY), NCW);
+    mbar_init(bar(B_AREADY), NCW * CG);
     mbar_init(bar(B_DDONE), 1);
     mbar_init(bar(B_D1READY0), 1);
     mbar_init(bar(B_D1READY1), 1);
     mbar_init(bar(B_D1FREE0), NCW);
     mbar_init(bar(B_D1FREE1), NCW);
-    mbar_init(bar(B_HREADY0), NCW);
-    mbar_init(bar(B_HREADY1), NCW);
+    mbar_init(bar(B_HREADY0), NCW * CG);
+    mbar_init(bar(B_HREADY1), NCW * CG);
     mbar_init(bar(B_HFREE0), 1);
     mbar_init(bar(B_HFREE1), 1);
     mbar_init(bar(B_TOKFULL0), NGW);
@@ -176,12 +212,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
     for (int s = 0; s < NSLOT; ++s) {
       mbar_init(bar(B_FULL0 + s), 1);
       mbar_init(bar(B_EMPTY0 + s), 1);
+      mbar_init(bar(B_PFULL0 + s), 1);
     }
     fence_barrier_init();
   }
-  if (warp == 0) tmem_alloc(sbase + OFF_TMEMPTR, 512);
+  if (warp == 0) {
+    if (CG == 2) tmem_alloc_pair(sbase + OFF_TMEMPTR, 512);
+    else tmem_alloc(sbase + OFF_TMEMPTR, 512);
+  }
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all();  // the peer's barriers are initialised before anything arrives on them
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(sgen + OFF_TMEMPTR);
 
@@ -203,21 +244,30 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
           ph_empty ^= 1u << slot;
           w_e += clock64() - t0;
           if (elect_one()) {
-            const uint8_t* src = p.wimg + (size_t)__ldg(p.order + (NPASS == 3 ? 0 : 3 * UNITS_PER_LAYER * 2) + g) * UNIT_PART_BYTES;
-            mbar_arrive_expect_tx(bar(B_FULL0 + slot), UNIT_PART_BYTES);
+            const uint32_t ord = __ldg(p.order + (NPASS == 3 ? 0 : 3 * UNITS_PER_LAYER * 2) + g);
+            const uint8_t* src = p.wimg + (size_t)(ord & ~ORDER_W2) * UNIT_PART_BYTES;
+            const uint32_t dst = sbase + OFF_RING + slot * SLOT_BYTES;
+            mbar_arrive_expect_tx(bar(B_FULL0 + slot), SLOT_BYTES);
+            if (CG == 1) {
 #pragma unroll
-            for (uint32_t part = 0; part < UNIT_PART_BYTES; part += 8192)
-              bulk_g2s(sbase + OFF_RING + slot * UNIT_PART_BYTES + part, src + part, 8192, bar(B_FULL0 + slot));
+              for (uint32_t part = 0; part < UNIT_PART_BYTES; part += 8192)
+                bulk_g2s(dst + part, src + part, 8192, bar(B_FULL0 + slot));
+            } else if (ord & ORDER_W2) {  // [128 n][64 k]: rows 64 rank .. +63 are contiguous
+              bulk_g2s(dst, src + rank * 8192, 8192, bar(B_FULL0 + slot));
+            } else {  // [2 k-blocks][64 n][64 k]: rows 32 rank .. +31 of each k-block
+              bulk_g2s(dst, src + rank * 4096, 4096, bar(B_FULL0 + slot));
+              bulk_g2s(dst + 4096, src + 8192 + rank * 4096, 4096, bar(B_FULL0 + slot));
+            }
           }
           __syncwarp();
           slot = (slot + 1 == NSLOT) ? 0 : slot + 1;
         }
       };
       int pending = 0;
-      for (long long tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      for (long long base = base_first; base < p.num_tiles; base += gridDim.x) {
         stream(0, TAIL_UNIT0 * NPART);  // layers 0,1 and the in_proj of layer 2
         ++pending;
-        if (pending == TAIL_SLOTS || tile + gridDim.x >= p.num_tiles) {
+        if (pending == TAIL_SLOTS || base + gridDim.x >= p.num_tiles) {
           stream(TAIL_UNIT0 * NPART, 3 * UNITS_PER_LAYER * NPART);  // tail pass: out_proj + FFN of layer 2
           pending = 0;
         }
@@ -227,8 +277,33 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
         atomicAdd(&g_prof[PF_PROD_TOTAL], (unsigned long long)(clock64() - t_start));
       }
     }
+  } else if (warp == NCW + 1 && !leader) {
+    // ===================================================================== peer CTA of a pair: slot relay
+    // tells the leader's MMA warp that this CTA's half of a ring slot has landed (the commit that frees the slot
+    // arrives on both CTAs' "empty" barriers)
+    uint32_t ph_full = 0;
+    int slot = 0;
+    auto relay = [&](int nparts) {
+#pragma unroll 1
+      for (int g = 0; g < nparts; ++g) {
+        mbar_wait(bar(B_FULL0 + slot), (ph_full >> slot) & 1u);
+        ph_full ^= 1u << slot;
+        if (lane == 0) mbar_arrive_cluster(mapa_u32(bar(B_PFULL0 + slot), 0));
+        __syncwarp();
+        slot = (slot + 1 == NSLOT) ? 0 : slot + 1;
+      }
+    };
+    int pending = 0;
+    for (long long base = base_first; base < p.num_tiles; base += gridDim.x) {
+      relay(TAIL_UNIT0 * NPART);
+      ++pending;
+      if (pending == TAIL_SLOTS || base + gridDim.x >= p.num_tiles) {
+        relay((3 * UNITS_PER_LAYER - TAIL_UNIT0) * NPART);
+        pending = 0;
+      }
+    }
   } else if (warp == NCW + 1) {
-    // ===================================================================== MMA issuer
+    // ===================================================================== MMA issuer (leader CTA of a pair)
     // the whole warp runs the control flow (waits are warp-uniform); one elected lane issues
     {
       uint32_t ph_a = 0, ph_full = 0, ph_hr = 0;  // parity bits (one per barrier / slot)
@@ -236,16 +311,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
       long long w_a = 0, w_full = 0, w_h = 0, w_d1 = 0;
       const long long t_start = clock64();
       const uint32_t ax_hi = sbase + OFF_AX_HI, ax_lo = sbase + OFF_AX_LO;
-      constexpr uint32_t ID64 = make_idesc_bf16(64), ID128 = make_idesc_bf16(128);
+      constexpr uint32_t ID64 = make_idesc_bf16(64, 128 * CG), ID128 = make_idesc_bf16(128, 128 * CG);
+      constexpr uint32_t BKB = 8192u / CG;  // k-block stride of this CTA's share of a [2][64 n][64 k] part
       auto wait_full = [&]() -> uint32_t {
         const long long t0 = clock64();
         mbar_wait(bar(B_FULL0 + slot), (ph_full >> slot) & 1u);
+        if (CG == 2) mbar_wait_cluster(bar(B_PFULL0 + slot), (ph_full >> slot) & 1u);
         ph_full ^= 1u << slot;
         w_full += clock64() - t0;
-        return sbase + OFF_RING + slot * UNIT_PART_BYTES;
+        return sbase + OFF_RING + slot * SLOT_BYTES;
       };
       auto commit = [&](int b) {
-        if (elect_one()) umma_commit(bar(b));
+        if (elect_one()) {
+          if (CG == 2) umma_commit_pair(bar(b));
+          else umma_commit(bar(b));
+        }
         __syncwarp();
       };
       auto release = [&]() {
@@ -260,20 +340,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
       auto unit_n64 = [&](uint32_t d_col, bool fresh) {
         uint32_t w = wait_full();
         tc_fence_after();
-        if (elect_one()) issue_part<(NPASS == 3 ? 2 : 1), 8, 16384u, 8192u, ID64>(tmem + d_col, ax_hi, ax_lo, w, fresh);
+        if (elect_one()) issue_part<CG, (NPASS == 3 ? 2 : 1), 8, 16384u, BKB, ID64>(tmem + d_col, ax_hi, ax_lo, w, fresh);
         __syncwarp();
         release();
         if (NPASS == 3) {
           w = wait_full();
           tc_fence_after();
-          if (elect_one()) issue_part<1, 8, 16384u, 8192u, ID64>(tmem + d_col, ax_hi, ax_hi, w, false);
+          if (elect_one()) issue_part<CG, 1, 8, 16384u, BKB, ID64>(tmem + d_col, ax_hi, ax_hi, w, false);
           __syncwarp();
           release();
         }
       };
       auto wait_a = [&]() {
         const long long t0 = clock64();
-        mbar_wait(bar(B_AREADY), ph_a);
+        wait_lead(B_AREADY, ph_a);
         w_a += clock64() - t0;
         ph_a ^= 1;
         tc_fence_after();
@@ -298,15 +378,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
             uint32_t w = wait_full();
             tc_fence_after();
             if (elect_one())
-              issue_part_ts<(NPASS == 3 ? 2 : 1), 8, 8192u, ID64>(tmem + TM_S + 64 * (c & 1), tmem + TM_AXT_HI,
-                                                                   tmem + TM_AXT_LO, w, true);
+              issue_part_ts<CG, (NPASS == 3 ? 2 : 1), 8, BKB, ID64>(tmem + TM_S + 64 * (c & 1), tmem + TM_AXT_HI,
+                                                                       tmem + TM_AXT_LO, w, true);
             __syncwarp();
             release();
             if (NPASS == 3) {
               w = wait_full();
               tc_fence_after();
               if (elect_one())
-                issue_part_ts<1, 8, 8192u, ID64>(tmem + TM_S + 64 * (c & 1), tmem + TM_AXT_HI, tmem + TM_AXT_HI, w, false);
+                issue_part_ts<CG, 1, 8, BKB, ID64>(tmem + TM_S + 64 * (c & 1), tmem + TM_AXT_HI, tmem + TM_AXT_HI, w, false);
               __syncwarp();
               release();
             }
@@ -317,17 +397,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
           const uint32_t h_hi = tmem + TM_HT + 64 * (c & 1), h_lo = h_hi + 32;  // H chunk operand in tensor memory
           uint32_t w = wait_full();
           const long long t0 = clock64();
-          mbar_wait(bar(B_HREADY0 + (c & 1)), (ph_hr >> (c & 1)) & 1u);
+          wait_lead(B_HREADY0 + (c & 1), (ph_hr >> (c & 1)) & 1u);
           ph_hr ^= 1u << (c & 1);
           w_h += clock64() - t0;
           tc_fence_after();
-          if (elect_one()) issue_part_ts<(NPASS == 3 ? 2 : 1), 4, 0u, ID128>(tmem + TM_R, h_hi, h_lo, w, false);
+          if (elect_one()) issue_part_ts<CG, (NPASS == 3 ? 2 : 1), 4, 0u, ID128>(tmem + TM_R, h_hi, h_lo, w, false);
           __syncwarp();
           release();
           if (NPASS == 3) {
             w = wait_full();
             tc_fence_after();
-            if (elect_one()) issue_part_ts<1, 4, 0u, ID128>(tmem + TM_R, h_hi, h_hi, w, false);
+            if (elect_one()) issue_part_ts<CG, 1, 4, 0u, ID128>(tmem + TM_R, h_hi, h_hi, w, false);
             __syncwarp();
             release();
           }
@@ -343,14 +423,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
         commit(B_DDONE);
       };
       int pending = 0;
-      for (long long tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      for (long long base = base_first; base < p.num_tiles; base += gridDim.x) {
         for (int layer = 0; layer < 2; ++layer) {
           mma_qkv();
           mma_out_ffn();
         }
         mma_qkv();  // last layer: only token 0 of every query is consumed downstream -> batched tail pass
         ++pending;
-        if (pending == TAIL_SLOTS || tile + gridDim.x >= p.num_tiles) {
+        if (pending == TAIL_SLOTS || base + gridDim.x >= p.num_tiles) {
           mma_out_ffn();
           pending = 0;
         }
@@ -438,7 +518,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
       float* const tokbase = p.scratch + (size_t)gridDim.x * (TAIL_SLOTS * TILE_Q) * 256 + (size_t)blockIdx.x * (2 * 128 * 128);
       uint32_t ph_te = 3u;  // "empty"-type: the first wait on each buffer passes
       int it = 0;
-      for (long long tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      for (long long tile = tile_first; tile - rank < p.num_tiles; tile += gridDim.x, ++it) {
         const int buf = it & 1;
         mbar_wait(bar(B_TOKEMPTY0 + buf), (ph_te >> buf) & 1u);
         ph_te ^= 1u << buf;
@@ -520,7 +600,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
       tmem_st_wait();
       tc_fence_before();
       fence_proxy_async_smem();
-      warp_arrive(bar(B_AREADY), lane);
+      arrive_lead(B_AREADY);
     };
 
     float* const tokbase = p.scratch + (size_t)gridDim.x * (TAIL_SLOTS * TILE_Q) * 256 + (size_t)blockIdx.x * (2 * 128 * 128);
@@ -673,7 +753,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
             for (int c = 0; c < 8; ++c) dst[c] = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
           }
         } else {
-          warp_arrive(bar(B_AREADY), lane);
+          arrive_lead(B_AREADY);
         }
         lap(PF_ATTN)
     };
@@ -730,7 +810,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
               tmem_st_wait();
             }
             tc_fence_before();  // orders this thread's D1 load / H store before the MMAs that follow the arrive
-            warp_arrive(bar(B_HREADY0 + bsel), lane);
+            arrive_lead(B_HREADY0 + bsel);
             lap(PF_FFN_STORE)
           }
         }
@@ -764,7 +844,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
     int pending = 0, tile_it = 0;
     uint32_t ph_tf = 0;
     long long batch_tile0 = 0;
-    for (long long tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+    for (long long tile = tile_first; tile - rank < p.num_tiles; tile += gridDim.x) {
       const long long q_idx = tile * TILE_Q + qi;
       const bool valid = (qi < TILE_Q) && (q_idx < p.n);
       // ------------------------------------------------------------------ token build
@@ -822,7 +902,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
       }
       if (pending == 0) batch_tile0 = tile;
       ++pending;
-      if (pending == TAIL_SLOTS || tile + gridDim.x >= p.num_tiles) {
+      if (pending == TAIL_SLOTS || tile - rank + gridDim.x >= p.num_tiles) {
         // ---------------------------------------------------------------- tail pass: token 0 of up to 126 queries
         named_bar_sync(1, NCT);  // scratch rows written by other threads are visible after the CTA barrier
         {
@@ -848,7 +928,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
           tmem_st_wait();
           tc_fence_before();
           fence_proxy_async_smem();
-          warp_arrive(bar(B_AREADY), lane);
+          arrive_lead(B_AREADY);
           post_attn(2, g == 0 && tvalid, tq);
         }
         pending = 0;
@@ -865,8 +945,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
 #undef lap
   }
   tc_fence_before();
-  __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem, 512);
+  if (CG == 2) cluster_sync_all();  // neither CTA frees tensor memory (or exits) while the pair's MMAs may touch it
+  else __syncthreads();
+  if (warp == 0) {
+    if (CG == 2) tmem_dealloc_pair(tmem, 512);
+    else tmem_dealloc(tmem, 512);
+  }
 }
 
 // ---- self-test: one 128-row UMMA tile against one weight unit ------------------------------------
@@ -910,15 +994,15 @@ __global__ void __launch_bounds__(128, 1) umma_selftest_kernel(const float* __re
     const uint32_t w = sbase + OFF_RING;
     if (mode == 0)
     {
-      issue_part<(NPASS == 3 ? 2 : 1), 8, 16384u, 8192u, make_idesc_bf16(64)>(tmem, sbase + OFF_AX_HI, sbase + OFF_AX_LO, w, true);
+      issue_part<1, (NPASS == 3 ? 2 : 1), 8, 16384u, 8192u, make_idesc_bf16(64)>(tmem, sbase + OFF_AX_HI, sbase + OFF_AX_LO, w, true);
       if (NPASS == 3)
-        issue_part<1, 8, 16384u, 8192u, make_idesc_bf16(64)>(tmem, sbase + OFF_AX_HI, sbase + OFF_AX_HI, w + UNIT_PART_BYTES, false);
+        issue_part<1, 1, 8, 16384u, 8192u, make_idesc_bf16(64)>(tmem, sbase + OFF_AX_HI, sbase + OFF_AX_HI, w + UNIT_PART_BYTES, false);
     }
     else
     {
-      issue_part<(NPASS == 3 ? 2 : 1), 4, 0u, 0u, make_idesc_bf16(128)>(tmem, sbase + OFF_AX_HI, sbase + OFF_AX_LO, w, true);
+      issue_part<1, (NPASS == 3 ? 2 : 1), 4, 0u, 0u, make_idesc_bf16(128)>(tmem, sbase + OFF_AX_HI, sbase + OFF_AX_LO, w, true);
       if (NPASS == 3)
-        issue_part<1, 4, 0u, 0u, make_idesc_bf16(128)>(tmem, sbase + OFF_AX_HI, sbase + OFF_AX_HI, w + UNIT_PART_BYTES, false);
+        issue_part<1, 1, 4, 0u, 0u, make_idesc_bf16(128)>(tmem, sbase + OFF_AX_HI, sbase + OFF_AX_HI, w + UNIT_PART_BYTES, false);
     }
     umma_commit(done);
   }
@@ -1041,8 +1125,11 @@ int dectc_pack(s3d_model* m, cudaStream_t st) {
   std::vector<uint32_t> order;
   for (int x3 = 1; x3 >= 0; --x3)
     for (int u = 0; u < 3 * UNITS_PER_LAYER; ++u) {
-      order.push_back(2u * u);
-      if (x3) order.push_back(2u * u + 1);
+      // FFN units follow the pipeline order W1_0, (W1_1, W2_0), ..., (W1_31, W2_30), W2_31 (see pack_w1 / pack_w2)
+      const int j = u % UNITS_PER_LAYER - 8;
+      const uint32_t w2 = (j == 2 * NCHUNK - 1 || (j > 0 && j % 2 == 0)) ? ORDER_W2 : 0u;
+      order.push_back((2u * u) | w2);
+      if (x3) order.push_back((2u * u + 1) | w2);
     }
   void* dord = nullptr;
   S3D_CUDA(cudaMalloc(&dord, order.size() * sizeof(uint32_t)));
@@ -1101,12 +1188,36 @@ int decoder_tc(const s3d_model* m, const float* planes, int S, const QueryCtx& q
     return S3D_ERR_WORKSPACE;
   }
   p.scratch = static_cast<float*>(ws);
-  if (precision == S3D_PREC_BF16X3) {
-    S3D_CUDA(cudaFuncSetAttribute(decoder_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    decoder_tc_kernel<3><<<grid, NTHREADS, SMEM_BYTES, st>>>(p);
+  // CTA pairs (cta_group::2) by default; S3D_TC_CG=1 selects the single-CTA kernel (kept for A/B measurements).
+  static const int cg = [] {
+    const char* e = getenv("S3D_TC_CG");
+    return (e && e[0] == '1') ? 1 : 2;
+  }();
+  auto launch = [&](auto kern, unsigned g, int cluster) -> int {
+    S3D_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(g);
+    cfg.blockDim = dim3(NTHREADS);
+    cfg.dynamicSmemBytes = SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = cluster;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    S3D_CUDA(cudaLaunchKernelEx(&cfg, kern, p));
+    return S3D_OK;
+  };
+  if (cg == 2) {
+    const long long pairs = (p.num_tiles + 1) / 2;
+    const unsigned g2 = 2u * (unsigned)(pairs < sms / 2 ? pairs : sms / 2);
+    if (precision == S3D_PREC_BF16X3) S3D_TRY(launch(decoder_tc_kernel<3, 2>, g2, 2));
+    else S3D_TRY(launch(decoder_tc_kernel<1, 2>, g2, 2));
   } else {
-    S3D_CUDA(cudaFuncSetAttribute(decoder_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    decoder_tc_kernel<1><<<grid, NTHREADS, SMEM_BYTES, st>>>(p);
+    if (precision == S3D_PREC_BF16X3) S3D_TRY(launch(decoder_tc_kernel<3, 1>, grid, 1));
+    else S3D_TRY(launch(decoder_tc_kernel<1, 1>, grid, 1));
   }
   S3D_LAUNCH_CHECK();
   return S3D_OK;
