@@ -132,7 +132,8 @@ int s3d_decoder_debug_tokens(const s3d_model* m, const void* planes_dev, int32_t
 /* Hardware self-test of the tensor-core plumbing the decoder relies on (UMMA shared-memory and
  * instruction descriptors, 128-byte-swizzled operand tiles, bulk async copy, TMEM load): one
  * 128-row tile against one weight unit, passes = 1 (bf16) or 3 (bf16 hi/lo split).
- *   mode 0: d[128][64]  = a[128][128] . w[64][128]^T      mode 1: d[128][128] = a[128][64] . w[128][64]^T
+ *   d[128][128] = a[128][128] . w[128][128]^T;  mode 0: A operand in shared memory, mode 1: A operand in
+ *   tensor memory (the two operand paths of the decoder).
  * a_dev, w_dev, d_dev are fp32 row-major device arrays.  Synchronises the stream. */
 int s3d_selftest_umma(int32_t mode, int32_t passes, const float* a_dev, const float* w_dev, float* d_dev,
                       void* stream);

@@ -101,8 +101,7 @@ def available_precisions():
 def selftest_umma(mode, passes, a, w):
     """d = a . w^T on one tcgen05 tile (see include/slice3d_b200.h); a, w fp32 CUDA tensors."""
     a, w = _f32c(a, "a"), _f32c(w, "w")
-    n = 64 if mode == 0 else 128
-    d = torch.empty(128, n, dtype=torch.float32, device=a.device)
+    d = torch.empty(128, 128, dtype=torch.float32, device=a.device)
     with torch.cuda.device(a.device):
         _check(lib().s3d_selftest_umma(mode, passes, a.data_ptr(), w.data_ptr(), d.data_ptr(), _stream(a.device)))
     return d

@@ -37,15 +37,17 @@ using namespace ptx;
 
 constexpr int TILE_Q = 9;    // queries per tile
 constexpr int NTOK = 13;     // tokens per query (K = 12 slices + the query token)
-constexpr int NSLOT_MAX = 10;  // weight ring: 80 KB = 5 slots of one 16 KB part, or (CTA pair) 10 slots of this CTA's 8 KB half
-constexpr uint32_t RING_BYTES = 81920;
-constexpr uint32_t ORDER_W2 = 0x80000000u;  // order[] flag: the part belongs to a linear2 unit ([128 n][64 k])
-constexpr int UNITS_PER_LAYER = 72;  // 6 (in_proj) + 2 (out_proj) + 32 (linear1) + 32 (linear2)
-constexpr int UNIT_PART_BYTES = 16384;  // one precision part (hi or lo) of a unit: 64x128 or 128x64 bf16
+constexpr int NSLOT = 5;       // weight ring: 5 slots of this CTA's half (16 KB) of one part
+constexpr uint32_t SLOT_BYTES = 16384;
+constexpr uint32_t RING_BYTES = NSLOT * SLOT_BYTES;
+// Every weight unit is a [128 n][128 k] block (tcgen05.mma needs N >= 128 per instruction to run at the pipe's
+// rate: N = 64 instructions were measured at 52-59 cycles against a 32-cycle floor, tools/mma_rate.cu).
+constexpr int UNITS_PER_LAYER = 36;  // 3 (in_proj) + 1 (out_proj) + 16 (linear1 chunks) + 16 (linear2 chunks)
+constexpr int UNIT_PART_BYTES = 32768;  // one precision part (hi or lo) of a unit: [2 k-blocks][128 n][64 k] bf16
 constexpr int UNIT_STRIDE_BYTES = 2 * UNIT_PART_BYTES;  // hi then lo in global memory
-constexpr int NCHUNK = 32;   // FFN hidden chunks of 64
+constexpr int NCHUNK = 16;   // FFN hidden chunks of 128
 constexpr int TAIL_SLOTS = 14;  // tiles whose token-0 rows are batched into one tail pass (14 x 9 = 126 rows)
-constexpr int TAIL_UNIT0 = 2 * UNITS_PER_LAYER + 6;  // first unit of the tail pass: layer 2 out_proj
+constexpr int TAIL_UNIT0 = 2 * UNITS_PER_LAYER + 3;  // first unit of the tail pass: layer 2 out_proj
 constexpr int NCW = 16;      // compute warps: warp w owns TMEM lanes 32*(w&3).. and column quarter w>>2
 constexpr int NCT = NCW * 32;
 constexpr int NGW = 2;       // gather warps (token build for the tile after next, fully asynchronous)
@@ -67,20 +69,19 @@ constexpr uint32_t OFF_BAR = OFF_RED + 4096;
 constexpr uint32_t SMEM_BYTES = OFF_BAR + 512 + 1024;              // + alignment slack
 
 // barrier indices (8 bytes each at OFF_BAR)
-enum { B_AREADY = 0, B_DDONE, B_D1READY0, B_D1READY1, B_D1FREE0, B_D1FREE1, B_HREADY0, B_HREADY1, B_HFREE0, B_HFREE1,
-       B_TOKFULL0, B_TOKFULL1, B_TOKEMPTY0, B_TOKEMPTY1, B_FULL0, B_EMPTY0 = B_FULL0 + NSLOT_MAX,
-       B_PFULL0 = B_EMPTY0 + NSLOT_MAX,  // leader CTA only: the peer's half of the slot has landed
-       B_COUNT = B_PFULL0 + NSLOT_MAX };
+enum { B_AREADY = 0, B_DDONE, B_D1READY, B_HREADY0, B_HREADY1,
+       B_TOKFULL0, B_TOKFULL1, B_TOKEMPTY0, B_TOKEMPTY1, B_FULL0, B_EMPTY0 = B_FULL0 + NSLOT,
+       B_PFULL0 = B_EMPTY0 + NSLOT,  // leader CTA only: the peer's half of the slot has landed
+       B_COUNT = B_PFULL0 + NSLOT };
 static_assert(8 * B_COUNT + 8 <= 512, "barrier area");
 constexpr uint32_t OFF_TMEMPTR = OFF_BAR + 8 * B_COUNT;
 
 // TMEM columns
 constexpr uint32_t TM_R = 0;      // residual / out-proj / FFN2 accumulator, 128 columns
 constexpr uint32_t TM_S = 128;    // QKV accumulators (384 columns), or during the FFN:
-                                  //   128..255  FFN1 chunk accumulators D1 (2 x 64)
-constexpr uint32_t TM_AXT_HI = 256;  // 256..319  X' (FFN input) as packed bf16 hi, K = 128 -> 64 columns  (A operand in TMEM)
-constexpr uint32_t TM_AXT_LO = 320;  // 320..383  ... lo
-constexpr uint32_t TM_HT = 384;      // 384..511  H chunk operand: 2 buffers x (hi 32 | lo 32 columns), K = 64
+constexpr uint32_t TM_D1 = 128;   //   128..255  FFN1 chunk accumulator D1 (128 hidden units)
+constexpr uint32_t TM_HT = 256;   //   256..511  H chunk as the A operand of linear2 (packed bf16, K = 128):
+                                  //             2 buffers x (hi 64 | lo 64 columns)
 
 // Phase-cycle counters (clock64 deltas summed over CTAs), read through s3d_debug_profile().
 enum { PF_TOKEN = 0, PF_VEC, PF_WAIT_QKV, PF_ATTN, PF_WAIT_OUT, PF_LN1, PF_FFN_WAIT_D1, PF_FFN_MATH, PF_FFN_WAIT_HFREE,
@@ -89,10 +90,9 @@ enum { PF_TOKEN = 0, PF_VEC, PF_WAIT_QKV, PF_ATTN, PF_WAIT_OUT, PF_LN1, PF_FFN_W
 __device__ unsigned long long g_prof[32];
 
 struct TcParams {
-  const uint8_t* wimg;  // [3 layers][72 units][hi 16 KB | lo 16 KB]
+  const uint8_t* wimg;  // [3 layers][36 units][hi 32 KB | lo 32 KB]
   const float* vecs;    // [3 layers][VEC_FLOATS]
   float* scratch;         // [grid][TAIL_SLOTS*9 rows][256] fp32: attention output | x + b_o of token-0 rows
-  const uint32_t* order;  // part stream: [bf16x3: 432 part indices][bf16: 216 part indices]
   const float* planes;
   int S;
   QueryCtx q;
@@ -101,6 +101,7 @@ struct TcParams {
   float* out;
   const float *fcp_wt, *fcp_b, *fcs_b, *fco_w, *fco_b, *b_o0;
   long long num_tiles;
+  int dbg;  // S3D_TC_DBG bit 0: the producer skips the weight copies (timing experiments only; results are garbage)
 };
 
 // ---- operand writes ------------------------------------------------------------------------
@@ -174,8 +175,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
   uint8_t* sgen = smem_raw + (sbase - raw);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   auto bar = [&](int i) { return sbase + OFF_BAR + 8u * i; };
-  constexpr int NSLOT = 5 * CG;
-  constexpr uint32_t SLOT_BYTES = UNIT_PART_BYTES / CG;
+  static_assert(CG == 2, "the decoder runs as CTA pairs");
   const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;
   const bool leader = rank == 0;
   // tiles of this CTA: base + rank for base = CG * group, CG * (group + #groups), ...
@@ -197,14 +197,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
   if (threadIdx.x == 0) {
     mbar_init(bar(B_AREADY), NCW * CG);
     mbar_init(bar(B_DDONE), 1);
-    mbar_init(bar(B_D1READY0), 1);
-    mbar_init(bar(B_D1READY1), 1);
-    mbar_init(bar(B_D1FREE0), NCW);
-    mbar_init(bar(B_D1FREE1), NCW);
+    mbar_init(bar(B_D1READY), 1);
     mbar_init(bar(B_HREADY0), NCW * CG);
     mbar_init(bar(B_HREADY1), NCW * CG);
-    mbar_init(bar(B_HFREE0), 1);
-    mbar_init(bar(B_HFREE1), 1);
     mbar_init(bar(B_TOKFULL0), NGW);
     mbar_init(bar(B_TOKFULL1), NGW);
     mbar_init(bar(B_TOKEMPTY0), NCW);
@@ -235,7 +230,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
       int slot = 0;
       long long w_e = 0;
       const long long t_start = clock64();
-      // parts [g0, g1) of the stream (order built on the host to match the issuer, see dectc_pack)
+      // parts [g0, g1) of the stream (the image is packed in the issuer's consumption order, see dectc_pack)
       auto stream = [&](int g0, int g1) {
 #pragma unroll 1
         for (int g = g0; g < g1; ++g) {
@@ -244,19 +239,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
           ph_empty ^= 1u << slot;
           w_e += clock64() - t0;
           if (elect_one()) {
-            const uint32_t ord = __ldg(p.order + (NPASS == 3 ? 0 : 3 * UNITS_PER_LAYER * 2) + g);
-            const uint8_t* src = p.wimg + (size_t)(ord & ~ORDER_W2) * UNIT_PART_BYTES;
+            // part g of the stream = image part g (bf16x3: hi, lo of every unit) or 2g (bf16: hi parts only);
+            // this CTA's half = rows 64 rank .. +63 of each of the two k-blocks ([128 n][64 k], 16 KB each)
+            const uint8_t* src = p.wimg + (size_t)(NPASS == 3 ? g : 2 * g) * UNIT_PART_BYTES + rank * 8192;
             const uint32_t dst = sbase + OFF_RING + slot * SLOT_BYTES;
-            mbar_arrive_expect_tx(bar(B_FULL0 + slot), SLOT_BYTES);
-            if (CG == 1) {
-#pragma unroll
-              for (uint32_t part = 0; part < UNIT_PART_BYTES; part += 8192)
-                bulk_g2s(dst + part, src + part, 8192, bar(B_FULL0 + slot));
-            } else if (ord & ORDER_W2) {  // [128 n][64 k]: rows 64 rank .. +63 are contiguous
-              bulk_g2s(dst, src + rank * 8192, 8192, bar(B_FULL0 + slot));
-            } else {  // [2 k-blocks][64 n][64 k]: rows 32 rank .. +31 of each k-block
-              bulk_g2s(dst, src + rank * 4096, 4096, bar(B_FULL0 + slot));
-              bulk_g2s(dst + 4096, src + 8192 + rank * 4096, 4096, bar(B_FULL0 + slot));
+            if (p.dbg & 1) {
+              mbar_arrive(bar(B_FULL0 + slot));
+            } else {
+              mbar_arrive_expect_tx(bar(B_FULL0 + slot), SLOT_BYTES);
+              bulk_g2s(dst, src, 8192, bar(B_FULL0 + slot));
+              bulk_g2s(dst + 8192, src + 16384, 8192, bar(B_FULL0 + slot));
             }
           }
           __syncwarp();
@@ -308,11 +300,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
     {
       uint32_t ph_a = 0, ph_full = 0, ph_hr = 0;  // parity bits (one per barrier / slot)
       int slot = 0;
-      long long w_a = 0, w_full = 0, w_h = 0, w_d1 = 0;
+      long long w_a = 0, w_full = 0, w_h = 0;
       const long long t_start = clock64();
       const uint32_t ax_hi = sbase + OFF_AX_HI, ax_lo = sbase + OFF_AX_LO;
-      constexpr uint32_t ID64 = make_idesc_bf16(64, 128 * CG), ID128 = make_idesc_bf16(128, 128 * CG);
-      constexpr uint32_t BKB = 8192u / CG;  // k-block stride of this CTA's share of a [2][64 n][64 k] part
+      constexpr uint32_t ID128 = make_idesc_bf16(128, 128 * CG);
+      constexpr uint32_t BKB = 8192u;  // k-block stride of this CTA's half of a part: [64 n][64 k]
       auto wait_full = [&]() -> uint32_t {
         const long long t0 = clock64();
         mbar_wait(bar(B_FULL0 + slot), (ph_full >> slot) & 1u);
@@ -333,20 +325,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
         slot = (slot + 1 == NSLOT) ? 0 : slot + 1;
       };
       // One weight unit = its hi part (passes A_hi.B_hi [, A_lo.B_hi]) then, for bf16x3, its lo part
-      // (pass A_hi.B_lo); each part is one ring slot, released as soon as its MMAs are issued.  (Splitting
-      // the accumulation into two interleaved chains was measured and did not help: the pipe already runs
-      // at ~86 % of its rate while the issuer is busy.)
-      // unit of 64 output columns over K = 128 (in_proj / out_proj / linear1), A = AX
-      auto unit_n64 = [&](uint32_t d_col, bool fresh) {
+      // (pass A_hi.B_lo); each part is one ring slot, released as soon as its MMAs are issued.
+      // D[:, d_col .. +127] (+)= AX . W^T, A = the activation tile in shared memory (K = 128)
+      auto unit_ss = [&](uint32_t d_col, bool fresh) {
         uint32_t w = wait_full();
         tc_fence_after();
-        if (elect_one()) issue_part<CG, (NPASS == 3 ? 2 : 1), 8, 16384u, BKB, ID64>(tmem + d_col, ax_hi, ax_lo, w, fresh);
+        if (elect_one()) issue_part<CG, (NPASS == 3 ? 2 : 1), 8, 16384u, BKB, ID128>(tmem + d_col, ax_hi, ax_lo, w, fresh);
         __syncwarp();
         release();
         if (NPASS == 3) {
           w = wait_full();
           tc_fence_after();
-          if (elect_one()) issue_part<CG, 1, 8, 16384u, BKB, ID64>(tmem + d_col, ax_hi, ax_hi, w, false);
+          if (elect_one()) issue_part<CG, 1, 8, 16384u, BKB, ID128>(tmem + d_col, ax_hi, ax_hi, w, false);
           __syncwarp();
           release();
         }
@@ -361,63 +351,47 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
       // QKV projection: S[:, 0:384] = X . Win^T
       auto mma_qkv = [&]() {
         wait_a();
-        for (int u = 0; u < 6; ++u) unit_n64(TM_S + 64 * u, true);
+        for (int u = 0; u < 3; ++u) unit_ss(TM_S + 128 * u, true);
         commit(B_DDONE);
       };
-      // out-proj: R += O . Wo^T (R pre-loaded with x + b_o), then the FFN:
-      // D1[c] = X' . W1_c^T (N=64) ; R += relu(D1[c] + b1) . W2_c^T (N=128, K=64)
+      // out-proj: R += O . Wo^T (R pre-loaded with x + b_o), then the FFN over 16 hidden chunks of 128:
+      // D1 = X' . W1_c^T (A = X' in shared memory) ; R += relu(D1 + b1) . W2_c^T (A = H chunk in tensor memory)
       auto mma_out_ffn = [&]() {
         wait_a();
-        for (int u = 0; u < 2; ++u) unit_n64(TM_R + 64 * u, false);
+        unit_ss(TM_R, false);
         commit(B_DDONE);
         wait_a();
-        auto issue1 = [&](int c) {
-          // D1[c&1] is free: the compute warps loaded chunk c-2 out of it before they arrived on h_ready(c-2),
-          // which this warp has already waited for (issue2(c-2) precedes issue1(c)).
-          {  // linear1 chunk: A = X' in tensor memory
-            uint32_t w = wait_full();
-            tc_fence_after();
-            if (elect_one())
-              issue_part_ts<CG, (NPASS == 3 ? 2 : 1), 8, BKB, ID64>(tmem + TM_S + 64 * (c & 1), tmem + TM_AXT_HI,
-                                                                       tmem + TM_AXT_LO, w, true);
-            __syncwarp();
-            release();
-            if (NPASS == 3) {
-              w = wait_full();
-              tc_fence_after();
-              if (elect_one())
-                issue_part_ts<CG, 1, 8, BKB, ID64>(tmem + TM_S + 64 * (c & 1), tmem + TM_AXT_HI, tmem + TM_AXT_HI, w, false);
-              __syncwarp();
-              release();
-            }
-          }
-          commit(B_D1READY0 + (c & 1));
+        auto issue1 = [&]() {
+          unit_ss(TM_D1, true);
+          commit(B_D1READY);
         };
         auto issue2 = [&](int c) {
-          const uint32_t h_hi = tmem + TM_HT + 64 * (c & 1), h_lo = h_hi + 32;  // H chunk operand in tensor memory
+          const uint32_t h_hi = tmem + TM_HT + 128 * (c & 1), h_lo = h_hi + 64;
           uint32_t w = wait_full();
-          const long long t0 = clock64();
-          wait_lead(B_HREADY0 + (c & 1), (ph_hr >> (c & 1)) & 1u);
-          ph_hr ^= 1u << (c & 1);
-          w_h += clock64() - t0;
           tc_fence_after();
-          if (elect_one()) issue_part_ts<CG, (NPASS == 3 ? 2 : 1), 4, 0u, ID128>(tmem + TM_R, h_hi, h_lo, w, false);
+          if (elect_one()) issue_part_ts<CG, (NPASS == 3 ? 2 : 1), 8, BKB, ID128>(tmem + TM_R, h_hi, h_lo, w, false);
           __syncwarp();
           release();
           if (NPASS == 3) {
             w = wait_full();
             tc_fence_after();
-            if (elect_one()) issue_part_ts<CG, 1, 4, 0u, ID128>(tmem + TM_R, h_hi, h_hi, w, false);
+            if (elect_one()) issue_part_ts<CG, 1, 8, BKB, ID128>(tmem + TM_R, h_hi, h_hi, w, false);
             __syncwarp();
             release();
           }
-          // no "H free" signal: d1_ready(c+2) is committed after MMA1_{c+2}, i.e. after these MMAs, and
-          // tcgen05.commit covers every earlier MMA -- the compute warps wait for it before rewriting H[c&1].
         };
-        issue1(0);
+        issue1();
 #pragma unroll 1
         for (int c = 0; c < NCHUNK; ++c) {
-          if (c + 1 < NCHUNK) issue1(c + 1);
+          // h_ready(c): the compute warps have drained D1 (chunk c) and written the H operand of chunk c
+          const long long t0 = clock64();
+          wait_lead(B_HREADY0 + (c & 1), (ph_hr >> (c & 1)) & 1u);
+          ph_hr ^= 1u << (c & 1);
+          w_h += clock64() - t0;
+          tc_fence_after();
+          // D1 is single-buffered: MMA1 of chunk c+1 goes first so that its epilogue overlaps MMA2 of chunk c.
+          // H[c&1] is rewritten for chunk c+2 only after d1_ready(c+2), which is committed after these MMA2s.
+          if (c + 1 < NCHUNK) issue1();
           issue2(c);
         }
         commit(B_DDONE);
@@ -439,7 +413,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
         atomicAdd(&g_prof[PF_MMA_WAIT_A], (unsigned long long)w_a);
         atomicAdd(&g_prof[PF_MMA_WAIT_FULL], (unsigned long long)w_full);
         atomicAdd(&g_prof[PF_MMA_WAIT_H], (unsigned long long)w_h);
-        atomicAdd(&g_prof[PF_MMA_WAIT_D1FREE], (unsigned long long)w_d1);
         atomicAdd(&g_prof[PF_MMA_TOTAL], (unsigned long long)(clock64() - t_start));
       }
     }
@@ -769,44 +742,37 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
           tmem_ld32(trow + TM_R + 32 * g, v);
           tmem_ld_wait();
           layer_norm(v, vec + V_LN1W, vec + V_LN1B);
-          {  // X' -> A operand of linear1, kept in tensor memory (packed bf16 hi / lo, 16 columns per thread)
-            uint32_t xh[16], xl[16];
-#pragma unroll
-            for (int c = 0; c < 4; ++c) split8<NPASS == 3>(v + 8 * c, xh + 4 * c, xl + 4 * c);
-            tmem_st16(trow + TM_AXT_HI + 16 * g, xh);
-            if (NPASS == 3) tmem_st16(trow + TM_AXT_LO + 16 * g, xl);
-          }
+          store_ax(v);  // X' -> A operand of linear1 (the activation tile is idle between out-proj and the next layer)
           publish(v, vec + V_B2);
         }
         lap(PF_LN1)
-        // -------------------------------------------------------------- FFN hidden chunks (16 columns per thread)
+        // -------------------------------------------------------------- FFN hidden chunks (32 columns per thread)
         {
 #pragma unroll 1
           for (int c = 0; c < NCHUNK; ++c) {
             const int bsel = c & 1;
-            mbar_wait(bar(B_D1READY0 + bsel), (ph_d1r >> bsel) & 1u);
-            ph_d1r ^= 1u << bsel;
+            mbar_wait(bar(B_D1READY), ph_d1r);
+            ph_d1r ^= 1u;
             tc_fence_after();
             lap(PF_FFN_WAIT_D1)
-            float d[16];
-            tmem_ld16(trow + TM_S + 64 * bsel + 16 * g, d);
+            float d[32];
+            tmem_ld32(trow + TM_D1 + 32 * g, d);
             tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float4 b4 = *reinterpret_cast<const float4*>(vec + V_B1 + c * 64 + 16 * g + 4 * j);
+            for (int j = 0; j < 8; ++j) {
+              const float4 b4 = *reinterpret_cast<const float4*>(vec + V_B1 + c * 128 + 32 * g + 4 * j);
               d[4 * j] = fmaxf(d[4 * j] + b4.x, 0.f);
               d[4 * j + 1] = fmaxf(d[4 * j + 1] + b4.y, 0.f);
               d[4 * j + 2] = fmaxf(d[4 * j + 2] + b4.z, 0.f);
               d[4 * j + 3] = fmaxf(d[4 * j + 3] + b4.w, 0.f);
             }
             lap(PF_FFN_MATH)
-
-            {  // H chunk -> A operand of linear2 in tensor memory (8 packed columns per thread, hi and lo)
-              uint32_t hh[8], hl[8];
-              split8<NPASS == 3>(d, hh, hl);
-              split8<NPASS == 3>(d + 8, hh + 4, hl + 4);
-              tmem_st8(trow + TM_HT + 64 * bsel + 8 * g, hh);
-              if (NPASS == 3) tmem_st8(trow + TM_HT + 64 * bsel + 32 + 8 * g, hl);
+            {  // H chunk -> A operand of linear2 in tensor memory (16 packed columns per thread, hi and lo)
+              uint32_t hh[16], hl[16];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) split8<NPASS == 3>(d + 8 * j, hh + 4 * j, hl + 4 * j);
+              tmem_st16(trow + TM_HT + 128 * bsel + 16 * g, hh);
+              if (NPASS == 3) tmem_st16(trow + TM_HT + 128 * bsel + 64 + 16 * g, hl);
               tmem_st_wait();
             }
             tc_fence_before();  // orders this thread's D1 load / H store before the MMAs that follow the arrive
@@ -953,9 +919,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
   }
 }
 
-// ---- self-test: one 128-row UMMA tile against one weight unit ------------------------------------
-// mode 0: D[128][64]  = A[128][128] . W[64][128]^T   (unit shape of in_proj / out_proj / linear1)
-// mode 1: D[128][128] = A[128][64]  . W[128][64]^T   (unit shape of linear2)
+// ---- self-test: one 128-row UMMA tile against one weight unit -------------------------------------
+// D[128][128] = A[128][128] . W[128][128]^T, single CTA (cta_group::1).
+// mode 0: A in shared memory (the QKV / out-proj / linear1 path); mode 1: A in tensor memory (the linear2 path).
 template <int NPASS>
 __global__ void __launch_bounds__(128, 1) umma_selftest_kernel(const float* __restrict__ A, const uint8_t* wimg, int mode,
                                                                float* __restrict__ D) {
@@ -965,7 +931,6 @@ __global__ void __launch_bounds__(128, 1) umma_selftest_kernel(const float* __re
   uint8_t* sgen = smem_raw + (sbase - raw);
   const int warp = threadIdx.x >> 5;
   const int r = threadIdx.x;
-  const int K = mode == 0 ? 128 : 64, N = mode == 0 ? 64 : 128;
   const uint32_t full = sbase + OFF_BAR, done = sbase + OFF_BAR + 8;
   if (threadIdx.x == 0) {
     mbar_init(full, 1);
@@ -977,43 +942,52 @@ __global__ void __launch_bounds__(128, 1) umma_selftest_kernel(const float* __re
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(sgen + OFF_TMEMPTR);
-  if (threadIdx.x == 0) {
+  const uint32_t trow = tmem + (static_cast<uint32_t>(warp * 32) << 16);
+  if (threadIdx.x == 0) {  // the whole unit (hi 32 KB | lo 32 KB) lands in the H + ring area
     mbar_arrive_expect_tx(full, UNIT_STRIDE_BYTES);
-    bulk_g2s(sbase + OFF_RING, wimg, UNIT_STRIDE_BYTES, full);
+    for (uint32_t o = 0; o < UNIT_STRIDE_BYTES; o += 16384) bulk_g2s(sbase + OFF_H + o, wimg + o, 16384, full);
   }
-  for (int kc = 0; kc < K / 8; ++kc) {
-    float v[8];
-    for (int i = 0; i < 8; ++i) v[i] = A[r * K + kc * 8 + i];
-    store_chunk<NPASS>(sgen + OFF_AX_HI + (kc >> 3) * 16384, sgen + OFF_AX_LO + (kc >> 3) * 16384, r, kc & 7, v);
+  if (mode == 0) {
+    for (int kc = 0; kc < 16; ++kc) {
+      float v[8];
+      for (int i = 0; i < 8; ++i) v[i] = A[r * 128 + kc * 8 + i];
+      store_chunk<NPASS>(sgen + OFF_AX_HI + (kc >> 3) * 16384, sgen + OFF_AX_LO + (kc >> 3) * 16384, r, kc & 7, v);
+    }
+    fence_proxy_async_smem();
+  } else {  // packed bf16 pairs, column = k / 2: hi at columns 256.., lo at 320..
+    for (int j = 0; j < 4; ++j) {
+      float v[32];
+      for (int i = 0; i < 32; ++i) v[i] = A[r * 128 + 32 * j + i];
+      uint32_t h[16], l[16];
+      for (int c = 0; c < 4; ++c) split8<NPASS == 3>(v + 8 * c, h + 4 * c, l + 4 * c);
+      tmem_st16(trow + TM_HT + 16 * j, h);
+      if (NPASS == 3) tmem_st16(trow + TM_HT + 64 + 16 * j, l);
+    }
+    tmem_st_wait();
+    tc_fence_before();
   }
-  fence_proxy_async_smem();
   __syncthreads();
   if (threadIdx.x == 0) {
     mbar_wait(full, 0);
     tc_fence_after();
-    const uint32_t w = sbase + OFF_RING;
-    if (mode == 0)
-    {
-      issue_part<1, (NPASS == 3 ? 2 : 1), 8, 16384u, 8192u, make_idesc_bf16(64)>(tmem, sbase + OFF_AX_HI, sbase + OFF_AX_LO, w, true);
-      if (NPASS == 3)
-        issue_part<1, 1, 8, 16384u, 8192u, make_idesc_bf16(64)>(tmem, sbase + OFF_AX_HI, sbase + OFF_AX_HI, w + UNIT_PART_BYTES, false);
-    }
-    else
-    {
-      issue_part<1, (NPASS == 3 ? 2 : 1), 4, 0u, 0u, make_idesc_bf16(128)>(tmem, sbase + OFF_AX_HI, sbase + OFF_AX_LO, w, true);
-      if (NPASS == 3)
-        issue_part<1, 1, 4, 0u, 0u, make_idesc_bf16(128)>(tmem, sbase + OFF_AX_HI, sbase + OFF_AX_HI, w + UNIT_PART_BYTES, false);
+    const uint32_t w = sbase + OFF_H;
+    constexpr uint32_t ID = make_idesc_bf16(128);
+    if (mode == 0) {
+      issue_part<1, (NPASS == 3 ? 2 : 1), 8, 16384u, 16384u, ID>(tmem, sbase + OFF_AX_HI, sbase + OFF_AX_LO, w, true);
+      if (NPASS == 3) issue_part<1, 1, 8, 16384u, 16384u, ID>(tmem, sbase + OFF_AX_HI, sbase + OFF_AX_HI, w + UNIT_PART_BYTES, false);
+    } else {
+      issue_part_ts<1, (NPASS == 3 ? 2 : 1), 8, 16384u, ID>(tmem, tmem + TM_HT, tmem + TM_HT + 64, w, true);
+      if (NPASS == 3) issue_part_ts<1, 1, 8, 16384u, ID>(tmem, tmem + TM_HT, tmem + TM_HT, w + UNIT_PART_BYTES, false);
     }
     umma_commit(done);
   }
   mbar_wait(done, 0);
   tc_fence_after();
-  const uint32_t trow = tmem + (static_cast<uint32_t>(warp * 32) << 16);
-  for (int j = 0; j < N / 32; ++j) {
+  for (int j = 0; j < 4; ++j) {
     float v[32];
     tmem_ld32(trow + 32 * j, v);
     tmem_ld_wait();
-    for (int c = 0; c < 32; ++c) D[r * N + 32 * j + c] = v[c];
+    for (int c = 0; c < 32; ++c) D[r * 128 + 32 * j + c] = v[c];
   }
   tc_fence_before();
   __syncthreads();
@@ -1069,16 +1043,16 @@ int dectc_pack(s3d_model* m, cudaStream_t st) {
     S3D_TRY(fetch(L.lin2, w2));
     uint8_t* dst = img.data() + (size_t)l * UNITS_PER_LAYER * UNIT_STRIDE_BYTES;
     int g = 0;
-    for (int u = 0; u < 6; ++u, ++g)
-      pack_unit([&](int n, int k) { return win[(size_t)k * 384 + 64 * u + n]; }, 64, 128, dst + (size_t)g * UNIT_STRIDE_BYTES);
-    for (int u = 0; u < 2; ++u, ++g)
-      pack_unit([&](int n, int k) { return wo[(size_t)k * 128 + 64 * u + n]; }, 64, 128, dst + (size_t)g * UNIT_STRIDE_BYTES);
-    auto pack_w1 = [&](int c) {
-      pack_unit([&](int n, int k) { return w1[(size_t)k * 2048 + 64 * c + n]; }, 64, 128, dst + (size_t)g * UNIT_STRIDE_BYTES);
+    for (int u = 0; u < 3; ++u, ++g)
+      pack_unit([&](int n, int k) { return win[(size_t)k * 384 + 128 * u + n]; }, 128, 128, dst + (size_t)g * UNIT_STRIDE_BYTES);
+    pack_unit([&](int n, int k) { return wo[(size_t)k * 128 + n]; }, 128, 128, dst + (size_t)g * UNIT_STRIDE_BYTES);
+    ++g;
+    auto pack_w1 = [&](int c) {  // hidden units 128c .. +127 as output columns
+      pack_unit([&](int n, int k) { return w1[(size_t)k * 2048 + 128 * c + n]; }, 128, 128, dst + (size_t)g * UNIT_STRIDE_BYTES);
       ++g;
     };
-    auto pack_w2 = [&](int c) {
-      pack_unit([&](int n, int k) { return w2[(size_t)(64 * c + k) * 128 + n]; }, 128, 64, dst + (size_t)g * UNIT_STRIDE_BYTES);
+    auto pack_w2 = [&](int c) {  // hidden units 128c .. +127 as the contraction index
+      pack_unit([&](int n, int k) { return w2[(size_t)(128 * c + k) * 128 + n]; }, 128, 128, dst + (size_t)g * UNIT_STRIDE_BYTES);
       ++g;
     };
     // consumption order of the FFN pipeline: W1_0, then (W1_{c+1}, W2_c) ...
@@ -1120,23 +1094,6 @@ int dectc_pack(s3d_model* m, cudaStream_t st) {
   S3D_CUDA(cudaMemcpyAsync(dv, vecs.data(), vecs.size() * sizeof(float), cudaMemcpyHostToDevice, st));
   S3D_CUDA(cudaStreamSynchronize(st));
   m->dectc.vec = static_cast<float*>(dv);
-  // part stream in consumption order: unit by unit, hi part then (bf16x3 only) lo part; unit u of layer l
-  // is parts 2*(72 l + u) (hi) and +1 (lo) of the image.
-  std::vector<uint32_t> order;
-  for (int x3 = 1; x3 >= 0; --x3)
-    for (int u = 0; u < 3 * UNITS_PER_LAYER; ++u) {
-      // FFN units follow the pipeline order W1_0, (W1_1, W2_0), ..., (W1_31, W2_30), W2_31 (see pack_w1 / pack_w2)
-      const int j = u % UNITS_PER_LAYER - 8;
-      const uint32_t w2 = (j == 2 * NCHUNK - 1 || (j > 0 && j % 2 == 0)) ? ORDER_W2 : 0u;
-      order.push_back((2u * u) | w2);
-      if (x3) order.push_back((2u * u + 1) | w2);
-    }
-  void* dord = nullptr;
-  S3D_CUDA(cudaMalloc(&dord, order.size() * sizeof(uint32_t)));
-  m->allocs.push_back(dord);
-  S3D_CUDA(cudaMemcpyAsync(dord, order.data(), order.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
-  S3D_CUDA(cudaStreamSynchronize(st));
-  m->dectc.order = static_cast<uint32_t*>(dord);
   return S3D_OK;
 }
 
@@ -1167,7 +1124,6 @@ int decoder_tc(const s3d_model* m, const float* planes, int S, const QueryCtx& q
   TcParams p{};
   p.wimg = reinterpret_cast<const uint8_t*>(m->dectc.wimg);
   p.vecs = m->dectc.vec;
-  p.order = m->dectc.order;
   p.planes = planes;
   p.S = S;
   p.q = q;
@@ -1182,17 +1138,11 @@ int decoder_tc(const s3d_model* m, const float* planes, int S, const QueryCtx& q
   S3D_CUDA(cudaGetDevice(&dev));
   S3D_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   if (sms > 256) sms = 256;
-  const unsigned grid = (unsigned)(p.num_tiles < sms ? p.num_tiles : sms);
   if (ws == nullptr || ws_bytes < decoder_tc_workspace_bytes(n)) {
     set_error("decoder: workspace too small");
     return S3D_ERR_WORKSPACE;
   }
   p.scratch = static_cast<float*>(ws);
-  // CTA pairs (cta_group::2) by default; S3D_TC_CG=1 selects the single-CTA kernel (kept for A/B measurements).
-  static const int cg = [] {
-    const char* e = getenv("S3D_TC_CG");
-    return (e && e[0] == '1') ? 1 : 2;
-  }();
   auto launch = [&](auto kern, unsigned g, int cluster) -> int {
     S3D_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     cudaLaunchConfig_t cfg{};
@@ -1210,14 +1160,11 @@ int decoder_tc(const s3d_model* m, const float* planes, int S, const QueryCtx& q
     S3D_CUDA(cudaLaunchKernelEx(&cfg, kern, p));
     return S3D_OK;
   };
-  if (cg == 2) {
+  {  // CTA pairs: clusters of 2, one pair per TPC
     const long long pairs = (p.num_tiles + 1) / 2;
     const unsigned g2 = 2u * (unsigned)(pairs < sms / 2 ? pairs : sms / 2);
     if (precision == S3D_PREC_BF16X3) S3D_TRY(launch(decoder_tc_kernel<3, 2>, g2, 2));
     else S3D_TRY(launch(decoder_tc_kernel<1, 2>, g2, 2));
-  } else {
-    if (precision == S3D_PREC_BF16X3) S3D_TRY(launch(decoder_tc_kernel<3, 1>, grid, 1));
-    else S3D_TRY(launch(decoder_tc_kernel<1, 1>, grid, 1));
   }
   S3D_LAUNCH_CHECK();
   return S3D_OK;
@@ -1229,7 +1176,7 @@ int umma_selftest(int mode, int passes, const float* a_dev, const float* w_dev, 
     set_error("selftest: bad argument");
     return S3D_ERR_BAD_ARG;
   }
-  const int N = mode == 0 ? 64 : 128, K = mode == 0 ? 128 : 64;
+  const int N = 128, K = 128;
   std::vector<float> w((size_t)N * K);
   S3D_CUDA(cudaMemcpyAsync(w.data(), w_dev, w.size() * sizeof(float), cudaMemcpyDeviceToHost, st));
   S3D_CUDA(cudaStreamSynchronize(st));

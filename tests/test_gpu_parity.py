@@ -177,7 +177,7 @@ def test_empty_and_ragged_queries():
 def test_umma_selftest(mode, passes):
     """One UMMA tile vs fp64: validates descriptors / swizzle / bulk copy / TMEM load."""
     g = torch.Generator().manual_seed(11 + mode)
-    k, n = (128, 64) if mode == 0 else (64, 128)
+    k, n = 128, 128  # mode 0: A operand in shared memory, mode 1: A operand in tensor memory
     a = torch.randn(128, k, generator=g)
     w = torch.randn(n, k, generator=g) * 0.2
     d = _native.selftest_umma(mode, passes, a.to(DEV), w.to(DEV)).cpu()
