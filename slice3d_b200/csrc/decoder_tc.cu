@@ -69,7 +69,7 @@ constexpr uint32_t OFF_BAR = OFF_RED + 4096;
 constexpr uint32_t SMEM_BYTES = OFF_BAR + 512 + 1024;              // + alignment slack
 
 // barrier indices (8 bytes each at OFF_BAR)
-enum { B_AREADY = 0, B_DDONE, B_D1READY, B_HREADY0, B_HREADY1,
+enum { B_AREADY = 0, B_DDONE, B_D1READY0, B_D1READY1, B_HREADY, B_HFREE,
        B_TOKFULL0, B_TOKFULL1, B_TOKEMPTY0, B_TOKEMPTY1, B_FULL0, B_EMPTY0 = B_FULL0 + NSLOT,
        B_PFULL0 = B_EMPTY0 + NSLOT,  // leader CTA only: the peer's half of the slot has landed
        B_COUNT = B_PFULL0 + NSLOT };
@@ -79,9 +79,9 @@ constexpr uint32_t OFF_TMEMPTR = OFF_BAR + 8 * B_COUNT;
 // TMEM columns
 constexpr uint32_t TM_R = 0;      // residual / out-proj / FFN2 accumulator, 128 columns
 constexpr uint32_t TM_S = 128;    // QKV accumulators (384 columns), or during the FFN:
-constexpr uint32_t TM_D1 = 128;   //   128..255  FFN1 chunk accumulator D1 (128 hidden units)
-constexpr uint32_t TM_HT = 256;   //   256..511  H chunk as the A operand of linear2 (packed bf16, K = 128):
-                                  //             2 buffers x (hi 64 | lo 64 columns)
+constexpr uint32_t TM_D1 = 128;   //   128..383  FFN1 chunk accumulators D1 (2 buffers x 128 hidden units)
+constexpr uint32_t TM_HT = 384;   //   384..511  H chunk as the A operand of linear2 (packed bf16, K = 128):
+                                  //             hi 64 | lo 64 columns
 
 // Phase-cycle counters (clock64 deltas summed over CTAs), read through s3d_debug_profile().
 enum { PF_TOKEN = 0, PF_VEC, PF_WAIT_QKV, PF_ATTN, PF_WAIT_OUT, PF_LN1, PF_FFN_WAIT_D1, PF_FFN_MATH, PF_FFN_WAIT_HFREE,
@@ -197,9 +197,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
   if (threadIdx.x == 0) {
     mbar_init(bar(B_AREADY), NCW * CG);
     mbar_init(bar(B_DDONE), 1);
-    mbar_init(bar(B_D1READY), 1);
-    mbar_init(bar(B_HREADY0), NCW * CG);
-    mbar_init(bar(B_HREADY1), NCW * CG);
+    mbar_init(bar(B_D1READY0), 1);
+    mbar_init(bar(B_D1READY1), 1);
+    mbar_init(bar(B_HREADY), NCW * CG);
+    mbar_init(bar(B_HFREE), 1);
     mbar_init(bar(B_TOKFULL0), NGW);
     mbar_init(bar(B_TOKFULL1), NGW);
     mbar_init(bar(B_TOKEMPTY0), NCW);
@@ -361,12 +362,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
         unit_ss(TM_R, false);
         commit(B_DDONE);
         wait_a();
-        auto issue1 = [&]() {
-          unit_ss(TM_D1, true);
-          commit(B_D1READY);
+        // D1 is double-buffered, H single: the part of a chunk's epilogue that sits between two MMAs of the pipe
+        // is only "h_free -> store H -> h_ready", and it is covered by MMA1 of the chunk after next.
+        auto issue1 = [&](int c) {
+          unit_ss(TM_D1 + 128 * (c & 1), true);
+          commit(B_D1READY0 + (c & 1));
         };
         auto issue2 = [&](int c) {
-          const uint32_t h_hi = tmem + TM_HT + 128 * (c & 1), h_lo = h_hi + 64;
+          const uint32_t h_hi = tmem + TM_HT, h_lo = h_hi + 64;
           uint32_t w = wait_full();
           tc_fence_after();
           if (elect_one()) issue_part_ts<CG, (NPASS == 3 ? 2 : 1), 8, BKB, ID128>(tmem + TM_R, h_hi, h_lo, w, false);
@@ -380,19 +383,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
             release();
           }
         };
-        issue1();
+        issue1(0);
+        issue1(1);
 #pragma unroll 1
         for (int c = 0; c < NCHUNK; ++c) {
-          // h_ready(c): the compute warps have drained D1 (chunk c) and written the H operand of chunk c
+          // h_ready(c): the compute warps have drained D1[c&1] and written the H operand of chunk c
           const long long t0 = clock64();
-          wait_lead(B_HREADY0 + (c & 1), (ph_hr >> (c & 1)) & 1u);
-          ph_hr ^= 1u << (c & 1);
+          wait_lead(B_HREADY, ph_hr);
+          ph_hr ^= 1u;
           w_h += clock64() - t0;
           tc_fence_after();
-          // D1 is single-buffered: MMA1 of chunk c+1 goes first so that its epilogue overlaps MMA2 of chunk c.
-          // H[c&1] is rewritten for chunk c+2 only after d1_ready(c+2), which is committed after these MMA2s.
-          if (c + 1 < NCHUNK) issue1();
           issue2(c);
+          if (c + 1 < NCHUNK) commit(B_HFREE);  // H may be rewritten once MMA2 of chunk c has completed
+          if (c + 2 < NCHUNK) issue1(c + 2);
         }
         commit(B_DDONE);
       };
@@ -514,7 +517,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
     const float* vec = reinterpret_cast<const float*>(sgen + OFF_VEC);
     float* red0 = reinterpret_cast<float*>(sgen + OFF_RED);
     float* red1 = red0 + 512;
-    uint32_t ph_d = 0, ph_d1r = 0;
+    uint32_t ph_d = 0, ph_d1r = 0, ph_hf = 0;
     const int qi = r / NTOK, tk = r - qi * NTOK;
     uint32_t pf[16];
 #pragma unroll
@@ -751,12 +754,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
 #pragma unroll 1
           for (int c = 0; c < NCHUNK; ++c) {
             const int bsel = c & 1;
-            mbar_wait(bar(B_D1READY), ph_d1r);
-            ph_d1r ^= 1u;
+            mbar_wait(bar(B_D1READY0 + bsel), (ph_d1r >> bsel) & 1u);
+            ph_d1r ^= 1u << bsel;
             tc_fence_after();
             lap(PF_FFN_WAIT_D1)
             float d[32];
-            tmem_ld32(trow + TM_D1 + 32 * g, d);
+            tmem_ld32(trow + TM_D1 + 128 * bsel + 32 * g, d);
             tmem_ld_wait();
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -771,12 +774,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
               uint32_t hh[16], hl[16];
 #pragma unroll
               for (int j = 0; j < 4; ++j) split8<NPASS == 3>(d + 8 * j, hh + 4 * j, hl + 4 * j);
-              tmem_st16(trow + TM_HT + 128 * bsel + 16 * g, hh);
-              if (NPASS == 3) tmem_st16(trow + TM_HT + 128 * bsel + 64 + 16 * g, hl);
+              if (c > 0) {  // MMA2 of the previous chunk has finished reading H
+                mbar_wait(bar(B_HFREE), ph_hf);
+                ph_hf ^= 1u;
+                tc_fence_after();
+              }
+              lap(PF_FFN_WAIT_HFREE)
+              tmem_st16(trow + TM_HT + 16 * g, hh);
+              if (NPASS == 3) tmem_st16(trow + TM_HT + 64 + 16 * g, hl);
               tmem_st_wait();
             }
             tc_fence_before();  // orders this thread's D1 load / H store before the MMAs that follow the arrive
-            arrive_lead(B_HREADY0 + bsel);
+            arrive_lead(B_HREADY);
             lap(PF_FFN_STORE)
           }
         }
@@ -954,7 +963,7 @@ __global__ void __launch_bounds__(128, 1) umma_selftest_kernel(const float* __re
       store_chunk<NPASS>(sgen + OFF_AX_HI + (kc >> 3) * 16384, sgen + OFF_AX_LO + (kc >> 3) * 16384, r, kc & 7, v);
     }
     fence_proxy_async_smem();
-  } else {  // packed bf16 pairs, column = k / 2: hi at columns 256.., lo at 320..
+  } else {  // packed bf16 pairs, column = k / 2: hi at columns TM_HT.., lo at TM_HT + 64..
     for (int j = 0; j < 4; ++j) {
       float v[32];
       for (int i = 0; i < 32; ++i) v[i] = A[r * 128 + 32 * j + i];
@@ -1055,11 +1064,12 @@ int dectc_pack(s3d_model* m, cudaStream_t st) {
       pack_unit([&](int n, int k) { return w2[(size_t)(128 * c + k) * 128 + n]; }, 128, 128, dst + (size_t)g * UNIT_STRIDE_BYTES);
       ++g;
     };
-    // consumption order of the FFN pipeline: W1_0, then (W1_{c+1}, W2_c) ...
+    // consumption order of the FFN pipeline: W1_0, W1_1, then (W2_c, W1_{c+2}) ...
     pack_w1(0);
+    pack_w1(1);
     for (int c = 0; c < NCHUNK; ++c) {
-      if (c + 1 < NCHUNK) pack_w1(c + 1);
       pack_w2(c);
+      if (c + 2 < NCHUNK) pack_w1(c + 2);
     }
   }
   void* d = nullptr;
