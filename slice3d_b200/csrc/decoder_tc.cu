@@ -50,7 +50,10 @@ constexpr int TAIL_SLOTS = 14;  // tiles whose token-0 rows are batched into one
 constexpr int TAIL_UNIT0 = 2 * UNITS_PER_LAYER + 3;  // first unit of the tail pass: layer 2 out_proj
 constexpr int NCW = 16;      // compute warps: warp w owns TMEM lanes 32*(w&3).. and column quarter w>>2
 constexpr int NCT = NCW * 32;
-constexpr int NGW = 2;       // gather warps (token build for the tile after next, fully asynchronous)
+constexpr int NGW = 2;       // gather warps (token build for the next tiles, fully asynchronous): warps 18-19
+// 20 warps x 96 registers.  (24 warps with setmaxnreg re-budgeting -- 96 for the compute warps, 40/56 for the
+// service warpgroups, 4 gather warps -- was measured: the MMA issuer spills at 40 registers and starves the pipe in
+// bf16x3 mode; 8 % slower there, equal in bf16 mode.)
 constexpr int NTHREADS = NCT + 64 + NGW * 32;  // + producer warp + MMA warp + gather warps
 
 // per-layer fp32 vector block staged in shared memory (floats)
@@ -69,7 +72,7 @@ constexpr uint32_t OFF_BAR = OFF_RED + 4096;
 constexpr uint32_t SMEM_BYTES = OFF_BAR + 512 + 1024;              // + alignment slack
 
 // barrier indices (8 bytes each at OFF_BAR)
-enum { B_AREADY = 0, B_DDONE, B_D1READY0, B_D1READY1, B_HREADY, B_HFREE,
+enum { B_AREADY = 0, B_DDONE, B_KDONE, B_QDONE, B_D1READY0, B_D1READY1, B_HREADY, B_HFREE,
        B_TOKFULL0, B_TOKFULL1, B_TOKEMPTY0, B_TOKEMPTY1, B_FULL0, B_EMPTY0 = B_FULL0 + NSLOT,
        B_PFULL0 = B_EMPTY0 + NSLOT,  // leader CTA only: the peer's half of the slot has landed
        B_COUNT = B_PFULL0 + NSLOT };
@@ -117,24 +120,35 @@ __device__ __forceinline__ void store_chunk(uint8_t* tile_hi, uint8_t* tile_lo, 
 }
 
 // ---- MMA issue -----------------------------------------------------------------------------
-// One 16 KB weight part (B) against NA activation operands (a0 [, a1]): D += a0.B [+ a1.B], KS k-steps
-// of 16 each, fully unrolled with compile-time descriptor increments.
+// One weight part (B) against NA activation operands (a0 [, a1]): D += a0.B [+ a1.B], KS k-steps of 16 each,
+// unrolled (a rolled loop was measured to starve the pipe: the issuer shares its scheduler with busy warps),
+// with 32-bit descriptor words so that the unrolled sequence stays small in registers.
 //   *_KB: byte stride between 64-wide k-blocks of the A / B tiles.
 template <int CG, int NA, int KS, uint32_t A_KB, uint32_t B_KB, uint32_t IDESC>
 __device__ __forceinline__ void issue_part(uint32_t d_tmem, uint32_t a0, uint32_t a1, uint32_t b, bool fresh) {
-  const uint64_t ad0 = make_desc_sw128(a0), ad1 = make_desc_sw128(a1), bd = make_desc_sw128(b);
+  if (CG == 2) {
+    const uint32_t bl = make_desc_lo(b);
 #pragma unroll
-  for (int pass = 0; pass < NA; ++pass) {
-    const uint64_t ad = (pass == 1) ? ad1 : ad0;
+    for (int pass = 0; pass < NA; ++pass) {
+      const uint32_t al = make_desc_lo(pass == 1 ? a1 : a0);
 #pragma unroll
-    for (int ks = 0; ks < KS; ++ks) {
-      const uint32_t kb = ks >> 2, kin = (ks & 3) * 32;
-      if (CG == 2)
-        umma_bf16_pair(d_tmem, ad + ((kb * A_KB + kin) >> 4), bd + ((kb * B_KB + kin) >> 4), IDESC,
-                       (pass == 0 && ks == 0 && fresh) ? 0u : 1u);
-      else
+      for (int ks = 0; ks < KS; ++ks) {
+        const uint32_t kb = ks >> 2, kin = (ks & 3) * 32;
+        umma_pair_lo(d_tmem, al + ((kb * A_KB + kin) >> 4), bl + ((kb * B_KB + kin) >> 4), IDESC,
+                     (pass == 0 && ks == 0 && fresh) ? 0u : 1u);
+      }
+    }
+  } else {
+    const uint64_t ad0 = make_desc_sw128(a0), ad1 = make_desc_sw128(a1), bd = make_desc_sw128(b);
+#pragma unroll
+    for (int pass = 0; pass < NA; ++pass) {
+      const uint64_t ad = (pass == 1) ? ad1 : ad0;
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks) {
+        const uint32_t kb = ks >> 2, kin = (ks & 3) * 32;
         umma_bf16(d_tmem, ad + ((kb * A_KB + kin) >> 4), bd + ((kb * B_KB + kin) >> 4), IDESC,
                   (pass == 0 && ks == 0 && fresh) ? 0u : 1u);
+      }
     }
   }
 }
@@ -142,17 +156,27 @@ __device__ __forceinline__ void issue_part(uint32_t d_tmem, uint32_t a0, uint32_
 // Same with the A operand(s) in tensor memory (8 columns per k-step).
 template <int CG, int NA, int KS, uint32_t B_KB, uint32_t IDESC>
 __device__ __forceinline__ void issue_part_ts(uint32_t d_tmem, uint32_t a0_tmem, uint32_t a1_tmem, uint32_t b, bool fresh) {
-  const uint64_t bd = make_desc_sw128(b);
+  if (CG == 2) {
+    const uint32_t bl = make_desc_lo(b);
 #pragma unroll
-  for (int pass = 0; pass < NA; ++pass) {
-    const uint32_t at = (pass == 1) ? a1_tmem : a0_tmem;
+    for (int pass = 0; pass < NA; ++pass) {
+      const uint32_t at = (pass == 1) ? a1_tmem : a0_tmem;
 #pragma unroll
-    for (int ks = 0; ks < KS; ++ks) {
-      const uint32_t kb = ks >> 2, kin = (ks & 3) * 32;
-      if (CG == 2)
-        umma_bf16_ts_pair(d_tmem, at + 8 * ks, bd + ((kb * B_KB + kin) >> 4), IDESC, (pass == 0 && ks == 0 && fresh) ? 0u : 1u);
-      else
+      for (int ks = 0; ks < KS; ++ks) {
+        const uint32_t kb = ks >> 2, kin = (ks & 3) * 32;
+        umma_ts_pair_lo(d_tmem, at + 8 * ks, bl + ((kb * B_KB + kin) >> 4), IDESC, (pass == 0 && ks == 0 && fresh) ? 0u : 1u);
+      }
+    }
+  } else {
+    const uint64_t bd = make_desc_sw128(b);
+#pragma unroll
+    for (int pass = 0; pass < NA; ++pass) {
+      const uint32_t at = (pass == 1) ? a1_tmem : a0_tmem;
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks) {
+        const uint32_t kb = ks >> 2, kin = (ks & 3) * 32;
         umma_bf16_ts(d_tmem, at + 8 * ks, bd + ((kb * B_KB + kin) >> 4), IDESC, (pass == 0 && ks == 0 && fresh) ? 0u : 1u);
+      }
     }
   }
 }
@@ -197,6 +221,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
   if (threadIdx.x == 0) {
     mbar_init(bar(B_AREADY), NCW * CG);
     mbar_init(bar(B_DDONE), 1);
+    mbar_init(bar(B_KDONE), 1);
+    mbar_init(bar(B_QDONE), 1);
     mbar_init(bar(B_D1READY0), 1);
     mbar_init(bar(B_D1READY1), 1);
     mbar_init(bar(B_HREADY), NCW * CG);
@@ -224,21 +250,128 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
 
   constexpr int NPART = (NPASS == 3) ? 2 : 1;  // ring parts per weight unit (hi [, lo])
 
+  if (warp >= NCW + 2) {
+    // ===================================================================== gather warps
+    // They run up to two tiles ahead of the compute warps (double-buffered token scratch), so the L2 latency
+    // of the bilinear taps is off the critical path.
+    // Token gather, decoupled from row ownership.  The 108 (slice, query, 32-channel block) tasks of a tile are
+    // dealt four to a warp-step (one per quarter-warp, 16 bytes per lane; the four quarter-warps of a step take
+    // the same slice and channel block of four consecutive queries, whose texels coincide or neighbour each
+    // other, so their requests coalesce), 56 steps for each of the two gather warps.  Each step issues the 12 tap loads of plane scales
+    // 0-2 together, then the 8 of scales 3-4 (two L2 round trips per step instead of five: with ~226 KB of shared
+    // memory in use there is no L1 to speak of and the gather is bound by L2 latency x loads in flight).  The
+    // 16-byte token pieces go to this CTA's global token scratch [128 rows][128] (L2-resident); the row owners
+    // pick them up after a CTA barrier.
+    float qgu = 0.f, qgv = 0.f;  // lane l < 9: grid_sample coordinates of query l of the current tile
+    auto gather_step = [&](long long gt, int idx, float* tokbuf) {  // idx 0..111
+      const int qtr = lane >> 3, l8 = lane & 7;
+      int q, k, cb;
+      if (idx < 96) {  // steps 0..5: queries 0..7, four per step
+        cb = idx & 3;
+        const int grp = idx >> 2;  // 0..23
+        k = grp >> 1;
+        q = 4 * (grp & 1) + qtr;
+      } else {  // step 6: the 48 tasks of query 8, four slices per step
+        const int t = (idx - 96) * 4 + qtr;  // 0..63, 48 real
+        cb = t & 3;
+        k = t >> 2;
+        q = 8;
+      }
+      const long long gq = gt * TILE_Q + q;
+      const float gu = __shfl_sync(0xffffffffu, qgu, q), gv = __shfl_sync(0xffffffffu, qgv, q);
+      if (k >= 12 || gq >= p.n) return;
+      const int ch = 32 * cb + l8 * 4;
+      float4 acc = __ldg(reinterpret_cast<const float4*>(p.fcs_b + ch));
+      const int R0 = plane_res(p.S, 0);
+      const float* P = p.planes + (size_t)k * R0 * R0 * 128 + ch;
+      auto fold = [&](const float4* v, const Taps& t) {
+        acc.x += v[0].x * t.w00 + v[1].x * t.w01 + v[2].x * t.w10 + v[3].x * t.w11;
+        acc.y += v[0].y * t.w00 + v[1].y * t.w01 + v[2].y * t.w10 + v[3].y * t.w11;
+        acc.z += v[0].z * t.w00 + v[1].z * t.w01 + v[2].z * t.w10 + v[3].z * t.w11;
+        acc.w += v[0].w * t.w00 + v[1].w * t.w01 + v[2].w * t.w10 + v[3].w * t.w11;
+      };
+      auto issue = [&](float4* v, const Taps& t, const float* base) {
+        v[0] = __ldg(reinterpret_cast<const float4*>(base + (size_t)t.o00 * 128));
+        v[1] = __ldg(reinterpret_cast<const float4*>(base + (size_t)t.o01 * 128));
+        v[2] = __ldg(reinterpret_cast<const float4*>(base + (size_t)t.o10 * 128));
+        v[3] = __ldg(reinterpret_cast<const float4*>(base + (size_t)t.o11 * 128));
+      };
+      // plane of scale s for slice k starts at P + (12 * sum_{i<s} R_i^2 + k * (R_s^2 - R_0^2)) * 128
+      const size_t r2 = (size_t)R0 * R0;
+      {  // 12 + 8 loads in flight per lane: two L2 round trips per step
+        float4 v0[4], v1[4], v2[4];
+        const Taps t0 = make_taps(gu, gv, R0), t1 = make_taps(gu, gv, 2 * R0), t2 = make_taps(gu, gv, 4 * R0);
+        issue(v0, t0, P);
+        issue(v1, t1, P + (12 * r2 + (size_t)k * 3 * r2) * 128);
+        issue(v2, t2, P + (12 * 5 * r2 + (size_t)k * 15 * r2) * 128);
+        fold(v0, t0);
+        fold(v1, t1);
+        fold(v2, t2);
+      }
+      {
+        float4 v3[4], v4[4];
+        const Taps t3 = make_taps(gu, gv, 8 * R0), t4 = make_taps(gu, gv, 16 * R0);
+        issue(v3, t3, P + (12 * 21 * r2 + (size_t)k * 63 * r2) * 128);
+        issue(v4, t4, P + (12 * 85 * r2 + (size_t)k * 255 * r2) * 128);
+        fold(v3, t3);
+        fold(v4, t4);
+      }
+      __stcg(reinterpret_cast<float4*>(tokbuf + (size_t)(NTOK * q + 1 + k) * 128 + ch), acc);
+    };
+
+    {
+      float* const tokbase = p.scratch + (size_t)gridDim.x * (TAIL_SLOTS * TILE_Q) * 256 + (size_t)blockIdx.x * (2 * 128 * 128);
+      uint32_t ph_te = 3u;  // "empty"-type: the first wait on each buffer passes
+      int it = 0;
+      for (long long tile = tile_first; tile - rank < p.num_tiles; tile += gridDim.x, ++it) {
+        const int buf = it & 1;
+        mbar_wait(bar(B_TOKEMPTY0 + buf), (ph_te >> buf) & 1u);
+        ph_te ^= 1u << buf;
+        float* const tokbuf = tokbase + (size_t)buf * (128 * 128);
+        {  // the tile's 9 queries: one per lane (the dependent loads of load_query happen once per tile, not per step)
+          const int ql = lane < TILE_Q ? lane : TILE_Q - 1;
+          const long long gq = tile * TILE_Q + ql;
+          float qx = 0.f, qy = 0.f, qz = 0.f;
+          if (gq < p.n) load_query(p.q, gq, qx, qy, qz, qgu, qgv);
+          // query tokens fc_p(q) (models.py:79): rows 13 q of the tile, 4 channels per lane
+          const int gw = warp - NCW - 2;
+          const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.fcp_b) + lane);
+          const float4 w0 = __ldg(reinterpret_cast<const float4*>(p.fcp_wt) + lane);
+          const float4 w1 = __ldg(reinterpret_cast<const float4*>(p.fcp_wt + 128) + lane);
+          const float4 w2 = __ldg(reinterpret_cast<const float4*>(p.fcp_wt + 256) + lane);
+#pragma unroll
+          for (int q = gw; q < TILE_Q; q += NGW) {
+            const float px = __shfl_sync(0xffffffffu, qx, q), py = __shfl_sync(0xffffffffu, qy, q),
+                        pz = __shfl_sync(0xffffffffu, qz, q);
+            if (tile * TILE_Q + q < p.n)
+              __stcg(reinterpret_cast<float4*>(tokbuf + (size_t)(NTOK * q) * 128) + lane,
+                     make_float4(b4.x + px * w0.x + py * w1.x + pz * w2.x, b4.y + px * w0.y + py * w1.y + pz * w2.y,
+                                 b4.z + px * w0.z + py * w1.z + pz * w2.z, b4.w + px * w0.w + py * w1.w + pz * w2.w));
+          }
+        }
+#pragma unroll 1
+        for (int idx = warp - NCW - 2; idx < 112; idx += NGW) gather_step(tile, idx, tokbuf);
+        __threadfence_block();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar(B_TOKFULL0 + buf));
+      }
+    }
+  } else if (warp >= NCW) {
   if (warp == NCW) {
     // ===================================================================== weight producer
     {
       uint32_t ph_empty = 0xffffffffu;  // one parity bit per slot ("empty"-type: first wait passes)
       int slot = 0;
-      long long w_e = 0;
-      const long long t_start = clock64();
+      uint32_t w_e = 0;
+      const uint32_t t_start = (uint32_t)clock();
       // parts [g0, g1) of the stream (the image is packed in the issuer's consumption order, see dectc_pack)
       auto stream = [&](int g0, int g1) {
 #pragma unroll 1
         for (int g = g0; g < g1; ++g) {
-          const long long t0 = clock64();
+          const uint32_t t0 = (uint32_t)clock();
           mbar_wait(bar(B_EMPTY0 + slot), (ph_empty >> slot) & 1u);
           ph_empty ^= 1u << slot;
-          w_e += clock64() - t0;
+          w_e += (uint32_t)clock() - t0;
           if (elect_one()) {
             // part g of the stream = image part g (bf16x3: hi, lo of every unit) or 2g (bf16: hi parts only);
             // this CTA's half = rows 64 rank .. +63 of each of the two k-blocks ([128 n][64 k], 16 KB each)
@@ -267,7 +400,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
       }
       if (lane == 0) {
         atomicAdd(&g_prof[PF_PROD_WAIT_EMPTY], (unsigned long long)w_e);
-        atomicAdd(&g_prof[PF_PROD_TOTAL], (unsigned long long)(clock64() - t_start));
+        atomicAdd(&g_prof[PF_PROD_TOTAL], (unsigned long long)((uint32_t)clock() - t_start));
       }
     }
   } else if (warp == NCW + 1 && !leader) {
@@ -301,17 +434,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
     {
       uint32_t ph_a = 0, ph_full = 0, ph_hr = 0;  // parity bits (one per barrier / slot)
       int slot = 0;
-      long long w_a = 0, w_full = 0, w_h = 0;
-      const long long t_start = clock64();
+      uint32_t w_a = 0, w_full = 0, w_h = 0;  // 32-bit cycle sums (wrap after ~2 s; only read in profiling runs)
+      const uint32_t t_start = (uint32_t)clock();
       const uint32_t ax_hi = sbase + OFF_AX_HI, ax_lo = sbase + OFF_AX_LO;
       constexpr uint32_t ID128 = make_idesc_bf16(128, 128 * CG);
       constexpr uint32_t BKB = 8192u;  // k-block stride of this CTA's half of a part: [64 n][64 k]
       auto wait_full = [&]() -> uint32_t {
-        const long long t0 = clock64();
+        const uint32_t t0 = (uint32_t)clock();
         mbar_wait(bar(B_FULL0 + slot), (ph_full >> slot) & 1u);
         if (CG == 2) mbar_wait_cluster(bar(B_PFULL0 + slot), (ph_full >> slot) & 1u);
         ph_full ^= 1u << slot;
-        w_full += clock64() - t0;
+        w_full += (uint32_t)clock() - t0;
         return sbase + OFF_RING + slot * SLOT_BYTES;
       };
       auto commit = [&](int b) {
@@ -343,16 +476,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
         }
       };
       auto wait_a = [&]() {
-        const long long t0 = clock64();
+        const uint32_t t0 = (uint32_t)clock();
         wait_lead(B_AREADY, ph_a);
-        w_a += clock64() - t0;
+        w_a += (uint32_t)clock() - t0;
         ph_a ^= 1;
         tc_fence_after();
       };
-      // QKV projection: S[:, 0:384] = X . Win^T
+      // QKV projection: S[:, 0:384] = X . Win^T, issued K, Q, V with a commit each: the compute warps stage K
+      // while Q is in the pipe and compute the scores while V is
       auto mma_qkv = [&]() {
         wait_a();
-        for (int u = 0; u < 3; ++u) unit_ss(TM_S + 128 * u, true);
+        unit_ss(TM_S + 128, true);
+        commit(B_KDONE);
+        unit_ss(TM_S, true);
+        commit(B_QDONE);
+        unit_ss(TM_S + 256, true);
         commit(B_DDONE);
       };
       // out-proj: R += O . Wo^T (R pre-loaded with x + b_o), then the FFN over 16 hidden chunks of 128:
@@ -388,10 +526,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
 #pragma unroll 1
         for (int c = 0; c < NCHUNK; ++c) {
           // h_ready(c): the compute warps have drained D1[c&1] and written the H operand of chunk c
-          const long long t0 = clock64();
+          const uint32_t t0 = (uint32_t)clock();
           wait_lead(B_HREADY, ph_hr);
           ph_hr ^= 1u;
-          w_h += clock64() - t0;
+          w_h += (uint32_t)clock() - t0;
           tc_fence_after();
           issue2(c);
           if (c + 1 < NCHUNK) commit(B_HFREE);  // H may be rewritten once MMA2 of chunk c has completed
@@ -416,95 +554,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
         atomicAdd(&g_prof[PF_MMA_WAIT_A], (unsigned long long)w_a);
         atomicAdd(&g_prof[PF_MMA_WAIT_FULL], (unsigned long long)w_full);
         atomicAdd(&g_prof[PF_MMA_WAIT_H], (unsigned long long)w_h);
-        atomicAdd(&g_prof[PF_MMA_TOTAL], (unsigned long long)(clock64() - t_start));
+        atomicAdd(&g_prof[PF_MMA_TOTAL], (unsigned long long)((uint32_t)clock() - t_start));
       }
     }
-  } else if (warp >= NCW + 2) {
-    // ===================================================================== gather warps
-    // They run up to two tiles ahead of the compute warps (double-buffered token scratch), so the L2 latency
-    // of the bilinear taps is off the critical path.
-    // Token gather, decoupled from row ownership.  The 108 (slice, query, 32-channel block) tasks of a tile are
-    // dealt four to a warp-step (one per quarter-warp, 16 bytes per lane; the four quarter-warps of a step take
-    // the same slice and channel block of four consecutive queries, whose texels coincide or neighbour each
-    // other, so their requests coalesce), 56 steps for each of the two gather warps.  Each step issues the 12 tap loads of plane scales
-    // 0-2 together, then the 8 of scales 3-4 (two L2 round trips per step instead of five: with ~226 KB of shared
-    // memory in use there is no L1 to speak of and the gather is bound by L2 latency x loads in flight).  The
-    // 16-byte token pieces go to this CTA's global token scratch [128 rows][128] (L2-resident); the row owners
-    // pick them up after a CTA barrier.
-    constexpr int GATHER_STEPS = 112 / NGW;
-    auto gather_step = [&](long long gt, int step, float* tokbuf) {
-      const int qtr = lane >> 3, l8 = lane & 7;
-      int q, k, cb;
-      const int idx = step * NGW + (warp - NCW - 2);  // 0..111
-      if (idx < 96) {  // steps 0..5: queries 0..7, four per step
-        cb = idx & 3;
-        const int grp = idx >> 2;  // 0..23
-        k = grp >> 1;
-        q = 4 * (grp & 1) + qtr;
-      } else {  // step 6: the 48 tasks of query 8, four slices per step
-        const int t = (idx - 96) * 4 + qtr;  // 0..63, 48 real
-        cb = t & 3;
-        k = t >> 2;
-        q = 8;
-      }
-      const long long gq = gt * TILE_Q + q;
-      if (k >= 12 || gq >= p.n) return;
-      const int ch = 32 * cb + l8 * 4;
-      float x, y, z, gu, gv;
-      load_query(p.q, gq, x, y, z, gu, gv);
-      float4 acc = __ldg(reinterpret_cast<const float4*>(p.fcs_b + ch));
-      const int R0 = plane_res(p.S, 0);
-      const float* P = p.planes + (size_t)k * R0 * R0 * 128 + ch;
-      auto fold = [&](const float4* v, const Taps& t) {
-        acc.x += v[0].x * t.w00 + v[1].x * t.w01 + v[2].x * t.w10 + v[3].x * t.w11;
-        acc.y += v[0].y * t.w00 + v[1].y * t.w01 + v[2].y * t.w10 + v[3].y * t.w11;
-        acc.z += v[0].z * t.w00 + v[1].z * t.w01 + v[2].z * t.w10 + v[3].z * t.w11;
-        acc.w += v[0].w * t.w00 + v[1].w * t.w01 + v[2].w * t.w10 + v[3].w * t.w11;
-      };
-      auto issue = [&](float4* v, const Taps& t, const float* base) {
-        v[0] = __ldg(reinterpret_cast<const float4*>(base + (size_t)t.o00 * 128));
-        v[1] = __ldg(reinterpret_cast<const float4*>(base + (size_t)t.o01 * 128));
-        v[2] = __ldg(reinterpret_cast<const float4*>(base + (size_t)t.o10 * 128));
-        v[3] = __ldg(reinterpret_cast<const float4*>(base + (size_t)t.o11 * 128));
-      };
-      // plane of scale s for slice k starts at P + (12 * sum_{i<s} R_i^2 + k * (R_s^2 - R_0^2)) * 128
-      const size_t r2 = (size_t)R0 * R0;
-      {
-        float4 v0[4], v1[4], v2[4];
-        const Taps t0 = make_taps(gu, gv, R0), t1 = make_taps(gu, gv, 2 * R0), t2 = make_taps(gu, gv, 4 * R0);
-        issue(v0, t0, P);
-        issue(v1, t1, P + (12 * r2 + (size_t)k * 3 * r2) * 128);
-        issue(v2, t2, P + (12 * 5 * r2 + (size_t)k * 15 * r2) * 128);
-        fold(v0, t0);
-        fold(v1, t1);
-        fold(v2, t2);
-      }
-      {
-        float4 v3[4], v4[4];
-        const Taps t3 = make_taps(gu, gv, 8 * R0), t4 = make_taps(gu, gv, 16 * R0);
-        issue(v3, t3, P + (12 * 21 * r2 + (size_t)k * 63 * r2) * 128);
-        issue(v4, t4, P + (12 * 85 * r2 + (size_t)k * 255 * r2) * 128);
-        fold(v3, t3);
-        fold(v4, t4);
-      }
-      __stcg(reinterpret_cast<float4*>(tokbuf + (size_t)(NTOK * q + 1 + k) * 128 + ch), acc);
-    };
-
-    {
-      float* const tokbase = p.scratch + (size_t)gridDim.x * (TAIL_SLOTS * TILE_Q) * 256 + (size_t)blockIdx.x * (2 * 128 * 128);
-      uint32_t ph_te = 3u;  // "empty"-type: the first wait on each buffer passes
-      int it = 0;
-      for (long long tile = tile_first; tile - rank < p.num_tiles; tile += gridDim.x, ++it) {
-        const int buf = it & 1;
-        mbar_wait(bar(B_TOKEMPTY0 + buf), (ph_te >> buf) & 1u);
-        ph_te ^= 1u << buf;
-#pragma unroll 1
-        for (int st = 0; st < GATHER_STEPS; ++st) gather_step(tile, st, tokbase + (size_t)buf * (128 * 128));
-        __threadfence_block();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar(B_TOKFULL0 + buf));
-      }
-    }
+  }
   } else {
     // ===================================================================== compute warps
     // thread = (tile row r = TMEM lane, column quarter g): 32 of the 128 model channels per thread
@@ -517,7 +570,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
     const float* vec = reinterpret_cast<const float*>(sgen + OFF_VEC);
     float* red0 = reinterpret_cast<float*>(sgen + OFF_RED);
     float* red1 = red0 + 512;
-    uint32_t ph_d = 0, ph_d1r = 0, ph_hf = 0;
+    uint32_t ph_d = 0, ph_d1r = 0, ph_hf = 0, ph_kq = 0;
     const int qi = r / NTOK, tk = r - qi * NTOK;
     uint32_t pf[16];
 #pragma unroll
@@ -606,6 +659,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
             }
           }
           named_bar_sync(1, NCT);
+          mbar_wait(bar(B_QDONE), ph_kq);
+          ph_kq ^= 1u;
+          tc_fence_after();
           lap(12)
           {
 #pragma unroll
@@ -667,6 +723,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
           }
           lap(13)
           named_bar_sync(1, NCT);  // everyone has read K
+          mbar_wait(bar(B_DDONE), ph_d);  // V projected
+          ph_d ^= 1;
+          tc_fence_after();
           {
             float vv[32];
             tmem_ld32(trow + TM_S + 256 + 32 * h, vv);
@@ -816,7 +875,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
         }
         lap(PF_LN2)
     };
-    int pending = 0, tile_it = 0;
+    int pending = 0, tile_it = 0, tiles_done = 0;
     uint32_t ph_tf = 0;
     long long batch_tile0 = 0;
     for (long long tile = tile_first; tile - rank < p.num_tiles; tile += gridDim.x) {
@@ -832,18 +891,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
           float4 t4 = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (valid && tk > 0) t4 = __ldcg(reinterpret_cast<const float4*>(tokbuf + (size_t)r * 128 + 32 * g) + c);
+          if (valid) t4 = __ldcg(reinterpret_cast<const float4*>(tokbuf + (size_t)r * 128 + 32 * g) + c);
           v[4 * c] = t4.x; v[4 * c + 1] = t4.y; v[4 * c + 2] = t4.z; v[4 * c + 3] = t4.w;
-        }
-        if (valid && tk == 0) {  // query token: fc_p(q) (models.py:79)
-          float px, py, pz, gu, gv;
-          load_query(p.q, q_idx, px, py, pz, gu, gv);
-#pragma unroll
-          for (int c = 0; c < 32; ++c) {
-            const int cc = 32 * g + c;
-            v[c] = __ldg(p.fcp_b + cc) + px * __ldg(p.fcp_wt + cc) + py * __ldg(p.fcp_wt + 128 + cc) +
-                   pz * __ldg(p.fcp_wt + 256 + cc);
-          }
         }
         warp_arrive(bar(B_TOKEMPTY0 + tbuf), lane);  // this warp has read its tokens: the buffer may be refilled
         store_ax(v);
@@ -864,8 +913,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
         named_bar_sync(1, NCT);
         lap(PF_VEC)
         // -------------------------------------------------------------- attention (13x13 per query and head)
-        mbar_wait(bar(B_DDONE), ph_d);
-        ph_d ^= 1;
+        mbar_wait(bar(B_KDONE), ph_kq);  // K projected (Q and V follow, see mma_qkv)
         tc_fence_after();
         lap(PF_WAIT_QKV)
         if (layer < 2) {
@@ -908,14 +956,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
         }
         pending = 0;
       }
-      if (tid == 0) {
-        atomicAdd(&g_prof[PF_TILES], 1ull);
+      ++tiles_done;
+    }
+    if (tid == 0) {  // phase counters of this CTA's warp 0 (cycles; 32-bit sums are enough for ~10^4 tiles per CTA)
+      atomicAdd(&g_prof[PF_TILES], (unsigned long long)tiles_done);
 #pragma unroll
-        for (int i = 0; i < 12; ++i) atomicAdd(&g_prof[i], (unsigned long long)pf[i]);
-        for (int i = 12; i < 16; ++i) atomicAdd(&g_prof[i + 8], (unsigned long long)pf[i]);
-      }
-#pragma unroll
-      for (int i = 0; i < 16; ++i) pf[i] = 0;
+      for (int i = 0; i < 12; ++i) atomicAdd(&g_prof[i], (unsigned long long)pf[i]);
+      for (int i = 12; i < 16; ++i) atomicAdd(&g_prof[i + 8], (unsigned long long)pf[i]);
     }
 #undef lap
   }
@@ -1052,8 +1099,10 @@ int dectc_pack(s3d_model* m, cudaStream_t st) {
     S3D_TRY(fetch(L.lin2, w2));
     uint8_t* dst = img.data() + (size_t)l * UNITS_PER_LAYER * UNIT_STRIDE_BYTES;
     int g = 0;
-    for (int u = 0; u < 3; ++u, ++g)
+    for (int u : {1, 0, 2}) {  // issue order of the QKV projection: K, Q, V
       pack_unit([&](int n, int k) { return win[(size_t)k * 384 + 128 * u + n]; }, 128, 128, dst + (size_t)g * UNIT_STRIDE_BYTES);
+      ++g;
+    }
     pack_unit([&](int n, int k) { return wo[(size_t)k * 128 + n]; }, 128, 128, dst + (size_t)g * UNIT_STRIDE_BYTES);
     ++g;
     auto pack_w1 = [&](int c) {  // hidden units 128c .. +127 as output columns
