@@ -10,7 +10,7 @@ import os
 import torch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "_lib", "libslice3d_b200.so")
+LIB_PATH = os.environ.get("S3D_LIB") or os.path.join(HERE, "_lib", "libslice3d_b200.so")  # S3D_LIB: kernel experiments
 
 PREC_FP32, PREC_BF16X3, PREC_BF16 = 0, 1, 2
 PRECISIONS = {"fp32": PREC_FP32, "bf16x3": PREC_BF16X3, "bf16": PREC_BF16}

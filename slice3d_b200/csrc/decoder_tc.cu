@@ -50,7 +50,10 @@ constexpr int TAIL_SLOTS = 14;  // tiles whose token-0 rows are batched into one
 constexpr int TAIL_UNIT0 = 2 * UNITS_PER_LAYER + 3;  // first unit of the tail pass: layer 2 out_proj
 constexpr int NCW = 16;      // compute warps: warp w owns TMEM lanes 32*(w&3).. and column quarter w>>2
 constexpr int NCT = NCW * 32;
-constexpr int NGW = 2;       // gather warps (token build for the next tiles, fully asynchronous): warps 18-19
+#ifndef S3D_NGW
+#define S3D_NGW 2
+#endif
+constexpr int NGW = S3D_NGW;       // gather warps (token build for the next tiles, fully asynchronous): warps 18-19
 // 20 warps x 96 registers.  (24 warps with setmaxnreg re-budgeting -- 96 for the compute warps, 40/56 for the
 // service warpgroups, 4 gather warps -- was measured: the MMA issuer spills at 40 registers and starves the pipe in
 // bf16x3 mode; 8 % slower there, equal in bf16 mode.)
@@ -59,6 +62,9 @@ constexpr int NTHREADS = NCT + 64 + NGW * 32;  // + producer warp + MMA warp + g
 // per-layer fp32 vector block staged in shared memory (floats)
 constexpr int V_BIN = 0, V_BONEXT = 384, V_LN1W = 512, V_LN1B = 640, V_B2 = 768, V_LN2W = 896, V_LN2B = 1024,
               V_B1 = 1152, VEC_FLOATS = 3200, V_SMEM_FLOATS = VEC_FLOATS;
+constexpr int V_PART_B = 384;  // floats [0, 384) = b_in (attention phase); the rest is used from LayerNorm 1 on
+// K/V staging for attention: fp32 [117 rows][ST_PITCH] in the H region (+ the last layer's [9][4][13] scores)
+constexpr int ST_PITCH = 132;
 
 // shared memory map (bytes from the 1024-aligned base)
 constexpr uint32_t OFF_AX_HI = 0;                 // [2 k-blocks][128 rows][64] bf16 = 32 KB
@@ -66,9 +72,11 @@ constexpr uint32_t OFF_AX_LO = 32768;             // 32 KB
 constexpr uint32_t OFF_H = 65536;                 // 2 x (H chunk hi 16 KB + lo 16 KB) | K/V staging [128][128] fp32 | gather scratch
 constexpr uint32_t H_BUF_BYTES = 32768;
 constexpr uint32_t OFF_RING = OFF_H + 2 * H_BUF_BYTES;  // 131072
+constexpr uint32_t OFF_SC = OFF_H + TILE_Q * NTOK * ST_PITCH * 4;
+static_assert(OFF_SC + TILE_Q * 4 * NTOK * 4 <= OFF_RING, "attention staging");
 constexpr uint32_t OFF_VEC = OFF_RING + RING_BYTES;  // 212992
-constexpr uint32_t OFF_RED = OFF_VEC + V_SMEM_FLOATS * 4;          // 2 x [128][4] fp32 LayerNorm partials
-constexpr uint32_t OFF_BAR = OFF_RED + 4096;
+constexpr uint32_t OFF_RED = OFF_VEC + V_SMEM_FLOATS * 4;          // [128][4] x (mean, M2) fp32 LayerNorm partials
+constexpr uint32_t OFF_BAR = OFF_RED + 5120;  // (last layer: [9][128] fp32 scaled queries of the token-0 rows)
 constexpr uint32_t SMEM_BYTES = OFF_BAR + 512 + 1024;              // + alignment slack
 
 // barrier indices (8 bytes each at OFF_BAR)
@@ -569,7 +577,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
     uint8_t* ax_lo = sgen + OFF_AX_LO;
     const float* vec = reinterpret_cast<const float*>(sgen + OFF_VEC);
     float* red0 = reinterpret_cast<float*>(sgen + OFF_RED);
-    float* red1 = red0 + 512;
     uint32_t ph_d = 0, ph_d1r = 0, ph_hf = 0, ph_kq = 0;
     const int qi = r / NTOK, tk = r - qi * NTOK;
     uint32_t pf[16];
@@ -583,33 +590,36 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
     tprev = t_;                           \
   }
 
-    // LayerNorm over the 128 channels of row r, 32 of them in v[] (partials exchanged through smem)
+    // LayerNorm over the 128 channels of row r, 32 of them in v[].  Each of the row's four threads reduces its own
+    // 32 values to (mean, M2 = sum of squared deviations); the pairs are exchanged through smem with ONE barrier and
+    // combined exactly (Chan's parallel variance): mean = avg(m_i), M2 = sum(M2_i) + 32 sum((m_i - mean)^2).
     auto layer_norm = [&](float* v, const float* w, const float* b) {
       float s = 0.f;
 #pragma unroll
       for (int c = 0; c < 32; ++c) s += v[c];
-      red0[r * 4 + g] = s;
-      named_bar_sync(1, NCT);
-      const float4 s4 = *reinterpret_cast<const float4*>(red0 + r * 4);
-      const float mean = (s4.x + s4.y + s4.z + s4.w) * (1.f / 128.f);
+      const float m = s * (1.f / 32.f);
       float d2 = 0.f;
 #pragma unroll
       for (int c = 0; c < 32; ++c) {
-        v[c] -= mean;
-        d2 = fmaf(v[c], v[c], d2);
+        const float d = v[c] - m;
+        d2 = fmaf(d, d, d2);
       }
-      red1[r * 4 + g] = d2;
+      reinterpret_cast<float2*>(red0)[r * 4 + g] = make_float2(m, d2);
       named_bar_sync(1, NCT);
-      const float4 d4 = *reinterpret_cast<const float4*>(red1 + r * 4);
-      const float rstd = rsqrtf((d4.x + d4.y + d4.z + d4.w) * (1.f / 128.f) + 1e-5f);
+      const float4 p0 = *reinterpret_cast<const float4*>(red0 + r * 8);
+      const float4 p1 = *reinterpret_cast<const float4*>(red0 + r * 8 + 4);
+      const float mean = (p0.x + p0.z + p1.x + p1.z) * 0.25f;
+      const float e0 = p0.x - mean, e1 = p0.z - mean, e2 = p1.x - mean, e3 = p1.z - mean;
+      const float M2 = (p0.y + p0.w + p1.y + p1.w) + 32.f * (e0 * e0 + e1 * e1 + e2 * e2 + e3 * e3);
+      const float rstd = rsqrtf(M2 * (1.f / 128.f) + 1e-5f);
 #pragma unroll
       for (int c = 0; c < 32; c += 4) {
         const float4 w4 = *reinterpret_cast<const float4*>(w + 32 * g + c);
         const float4 b4 = *reinterpret_cast<const float4*>(b + 32 * g + c);
-        v[c] = fmaf(v[c] * rstd, w4.x, b4.x);
-        v[c + 1] = fmaf(v[c + 1] * rstd, w4.y, b4.y);
-        v[c + 2] = fmaf(v[c + 2] * rstd, w4.z, b4.z);
-        v[c + 3] = fmaf(v[c + 3] * rstd, w4.w, b4.w);
+        v[c] = fmaf((v[c] - mean) * rstd, w4.x, b4.x);
+        v[c + 1] = fmaf((v[c + 1] - mean) * rstd, w4.y, b4.y);
+        v[c + 2] = fmaf((v[c + 2] - mean) * rstd, w4.z, b4.z);
+        v[c + 3] = fmaf((v[c + 3] - mean) * rstd, w4.w, b4.w);
       }
     };
     // v[0..31] = channels 32g.. of row r -> operand A (k-block g/2, chunks 4*(g&1)..+3)
@@ -633,164 +643,250 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
     };
 
     float* const tokbase = p.scratch + (size_t)gridDim.x * (TAIL_SLOTS * TILE_Q) * 256 + (size_t)blockIdx.x * (2 * 128 * 128);
-    // Self-attention over the 13 tokens of each query, 4 heads (one per column group).  tok0_only: last
-    // layer -- only token 0 of a query is consumed downstream (models.py:83), so only those rows attend and
-    // their output (and residual) is parked in the CTA's global scratch row `slot*9 + qi` for the tail pass.
-    auto attention = [&](bool tok0_only, bool valid, int slot) {
-      const bool act = valid && (!tok0_only || tk == 0);
-      float* tail_row = p.scratch + ((size_t)blockIdx.x * (TAIL_SLOTS * TILE_Q) + (size_t)slot * TILE_Q + (qi < TILE_Q ? qi : 0)) * 256;
-        {
-          // column group g takes head g.  K (then V) of all heads is staged as one [128][128] fp32 matrix in
-          // the H region; 16-byte chunk c4 of row q is stored at chunk (c4 ^ (q & 7)) so that the four
-          // queries a warp touches at once hit distinct banks without padding.
-          float* st = reinterpret_cast<float*>(sgen + OFF_H);
-          const float* b_in = vec + V_BIN;
-          const int h = g;
-          float sc[NTOK];
-          {
-            float kk[32];
-            tmem_ld32(trow + TM_S + 128 + 32 * h, kk);
-            tmem_ld_wait();
+    // Self-attention over the 13 tokens of each query, 4 heads (one per column group = per thread of a row).
+    // K (then V) of all heads is staged as an fp32 matrix [117 rows][ST_PITCH] in the H region.  The pitch of
+    // 132 floats puts the key rows of the (at most four) queries a warp touches at once in distinct banks, and
+    // every address is "row base of my query + compile-time offset": no address arithmetic in the loops.
+    // The dot products run as packed fp32 FMAs (FFMA2).
+    float* const st = reinterpret_cast<float*>(sgen + OFF_H);
+    const float* const qrows = st + (qi < TILE_Q ? qi : 0) * (NTOK * ST_PITCH) + 32 * g;  // key/value rows of my query, my head
+    // S[:, col + 32g ..+31] + bias -> my row of the staging matrix
+    auto stage_kv = [&](uint32_t col, const float* bias) {
+      float kk[32];
+      tmem_ld32(trow + col + 32 * g, kk);
+      tmem_ld_wait();
+      if (r < TILE_Q * NTOK) {
+        float4* dst = reinterpret_cast<float4*>(st + r * ST_PITCH + 32 * g);
 #pragma unroll
-            for (int c = 0; c < 32; c += 4) {
-              const float4 b4 = *reinterpret_cast<const float4*>(b_in + 128 + 32 * h + c);
-              *reinterpret_cast<float4*>(st + r * 128 + ((((32 * h + c) >> 2) ^ (r & 7)) << 2)) =
-                  make_float4(kk[c] + b4.x, kk[c + 1] + b4.y, kk[c + 2] + b4.z, kk[c + 3] + b4.w);
-            }
-          }
-          named_bar_sync(1, NCT);
-          mbar_wait(bar(B_QDONE), ph_kq);
-          ph_kq ^= 1u;
-          tc_fence_after();
-          lap(12)
-          {
-#pragma unroll
-            for (int j = 0; j < NTOK; ++j) sc[j] = 0.f;
-            // head dim in two halves of 16: small live state (q 16 + k 16) lets the compiler keep several
-            // K rows of loads in flight under the 96-register cap
-#pragma unroll
-            for (int hf = 0; hf < 2; ++hf) {
-              float qq[16];
-              tmem_ld16(trow + TM_S + 32 * h + 16 * hf, qq);
-              tmem_ld_wait();
-#pragma unroll
-              for (int c = 0; c < 16; c += 4) {
-                const float4 b4 = *reinterpret_cast<const float4*>(b_in + 32 * h + 16 * hf + c);
-                qq[c] = (qq[c] + b4.x) * 0.17677669529663687f;
-                qq[c + 1] = (qq[c + 1] + b4.y) * 0.17677669529663687f;
-                qq[c + 2] = (qq[c + 2] + b4.z) * 0.17677669529663687f;
-                qq[c + 3] = (qq[c + 3] + b4.w) * 0.17677669529663687f;
-              }
-              if (act) {
-#pragma unroll
-                for (int j = 0; j < NTOK; ++j) {
-                  const int row = qi * NTOK + j;
-                  const float* kb = st + row * 128;
-                  float4 k4[4];
-#pragma unroll
-                  for (int c = 0; c < 4; ++c)
-                    k4[c] = *reinterpret_cast<const float4*>(kb + (((8 * h + 4 * hf + c) ^ (row & 7)) << 2));
-                  float s0 = 0.f, s1 = 0.f;
-#pragma unroll
-                  for (int c = 0; c < 4; c += 2) {
-                    s0 = fmaf(qq[4 * c], k4[c].x, s0);
-                    s1 = fmaf(qq[4 * c + 4], k4[c + 1].x, s1);
-                    s0 = fmaf(qq[4 * c + 1], k4[c].y, s0);
-                    s1 = fmaf(qq[4 * c + 5], k4[c + 1].y, s1);
-                    s0 = fmaf(qq[4 * c + 2], k4[c].z, s0);
-                    s1 = fmaf(qq[4 * c + 6], k4[c + 1].z, s1);
-                    s0 = fmaf(qq[4 * c + 3], k4[c].w, s0);
-                    s1 = fmaf(qq[4 * c + 7], k4[c + 1].w, s1);
-                  }
-                  sc[j] += s0 + s1;
-                }
-              }
-            }
-            if (act) {
-              float mx = sc[0];
-#pragma unroll
-              for (int j = 1; j < NTOK; ++j) mx = fmaxf(mx, sc[j]);
-              float sum = 0.f;
-#pragma unroll
-              for (int j = 0; j < NTOK; ++j) {
-                sc[j] = __expf(sc[j] - mx);
-                sum += sc[j];
-              }
-              const float inv = 1.f / sum;
-#pragma unroll
-              for (int j = 0; j < NTOK; ++j) sc[j] *= inv;
-            }
-          }
-          lap(13)
-          named_bar_sync(1, NCT);  // everyone has read K
-          mbar_wait(bar(B_DDONE), ph_d);  // V projected
-          ph_d ^= 1;
-          tc_fence_after();
-          {
-            float vv[32];
-            tmem_ld32(trow + TM_S + 256 + 32 * h, vv);
-            tmem_ld_wait();
-#pragma unroll
-            for (int c = 0; c < 32; c += 4) {
-              const float4 b4 = *reinterpret_cast<const float4*>(b_in + 256 + 32 * h + c);
-              *reinterpret_cast<float4*>(st + r * 128 + ((((32 * h + c) >> 2) ^ (r & 7)) << 2)) =
-                  make_float4(vv[c] + b4.x, vv[c + 1] + b4.y, vv[c + 2] + b4.z, vv[c + 3] + b4.w);
-            }
-          }
-          named_bar_sync(1, NCT);
-          lap(14)
-          {
-            // O[:, 32h:32h+32] in two halves of 16 -> operand A chunks (k-block h/2, chunks 4*(h&1) + 2*hf ..+1)
-#pragma unroll
-            for (int hf = 0; hf < 2; ++hf) {
-              float o[16];
-#pragma unroll
-              for (int c = 0; c < 16; ++c) o[c] = 0.f;
-              if (act) {
-#pragma unroll
-                for (int j = 0; j < NTOK; ++j) {
-                  const int row = qi * NTOK + j;
-                  const float* vb = st + row * 128;
-                  float4 v4[4];
-#pragma unroll
-                  for (int c = 0; c < 4; ++c)
-                    v4[c] = *reinterpret_cast<const float4*>(vb + (((8 * h + 4 * hf + c) ^ (row & 7)) << 2));
-#pragma unroll
-                  for (int c = 0; c < 4; ++c) {
-                    o[4 * c] = fmaf(sc[j], v4[c].x, o[4 * c]);
-                    o[4 * c + 1] = fmaf(sc[j], v4[c].y, o[4 * c + 1]);
-                    o[4 * c + 2] = fmaf(sc[j], v4[c].z, o[4 * c + 2]);
-                    o[4 * c + 3] = fmaf(sc[j], v4[c].w, o[4 * c + 3]);
-                  }
-                }
-              }
-              if (!tok0_only) {
-                store_chunk<NPASS>(ax_hi + (h >> 1) * 16384, ax_lo + (h >> 1) * 16384, r, (h & 1) * 4 + 2 * hf, o);
-                store_chunk<NPASS>(ax_hi + (h >> 1) * 16384, ax_lo + (h >> 1) * 16384, r, (h & 1) * 4 + 2 * hf + 1, o + 8);
-              } else if (act) {  // last layer: park the attention output of token 0 for the tail pass
-                float4* dst = reinterpret_cast<float4*>(tail_row + 32 * h + 16 * hf);
-#pragma unroll
-                for (int c = 0; c < 4; ++c) dst[c] = make_float4(o[4 * c], o[4 * c + 1], o[4 * c + 2], o[4 * c + 3]);
-              }
-            }
-          }
-          lap(15)
-          // (the staging region is next written by the FFN epilogue, after LayerNorm 1's barriers)
-          fence_proxy_async_smem();
+        for (int c = 0; c < 8; ++c) {
+          const float4 b4 = *reinterpret_cast<const float4*>(bias + 32 * g + 4 * c);
+          dst[c] = make_float4(kk[4 * c] + b4.x, kk[4 * c + 1] + b4.y, kk[4 * c + 2] + b4.z, kk[4 * c + 3] + b4.w);
         }
-        if (tok0_only) {
-          float v[32];
-          tmem_ld32(trow + TM_R + 32 * g, v);  // x + b_o of this row (pre-loaded accumulator of out-proj)
+      }
+    };
+    // b_in of the next layer replaces this layer's once every thread is past its last use (after the "V staged"
+    // barrier); the FFN-phase vectors of this layer are fetched at the start of attention and stored after the
+    // "K staged" barrier (every thread is past LayerNorm 2 of the previous layer by then).
+    auto vecB_fetch = [&](int layer, float4* v2) {
+      const float4* src = reinterpret_cast<const float4*>(p.vecs + (size_t)layer * VEC_FLOATS) + V_PART_B / 4;
+      v2[0] = __ldg(src + tid);
+      v2[1] = (tid + NCT < (VEC_FLOATS - V_PART_B) / 4) ? __ldg(src + tid + NCT) : make_float4(0.f, 0.f, 0.f, 0.f);
+    };
+    auto vecB_store = [&](const float4* v2) {
+      float4* dst = reinterpret_cast<float4*>(sgen + OFF_VEC) + V_PART_B / 4;
+      dst[tid] = v2[0];
+      if (tid + NCT < (VEC_FLOATS - V_PART_B) / 4) dst[tid + NCT] = v2[1];
+    };
+    auto vecA_next = [&](int layer) {  // b_in of the layer after `layer`
+      if (tid < V_PART_B / 4) {
+        const int nl = layer == 2 ? 0 : layer + 1;
+        reinterpret_cast<float4*>(sgen + OFF_VEC)[tid] =
+            __ldg(reinterpret_cast<const float4*>(p.vecs + (size_t)nl * VEC_FLOATS) + tid);
+      }
+    };
+    auto attention = [&](int layer, bool valid) {
+      const float* b_in = vec + V_BIN;
+      float sc[NTOK];
+      {
+        float4 vb[2];
+        vecB_fetch(layer, vb);
+        stage_kv(TM_S + 128, b_in + 128);
+        named_bar_sync(1, NCT);
+        vecB_store(vb);
+      }
+      mbar_wait(bar(B_QDONE), ph_kq);
+      ph_kq ^= 1u;
+      tc_fence_after();
+      lap(12)
+      {
+#pragma unroll
+        for (int j = 0; j < NTOK; ++j) sc[j] = 0.f;
+        // head dim in two halves of 16: small live state lets the compiler keep several key rows in flight
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          float qq[16];
+          tmem_ld16(trow + TM_S + 32 * g + 16 * hf, qq);
           tmem_ld_wait();
-          if (act) {
-            float4* dst = reinterpret_cast<float4*>(tail_row + 128 + 32 * g);
 #pragma unroll
-            for (int c = 0; c < 8; ++c) dst[c] = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+          for (int c = 0; c < 16; c += 4) {
+            const float4 b4 = *reinterpret_cast<const float4*>(b_in + 32 * g + 16 * hf + c);
+            qq[c] = (qq[c] + b4.x) * 0.17677669529663687f;
+            qq[c + 1] = (qq[c + 1] + b4.y) * 0.17677669529663687f;
+            qq[c + 2] = (qq[c + 2] + b4.z) * 0.17677669529663687f;
+            qq[c + 3] = (qq[c + 3] + b4.w) * 0.17677669529663687f;
           }
-        } else {
-          arrive_lead(B_AREADY);
+          if (valid) {
+#pragma unroll
+            for (int j = 0; j < NTOK; ++j) {
+              const float4* kb = reinterpret_cast<const float4*>(qrows + j * ST_PITCH + 16 * hf);
+              float2 a0 = make_float2(0.f, 0.f), a1 = make_float2(0.f, 0.f);
+#pragma unroll
+              for (int c = 0; c < 4; ++c) {
+                const float4 k4 = kb[c];
+                ffma2(a0, make_float2(qq[4 * c], qq[4 * c + 1]), make_float2(k4.x, k4.y));
+                ffma2(a1, make_float2(qq[4 * c + 2], qq[4 * c + 3]), make_float2(k4.z, k4.w));
+              }
+              sc[j] += (a0.x + a0.y) + (a1.x + a1.y);
+            }
+          }
         }
-        lap(PF_ATTN)
+        if (valid) {
+          float mx = sc[0];
+#pragma unroll
+          for (int j = 1; j < NTOK; ++j) mx = fmaxf(mx, sc[j]);
+          float sum = 0.f;
+#pragma unroll
+          for (int j = 0; j < NTOK; ++j) {
+            sc[j] = __expf(sc[j] - mx);
+            sum += sc[j];
+          }
+          const float inv = 1.f / sum;
+#pragma unroll
+          for (int j = 0; j < NTOK; ++j) sc[j] *= inv;
+        }
+      }
+      lap(13)
+      named_bar_sync(1, NCT);  // everyone has read K
+      mbar_wait(bar(B_DDONE), ph_d);  // V projected
+      ph_d ^= 1;
+      tc_fence_after();
+      stage_kv(TM_S + 256, b_in + 256);
+      named_bar_sync(1, NCT);
+      vecA_next(layer);
+      lap(14)
+      {
+        // O[:, 32g:32g+32] in two halves of 16 -> operand A chunks (k-block g/2, chunks 4*(g&1) + 2*hf ..+1)
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          float2 o2[8];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) o2[c] = make_float2(0.f, 0.f);
+          if (valid) {
+#pragma unroll
+            for (int j = 0; j < NTOK; ++j) {
+              const float4* vb = reinterpret_cast<const float4*>(qrows + j * ST_PITCH + 16 * hf);
+              const float2 p2 = make_float2(sc[j], sc[j]);
+#pragma unroll
+              for (int c = 0; c < 4; ++c) {
+                const float4 v4 = vb[c];
+                ffma2(o2[2 * c], p2, make_float2(v4.x, v4.y));
+                ffma2(o2[2 * c + 1], p2, make_float2(v4.z, v4.w));
+              }
+            }
+          }
+          float o[16];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            o[2 * c] = o2[c].x;
+            o[2 * c + 1] = o2[c].y;
+          }
+          store_chunk<NPASS>(ax_hi + (g >> 1) * 16384, ax_lo + (g >> 1) * 16384, r, (g & 1) * 4 + 2 * hf, o);
+          store_chunk<NPASS>(ax_hi + (g >> 1) * 16384, ax_lo + (g >> 1) * 16384, r, (g & 1) * 4 + 2 * hf + 1, o + 8);
+        }
+      }
+      lap(15)
+      fence_proxy_async_smem();
+      arrive_lead(B_AREADY);
+      lap(PF_ATTN)
+    };
+    // Last layer: only token 0 of a query is consumed downstream (models.py:83), so only those 9 rows attend.  The
+    // work is re-dealt over the CTA instead of leaving it with the 9 row owners: 468 threads take one (query, head,
+    // key) dot product each, 288 threads one float4 of the output.  The attention output and the residual (x + b_o)
+    // of the token-0 rows are parked in the CTA's global scratch rows `slot*9 + q` for the tail pass.
+    auto attention_tok0 = [&](long long tile, int slot) {
+      const float* b_in = vec + V_BIN;
+      float* const qs = reinterpret_cast<float*>(sgen + OFF_RED);  // [9][128] scaled queries of the token-0 rows
+      float* const scs = reinterpret_cast<float*>(sgen + OFF_SC);  // [9][4][13] scores
+      float* const tail0 = p.scratch + ((size_t)blockIdx.x * (TAIL_SLOTS * TILE_Q) + (size_t)slot * TILE_Q) * 256;
+      {
+        float4 vb[2];
+        vecB_fetch(2, vb);
+        stage_kv(TM_S + 128, b_in + 128);
+        mbar_wait(bar(B_QDONE), ph_kq);
+        ph_kq ^= 1u;
+        tc_fence_after();
+        {
+          float qq[32];
+          tmem_ld32(trow + TM_S + 32 * g, qq);
+          tmem_ld_wait();
+          if (tk == 0 && qi < TILE_Q) {
+            float4* dst = reinterpret_cast<float4*>(qs + qi * 128 + 32 * g);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              const float4 b4 = *reinterpret_cast<const float4*>(b_in + 32 * g + 4 * c);
+              dst[c] = make_float4((qq[4 * c] + b4.x) * 0.17677669529663687f, (qq[4 * c + 1] + b4.y) * 0.17677669529663687f,
+                                   (qq[4 * c + 2] + b4.z) * 0.17677669529663687f, (qq[4 * c + 3] + b4.w) * 0.17677669529663687f);
+            }
+          }
+        }
+        named_bar_sync(1, NCT);
+        vecB_store(vb);
+      }
+      lap(12)
+      if (tid < TILE_Q * 4 * NTOK) {
+        const int q = tid / (4 * NTOK), rem = tid - q * (4 * NTOK), hh = rem / NTOK, j = rem - hh * NTOK;
+        const float4* qp = reinterpret_cast<const float4*>(qs + q * 128 + 32 * hh);
+        const float4* kp = reinterpret_cast<const float4*>(st + (q * NTOK + j) * ST_PITCH + 32 * hh);
+        float2 a0 = make_float2(0.f, 0.f), a1 = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const float4 q4v = qp[c], k4 = kp[c];
+          ffma2(a0, make_float2(q4v.x, q4v.y), make_float2(k4.x, k4.y));
+          ffma2(a1, make_float2(q4v.z, q4v.w), make_float2(k4.z, k4.w));
+        }
+        scs[tid] = (a0.x + a0.y) + (a1.x + a1.y);
+      }
+      lap(13)
+      mbar_wait(bar(B_DDONE), ph_d);  // V projected
+      ph_d ^= 1;
+      tc_fence_after();
+      named_bar_sync(1, NCT);  // scores written, everyone has read K
+      stage_kv(TM_S + 256, b_in + 256);
+      {  // residual x + b_o of the token-0 rows (the pre-loaded accumulator of out-proj)
+        float v[32];
+        tmem_ld32(trow + TM_R + 32 * g, v);
+        tmem_ld_wait();
+        if (tk == 0 && qi < TILE_Q) {
+          float4* dst = reinterpret_cast<float4*>(tail0 + (size_t)qi * 256 + 128 + 32 * g);
+#pragma unroll
+          for (int c = 0; c < 8; ++c) dst[c] = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+        }
+      }
+      named_bar_sync(1, NCT);
+      vecA_next(2);
+      lap(14)
+      if (tid < TILE_Q * 32) {
+        const int q = tid >> 5, c4 = tid & 31, hh = c4 >> 3;
+        const float* sp = scs + q * (4 * NTOK) + hh * NTOK;
+        float pj[NTOK];
+        float mx = sp[0];
+#pragma unroll
+        for (int j = 0; j < NTOK; ++j) {
+          pj[j] = sp[j];
+          mx = fmaxf(mx, pj[j]);
+        }
+        float sum = 0.f;
+#pragma unroll
+        for (int j = 0; j < NTOK; ++j) {
+          pj[j] = __expf(pj[j] - mx);
+          sum += pj[j];
+        }
+        const float inv = 1.f / sum;
+        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float* vp = st + (q * NTOK) * ST_PITCH + 4 * c4;
+#pragma unroll
+        for (int j = 0; j < NTOK; ++j) {
+          const float4 v4 = *reinterpret_cast<const float4*>(vp + j * ST_PITCH);
+          o.x = fmaf(pj[j], v4.x, o.x);
+          o.y = fmaf(pj[j], v4.y, o.y);
+          o.z = fmaf(pj[j], v4.z, o.z);
+          o.w = fmaf(pj[j], v4.w, o.w);
+        }
+        if (tile * TILE_Q + q < p.n)
+          *reinterpret_cast<float4*>(tail0 + (size_t)q * 256 + 4 * c4) = make_float4(o.x * inv, o.y * inv, o.z * inv, o.w * inv);
+      }
+      lap(15)
+      lap(PF_ATTN)
     };
     // out-proj result + residual -> LayerNorm 1 -> FFN -> LayerNorm 2 -> next layer's operand / fc_out head
     auto post_attn = [&](int layer, bool head_valid, long long head_q) {
@@ -865,6 +961,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
             float acc = 0.f;
 #pragma unroll
             for (int c = 0; c < 32; ++c) acc = fmaf(v[c], __ldg(p.fco_w + 32 * g + c), acc);
+            named_bar_sync(1, NCT);  // everyone has read the LayerNorm partials
             red0[r * 4 + g] = acc;
             named_bar_sync(1, NCT);
             if (head_valid) {
@@ -875,6 +972,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
         }
         lap(PF_LN2)
     };
+    if (tid < V_PART_B / 4)  // b_in of layer 0 (later layers / tiles: staged by vecA_next during the previous attention)
+      reinterpret_cast<float4*>(sgen + OFF_VEC)[tid] = __ldg(reinterpret_cast<const float4*>(p.vecs) + tid);
+    named_bar_sync(1, NCT);
     int pending = 0, tile_it = 0, tiles_done = 0;
     uint32_t ph_tf = 0;
     long long batch_tile0 = 0;
@@ -903,24 +1003,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
 
 #pragma unroll 1
       for (int layer = 0; layer < 3; ++layer) {
-        // -------------------------------------------------------------- stage this layer's vectors
-        named_bar_sync(1, NCT);  // everyone is done with the previous layer's vectors
-        {
-          const float4* src = reinterpret_cast<const float4*>(p.vecs + (size_t)layer * VEC_FLOATS);
-          float4* dst = reinterpret_cast<float4*>(sgen + OFF_VEC);
-          for (int i = tid; i < V_SMEM_FLOATS / 4; i += NCT) dst[i] = __ldg(src + i);
-        }
-        named_bar_sync(1, NCT);
-        lap(PF_VEC)
+        // (this layer's vectors: b_in was staged during the previous layer's attention, the FFN-phase block is
+        // staged inside attention -- no barrier here)
         // -------------------------------------------------------------- attention (13x13 per query and head)
         mbar_wait(bar(B_KDONE), ph_kq);  // K projected (Q and V follow, see mma_qkv)
         tc_fence_after();
         lap(PF_WAIT_QKV)
         if (layer < 2) {
-          attention(false, valid, 0);
+          attention(layer, valid);
           post_attn(layer, false, 0);
         } else {
-          attention(true, valid, pending);
+          attention_tok0(tile, pending);
         }
       }
       if (pending == 0) batch_tile0 = tile;
