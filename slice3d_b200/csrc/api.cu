@@ -308,7 +308,8 @@ int s3d_model_create(s3d_model** out, const s3d_tensor* tensors, int32_t n_tenso
     s3d_model_destroy(m);
     return missing ? S3D_ERR_MISSING_TENSOR : S3D_ERR_BAD_ARG;
   }
-  int r = dectc_pack(m, static_cast<cudaStream_t>(stream));
+  int r = enctc_pack(m, static_cast<cudaStream_t>(stream));
+  if (r == S3D_OK) r = dectc_pack(m, static_cast<cudaStream_t>(stream));
   if (r != S3D_OK) {
     s3d_model_destroy(m);
     return r;

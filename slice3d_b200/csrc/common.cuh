@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <atomic>
@@ -55,6 +56,21 @@ struct ConvW {
   int k = 0, kpad = 0;
 };
 
+// A convolution lowered to the tcgen05 implicit GEMM (conv_tc.cu): fp16 hi/lo weight tiles (of w * 2^e, so that
+// the lo parts are normal fp16 numbers; acc_scale = 2^-e undoes it) in the UMMA shared-memory layout;
+// scale/shift alias the fp32 epilogue vectors of the ConvW it was packed from.
+struct ConvTC {
+  uint8_t* wimg = nullptr;
+  int cinp = 0;     // input channels padded to a multiple of 64 (pitch of the split NHWC input)
+  int cout = 0;     // real output channels
+  int bn = 128;     // output-channel tile (64 or 128)
+  int n_tiles = 0;
+  int taps = 9;
+  float acc_scale = 1.f;
+  const float* scale = nullptr;
+  const float* shift = nullptr;
+};
+
 struct DecLayerF32 {
   ConvW in_proj;   // 128 -> 384, shift = in_proj_bias
   ConvW out_proj;  // 128 -> 128
@@ -98,6 +114,12 @@ struct s3d_model {
   float* outc_w = nullptr;     // [3][32]
   float* outc_b = nullptr;     // [3]
   s3d::ConvW fcs[5];           // fc_s hoisted per scale: [C_s][128], no bias
+  // tensor-core encoder (conv_tc.cu): the 3x3 convolutions; dc1 is split into its slice-independent skip half
+  // (dc1s, run once per view on the fp32 path) and its per-slice half (tdc1)
+  s3d::ConvTC tvgg[13];        // [0] unused (3 input channels: fp32 path)
+  s3d::ConvTC tdc1[4], tdc2[4];
+  s3d::ConvW dc1s[4];
+  int enc_simt = 0;            // S3D_ENCODER=simt: whole encoder on the fp32 CUDA-core path (debugging)
   // decoder
   s3d::DecF32 dec32;
   s3d::DecTC dectc;
@@ -121,6 +143,12 @@ static inline size_t plane_offset_floats(int K, int S, int s) {
 int encoder_fwd(const s3d_model* m, const float* img, int B, int S, void* planes, float* const* feats_nchw,
                 float* slices_rec, void* ws, size_t ws_bytes, cudaStream_t st);
 size_t encoder_workspace_bytes(int B, int K, int S);
+
+// conv_tc.cu
+int convtc_pack(s3d_model* m, const ConvW& cw, int src_cin, int ci0, int cin, ConvTC& out, cudaStream_t st);
+int conv_tc(const ConvTC& w, const __half* in_hi, const __half* in_lo, int NI, int H, int W, const float* add,
+            int add_div, int relu, float* out_f32, int ldf, __half* out_hi, __half* out_lo, int lds, cudaStream_t st);
+int enctc_pack(s3d_model* m, cudaStream_t st);
 
 // ---- queries ----------------------------------------------------------------------
 struct QueryCtx {

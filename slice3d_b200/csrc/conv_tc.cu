@@ -1,0 +1,420 @@
+// 3x3 / 1x1 convolution of the plane encoder as a TMA-staged tcgen05 implicit GEMM (sm_100a).
+//
+//   out[pixel][co] = epilogue( sum_{tap, ci} in[pixel + tap offset][ci] * W[co][tap][ci] )
+//
+// reference: every Conv2d(3x3, padding=1) of reg_slices/src/unet_custom.py:15-19 (VGG16-BN trunk) and of
+// reg_slices/src/unet_parts.py:8-25 (DoubleConv of the four Up stages), eval mode, BatchNorm folded.
+//
+// Activations live in HBM as "split" NHWC tensors: two fp16 arrays hi = fp16(x), lo = fp16(x - hi)
+// (x = hi + lo + O(2^-22 |x|); bf16 pairs only give 2^-17, measured as 2.5e-4 max-abs on the planes after the ~20
+// convolutions between the image and the last plane, against the 1e-4 bar), written by the producing kernel's epilogue.  One CTA computes a tile of 128 output
+// pixels (a BW x BH patch of one image) x BN output channels:
+//
+//   producer warp   per k-block (one filter tap x 64 input channels): two 4-D tiled TMA loads (hi, lo) of the
+//                   patch shifted by the tap offset -- out-of-bounds rows/columns are zero-filled by the TMA unit,
+//                   which IS the convolution's zero padding -- landing as [128 pixels][64 ch] K-major tiles in the
+//                   128-byte-swizzle layout UMMA reads; plus one bulk copy of the pre-swizzled weight tile
+//                   ([BN][64] hi | lo).  NST-stage ring, mbarrier complete_tx.
+//   MMA warp        per k-block 4 k-steps x 3 passes (lo.hi + hi.lo + hi.hi) into one of two TMEM accumulators;
+//                   tcgen05.commit frees the stage and hands the accumulator to the epilogue warps.
+//   8 epilogue warps  drain every k-block's accumulator into fp32 registers (round-to-nearest running sum, see the
+//                   note at the kernel), then (+ slice-independent addend) * scale + shift, ReLU -> fp32 NHWC
+//                   and / or split fp16 NHWC for the next convolution.
+#include <cuda.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include "common.cuh"
+#include "tc_ptx.cuh"
+
+namespace s3d {
+
+namespace {
+
+using namespace ptx;
+
+constexpr int CT_EPI_WARPS = 8;
+constexpr int CT_THREADS = 64 + 32 * CT_EPI_WARPS;
+constexpr uint32_t CT_A_PART = 16384;  // [128 pixels][64 ch] fp16
+
+struct ConvTcParams {
+  int H, W, NI;
+  int bw_log2, BW, BH, tiles_x, tiles_y;
+  int ncb;   // input channel blocks of 64
+  int taps;  // 9 (3x3, pad 1) or 1
+  int nkb;   // taps * ncb
+  const uint8_t* wimg;
+  int Cout;  // real output channels (multiple of 32)
+  const float* scale;
+  const float* shift;
+  const float* add;  // optional fp32 [NI / add_div][H][W][Cout], added before scale/shift
+  int add_div;
+  int relu;
+  float acc_scale;  // 2^-e: the weights are packed as w * 2^e
+  float* out_f32;  // fp32 NHWC, row pitch ldf (or null)
+  int ldf;
+  __half* out_hi;  // split NHWC, row pitch lds >= Cout; channels [Cout, lds) are written as zero (or null)
+  __half* out_lo;
+  int lds;
+};
+
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, int c2, int c3, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar)
+      : "memory");
+}
+
+template <int BN, int NST>
+struct CtSmem {
+  static constexpr uint32_t B_PART = BN * 128;                    // [BN][64] fp16
+  static constexpr uint32_t STAGE = 2 * CT_A_PART + 2 * B_PART;   // A hi | A lo | B hi | B lo
+  static constexpr uint32_t OFF_BAR = NST * STAGE;
+  static constexpr uint32_t OFF_TMEMPTR = OFF_BAR + 8 * (2 * NST + 4);
+  static constexpr uint32_t BYTES = OFF_TMEMPTR + 16 + 1024;      // + alignment slack
+};
+
+// Accumulation: the tensor core adds every MMA's products into the fp32 TMEM accumulator with truncation, a
+// bias of ~2^-24 of the accumulator per instruction; over the 864 instructions of a K = 4608 contraction that
+// was measured as ~1e-4 relative error after the 13-convolution trunk.  So a TMEM accumulator only ever holds ONE
+// k-block (12 instructions); the epilogue warps drain it (double-buffered) and keep the running sum in registers
+// with round-to-nearest fp32 adds.
+template <int BN, int NST>
+__global__ void __launch_bounds__(CT_THREADS, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo, const ConvTcParams p) {
+  using L = CtSmem<BN, NST>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t sbase = (raw + 1023u) & ~1023u;
+  uint8_t* sgen = smem_raw + (sbase - raw);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  auto full = [&](int s) { return sbase + L::OFF_BAR + 8u * s; };
+  auto empty = [&](int s) { return sbase + L::OFF_BAR + 8u * (NST + s); };
+  auto acc_full = [&](int b) { return sbase + L::OFF_BAR + 8u * (2 * NST + b); };
+  auto acc_empty = [&](int b) { return sbase + L::OFF_BAR + 8u * (2 * NST + 2 + b); };
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NST; ++s) {
+      mbar_init(full(s), 1);
+      mbar_init(empty(s), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(acc_full(b), 1);
+      mbar_init(acc_empty(b), CT_EPI_WARPS);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(sbase + L::OFF_TMEMPTR, 2 * BN);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(sgen + L::OFF_TMEMPTR);
+
+  // tile -> (image, patch origin)
+  const int tiles_img = p.tiles_x * p.tiles_y;
+  const int img = blockIdx.x / tiles_img;
+  const int trem = blockIdx.x - img * tiles_img;
+  const int tyi = trem / p.tiles_x, txi = trem - tyi * p.tiles_x;
+  const int x0 = txi * p.BW, y0 = tyi * p.BH;
+  const int n_tile = blockIdx.y;
+
+  if (warp == 0) {
+    // ===================================================================== producer
+    const uint8_t* wsrc = p.wimg + (size_t)n_tile * p.nkb * (2 * L::B_PART);
+#pragma unroll 1
+    for (int kb = 0; kb < p.nkb; ++kb) {
+      const int s = kb % NST, it = kb / NST;
+      mbar_wait(empty(s), (it & 1) ^ 1u);  // "empty"-type: the first pass over the ring does not block
+      if (lane == 0) {
+        const int tap = kb / p.ncb, cb = kb - tap * p.ncb;
+        int dy = 0, dx = 0;
+        if (p.taps == 9) {
+          dy = tap / 3 - 1;
+          dx = tap - (tap / 3) * 3 - 1;
+        }
+        const uint32_t st = sbase + s * L::STAGE;
+        mbar_arrive_expect_tx(full(s), L::STAGE);
+        tma_load_4d(st, &tm_hi, cb * 64, x0 + dx, y0 + dy, img, full(s));
+        tma_load_4d(st + CT_A_PART, &tm_lo, cb * 64, x0 + dx, y0 + dy, img, full(s));
+        bulk_g2s(st + 2 * CT_A_PART, wsrc + (size_t)kb * (2 * L::B_PART), 2 * L::B_PART, full(s));
+      }
+      __syncwarp();
+    }
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer
+    constexpr uint32_t IDESC = make_idesc_f16(BN, 128);
+#pragma unroll 1
+    for (int kb = 0; kb < p.nkb; ++kb) {
+      const int s = kb % NST, it = kb / NST;
+      const int buf = kb & 1;
+      mbar_wait(acc_empty(buf), ((kb >> 1) & 1) ^ 1u);  // the epilogue has drained this accumulator
+      mbar_wait(full(s), it & 1);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t st = sbase + s * L::STAGE;
+        const uint32_t d = tmem + buf * BN;
+        const uint64_t a_hi = make_desc_sw128(st), a_lo = make_desc_sw128(st + CT_A_PART);
+        const uint64_t b_hi = make_desc_sw128(st + 2 * CT_A_PART), b_lo = make_desc_sw128(st + 2 * CT_A_PART + L::B_PART);
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          const uint64_t o = (uint64_t)((ks * 32) >> 4);
+          // correction terms first: they are ~2^-9 of the leading term
+          umma_bf16(d, a_lo + o, b_hi + o, IDESC, ks == 0 ? 0u : 1u);
+          umma_bf16(d, a_hi + o, b_lo + o, IDESC, 1u);
+        }
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          const uint64_t o = (uint64_t)((ks * 32) >> 4);
+          umma_bf16(d, a_hi + o, b_hi + o, IDESC, 1u);
+        }
+        umma_commit(empty(s));
+        umma_commit(acc_full(buf));
+      }
+      __syncwarp();
+    }
+  } else {
+    // ===================================================================== epilogue (warps 2..9)
+    constexpr int NC = BN / 2;  // columns per thread: the two warps of a TMEM lane quarter take half of the tile each
+    const int q = warp & 3;     // TMEM lane quarter this warp may access
+    const int ch = (warp - 2) >> 2;
+    const int row = 32 * q + lane;
+    const int bx = row & (p.BW - 1), by = row >> p.bw_log2;
+    const int x = x0 + bx, y = y0 + by;
+    const bool valid = (x < p.W) && (y < p.H);
+    const size_t pix = ((size_t)img * p.H + (valid ? y : 0)) * p.W + (valid ? x : 0);
+    const float* addp = p.add ? p.add + (((size_t)(img / p.add_div) * p.H + (valid ? y : 0)) * p.W + (valid ? x : 0)) * p.Cout : nullptr;
+    const uint32_t tsrc = tmem + (static_cast<uint32_t>(32 * q) << 16) + ch * NC;
+    float acc[NC];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) acc[c] = 0.f;
+#pragma unroll 1
+    for (int kb = 0; kb < p.nkb; ++kb) {
+      const int buf = kb & 1;
+      mbar_wait(acc_full(buf), (kb >> 1) & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int j = 0; j < NC / 32; ++j) {
+        float v[32];
+        tmem_ld32(tsrc + buf * BN + 32 * j, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < 32; ++c) acc[32 * j + c] += v[c];
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_empty(buf));
+    }
+    if (valid) {
+#pragma unroll
+      for (int j = 0; j < NC / 32; ++j) {
+        float* v = acc + 32 * j;
+        const int n0 = n_tile * BN + ch * NC + 32 * j;
+        if (n0 < p.Cout) {
+#pragma unroll
+          for (int c = 0; c < 32; c += 4) {
+            float4 t = make_float4(v[c] * p.acc_scale, v[c + 1] * p.acc_scale, v[c + 2] * p.acc_scale, v[c + 3] * p.acc_scale);
+            if (addp) {
+              const float4 a4 = __ldg(reinterpret_cast<const float4*>(addp + n0 + c));
+              t.x += a4.x; t.y += a4.y; t.z += a4.z; t.w += a4.w;
+            }
+            if (p.scale) {
+              const float4 s4 = __ldg(reinterpret_cast<const float4*>(p.scale + n0 + c));
+              t.x *= s4.x; t.y *= s4.y; t.z *= s4.z; t.w *= s4.w;
+            }
+            if (p.shift) {
+              const float4 s4 = __ldg(reinterpret_cast<const float4*>(p.shift + n0 + c));
+              t.x += s4.x; t.y += s4.y; t.z += s4.z; t.w += s4.w;
+            }
+            if (p.relu) {
+              t.x = fmaxf(t.x, 0.f); t.y = fmaxf(t.y, 0.f); t.z = fmaxf(t.z, 0.f); t.w = fmaxf(t.w, 0.f);
+            }
+            v[c] = t.x; v[c + 1] = t.y; v[c + 2] = t.z; v[c + 3] = t.w;
+          }
+          if (p.out_f32) {
+            float4* dst = reinterpret_cast<float4*>(p.out_f32 + pix * p.ldf + n0);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) dst[c] = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+          }
+          if (p.out_hi) {
+            uint4* dh = reinterpret_cast<uint4*>(p.out_hi + pix * p.lds + n0);
+            uint4* dl = reinterpret_cast<uint4*>(p.out_lo + pix * p.lds + n0);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              uint32_t h[4], l[4];
+              split8_h(v + 8 * c, h, l);
+              dh[c] = make_uint4(h[0], h[1], h[2], h[3]);
+              dl[c] = make_uint4(l[0], l[1], l[2], l[3]);
+            }
+          }
+        } else if (p.out_hi && n0 < p.lds) {  // zero the channel padding the next convolution's TMA will read
+          uint4* dh = reinterpret_cast<uint4*>(p.out_hi + pix * p.lds + n0);
+          uint4* dl = reinterpret_cast<uint4*>(p.out_lo + pix * p.lds + n0);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            dh[c] = make_uint4(0, 0, 0, 0);
+            dl[c] = make_uint4(0, 0, 0, 0);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 2 * BN);
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      f = nullptr;
+    return reinterpret_cast<EncodeTiledFn>(f);
+  }();
+  return fn;
+}
+
+// fp16 NHWC [NI][H][W][C] -> 4-D tensor map with a (64 ch, BW, BH, 1) box, 128-byte swizzle, zero OOB fill.
+int make_tmap(CUtensorMap* tm, const __half* base, int NI, int H, int W, int C, int BW, int BH) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn) {
+    set_error("conv_tc: cuTensorMapEncodeTiled is not available from this driver");
+    return S3D_ERR_CUDA;
+  }
+  const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)NI};
+  const cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  const cuuint32_t box[4] = {64, (cuuint32_t)BW, (cuuint32_t)BH, 1};
+  const cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<__half*>(base), dims, strides, box, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("conv_tc: cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
+    return S3D_ERR_CUDA;
+  }
+  return S3D_OK;
+}
+
+inline uint16_t f16_bits_h(float x) { return __half_as_ushort(__float2half_rn(x)); }
+inline float f16_val_h(uint16_t b) { return __half2float(__ushort_as_half(b)); }
+
+}  // namespace
+
+// Weight image of one convolution: [n_tile][k-block = tap x 64-channel block][hi BN x 64 | lo BN x 64] bf16, every
+// [BN][64] tile in the K-major 128-byte-swizzle layout (so a plain bulk copy lands a ready UMMA B operand).
+// `src` is the fp32 GEMM matrix [(tap*src_cin + ci)][src_ld] of the SIMT path (device); input channels
+// [ci0, ci0 + cin) of it are used and padded with zeros to a multiple of 64; output channels padded to BN.
+int convtc_pack(s3d_model* m, const ConvW& cw, int src_cin, int ci0, int cin, ConvTC& out, cudaStream_t st) {
+  const int taps = cw.ks * cw.ks, cout = cw.ncols;
+  const int cinp = (cin + 63) / 64 * 64;
+  const int bn = cout >= 128 ? 128 : 64;
+  const int n_tiles = (cout + bn - 1) / bn;
+  const int ncb = cinp / 64, nkb = taps * ncb;
+  std::vector<float> h((size_t)cw.kpad * cout);
+  S3D_CUDA(cudaMemcpyAsync(h.data(), cw.w, h.size() * sizeof(float), cudaMemcpyDeviceToHost, st));
+  S3D_CUDA(cudaStreamSynchronize(st));
+  // scale the weights by a power of two so that max |w| lands in [128, 256): hi and lo are then normal fp16 numbers
+  float wmax = 0.f;
+  for (int tap = 0; tap < taps; ++tap)
+    for (int ci = 0; ci < cin; ++ci)
+      for (int co = 0; co < cout; ++co) wmax = std::max(wmax, std::fabs(h[((size_t)tap * src_cin + ci0 + ci) * cout + co]));
+  int e = 0;
+  if (wmax > 0.f && std::isfinite(wmax)) {
+    int ex;
+    std::frexp(wmax, &ex);  // wmax = f * 2^ex, f in [0.5, 1)
+    e = 8 - ex;
+  }
+  const float wmul = std::ldexp(1.f, e);
+  out.acc_scale = std::ldexp(1.f, -e);
+  const size_t tile_bytes = (size_t)bn * 256;
+  std::vector<uint8_t> img((size_t)n_tiles * nkb * tile_bytes, 0);
+  for (int nt = 0; nt < n_tiles; ++nt)
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int tap = kb / ncb, cb = kb % ncb;
+      uint16_t* hi = reinterpret_cast<uint16_t*>(img.data() + ((size_t)nt * nkb + kb) * tile_bytes);
+      uint16_t* lo = hi + (size_t)bn * 64;
+      for (int n = 0; n < bn; ++n) {
+        const int co = nt * bn + n;
+        if (co >= cout) continue;
+        for (int k = 0; k < 64; ++k) {
+          const int ci = cb * 64 + k;
+          if (ci >= cin) continue;
+          const float w = h[((size_t)tap * src_cin + ci0 + ci) * cout + co] * wmul;
+          const uint16_t hb = f16_bits_h(w);
+          const uint16_t lb = f16_bits_h(w - f16_val_h(hb));
+          const size_t off = (ptx::sw128_chunk_off(n, k >> 3) + (k & 7) * 2) / 2;
+          hi[off] = hb;
+          lo[off] = lb;
+        }
+      }
+    }
+  void* d = nullptr;
+  S3D_CUDA(cudaMalloc(&d, img.size()));
+  m->allocs.push_back(d);
+  S3D_CUDA(cudaMemcpyAsync(d, img.data(), img.size(), cudaMemcpyHostToDevice, st));
+  S3D_CUDA(cudaStreamSynchronize(st));
+  out.wimg = static_cast<uint8_t*>(d);
+  out.cinp = cinp;
+  out.cout = cout;
+  out.bn = bn;
+  out.n_tiles = n_tiles;
+  out.taps = taps;
+  out.scale = cw.scale;
+  out.shift = cw.shift;
+  return S3D_OK;
+}
+
+// in: split NHWC [NI][H][W][w.cinp] (hi, lo).  Outputs: fp32 NHWC (pitch ldf) and / or split NHWC (pitch lds).
+int conv_tc(const ConvTC& w, const __half* in_hi, const __half* in_lo, int NI, int H, int W, const float* add,
+            int add_div, int relu, float* out_f32, int ldf, __half* out_hi, __half* out_lo, int lds,
+            cudaStream_t st) {
+  if (NI <= 0) return S3D_OK;
+  int BW = 1, lg = 0;
+  while (BW * 2 <= W && BW < 128) {
+    BW *= 2;
+    ++lg;
+  }
+  const int BH = 128 / BW;
+  ConvTcParams p{};
+  p.H = H; p.W = W; p.NI = NI;
+  p.BW = BW; p.bw_log2 = lg; p.BH = BH;
+  p.tiles_x = (W + BW - 1) / BW;
+  p.tiles_y = (H + BH - 1) / BH;
+  p.ncb = w.cinp / 64;
+  p.taps = w.taps;
+  p.nkb = p.taps * p.ncb;
+  p.wimg = w.wimg;
+  p.Cout = w.cout;
+  p.scale = w.scale; p.shift = w.shift;
+  p.add = add; p.add_div = add_div > 0 ? add_div : 1;
+  p.relu = relu;
+  p.acc_scale = w.acc_scale;
+  p.out_f32 = out_f32; p.ldf = ldf;
+  p.out_hi = out_hi; p.out_lo = out_lo; p.lds = lds;
+  CUtensorMap tm_hi, tm_lo;
+  S3D_TRY(make_tmap(&tm_hi, in_hi, NI, H, W, w.cinp, BW, BH));
+  S3D_TRY(make_tmap(&tm_lo, in_lo, NI, H, W, w.cinp, BW, BH));
+  dim3 grid((unsigned)(p.tiles_x * p.tiles_y * NI), (unsigned)w.n_tiles);
+  if (w.bn == 128) {
+    using L = CtSmem<128, 3>;
+    auto kern = conv_tc_kernel<128, 3>;
+    S3D_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::BYTES));
+    kern<<<grid, CT_THREADS, L::BYTES, st>>>(tm_hi, tm_lo, p);
+  } else {
+    using L = CtSmem<64, 4>;
+    auto kern = conv_tc_kernel<64, 4>;
+    S3D_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::BYTES));
+    kern<<<grid, CT_THREADS, L::BYTES, st>>>(tm_hi, tm_lo, p);
+  }
+  S3D_LAUNCH_CHECK();
+  return S3D_OK;
+}
+
+}  // namespace s3d

@@ -7,6 +7,9 @@
 // Work the reference repeats 12x (the 1x1 skip adapters trans_up1..4 and the trans_c
 // contribution of x5 run on the slice-tiled batch, unet_custom.py:57-66) is done once per
 // input view here; the results are identical because those operands do not depend on the slice.
+#include <cstdlib>
+#include <cstring>
+
 #include "gemm_simt.cuh"
 
 namespace s3d {
@@ -48,6 +51,36 @@ __global__ void k_bn_relu_pool(const float* __restrict__ in, float* __restrict__
       m.w = fmaxf(m.w, fmaf(v.w, sc.w, sh.w));
     }
   *reinterpret_cast<float4*>(out + (((size_t)b * Ho + yo) * Wo + xo) * C + c) = m;
+}
+
+// Same, written in the split-fp16 format the tensor-core convolutions read.
+__global__ void k_bn_relu_pool_split(const float* __restrict__ in, __half* __restrict__ hi, __half* __restrict__ lo,
+                                     const float* __restrict__ scale, const float* __restrict__ shift, int B, int H, int W,
+                                     int C) {
+  const int Ho = H / 2, Wo = W / 2, C4 = C / 4;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long total = (long long)B * Ho * Wo * C4;
+  if (i >= total) return;
+  int c = (int)(i % C4) * 4;
+  long long t = i / C4;
+  int xo = (int)(t % Wo);
+  t /= Wo;
+  int yo = (int)(t % Ho);
+  int b = (int)(t / Ho);
+  float4 sc = *reinterpret_cast<const float4*>(scale + c);
+  float4 sh = *reinterpret_cast<const float4*>(shift + c);
+  float m[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+    for (int dx = 0; dx < 2; ++dx) {
+      float4 v = *reinterpret_cast<const float4*>(in + (((size_t)b * H + 2 * yo + dy) * W + 2 * xo + dx) * C + c);
+      m[0] = fmaxf(m[0], fmaf(v.x, sc.x, sh.x));
+      m[1] = fmaxf(m[1], fmaf(v.y, sc.y, sh.y));
+      m[2] = fmaxf(m[2], fmaf(v.z, sc.z, sh.z));
+      m[3] = fmaxf(m[3], fmaf(v.w, sc.w, sh.w));
+    }
+  store_split4(hi, lo, (((size_t)b * Ho + yo) * Wo + xo) * C + c, m);
 }
 
 // latent[b,k,p,:] = base[b,p,:] + e[k,:]   (trans_c split into its x5 part and its slice-embedding part)
@@ -123,8 +156,17 @@ struct Bump {
 };
 
 struct EncBufs {
-  float *x0, *ta, *tb, *x[6], *base5, *skip[5], *feat[5], *u, *d;
+  float *x0, *ta, *tb, *x[6], *base5, *skip[5], *pskip[5], *feat[5], *u, *d;
 };
+
+// A split-fp16 activation tensor carved from `elems` floats of workspace: hi then lo, `elems` bf16 each.
+struct Split {
+  __half *hi, *lo;
+};
+inline Split split_of(float* base, size_t elems) {
+  __half* h = reinterpret_cast<__half*>(base);
+  return Split{h, h + elems};
+}
 
 // The single place that lays out the encoder workspace; called with base == nullptr to size it.
 void carve(Bump& bp, EncBufs& e, int B, int K, int S) {
@@ -137,9 +179,10 @@ void carve(Bump& bp, EncBufs& e, int B, int K, int S) {
   const int R0 = S / 16;
   e.base5 = bp.take((size_t)B * R0 * R0 * 512);
   for (int n = 1; n <= 4; ++n) e.skip[n] = bp.take((size_t)B * plane_res(S, n) * plane_res(S, n) * kPlaneC[n]);
+  for (int n = 1; n <= 4; ++n) e.pskip[n] = bp.take((size_t)B * plane_res(S, n) * plane_res(S, n) * kPlaneC[n]);
   for (int s = 0; s < 5; ++s) e.feat[s] = bp.take((size_t)B * K * plane_res(S, s) * plane_res(S, s) * kPlaneC[s]);
-  e.u = bp.take((size_t)B * K * S2 * 32);
-  e.d = bp.take((size_t)B * K * S2 * 32);
+  e.u = bp.take((size_t)B * K * S2 * 64);  // (split tensors with the channel pitch padded to 64 at the last stage)
+  e.d = bp.take((size_t)B * K * S2 * 64);
 }
 
 int conv(const ConvW& w, const float* src0, int c0, int bcast0, const float* src1, int c1, int NI, int H, int W,
@@ -157,6 +200,120 @@ int dense(const ConvW& w, const float* a, long long M, float* out, int relu, cud
 
 inline unsigned blocks_for(long long n, int t) { return (unsigned)((n + t - 1) / t); }
 
+
+// The encoder with every 3x3 convolution except the first (3 input channels) on the tensor cores (conv_tc.cu).
+// Activations that feed a tensor-core convolution are written in the split-fp16 format by their producer; the taps
+// x1..x5, the skip adapters and the feature planes stay fp32 (they feed fp32 consumers).  DoubleConv's first
+// convolution over cat([skip, up]) (unet_parts.py:73) is split by input-channel half: the skip half does not depend
+// on the slice, so it is evaluated once per view (fp32 path, B images) and added in the epilogue of the per-slice
+// half (B*K images) -- half of that convolution's work, 12x less of it, same result.
+int trunk_and_up_tc(const s3d_model* m, const float* img, int B, int S, EncBufs& e, cudaStream_t st) {
+  const int K = m->K;
+  const size_t S2 = (size_t)S * S;
+  k_nchw3_to_nhwc4<<<blocks_for((long long)B * S * S, 256), 256, 0, st>>>(img, e.x0, B, S * S);
+  S3D_LAUNCH_CHECK();
+  int H = S;
+  Split sa = split_of(e.ta, B * S2 * 64), sb = split_of(e.tb, B * S2 * 64);
+  {  // down1: conv0 on the fp32 path (K = 27), written split; conv1 -> tap x1 (fp32, pre-BN)
+    const ConvW& w = m->vgg[0];
+    LoadConv L{e.x0, nullptr, B * H * H, w.k, H, H, 4, 0, 1, w.ks};
+    EpiAffineSplit E{sa.hi, sa.lo, w.scale, w.shift, w.ncols, 1};
+    S3D_TRY(launch_gemm(L, w.w, w.ncols, w.kpad, E, st));
+    S3D_TRY(conv_tc(m->tvgg[1], sa.hi, sa.lo, B, H, H, nullptr, 1, 0, e.x[1], 64, nullptr, nullptr, 0, st));
+  }
+  const int first_conv[4] = {2, 4, 7, 10};
+  const int n_conv[4] = {2, 3, 3, 3};
+  const int cprev[4] = {64, 128, 256, 512};
+  for (int b = 0; b < 4; ++b) {
+    long long tot = (long long)B * (H / 2) * (H / 2) * (cprev[b] / 4);
+    H /= 2;
+    Split cur = split_of(e.ta, (size_t)B * H * H * cprev[b]);
+    k_bn_relu_pool_split<<<blocks_for(tot, 256), 256, 0, st>>>(e.x[b + 1], cur.hi, cur.lo, m->bn_scale[b], m->bn_shift[b], B,
+                                                               2 * H, 2 * H, cprev[b]);
+    S3D_LAUNCH_CHECK();
+    float* nxt_base = e.tb;
+    float* cur_base = e.ta;
+    for (int j = 0; j < n_conv[b]; ++j) {
+      const ConvTC& w = m->tvgg[first_conv[b] + j];
+      const bool last = (j == n_conv[b] - 1);
+      if (last) {
+        S3D_TRY(conv_tc(w, cur.hi, cur.lo, B, H, H, nullptr, 1, 0, e.x[b + 2], w.cout, nullptr, nullptr, 0, st));
+      } else {
+        Split nxt = split_of(nxt_base, (size_t)B * H * H * w.cout);
+        S3D_TRY(conv_tc(w, cur.hi, cur.lo, B, H, H, nullptr, 1, 1, nullptr, 0, nxt.hi, nxt.lo, w.cout, st));
+        cur = nxt;
+        float* t = cur_base;
+        cur_base = nxt_base;
+        nxt_base = t;
+      }
+    }
+  }
+  // latent = trans_c(cat[x5 tiled, slice embedding]) (unet_custom.py:52-57) -> feat[0]
+  const int R0 = S / 16;
+  S3D_TRY(dense(m->trans_c, e.x[5], (long long)B * R0 * R0, e.base5, 0, st));
+  {
+    long long tot = (long long)B * K * R0 * R0 * (512 / 4);
+    k_add_slice_bias<<<blocks_for(tot, 256), 256, 0, st>>>(e.base5, m->trans_c_e, e.feat[0], B, K, R0 * R0, 512);
+    S3D_LAUNCH_CHECK();
+  }
+  for (int n = 1; n <= 4; ++n) {
+    const int Rp = plane_res(S, n - 1), R = plane_res(S, n), C = kPlaneC[n];
+    const int CP = C < 64 ? 64 : C;  // channel pitch of the split tensors
+    const size_t elems = (size_t)B * K * R * R * CP;
+    Split su = split_of(e.u, elems), sd = split_of(e.d, elems);
+    // skip adapter on the un-tiled tap, then the skip half of DoubleConv's first convolution (raw sums)
+    S3D_TRY(dense(m->trans_up[n - 1], e.x[5 - n], (long long)B * R * R, e.skip[n], 0, st));
+    {
+      const ConvW& w = m->dc1s[n - 1];
+      LoadConv L{e.skip[n], nullptr, B * R * R, w.k, R, R, C, 0, 1, w.ks};
+      EpiAffine E{e.pskip[n], nullptr, nullptr, w.ncols, 0};
+      S3D_TRY(launch_gemm(L, w.w, w.ncols, w.kpad, E, st));
+    }
+    if (CP != C) S3D_CUDA(cudaMemsetAsync(e.u, 0, elems * 4, st));  // zero channel padding of `up`
+    {  // ConvTranspose2d 2x2 s2: GEMM with N = 4*C + pixel shuffle, written split
+      const ConvW& w = m->up_t[n - 1];
+      LoadPlain L{e.feat[n - 1], B * K * Rp * Rp, w.k, w.k};
+      EpiShuffle2xSplit E{su.hi, su.lo, w.shift, Rp, Rp, C, CP};
+      S3D_TRY(launch_gemm(L, w.w, w.ncols, w.kpad, E, st));
+    }
+    S3D_TRY(conv_tc(m->tdc1[n - 1], su.hi, su.lo, B * K, R, R, e.pskip[n], K, 1, nullptr, 0, sd.hi, sd.lo, CP, st));
+    S3D_TRY(conv_tc(m->tdc2[n - 1], sd.hi, sd.lo, B * K, R, R, nullptr, 1, 1, e.feat[n], C, nullptr, nullptr, 0, st));
+  }
+  return S3D_OK;
+}
+
+}  // namespace
+
+// Weight images of the tensor-core convolutions + the skip half of each DoubleConv (see trunk_and_up_tc).
+int enctc_pack(s3d_model* m, cudaStream_t st) {
+  const char* env = getenv("S3D_ENCODER");
+  m->enc_simt = (env && std::string(env) == "simt") ? 1 : 0;
+  for (int i = 1; i < 13; ++i) S3D_TRY(convtc_pack(m, m->vgg[i], m->vgg[i].cin, 0, m->vgg[i].cin, m->tvgg[i], st));
+  for (int n = 0; n < 4; ++n) {
+    const int C = kPlaneC[n + 1];
+    const ConvW& d1 = m->dc1[n];
+    S3D_TRY(convtc_pack(m, d1, 2 * C, C, C, m->tdc1[n], st));  // input channels [C, 2C) = the up-sampled half
+    S3D_TRY(convtc_pack(m, m->dc2[n], C, 0, C, m->tdc2[n], st));
+    // skip half: fp32 [9*C][C], raw sums (scale/shift are applied by the per-slice half's epilogue)
+    std::vector<float> h((size_t)d1.kpad * C), t((size_t)9 * C * C);
+    S3D_CUDA(cudaMemcpyAsync(h.data(), d1.w, h.size() * sizeof(float), cudaMemcpyDeviceToHost, st));
+    S3D_CUDA(cudaStreamSynchronize(st));
+    for (int tap = 0; tap < 9; ++tap)
+      for (int ci = 0; ci < C; ++ci)
+        std::memcpy(&t[((size_t)tap * C + ci) * C], &h[((size_t)tap * 2 * C + ci) * C], C * sizeof(float));
+    void* d = nullptr;
+    S3D_CUDA(cudaMalloc(&d, t.size() * sizeof(float)));
+    m->allocs.push_back(d);
+    S3D_CUDA(cudaMemcpyAsync(d, t.data(), t.size() * sizeof(float), cudaMemcpyHostToDevice, st));
+    S3D_CUDA(cudaStreamSynchronize(st));
+    ConvW& s = m->dc1s[n];
+    s.w = static_cast<float*>(d);
+    s.cin = C; s.ncols = C; s.ks = 3; s.k = 9 * C; s.kpad = 9 * C;
+  }
+  return S3D_OK;
+}
+
+namespace {
 }  // namespace
 
 size_t encoder_workspace_bytes(int B, int K, int S) {
@@ -185,63 +342,67 @@ int encoder_fwd(const s3d_model* m, const float* img, int B, int S, void* planes
   EncBufs e;
   carve(bp, e, B, K, S);
 
-  // ---- VGG16-BN trunk on the input view (unet_custom.py:42-48); taps x1..x5 are the
-  //      pre-BN outputs of the last convolution of each block (unet_custom.py:15-19).
-  k_nchw3_to_nhwc4<<<blocks_for((long long)B * S * S, 256), 256, 0, st>>>(img, e.x0, B, S * S);
-  S3D_LAUNCH_CHECK();
-  int H = S;
-  // down1
-  S3D_TRY(conv(m->vgg[0], e.x0, 4, 1, nullptr, 0, B, H, H, e.ta, 1, st));
-  S3D_TRY(conv(m->vgg[1], e.ta, 64, 1, nullptr, 0, B, H, H, e.x[1], 0, st));
-  // down2..down5: BN+ReLU+pool on the previous tap, then 2 or 3 convolutions
-  const int first_conv[4] = {2, 4, 7, 10};
-  const int n_conv[4] = {2, 3, 3, 3};
-  const int cprev[4] = {64, 128, 256, 512};
-  for (int b = 0; b < 4; ++b) {
-    long long tot = (long long)B * (H / 2) * (H / 2) * (cprev[b] / 4);
-    k_bn_relu_pool<<<blocks_for(tot, 256), 256, 0, st>>>(e.x[b + 1], e.ta, m->bn_scale[b], m->bn_shift[b], B, H, H,
-                                                         cprev[b]);
+  if (!m->enc_simt) {
+    S3D_TRY(trunk_and_up_tc(m, img, B, S, e, st));
+  } else {
+    // ---- VGG16-BN trunk on the input view (unet_custom.py:42-48); taps x1..x5 are the
+    //      pre-BN outputs of the last convolution of each block (unet_custom.py:15-19).
+    k_nchw3_to_nhwc4<<<blocks_for((long long)B * S * S, 256), 256, 0, st>>>(img, e.x0, B, S * S);
     S3D_LAUNCH_CHECK();
-    H /= 2;
-    float* cur = e.ta;
-    float* nxt = e.tb;
-    int cin = cprev[b];
-    for (int j = 0; j < n_conv[b]; ++j) {
-      const ConvW& w = m->vgg[first_conv[b] + j];
-      bool last = (j == n_conv[b] - 1);
-      float* dst = last ? e.x[b + 2] : nxt;
-      S3D_TRY(conv(w, cur, cin, 1, nullptr, 0, B, H, H, dst, last ? 0 : 1, st));
-      cin = w.ncols;
-      if (!last) {
-        float* t = cur;
-        cur = nxt;
-        nxt = t;
+    int H = S;
+    // down1
+    S3D_TRY(conv(m->vgg[0], e.x0, 4, 1, nullptr, 0, B, H, H, e.ta, 1, st));
+    S3D_TRY(conv(m->vgg[1], e.ta, 64, 1, nullptr, 0, B, H, H, e.x[1], 0, st));
+    // down2..down5: BN+ReLU+pool on the previous tap, then 2 or 3 convolutions
+    const int first_conv[4] = {2, 4, 7, 10};
+    const int n_conv[4] = {2, 3, 3, 3};
+    const int cprev[4] = {64, 128, 256, 512};
+    for (int b = 0; b < 4; ++b) {
+      long long tot = (long long)B * (H / 2) * (H / 2) * (cprev[b] / 4);
+      k_bn_relu_pool<<<blocks_for(tot, 256), 256, 0, st>>>(e.x[b + 1], e.ta, m->bn_scale[b], m->bn_shift[b], B, H, H,
+                                                           cprev[b]);
+      S3D_LAUNCH_CHECK();
+      H /= 2;
+      float* cur = e.ta;
+      float* nxt = e.tb;
+      int cin = cprev[b];
+      for (int j = 0; j < n_conv[b]; ++j) {
+        const ConvW& w = m->vgg[first_conv[b] + j];
+        bool last = (j == n_conv[b] - 1);
+        float* dst = last ? e.x[b + 2] : nxt;
+        S3D_TRY(conv(w, cur, cin, 1, nullptr, 0, B, H, H, dst, last ? 0 : 1, st));
+        cin = w.ncols;
+        if (!last) {
+          float* t = cur;
+          cur = nxt;
+          nxt = t;
+        }
       }
     }
-  }
-  // ---- latent = trans_c(cat[x5 tiled, slice embedding]) (unet_custom.py:52-57) -> feat[0]
-  const int R0 = S / 16;
-  S3D_TRY(dense(m->trans_c, e.x[5], (long long)B * R0 * R0, e.base5, 0, st));
-  {
-    long long tot = (long long)B * K * R0 * R0 * (512 / 4);
-    k_add_slice_bias<<<blocks_for(tot, 256), 256, 0, st>>>(e.base5, m->trans_c_e, e.feat[0], B, K, R0 * R0, 512);
-    S3D_LAUNCH_CHECK();
-  }
-  // ---- four Up stages (unet_custom.py:60-66, unet_parts.py:57-75)
-  for (int n = 1; n <= 4; ++n) {
-    const int Rp = plane_res(S, n - 1), R = plane_res(S, n), C = kPlaneC[n];
-    // skip adapter on the un-tiled tap x_{5-n}
-    S3D_TRY(dense(m->trans_up[n - 1], e.x[5 - n], (long long)B * R * R, e.skip[n], 0, st));
-    // ConvTranspose2d 2x2 s2: GEMM with N = 4*C + pixel shuffle
+    // ---- latent = trans_c(cat[x5 tiled, slice embedding]) (unet_custom.py:52-57) -> feat[0]
+    const int R0 = S / 16;
+    S3D_TRY(dense(m->trans_c, e.x[5], (long long)B * R0 * R0, e.base5, 0, st));
     {
-      const ConvW& w = m->up_t[n - 1];
-      LoadPlain L{e.feat[n - 1], B * K * Rp * Rp, w.k, w.k};
-      EpiShuffle2x E{e.u, w.shift, Rp, Rp, C};
-      S3D_TRY(launch_gemm(L, w.w, w.ncols, w.kpad, E, st));
+      long long tot = (long long)B * K * R0 * R0 * (512 / 4);
+      k_add_slice_bias<<<blocks_for(tot, 256), 256, 0, st>>>(e.base5, m->trans_c_e, e.feat[0], B, K, R0 * R0, 512);
+      S3D_LAUNCH_CHECK();
     }
-    // DoubleConv on cat([skip, up]) (skip first: unet_parts.py:73)
-    S3D_TRY(conv(m->dc1[n - 1], e.skip[n], C, K, e.u, C, B * K, R, R, e.d, 1, st));
-    S3D_TRY(conv(m->dc2[n - 1], e.d, C, 1, nullptr, 0, B * K, R, R, e.feat[n], 1, st));
+    // ---- four Up stages (unet_custom.py:60-66, unet_parts.py:57-75)
+    for (int n = 1; n <= 4; ++n) {
+      const int Rp = plane_res(S, n - 1), R = plane_res(S, n), C = kPlaneC[n];
+      // skip adapter on the un-tiled tap x_{5-n}
+      S3D_TRY(dense(m->trans_up[n - 1], e.x[5 - n], (long long)B * R * R, e.skip[n], 0, st));
+      // ConvTranspose2d 2x2 s2: GEMM with N = 4*C + pixel shuffle
+      {
+        const ConvW& w = m->up_t[n - 1];
+        LoadPlain L{e.feat[n - 1], B * K * Rp * Rp, w.k, w.k};
+        EpiShuffle2x E{e.u, w.shift, Rp, Rp, C};
+        S3D_TRY(launch_gemm(L, w.w, w.ncols, w.kpad, E, st));
+      }
+      // DoubleConv on cat([skip, up]) (skip first: unet_parts.py:73)
+      S3D_TRY(conv(m->dc1[n - 1], e.skip[n], C, K, e.u, C, B * K, R, R, e.d, 1, st));
+      S3D_TRY(conv(m->dc2[n - 1], e.d, C, 1, nullptr, 0, B * K, R, R, e.feat[n], 1, st));
+    }
   }
   // ---- outputs
   if (slices_rec) {

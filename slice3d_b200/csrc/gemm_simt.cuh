@@ -119,6 +119,60 @@ struct EpiShuffle2x {
   }
 };
 
+// Split-fp16 variants (hi = fp16(x) saturated, lo = fp16(x - hi); x = hi + lo + O(2^-22 |x|)): producers of the
+// tensor-core convolutions' inputs (conv_tc.cu).  ldc = channel pitch of the split tensor.
+__device__ __forceinline__ void store_split4(__half* hi, __half* lo, size_t o, const float* r) {
+  float c[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) c[i] = fminf(fmaxf(r[i], -65504.f), 65504.f);
+  const __half2 h01 = __floats2half2_rn(c[0], c[1]), h23 = __floats2half2_rn(c[2], c[3]);
+  const __half2 l01 = __floats2half2_rn(r[0] - __low2float(h01), r[1] - __high2float(h01));
+  const __half2 l23 = __floats2half2_rn(r[2] - __low2float(h23), r[3] - __high2float(h23));
+  uint2 hv, lv;
+  hv.x = *reinterpret_cast<const uint32_t*>(&h01); hv.y = *reinterpret_cast<const uint32_t*>(&h23);
+  lv.x = *reinterpret_cast<const uint32_t*>(&l01); lv.y = *reinterpret_cast<const uint32_t*>(&l23);
+  *reinterpret_cast<uint2*>(hi + o) = hv;
+  *reinterpret_cast<uint2*>(lo + o) = lv;
+}
+
+struct EpiAffineSplit {
+  __half* hi;
+  __half* lo;
+  const float* scale;
+  const float* shift;
+  int ldc, relu;
+  __device__ __forceinline__ void operator()(int m, int n, const float* v) const {
+    float r[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float t = v[i];
+      if (scale) t *= __ldg(scale + n + i);
+      if (shift) t += __ldg(shift + n + i);
+      if (relu) t = fmaxf(t, 0.f);
+      r[i] = t;
+    }
+    store_split4(hi, lo, (size_t)m * ldc + n, r);
+  }
+};
+
+struct EpiShuffle2xSplit {  // EpiShuffle2x writing the split format with channel pitch ldc >= Cout
+  __half* hi;
+  __half* lo;
+  const float* bias;
+  int H, W, Cout, ldc;
+  __device__ __forceinline__ void operator()(int m, int n, const float* v) const {
+    int x = m % W;
+    int t = m / W;
+    int y = t % H, img = t / H;
+    int q = n / Cout, co = n - q * Cout;
+    int dy = q >> 1, dx = q & 1;
+    const float r[4] = {v[0] + __ldg(bias + co), v[1] + __ldg(bias + co + 1), v[2] + __ldg(bias + co + 2),
+                        v[3] + __ldg(bias + co + 3)};
+    size_t o = (((size_t)img * (2 * H) + (2 * y + dy)) * (2 * W) + (2 * x + dx)) * ldc + co;
+    store_split4(hi, lo, o, r);
+  }
+};
+
 // ---------------------------------------------------------------- kernel
 template <int BN, class Loader, class Epi>
 __global__ void __launch_bounds__(GM_THREADS) gemm_simt_kernel(Loader L, const float* __restrict__ Wt, int N, int Kpad,

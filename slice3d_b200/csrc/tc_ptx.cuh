@@ -3,6 +3,7 @@
 // and the UMMA shared-memory + instruction descriptors.
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 
 namespace s3d {
@@ -330,6 +331,22 @@ __device__ __forceinline__ void split8(const float* v, uint32_t* h, uint32_t* l)
       l[i] = *reinterpret_cast<const uint32_t*>(&l2);
     }
   }
+}
+// fp16 flavour (the encoder's split activations): x = hi + lo + O(2^-22 |x|) for |x| within the fp16 range;
+// hi saturates at the largest finite fp16 instead of overflowing to infinity.
+__device__ __forceinline__ void split8_h(const float* v, uint32_t* h, uint32_t* l) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float a = fminf(fmaxf(v[2 * i], -65504.f), 65504.f), b = fminf(fmaxf(v[2 * i + 1], -65504.f), 65504.f);
+    const __half2 h2 = __floats2half2_rn(a, b);
+    h[i] = *reinterpret_cast<const uint32_t*>(&h2);
+    const __half2 l2 = __floats2half2_rn(v[2 * i] - __low2float(h2), v[2 * i + 1] - __high2float(h2));
+    l[i] = *reinterpret_cast<const uint32_t*>(&l2);
+  }
+}
+// Instruction descriptor, kind::f16 with fp16 operands (both K-major), fp32 accumulate.
+__host__ __device__ constexpr uint32_t make_idesc_f16(int n, int m = 128) {
+  return (1u << 4) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
 }
 __device__ __forceinline__ uint32_t pack2(__nv_bfloat16 a, __nv_bfloat16 b) {
   return static_cast<uint32_t>(__bfloat16_as_ushort(a)) | (static_cast<uint32_t>(__bfloat16_as_ushort(b)) << 16);
