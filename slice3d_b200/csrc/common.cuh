@@ -117,7 +117,8 @@ struct s3d_model {
   // tensor-core encoder (conv_tc.cu): the 3x3 convolutions; dc1 is split into its slice-independent skip half
   // (dc1s, run once per view on the fp32 path) and its per-slice half (tdc1)
   s3d::ConvTC tvgg[13];        // [0] unused (3 input channels: fp32 path)
-  s3d::ConvTC tdc1[4], tdc2[4];
+  s3d::ConvTC tdc1[4], tdc2[4], tdc1s[4];
+  s3d::ConvTC ttrans_c, ttrans_up[4], tup_t[4], tfcs[5];  // the 1x1 / transposed convolutions and the fc_s projection
   s3d::ConvW dc1s[4];
   int enc_simt = 0;            // S3D_ENCODER=simt: whole encoder on the fp32 CUDA-core path (debugging)
   // decoder
@@ -147,7 +148,8 @@ size_t encoder_workspace_bytes(int B, int K, int S);
 // conv_tc.cu
 int convtc_pack(s3d_model* m, const ConvW& cw, int src_cin, int ci0, int cin, ConvTC& out, cudaStream_t st);
 int conv_tc(const ConvTC& w, const __half* in_hi, const __half* in_lo, int NI, int H, int W, const float* add,
-            int add_div, int relu, float* out_f32, int ldf, __half* out_hi, __half* out_lo, int lds, cudaStream_t st);
+            int add_div, int relu, float* out_f32, int ldf, __half* out_hi, __half* out_lo, int lds, cudaStream_t st,
+            int shuffle_c = 0);
 int enctc_pack(s3d_model* m, cudaStream_t st);
 
 // ---- queries ----------------------------------------------------------------------

@@ -52,6 +52,9 @@ struct ConvTcParams {
   const float* add;  // optional fp32 [NI / add_div][H][W][Cout], added before scale/shift
   int add_div;
   int relu;
+  int shuffle;      // ConvTranspose2d(k=2, s=2) as a 1x1 "convolution" with N = 4*C (n = (dy*2+dx)*C + co): column n of
+                    // pixel (y, x) goes to channel co of pixel (2y+dy, 2x+dx) of a 2H x 2W image; shift is indexed by co
+  int Cq;           // shuffle: C
   float acc_scale;  // 2^-e: the weights are packed as w * 2^e
   float* out_f32;  // fp32 NHWC, row pitch ldf (or null)
   int ldf;
@@ -211,20 +214,27 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
       for (int j = 0; j < NC / 32; ++j) {
         float* v = acc + 32 * j;
         const int n0 = n_tile * BN + ch * NC + 32 * j;
+        int nb = n0;         // index into scale / shift / add and output channel
+        size_t opix = pix;   // output pixel
+        if (p.shuffle) {
+          const int qd = n0 / p.Cq;
+          nb = n0 - qd * p.Cq;
+          opix = ((size_t)img * (2 * p.H) + (2 * y + (qd >> 1))) * (2 * p.W) + (2 * x + (qd & 1));
+        }
         if (n0 < p.Cout) {
 #pragma unroll
           for (int c = 0; c < 32; c += 4) {
             float4 t = make_float4(v[c] * p.acc_scale, v[c + 1] * p.acc_scale, v[c + 2] * p.acc_scale, v[c + 3] * p.acc_scale);
             if (addp) {
-              const float4 a4 = __ldg(reinterpret_cast<const float4*>(addp + n0 + c));
+              const float4 a4 = __ldg(reinterpret_cast<const float4*>(addp + nb + c));
               t.x += a4.x; t.y += a4.y; t.z += a4.z; t.w += a4.w;
             }
             if (p.scale) {
-              const float4 s4 = __ldg(reinterpret_cast<const float4*>(p.scale + n0 + c));
+              const float4 s4 = __ldg(reinterpret_cast<const float4*>(p.scale + nb + c));
               t.x *= s4.x; t.y *= s4.y; t.z *= s4.z; t.w *= s4.w;
             }
             if (p.shift) {
-              const float4 s4 = __ldg(reinterpret_cast<const float4*>(p.shift + n0 + c));
+              const float4 s4 = __ldg(reinterpret_cast<const float4*>(p.shift + nb + c));
               t.x += s4.x; t.y += s4.y; t.z += s4.z; t.w += s4.w;
             }
             if (p.relu) {
@@ -233,13 +243,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
             v[c] = t.x; v[c + 1] = t.y; v[c + 2] = t.z; v[c + 3] = t.w;
           }
           if (p.out_f32) {
-            float4* dst = reinterpret_cast<float4*>(p.out_f32 + pix * p.ldf + n0);
+            float4* dst = reinterpret_cast<float4*>(p.out_f32 + opix * p.ldf + nb);
 #pragma unroll
             for (int c = 0; c < 8; ++c) dst[c] = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
           }
           if (p.out_hi) {
-            uint4* dh = reinterpret_cast<uint4*>(p.out_hi + pix * p.lds + n0);
-            uint4* dl = reinterpret_cast<uint4*>(p.out_lo + pix * p.lds + n0);
+            uint4* dh = reinterpret_cast<uint4*>(p.out_hi + opix * p.lds + nb);
+            uint4* dl = reinterpret_cast<uint4*>(p.out_lo + opix * p.lds + nb);
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
               uint32_t h[4], l[4];
@@ -248,7 +258,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
               dl[c] = make_uint4(l[0], l[1], l[2], l[3]);
             }
           }
-        } else if (p.out_hi && n0 < p.lds) {  // zero the channel padding the next convolution's TMA will read
+        } else if (p.out_hi && !p.shuffle && n0 < p.lds) {  // zero the channel padding the next convolution's TMA will read
           uint4* dh = reinterpret_cast<uint4*>(p.out_hi + pix * p.lds + n0);
           uint4* dl = reinterpret_cast<uint4*>(p.out_lo + pix * p.lds + n0);
 #pragma unroll
@@ -374,7 +384,7 @@ int convtc_pack(s3d_model* m, const ConvW& cw, int src_cin, int ci0, int cin, Co
 // in: split NHWC [NI][H][W][w.cinp] (hi, lo).  Outputs: fp32 NHWC (pitch ldf) and / or split NHWC (pitch lds).
 int conv_tc(const ConvTC& w, const __half* in_hi, const __half* in_lo, int NI, int H, int W, const float* add,
             int add_div, int relu, float* out_f32, int ldf, __half* out_hi, __half* out_lo, int lds,
-            cudaStream_t st) {
+            cudaStream_t st, int shuffle_c) {
   if (NI <= 0) return S3D_OK;
   int BW = 1, lg = 0;
   while (BW * 2 <= W && BW < 128) {
@@ -395,6 +405,8 @@ int conv_tc(const ConvTC& w, const __half* in_hi, const __half* in_lo, int NI, i
   p.scale = w.scale; p.shift = w.shift;
   p.add = add; p.add_div = add_div > 0 ? add_div : 1;
   p.relu = relu;
+  p.shuffle = shuffle_c > 0 ? 1 : 0;
+  p.Cq = shuffle_c > 0 ? shuffle_c : 1;
   p.acc_scale = w.acc_scale;
   p.out_f32 = out_f32; p.ldf = ldf;
   p.out_hi = out_hi; p.out_lo = out_lo; p.lds = lds;

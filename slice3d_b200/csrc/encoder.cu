@@ -85,7 +85,8 @@ __global__ void k_bn_relu_pool_split(const float* __restrict__ in, __half* __res
 
 // latent[b,k,p,:] = base[b,p,:] + e[k,:]   (trans_c split into its x5 part and its slice-embedding part)
 __global__ void k_add_slice_bias(const float* __restrict__ base, const float* __restrict__ e, float* __restrict__ out,
-                                 int B, int K, int HW, int C) {
+                                 int B, int K, int HW, int C, __half* __restrict__ hi = nullptr,
+                                 __half* __restrict__ lo = nullptr) {
   const int C4 = C / 4;
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long total = (long long)B * K * HW * C4;
@@ -98,7 +99,9 @@ __global__ void k_add_slice_bias(const float* __restrict__ base, const float* __
   int b = (int)(t / K);
   float4 a = *reinterpret_cast<const float4*>(base + ((size_t)b * HW + p) * C + c);
   float4 v = *reinterpret_cast<const float4*>(e + (size_t)k * C + c);
-  *reinterpret_cast<float4*>(out + i * 4) = make_float4(a.x + v.x, a.y + v.y, a.z + v.z, a.w + v.w);
+  const float r[4] = {a.x + v.x, a.y + v.y, a.z + v.z, a.w + v.w};
+  *reinterpret_cast<float4*>(out + i * 4) = make_float4(r[0], r[1], r[2], r[3]);
+  if (hi) store_split4(hi, lo, (size_t)i * 4, r);
 }
 
 // slices_rec = tanh(conv1x1 32->3) written NCHW (unet_parts.py:78-84).
@@ -157,6 +160,7 @@ struct Bump {
 
 struct EncBufs {
   float *x0, *ta, *tb, *x[6], *base5, *skip[5], *pskip[5], *feat[5], *u, *d;
+  float *xs[6], *fs[5];  // split copies of the taps / feature planes (inputs of tensor-core GEMMs)
 };
 
 // A split-fp16 activation tensor carved from `elems` floats of workspace: hi then lo, `elems` bf16 each.
@@ -178,7 +182,11 @@ void carve(Bump& bp, EncBufs& e, int B, int K, int S) {
   for (int i = 1; i <= 5; ++i) e.x[i] = bp.take(B * (S2 >> (2 * (i - 1))) * xc[i]);
   const int R0 = S / 16;
   e.base5 = bp.take((size_t)B * R0 * R0 * 512);
-  for (int n = 1; n <= 4; ++n) e.skip[n] = bp.take((size_t)B * plane_res(S, n) * plane_res(S, n) * kPlaneC[n]);
+  for (int i = 1; i <= 5; ++i) e.xs[i] = bp.take(B * (S2 >> (2 * (i - 1))) * xc[i]);
+  for (int s = 0; s < 5; ++s)
+    e.fs[s] = bp.take((size_t)B * K * plane_res(S, s) * plane_res(S, s) * (kPlaneC[s] < 64 ? 64 : kPlaneC[s]));
+  for (int n = 1; n <= 4; ++n)
+    e.skip[n] = bp.take((size_t)B * plane_res(S, n) * plane_res(S, n) * (kPlaneC[n] < 64 ? 64 : kPlaneC[n]));
   for (int n = 1; n <= 4; ++n) e.pskip[n] = bp.take((size_t)B * plane_res(S, n) * plane_res(S, n) * kPlaneC[n]);
   for (int s = 0; s < 5; ++s) e.feat[s] = bp.take((size_t)B * K * plane_res(S, s) * plane_res(S, s) * kPlaneC[s]);
   e.u = bp.take((size_t)B * K * S2 * 64);  // (split tensors with the channel pitch padded to 64 at the last stage)
@@ -201,25 +209,29 @@ int dense(const ConvW& w, const float* a, long long M, float* out, int relu, cud
 inline unsigned blocks_for(long long n, int t) { return (unsigned)((n + t - 1) / t); }
 
 
-// The encoder with every 3x3 convolution except the first (3 input channels) on the tensor cores (conv_tc.cu).
-// Activations that feed a tensor-core convolution are written in the split-fp16 format by their producer; the taps
-// x1..x5, the skip adapters and the feature planes stay fp32 (they feed fp32 consumers).  DoubleConv's first
-// convolution over cat([skip, up]) (unet_parts.py:73) is split by input-channel half: the skip half does not depend
-// on the slice, so it is evaluated once per view (fp32 path, B images) and added in the epilogue of the per-slice
-// half (B*K images) -- half of that convolution's work, 12x less of it, same result.
+// The encoder on the tensor cores (conv_tc.cu): every convolution except the first (3 input channels), the
+// transposed convolutions, the 1x1 adapters and the hoisted fc_s projection.  Activations that feed a tensor-core
+// GEMM are written in the split-fp16 format by their producer; taps and feature planes are also kept in fp32 for
+// their fp32 consumers (BatchNorm+pool, tanh head, export).  DoubleConv's first convolution over cat([skip, up])
+// (unet_parts.py:73) is split by input-channel half: the skip half does not depend on the slice, so it is evaluated
+// once per view (B images) and added in the epilogue of the per-slice half (B*K images) -- half of that
+// convolution's work, 12x less of it, same result.
 int trunk_and_up_tc(const s3d_model* m, const float* img, int B, int S, EncBufs& e, cudaStream_t st) {
   const int K = m->K;
   const size_t S2 = (size_t)S * S;
   k_nchw3_to_nhwc4<<<blocks_for((long long)B * S * S, 256), 256, 0, st>>>(img, e.x0, B, S * S);
   S3D_LAUNCH_CHECK();
   int H = S;
-  Split sa = split_of(e.ta, B * S2 * 64), sb = split_of(e.tb, B * S2 * 64);
-  {  // down1: conv0 on the fp32 path (K = 27), written split; conv1 -> tap x1 (fp32, pre-BN)
+  const int xc[6] = {0, 64, 128, 256, 512, 512};
+  auto xs_of = [&](int i) { return split_of(e.xs[i], B * (S2 >> (2 * (i - 1))) * xc[i]); };
+  Split sa = split_of(e.ta, B * S2 * 64);
+  {  // down1: conv0 on the fp32 path (K = 27), written split; conv1 -> tap x1 (pre-BN)
     const ConvW& w = m->vgg[0];
     LoadConv L{e.x0, nullptr, B * H * H, w.k, H, H, 4, 0, 1, w.ks};
     EpiAffineSplit E{sa.hi, sa.lo, w.scale, w.shift, w.ncols, 1};
     S3D_TRY(launch_gemm(L, w.w, w.ncols, w.kpad, E, st));
-    S3D_TRY(conv_tc(m->tvgg[1], sa.hi, sa.lo, B, H, H, nullptr, 1, 0, e.x[1], 64, nullptr, nullptr, 0, st));
+    Split x1 = xs_of(1);
+    S3D_TRY(conv_tc(m->tvgg[1], sa.hi, sa.lo, B, H, H, nullptr, 1, 0, e.x[1], 64, x1.hi, x1.lo, 64, st));
   }
   const int first_conv[4] = {2, 4, 7, 10};
   const int n_conv[4] = {2, 3, 3, 3};
@@ -237,7 +249,8 @@ int trunk_and_up_tc(const s3d_model* m, const float* img, int B, int S, EncBufs&
       const ConvTC& w = m->tvgg[first_conv[b] + j];
       const bool last = (j == n_conv[b] - 1);
       if (last) {
-        S3D_TRY(conv_tc(w, cur.hi, cur.lo, B, H, H, nullptr, 1, 0, e.x[b + 2], w.cout, nullptr, nullptr, 0, st));
+        Split xo = xs_of(b + 2);
+        S3D_TRY(conv_tc(w, cur.hi, cur.lo, B, H, H, nullptr, 1, 0, e.x[b + 2], w.cout, xo.hi, xo.lo, w.cout, st));
       } else {
         Split nxt = split_of(nxt_base, (size_t)B * H * H * w.cout);
         S3D_TRY(conv_tc(w, cur.hi, cur.lo, B, H, H, nullptr, 1, 1, nullptr, 0, nxt.hi, nxt.lo, w.cout, st));
@@ -250,10 +263,16 @@ int trunk_and_up_tc(const s3d_model* m, const float* img, int B, int S, EncBufs&
   }
   // latent = trans_c(cat[x5 tiled, slice embedding]) (unet_custom.py:52-57) -> feat[0]
   const int R0 = S / 16;
-  S3D_TRY(dense(m->trans_c, e.x[5], (long long)B * R0 * R0, e.base5, 0, st));
+  auto fs_of = [&](int s) {
+    const int R = plane_res(S, s), CP = kPlaneC[s] < 64 ? 64 : kPlaneC[s];
+    return split_of(e.fs[s], (size_t)B * K * R * R * CP);
+  };
   {
+    Split x5 = xs_of(5);
+    S3D_TRY(conv_tc(m->ttrans_c, x5.hi, x5.lo, B, R0, R0, nullptr, 1, 0, e.base5, 512, nullptr, nullptr, 0, st));
     long long tot = (long long)B * K * R0 * R0 * (512 / 4);
-    k_add_slice_bias<<<blocks_for(tot, 256), 256, 0, st>>>(e.base5, m->trans_c_e, e.feat[0], B, K, R0 * R0, 512);
+    Split f0 = fs_of(0);
+    k_add_slice_bias<<<blocks_for(tot, 256), 256, 0, st>>>(e.base5, m->trans_c_e, e.feat[0], B, K, R0 * R0, 512, f0.hi, f0.lo);
     S3D_LAUNCH_CHECK();
   }
   for (int n = 1; n <= 4; ++n) {
@@ -261,24 +280,33 @@ int trunk_and_up_tc(const s3d_model* m, const float* img, int B, int S, EncBufs&
     const int CP = C < 64 ? 64 : C;  // channel pitch of the split tensors
     const size_t elems = (size_t)B * K * R * R * CP;
     Split su = split_of(e.u, elems), sd = split_of(e.d, elems);
+    Split sk = split_of(e.skip[n], (size_t)B * R * R * CP);
+    Split xin = xs_of(5 - n), fin = fs_of(n - 1), fout = fs_of(n);
     // skip adapter on the un-tiled tap, then the skip half of DoubleConv's first convolution (raw sums)
-    S3D_TRY(dense(m->trans_up[n - 1], e.x[5 - n], (long long)B * R * R, e.skip[n], 0, st));
-    {
-      const ConvW& w = m->dc1s[n - 1];
-      LoadConv L{e.skip[n], nullptr, B * R * R, w.k, R, R, C, 0, 1, w.ks};
-      EpiAffine E{e.pskip[n], nullptr, nullptr, w.ncols, 0};
-      S3D_TRY(launch_gemm(L, w.w, w.ncols, w.kpad, E, st));
-    }
+    S3D_TRY(conv_tc(m->ttrans_up[n - 1], xin.hi, xin.lo, B, R, R, nullptr, 1, 0, nullptr, 0, sk.hi, sk.lo, CP, st));
+    S3D_TRY(conv_tc(m->tdc1s[n - 1], sk.hi, sk.lo, B, R, R, nullptr, 1, 0, e.pskip[n], C, nullptr, nullptr, 0, st));
+    // ConvTranspose2d 2x2 s2: 1x1 GEMM with N = 4*C + pixel shuffle
     if (CP != C) S3D_CUDA(cudaMemsetAsync(e.u, 0, elems * 4, st));  // zero channel padding of `up`
-    {  // ConvTranspose2d 2x2 s2: GEMM with N = 4*C + pixel shuffle, written split
-      const ConvW& w = m->up_t[n - 1];
-      LoadPlain L{e.feat[n - 1], B * K * Rp * Rp, w.k, w.k};
-      EpiShuffle2xSplit E{su.hi, su.lo, w.shift, Rp, Rp, C, CP};
-      S3D_TRY(launch_gemm(L, w.w, w.ncols, w.kpad, E, st));
-    }
+    S3D_TRY(conv_tc(m->tup_t[n - 1], fin.hi, fin.lo, B * K, Rp, Rp, nullptr, 1, 0, nullptr, 0, su.hi, su.lo, CP, st, C));
+    // DoubleConv: per-slice half of the first convolution (+ skip half, BN, ReLU), then the second convolution
     S3D_TRY(conv_tc(m->tdc1[n - 1], su.hi, su.lo, B * K, R, R, e.pskip[n], K, 1, nullptr, 0, sd.hi, sd.lo, CP, st));
-    S3D_TRY(conv_tc(m->tdc2[n - 1], sd.hi, sd.lo, B * K, R, R, nullptr, 1, 1, e.feat[n], C, nullptr, nullptr, 0, st));
+    S3D_TRY(conv_tc(m->tdc2[n - 1], sd.hi, sd.lo, B * K, R, R, nullptr, 1, 1, e.feat[n], C, fout.hi, fout.lo, CP, st));
   }
+  return S3D_OK;
+}
+
+// Hoisted fc_s (models.py:80): plane_s = fc_s[:, scale-s columns] applied to feature plane s, a 1x1 GEMM per scale.
+int project_planes_tc(const s3d_model* m, int B, int S, EncBufs& e, float* pl, cudaStream_t st) {
+  const int K = m->K;
+  const size_t per_img = s3d_planes_bytes(1, K, S) / sizeof(float);
+  for (int b = 0; b < B; ++b)
+    for (int s = 0; s < 5; ++s) {
+      const int R = plane_res(S, s), CP = kPlaneC[s] < 64 ? 64 : kPlaneC[s];
+      Split f = split_of(e.fs[s], (size_t)B * K * R * R * CP);
+      const size_t o = (size_t)b * K * R * R * CP;
+      S3D_TRY(conv_tc(m->tfcs[s], f.hi + o, f.lo + o, K, R, R, nullptr, 1, 0, pl + b * per_img + plane_offset_floats(K, S, s), 128,
+                      nullptr, nullptr, 0, st));
+    }
   return S3D_OK;
 }
 
@@ -309,7 +337,12 @@ int enctc_pack(s3d_model* m, cudaStream_t st) {
     ConvW& s = m->dc1s[n];
     s.w = static_cast<float*>(d);
     s.cin = C; s.ncols = C; s.ks = 3; s.k = 9 * C; s.kpad = 9 * C;
+    S3D_TRY(convtc_pack(m, s, C, 0, C, m->tdc1s[n], st));
+    S3D_TRY(convtc_pack(m, m->trans_up[n], 2 * C, 0, 2 * C, m->ttrans_up[n], st));
+    S3D_TRY(convtc_pack(m, m->up_t[n], m->up_t[n].cin, 0, m->up_t[n].cin, m->tup_t[n], st));
   }
+  S3D_TRY(convtc_pack(m, m->trans_c, 512, 0, 512, m->ttrans_c, st));
+  for (int s = 0; s < 5; ++s) S3D_TRY(convtc_pack(m, m->fcs[s], kPlaneC[s], 0, kPlaneC[s], m->tfcs[s], st));
   return S3D_OK;
 }
 
@@ -411,7 +444,9 @@ int encoder_fwd(const s3d_model* m, const float* img, int B, int S, void* planes
                                                       S * S);
     S3D_LAUNCH_CHECK();
   }
-  if (planes) {
+  if (planes && !m->enc_simt) {
+    S3D_TRY(project_planes_tc(m, B, S, e, static_cast<float*>(planes), st));
+  } else if (planes) {
     float* pl = static_cast<float*>(planes);
     const size_t per_img = s3d_planes_bytes(1, K, S) / sizeof(float);
     for (int b = 0; b < B; ++b)
