@@ -45,6 +45,7 @@ struct ConvTcParams {
   int ncb;   // input channel blocks of 64
   int taps;  // 9 (3x3, pad 1) or 1
   int nkb;   // taps * ncb
+  int n_tiles;  // output-channel tiles of BN
   const uint8_t* wimg;
   int Cout;  // real output channels (multiple of 32)
   const float* scale;
@@ -115,67 +116,83 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
   tc_fence_after();
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(sgen + L::OFF_TMEMPTR);
 
-  // tile -> (image, patch origin)
+  // Persistent CTAs: tile t = (pixel tile, n tile) with the n tile fastest (CTAs that run together share A tiles in
+  // L2).  The stage ring and the two accumulators keep rolling across tiles: while the epilogue warps finish a
+  // tile (affine, stores) the producer and the MMA warp are already in the next one.
   const int tiles_img = p.tiles_x * p.tiles_y;
-  const int img = blockIdx.x / tiles_img;
-  const int trem = blockIdx.x - img * tiles_img;
-  const int tyi = trem / p.tiles_x, txi = trem - tyi * p.tiles_x;
-  const int x0 = txi * p.BW, y0 = tyi * p.BH;
-  const int n_tile = blockIdx.y;
+  const int n_tiles = p.n_tiles;
+  const int total_tiles = tiles_img * p.NI * n_tiles;
+  auto decode = [&](int t, int& img, int& x0, int& y0, int& n_tile) {
+    n_tile = t % n_tiles;
+    const int mt = t / n_tiles;
+    img = mt / tiles_img;
+    const int trem = mt - img * tiles_img;
+    const int tyi = trem / p.tiles_x, txi = trem - tyi * p.tiles_x;
+    x0 = txi * p.BW;
+    y0 = tyi * p.BH;
+  };
 
   if (warp == 0) {
     // ===================================================================== producer
-    const uint8_t* wsrc = p.wimg + (size_t)n_tile * p.nkb * (2 * L::B_PART);
+    uint32_t g = 0;  // k-blocks issued so far (ring position)
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      int img, x0, y0, n_tile;
+      decode(t, img, x0, y0, n_tile);
+      const uint8_t* wsrc = p.wimg + (size_t)n_tile * p.nkb * (2 * L::B_PART);
 #pragma unroll 1
-    for (int kb = 0; kb < p.nkb; ++kb) {
-      const int s = kb % NST, it = kb / NST;
-      mbar_wait(empty(s), (it & 1) ^ 1u);  // "empty"-type: the first pass over the ring does not block
-      if (lane == 0) {
-        const int tap = kb / p.ncb, cb = kb - tap * p.ncb;
-        int dy = 0, dx = 0;
-        if (p.taps == 9) {
-          dy = tap / 3 - 1;
-          dx = tap - (tap / 3) * 3 - 1;
+      for (int kb = 0; kb < p.nkb; ++kb, ++g) {
+        const uint32_t s = g % NST, it = g / NST;
+        mbar_wait(empty(s), (it & 1) ^ 1u);  // "empty"-type: the first pass over the ring does not block
+        if (lane == 0) {
+          const int tap = kb / p.ncb, cb = kb - tap * p.ncb;
+          int dy = 0, dx = 0;
+          if (p.taps == 9) {
+            dy = tap / 3 - 1;
+            dx = tap - (tap / 3) * 3 - 1;
+          }
+          const uint32_t st = sbase + s * L::STAGE;
+          mbar_arrive_expect_tx(full(s), L::STAGE);
+          tma_load_4d(st, &tm_hi, cb * 64, x0 + dx, y0 + dy, img, full(s));
+          tma_load_4d(st + CT_A_PART, &tm_lo, cb * 64, x0 + dx, y0 + dy, img, full(s));
+          bulk_g2s(st + 2 * CT_A_PART, wsrc + (size_t)kb * (2 * L::B_PART), 2 * L::B_PART, full(s));
         }
-        const uint32_t st = sbase + s * L::STAGE;
-        mbar_arrive_expect_tx(full(s), L::STAGE);
-        tma_load_4d(st, &tm_hi, cb * 64, x0 + dx, y0 + dy, img, full(s));
-        tma_load_4d(st + CT_A_PART, &tm_lo, cb * 64, x0 + dx, y0 + dy, img, full(s));
-        bulk_g2s(st + 2 * CT_A_PART, wsrc + (size_t)kb * (2 * L::B_PART), 2 * L::B_PART, full(s));
+        __syncwarp();
       }
-      __syncwarp();
     }
   } else if (warp == 1) {
     // ===================================================================== MMA issuer
     constexpr uint32_t IDESC = make_idesc_f16(BN, 128);
+    uint32_t g = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
 #pragma unroll 1
-    for (int kb = 0; kb < p.nkb; ++kb) {
-      const int s = kb % NST, it = kb / NST;
-      const int buf = kb & 1;
-      mbar_wait(acc_empty(buf), ((kb >> 1) & 1) ^ 1u);  // the epilogue has drained this accumulator
-      mbar_wait(full(s), it & 1);
-      tc_fence_after();
-      if (elect_one()) {
-        const uint32_t st = sbase + s * L::STAGE;
-        const uint32_t d = tmem + buf * BN;
-        const uint64_t a_hi = make_desc_sw128(st), a_lo = make_desc_sw128(st + CT_A_PART);
-        const uint64_t b_hi = make_desc_sw128(st + 2 * CT_A_PART), b_lo = make_desc_sw128(st + 2 * CT_A_PART + L::B_PART);
+      for (int kb = 0; kb < p.nkb; ++kb, ++g) {
+        const uint32_t s = g % NST, it = g / NST;
+        const uint32_t buf = g & 1;
+        mbar_wait(acc_empty(buf), ((g >> 1) & 1) ^ 1u);  // the epilogue has drained this accumulator
+        mbar_wait(full(s), it & 1);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t st = sbase + s * L::STAGE;
+          const uint32_t d = tmem + buf * BN;
+          const uint64_t a_hi = make_desc_sw128(st), a_lo = make_desc_sw128(st + CT_A_PART);
+          const uint64_t b_hi = make_desc_sw128(st + 2 * CT_A_PART), b_lo = make_desc_sw128(st + 2 * CT_A_PART + L::B_PART);
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {
-          const uint64_t o = (uint64_t)((ks * 32) >> 4);
-          // correction terms first: they are ~2^-9 of the leading term
-          umma_bf16(d, a_lo + o, b_hi + o, IDESC, ks == 0 ? 0u : 1u);
-          umma_bf16(d, a_hi + o, b_lo + o, IDESC, 1u);
-        }
+          for (int ks = 0; ks < 4; ++ks) {
+            const uint64_t o = (uint64_t)((ks * 32) >> 4);
+            // correction terms first: they are ~2^-11 of the leading term
+            umma_bf16(d, a_lo + o, b_hi + o, IDESC, ks == 0 ? 0u : 1u);
+            umma_bf16(d, a_hi + o, b_lo + o, IDESC, 1u);
+          }
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {
-          const uint64_t o = (uint64_t)((ks * 32) >> 4);
-          umma_bf16(d, a_hi + o, b_hi + o, IDESC, 1u);
+          for (int ks = 0; ks < 4; ++ks) {
+            const uint64_t o = (uint64_t)((ks * 32) >> 4);
+            umma_bf16(d, a_hi + o, b_hi + o, IDESC, 1u);
+          }
+          umma_commit(empty(s));
+          umma_commit(acc_full(buf));
         }
-        umma_commit(empty(s));
-        umma_commit(acc_full(buf));
+        __syncwarp();
       }
-      __syncwarp();
     }
   } else {
     // ===================================================================== epilogue (warps 2..9)
@@ -184,18 +201,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
     const int ch = (warp - 2) >> 2;
     const int row = 32 * q + lane;
     const int bx = row & (p.BW - 1), by = row >> p.bw_log2;
+    const uint32_t tsrc = tmem + (static_cast<uint32_t>(32 * q) << 16) + ch * NC;
+    uint32_t g = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+    int img, x0, y0, n_tile;
+    decode(t, img, x0, y0, n_tile);
     const int x = x0 + bx, y = y0 + by;
     const bool valid = (x < p.W) && (y < p.H);
     const size_t pix = ((size_t)img * p.H + (valid ? y : 0)) * p.W + (valid ? x : 0);
     const float* addp = p.add ? p.add + (((size_t)(img / p.add_div) * p.H + (valid ? y : 0)) * p.W + (valid ? x : 0)) * p.Cout : nullptr;
-    const uint32_t tsrc = tmem + (static_cast<uint32_t>(32 * q) << 16) + ch * NC;
     float acc[NC];
 #pragma unroll
     for (int c = 0; c < NC; ++c) acc[c] = 0.f;
 #pragma unroll 1
-    for (int kb = 0; kb < p.nkb; ++kb) {
-      const int buf = kb & 1;
-      mbar_wait(acc_full(buf), (kb >> 1) & 1);
+    for (int kb = 0; kb < p.nkb; ++kb, ++g) {
+      const uint32_t buf = g & 1;
+      mbar_wait(acc_full(buf), (g >> 1) & 1);
       tc_fence_after();
 #pragma unroll
       for (int j = 0; j < NC / 32; ++j) {
@@ -269,6 +290,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
         }
       }
     }
+    }  // tile loop
   }
   tc_fence_before();
   __syncthreads();
@@ -400,6 +422,7 @@ int conv_tc(const ConvTC& w, const __half* in_hi, const __half* in_lo, int NI, i
   p.ncb = w.cinp / 64;
   p.taps = w.taps;
   p.nkb = p.taps * p.ncb;
+  p.n_tiles = w.n_tiles;
   p.wimg = w.wimg;
   p.Cout = w.cout;
   p.scale = w.scale; p.shift = w.shift;
@@ -413,7 +436,14 @@ int conv_tc(const ConvTC& w, const __half* in_hi, const __half* in_lo, int NI, i
   CUtensorMap tm_hi, tm_lo;
   S3D_TRY(make_tmap(&tm_hi, in_hi, NI, H, W, w.cinp, BW, BH));
   S3D_TRY(make_tmap(&tm_lo, in_lo, NI, H, W, w.cinp, BW, BH));
-  dim3 grid((unsigned)(p.tiles_x * p.tiles_y * NI), (unsigned)w.n_tiles);
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    S3D_CUDA(cudaGetDevice(&dev));
+    S3D_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const long long total = (long long)p.tiles_x * p.tiles_y * NI * w.n_tiles;
+  dim3 grid((unsigned)(total < sms ? total : sms));
   if (w.bn == 128) {
     using L = CtSmem<128, 3>;
     auto kern = conv_tc_kernel<128, 3>;
