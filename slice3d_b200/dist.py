@@ -50,3 +50,19 @@ def all_gather_slabs(vol_flat, nx, group=None):
             for r in range(world):  # ragged slabs: one broadcast per owner
                 dist.broadcast(outs[r], src=dist.get_global_rank(group, r) if group is not None else r, group=group)
     return vol_flat
+
+
+def all_gather_ranges(flat, n, group=None):
+    """In place: rank r has filled ``flat[slab_range(n, r, world)]``; afterwards every rank holds all n values."""
+    rank, world = rank_world(group)
+    if world == 1:
+        return flat
+    b = slab_bounds(n, world)
+    if n % world == 0:
+        lo, hi = b[rank], b[rank + 1]
+        dist.all_gather_into_tensor(flat, flat[lo:hi].clone(), group=group)
+    else:
+        for r in range(world):  # ragged shares: one broadcast per owner
+            if b[r + 1] > b[r]:
+                dist.broadcast(flat[b[r]:b[r + 1]], src=dist.get_global_rank(group, r) if group is not None else r, group=group)
+    return flat
