@@ -40,6 +40,35 @@ def test_encoder_planes_match_reference(name):
     assert helpers.maxabs(rec[:, :, ::helpers.REC_STRIDE, ::helpers.REC_STRIDE], case["slices_rec_sub"]) < TOL
 
 
+@pytest.mark.parametrize("S,K,B", [(48, 12, 1), (80, 5, 2), (32, 1, 1)])
+def test_encoder_odd_sizes_match_oracle(S, K, B):
+    """Plane resolutions that are not powers of two (partial TMA tiles, boxes larger than the image, out-of-bounds
+    fill on every side), K < 12, batch > 1: feature planes, projected planes and slices_rec against the CPU oracle."""
+    from slice3d_b200 import Slices3DRegModel
+    m = Slices3DRegModel(S, K, "test")
+    sd = synth.synthetic_state_dict(m.state_dict(), seed=3)
+    m.load_state_dict(sd)
+    m = m.to(DEV).eval()
+    feed = synth.synthetic_inputs(S, K, seed=3, batch=B)
+    with torch.no_grad():
+        want_feats, want_rec = oracle.unet_forward(sd, feed["img_input"], K)
+    planes, feats = m.native().encode(feed["img_input"].to(DEV), want_feats=True)
+    for i, (f, w) in enumerate(zip(feats, want_feats)):
+        assert f.shape == w.shape
+        assert helpers.maxabs(f.cpu(), w) < TOL, f"feature plane {i}"
+    assert helpers.maxabs(planes.slices_rec.cpu().view(want_rec.shape), want_rec) < TOL
+    blob, off, c0 = planes.blob.cpu(), 0, 0
+    per_img = blob.numel() // B
+    for s, w in enumerate(want_feats):
+        n, c, h, _ = w.shape
+        proj = torch.einsum("nchw,oc->nhwo", w.double(), sd["fc_s.weight"][:, c0:c0 + c].double()).view(B, K, h, h, 128)
+        for b in range(B):
+            got = blob[b * per_img + off:b * per_img + off + K * h * h * 128].view(K, h, h, 128)
+            assert helpers.maxabs(got, proj[b]) < TOL, f"projected plane {s} image {b}"
+        off += K * h * h * 128
+        c0 += c
+
+
 def test_projected_planes_are_fc_s_of_feature_planes():
     """The hoisted fc_s projection: plane_s = fc_s[:, scale s columns] . feature plane s."""
     case = helpers.load_case("k12_s128_g128")
