@@ -24,6 +24,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 FLOP_PER_QUERY = 32.82e6  # minimal exact algorithm (contract figure)
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE decoder launch from `ncu --set full` captures of the same
+# configuration (profiles/r1_e_summary.md); keyed by (grid, precision, queries in the launch).  Not measured -> null.
+DECODER_DRAM_BYTES = {(256, "bf16x3", 256 ** 3): 67.477e9 + 18.064e9}
 METRIC = "occupancy_queries_per_sec"
 UNIT = "queries/s"
 
@@ -305,7 +308,8 @@ def run_native(args):
                 "d2h_bytes_per_step": int(nx ** 3 * 4), "ms_per_step": e2e_ms / args.steps},
         "gpu_launches": int(launches),
         "roofline": {"bound": "tensor", "achieved": dec_tflops, "peak": sustained, "unit": "TFLOP/s",
-                     "frac": dec_tflops / sustained, "traffic": None,
+                     "frac": dec_tflops / sustained,
+                     "traffic": DECODER_DRAM_BYTES.get((nx, prec, count)), "traffic_unit": "bytes per launch (ncu dram read+write)",
                      "kernel": "decoder (all launches of one decode_grid call)", "kernel_ms": dec_ms,
                      "kernel_ms_max_over_ranks": dec_ms_max, "flop_per_query": FLOP_PER_QUERY, "queries_per_launch": count,
                      "peak_source": how + " sustained bf16"},
