@@ -647,7 +647,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
     // K (then V) of all heads is staged as an fp32 matrix [117 rows][ST_PITCH] in the H region.  The pitch of
     // 132 floats puts the key rows of the (at most four) queries a warp touches at once in distinct banks, and
     // every address is "row base of my query + compile-time offset": no address arithmetic in the loops.
-    // The dot products run as packed fp32 FMAs (FFMA2).
+    // The dot products run as packed fp32 FMAs (FFMA2).  (Measured and rejected: two rows of a query per thread, 252
+    // tasks on 8 warps with Q staged to shared memory as well -- halves the LDS traffic, but the extra staging pass, the
+    // wait for the V projection before it and the lower occupancy of the loops cost more: 186.5 vs 183.3 kcycles.)
     float* const st = reinterpret_cast<float*>(sgen + OFF_H);
     const float* const qrows = st + (qi < TILE_Q ? qi : 0) * (NTOK * ST_PITCH) + 32 * g;  // key/value rows of my query, my head
     // S[:, col + 32g ..+31] + bias -> my row of the staging matrix
