@@ -291,3 +291,30 @@ def test_full_size_dense_grid_256_bf16x3():
     pts = torch.stack([ax[ix], ax[iy], ax[iz]], -1).contiguous()
     ref = nat.decode(planes, 0, pts, T, out_scale=-1.0, precision="fp32")
     assert helpers.maxabs(flat[sub].cpu(), ref.cpu()) < TOL
+
+
+def test_tc_decoder_ragged_empty_and_unsupported():
+    """Edge cases of the tensor-core path: empty query set, fewer queries than one tile (9), ragged last tile, a
+    count that leaves one CTA of a pair without work, and K != 12 (served by the fp32 path only: loud error)."""
+    case = helpers.load_case("k12_s128_g128")
+    m, _ = _model(case)
+    feed = _feed(case)
+    nat = m.native()
+    planes = m.encode(feed["img_input"])
+    T = feed["trans_mat_wo_rot_tp"][0]
+    pts = torch.from_numpy(case["pts_g128"]).to(DEV)
+    assert nat.decode(planes, 0, torch.empty(0, 3, device=DEV), T, precision="bf16x3").numel() == 0
+    full = nat.decode(planes, 0, pts, T, precision="bf16x3")
+    ref = nat.decode(planes, 0, pts, T, precision="fp32")
+    assert helpers.maxabs(full.cpu(), ref.cpu()) < TOL
+    for n in (1, 7, 9, 10, 130, 1333):
+        part = nat.decode(planes, 0, pts[:n].contiguous(), T, precision="bf16x3")
+        # the same queries in a different tile / CTA-pair arrangement: same arithmetic per row
+        assert helpers.maxabs(part.cpu(), full[:n].cpu()) < 1e-6, n
+    case4 = helpers.load_case("cfg0_k4_s128_g64")
+    m4, _ = _model(case4)
+    f4 = _feed(case4)
+    p4 = m4.encode(f4["img_input"])
+    q4 = torch.from_numpy(case4["pts_g64"]).to(DEV)
+    with pytest.raises(_native.NativeError):
+        m4.native().decode(p4, 0, q4, f4["trans_mat_wo_rot_tp"][0], precision="bf16x3")
