@@ -138,6 +138,16 @@ int s3d_decoder_debug_tokens(const s3d_model* m, const void* planes_dev, int32_t
 int s3d_selftest_umma(int32_t mode, int32_t passes, const float* a_dev, const float* w_dev, float* d_dev,
                       void* stream);
 
+/* VGG19 perceptual loss between two image batches a, b (N,3,S,S) fp32 in [-1,1] (NCHW, device):
+ * replaces VGGPerceptualLoss.forward (reg_slices/src/vgg_perceptual_loss.py:51-71), which the reference
+ * evaluates inside every Slices3DRegModel.forward, also at test time (reg_slices/src/models.py:90-92).
+ * loss_dev receives ONE float = sum_t w_t * mean|tap_t(a) - tap_t(b)| (the caller applies the 0.001 of
+ * models.py:92).  Needs a model created WITH the vggptlossfunc.* tensors (S3D_ERR_MISSING_TENSOR otherwise);
+ * S must be a multiple of 16. */
+size_t s3d_vgg_loss_workspace_bytes(int32_t N, int32_t S);
+int s3d_vgg_loss_fwd(const s3d_model* m, const float* a_dev, const float* b_dev, int32_t N, int32_t S, float* loss_dev,
+                     void* workspace_dev, size_t workspace_bytes, void* stream);
+
 /* Instrumentation of the tensor-core decoder: 32 cycle counters (clock64 deltas summed over CTAs since the
  * last reset; index meaning in slice3d_b200/_native.py PROFILE_FIELDS).  Synchronises the device. */
 int s3d_debug_profile(int64_t* out32, int32_t reset);

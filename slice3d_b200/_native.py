@@ -78,6 +78,11 @@ def lib():
     L.s3d_decoder_debug_tokens.restype = C.c_int
     L.s3d_decoder_debug_tokens.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p,
                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+    L.s3d_vgg_loss_workspace_bytes.restype = C.c_size_t
+    L.s3d_vgg_loss_workspace_bytes.argtypes = [C.c_int32, C.c_int32]
+    L.s3d_vgg_loss_fwd.restype = C.c_int
+    L.s3d_vgg_loss_fwd.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
+                                   C.c_size_t, C.c_void_p]
     L.s3d_selftest_umma.restype = C.c_int
     L.s3d_selftest_umma.argtypes = [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.s3d_debug_profile.restype = C.c_int
@@ -160,7 +165,7 @@ class NativeModel:
         L = lib()
         keep, arr = [], []
         for name, t in state_dict.items():
-            if t.dtype != torch.float32 or name.startswith(("vggptlossfunc.", "att_layer.")):
+            if t.dtype != torch.float32 or name.startswith("att_layer."):
                 continue
             t = t.detach().to(device=device).contiguous()
             keep.append(t)
@@ -212,6 +217,20 @@ class NativeModel:
                                      _stream(self.device)))
         planes = Planes(blob, B, K, S, rec)
         return (planes, feats) if want_feats else planes
+
+    # ---- perceptual loss --------------------------------------------------------
+    def vgg_loss(self, a, b):
+        """a, b (N,3,S,S) fp32 CUDA in [-1,1] -> 0-dim tensor: VGGPerceptualLoss.forward(a, b)['pt_c_loss']."""
+        a, b = _f32c(a, "input_img"), _f32c(b, "target_img")
+        if a.shape != b.shape or a.dim() != 4 or a.shape[1] != 3 or a.shape[2] != a.shape[3]:
+            raise NativeError("vgg_loss: a and b must both be (N,3,S,S)")
+        N, S, L = a.shape[0], a.shape[2], lib()
+        with torch.cuda.device(self.device):
+            out = torch.empty((), dtype=torch.float32, device=self.device)
+            ws = self._workspace("vgg", L.s3d_vgg_loss_workspace_bytes(N, S))
+            _check(L.s3d_vgg_loss_fwd(self._h, a.data_ptr(), b.data_ptr(), N, S, out.data_ptr(), ws.data_ptr(), ws.numel(),
+                                      _stream(self.device)))
+        return out
 
     # ---- decoder ----------------------------------------------------------------
     def decode(self, planes, b, qry, T, rot=None, flip_in_place=False, out_scale=1.0, precision="bf16x3", out=None):

@@ -210,6 +210,22 @@ struct Packer {
         c0 += kPlaneC[s];
       }
     }
+    // ---- VGG19 perceptual loss (optional; vgg_perceptual_loss.py:6-40: torchvision feature indices per slice)
+    if (by_name.count("vggptlossfunc.vgg.slice1.0.weight")) {
+      struct PC {
+        int slice, idx, cin, cout;
+      };
+      const PC pc[14] = {{1, 0, 3, 64},     {1, 2, 64, 64},    {2, 5, 64, 128},   {2, 7, 128, 128},  {3, 10, 128, 256},
+                         {3, 12, 256, 256}, {4, 14, 256, 256}, {4, 16, 256, 256}, {4, 19, 256, 512}, {4, 21, 512, 512},
+                         {5, 23, 512, 512}, {5, 25, 512, 512}, {5, 28, 512, 512}, {5, 30, 512, 512}};
+      for (int i = 0; i < 14; ++i) {
+        std::string p = "vggptlossfunc.vgg.slice" + std::to_string(pc[i].slice) + "." + std::to_string(pc[i].idx);
+        if (!pack_conv(p + ".weight", pc[i].cout, pc[i].cin, 3, m->pvgg[i])) return false;
+        if (!vec(p + ".bias", pc[i].cout, m->pvgg[i].shift)) return false;
+      }
+      if (!vec("vggptlossfunc.mean", 3, m->pvgg_mean) || !vec("vggptlossfunc.std", 3, m->pvgg_std)) return false;
+      m->has_pvgg = 1;
+    }
     // ---- decoder
     DecF32& d = m->dec32;
     {
@@ -388,6 +404,20 @@ int s3d_decoder_grid_fwd(const s3d_model* m, const void* planes_dev, int32_t S, 
   q.T = T_dev;
   return run_decoder(m, planes_dev, S, q, count, out_scale, out_dev, precision, nullptr, workspace_dev,
                      workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+
+size_t s3d_vgg_loss_workspace_bytes(int32_t N, int32_t S) {
+  if (N <= 0 || S <= 0) return 0;
+  return vgg_loss_workspace_bytes(N, S);
+}
+
+int s3d_vgg_loss_fwd(const s3d_model* m, const float* a_dev, const float* b_dev, int32_t N, int32_t S, float* loss_dev,
+                     void* workspace_dev, size_t workspace_bytes, void* stream) {
+  if (!m) {
+    set_error("vgg_loss: null model");
+    return S3D_ERR_BAD_ARG;
+  }
+  return vgg_loss_fwd(m, a_dev, b_dev, N, S, loss_dev, workspace_dev, workspace_bytes, static_cast<cudaStream_t>(stream));
 }
 
 int s3d_debug_profile(int64_t* out32, int32_t reset) { return debug_profile(reinterpret_cast<long long*>(out32), reset); }

@@ -120,6 +120,12 @@ struct s3d_model {
   s3d::ConvTC tdc1[4], tdc2[4], tdc1s[4];
   s3d::ConvTC ttrans_c, ttrans_up[4], tup_t[4], tfcs[5];  // the 1x1 / transposed convolutions and the fc_s projection
   s3d::ConvW dc1s[4];
+  // VGG19 perceptual loss (perceptual.cu); optional: present when the vggptlossfunc.* tensors were given
+  int has_pvgg = 0;
+  s3d::ConvW pvgg[14];         // conv1_1 .. conv5_2 (shift = bias)
+  s3d::ConvTC tpvgg[14];       // [0] unused
+  float* pvgg_mean = nullptr;
+  float* pvgg_std = nullptr;
   int enc_simt = 0;            // S3D_ENCODER=simt: whole encoder on the fp32 CUDA-core path (debugging)
   // decoder
   s3d::DecF32 dec32;
@@ -151,6 +157,11 @@ int conv_tc(const ConvTC& w, const __half* in_hi, const __half* in_lo, int NI, i
             int add_div, int relu, float* out_f32, int ldf, __half* out_hi, __half* out_lo, int lds, cudaStream_t st,
             int shuffle_c = 0);
 int enctc_pack(s3d_model* m, cudaStream_t st);
+
+// perceptual.cu
+size_t vgg_loss_workspace_bytes(int N, int S);
+int vgg_loss_fwd(const s3d_model* m, const float* a, const float* b, int N, int S, float* loss, void* ws, size_t ws_bytes,
+                 cudaStream_t st);
 
 // ---- queries ----------------------------------------------------------------------
 struct QueryCtx {

@@ -341,6 +341,8 @@ int enctc_pack(s3d_model* m, cudaStream_t st) {
     S3D_TRY(convtc_pack(m, m->trans_up[n], 2 * C, 0, 2 * C, m->ttrans_up[n], st));
     S3D_TRY(convtc_pack(m, m->up_t[n], m->up_t[n].cin, 0, m->up_t[n].cin, m->tup_t[n], st));
   }
+  if (m->has_pvgg)
+    for (int i = 1; i < 14; ++i) S3D_TRY(convtc_pack(m, m->pvgg[i], m->pvgg[i].cin, 0, m->pvgg[i].cin, m->tpvgg[i], st));
   S3D_TRY(convtc_pack(m, m->trans_c, 512, 0, 512, m->ttrans_c, st));
   for (int s = 0; s < 5; ++s) S3D_TRY(convtc_pack(m, m->fcs[s], kPlaneC[s], 0, kPlaneC[s], m->tfcs[s], st));
   return S3D_OK;

@@ -80,7 +80,9 @@ class Slices3DRegModel(nn.Module):
         if c["vgg"] is None or c["vgg"][0] != key:
             B, K, S = planes.B, planes.K, planes.S
             tgt = img_slices.view(B, K, 3, S, S).view(B * K, 3, S, S)
-            c["vgg"] = (key, self.vggptlossfunc(planes.slices_rec, tgt)["pt_c_loss"] * 0.001, img_slices)
+            # VGGPerceptualLoss.forward on the CUDA library (same tcgen05 convolution kernel as the encoder)
+            loss = self.native().vgg_loss(planes.slices_rec, tgt.float().contiguous())
+            c["vgg"] = (key, loss * 0.001, img_slices)
         return c["vgg"][1]
 
     # ------------------------------------------------------------------ forward

@@ -318,3 +318,23 @@ def test_tc_decoder_ragged_empty_and_unsupported():
     q4 = torch.from_numpy(case4["pts_g64"]).to(DEV)
     with pytest.raises(_native.NativeError):
         m4.native().decode(p4, 0, q4, f4["trans_mat_wo_rot_tp"][0], precision="bf16x3")
+
+
+@pytest.mark.parametrize("S,N", [(64, 3), (48, 1), (128, 12)])
+def test_vgg_perceptual_loss_matches_oracle(S, N):
+    """VGGPerceptualLoss.forward (vgg_perceptual_loss.py:51-71) on the CUDA library against the CPU oracle:
+    relative 1e-4 on the loss value (fp32 reference arithmetic itself differs by ~1e-6 between formulations)."""
+    from slice3d_b200 import Slices3DRegModel
+    m = Slices3DRegModel(S, 12, "test")
+    sd = synth.synthetic_state_dict(m.state_dict(), seed=7)
+    m.load_state_dict(sd)
+    m = m.to(DEV).eval()
+    g = torch.Generator().manual_seed(S + N)
+    a = torch.rand(N, 3, S, S, generator=g) * 2 - 1
+    b = (a + 0.3 * torch.randn(N, 3, S, S, generator=g)).clamp(-1, 1)
+    with torch.no_grad():
+        want = float(oracle.vgg_perceptual(sd, a, b))
+    got = float(m.native().vgg_loss(a.to(DEV), b.to(DEV)))
+    print(f"vgg loss S={S} N={N}: native {got:.7f} oracle {want:.7f}")
+    assert abs(got - want) <= 1e-4 * abs(want)
+    assert float(m.native().vgg_loss(a.to(DEV), a.to(DEV))) == 0.0
