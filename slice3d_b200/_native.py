@@ -20,7 +20,8 @@ ABI_VERSION = 1
 SYMBOLS = [
     "s3d_abi_version", "s3d_last_error", "s3d_model_create", "s3d_model_destroy", "s3d_model_n_slices",
     "s3d_planes_bytes", "s3d_encoder_workspace_bytes", "s3d_encoder_fwd", "s3d_decoder_workspace_bytes",
-    "s3d_decoder_fwd", "s3d_decoder_grid_fwd", "s3d_decoder_debug_tokens", "s3d_selftest_umma", "s3d_debug_profile", "s3d_launch_count",
+    "s3d_decoder_fwd", "s3d_decoder_grid_fwd", "s3d_decoder_debug_tokens", "s3d_vgg_loss_workspace_bytes",
+    "s3d_vgg_loss_fwd", "s3d_selftest_umma", "s3d_debug_profile", "s3d_launch_count",
 ]
 
 
