@@ -127,3 +127,58 @@ def test_slab_all_gather_world2_gloo(tmp_path):
     procs = [subprocess.Popen([sys.executable, str(script), ROOT, port, str(r)]) for r in range(2)]
     codes = [p.wait(timeout=120) for p in procs]
     assert codes == [0, 0]
+
+
+_DDP_WORKER = r"""
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from slice3d_b200 import Slices3DRegModel, synth
+rank = int(sys.argv[3])
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%s" % sys.argv[2], rank=rank, world_size=2)
+torch.manual_seed(0)
+torch.set_num_threads(2)
+m = Slices3DRegModel(32, 12, "train").train()
+for mod in m.modules():  # dropout off: the two runs below must see the same arithmetic
+    if isinstance(mod, torch.nn.Dropout):
+        mod.p = 0.0
+    if isinstance(mod, torch.nn.MultiheadAttention):
+        mod.dropout = 0.0
+feed = synth.synthetic_inputs(32, batch=2)
+g = torch.Generator().manual_seed(1)
+feed["qry_norot"] = torch.rand(2, 16, 3, generator=g) - 0.5
+feed["sdf"] = torch.randn(2, 16, generator=g) * 0.1
+def loss_of(model, f):
+    x = model(f)
+    return (torch.nn.functional.l1_loss(x["sdf_pred"], f["sdf"]) +
+            torch.nn.functional.l1_loss(x["slices_rec"], f["img_slices"]) + x["vgg_loss"])
+mine = {k: v[rank:rank + 1].clone() for k, v in feed.items()}
+# single-process gradients of each rank's sample, for the expected average
+ref = {}
+for r in range(2):
+    m.zero_grad()
+    loss_of(m, {k: v[r:r + 1].clone() for k, v in feed.items()}).backward()
+    for n, p in m.named_parameters():
+        if p.grad is not None:
+            ref[n] = ref.get(n, 0) + p.grad.detach().clone() / 2
+m.zero_grad()
+ddp = torch.nn.parallel.DistributedDataParallel(m, find_unused_parameters=True)  # 14 parameters never get a gradient
+loss_of(ddp, mine).backward()
+worst = 0.0
+for n, p in m.named_parameters():
+    if p.grad is not None and n in ref:
+        worst = max(worst, float((p.grad - ref[n]).abs().max() / (ref[n].abs().max() + 1e-12)))
+dist.destroy_process_group()
+sys.exit(0 if worst < 1e-4 else 3)
+"""
+
+
+def test_ddp_gradient_allreduce_world2_gloo(tmp_path):
+    """BASELINE configs[4] on CPU: one process per replica, batch split across ranks, bucketed gradient all-reduce
+    (DDP); per-replica BatchNorm statistics as in the reference's DataParallel (train.py:132).  The all-reduced
+    gradients equal the average of the per-sample single-process gradients."""
+    script = tmp_path / "ddp.py"
+    script.write_text(_DDP_WORKER)
+    port = str(31500 + os.getpid() % 2000)
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT, port, str(r)]) for r in range(2)]
+    codes = [p.wait(timeout=600) for p in procs]
+    assert codes == [0, 0]
