@@ -41,7 +41,7 @@ def parse():
     ap.add_argument("--img", type=int, default=256)
     ap.add_argument("--precision", default=None, help="fp32 | bf16x3 | bf16 (default: best <=1e-4 mode built)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-sample", type=int, default=6000, help="queries in the bounded CPU sample")
+    ap.add_argument("--cpu-sample", type=int, default=60000, help="queries in the bounded CPU sample (decoder-only leg)")
     return ap.parse_args()
 
 
@@ -122,7 +122,7 @@ def cpu_sample_points(nx, n, seed=0):
     return torch.stack([ax[ix], ax[iy], ax[iz]], -1)
 
 
-def cpu_baseline(S, nx, n_sample, as_written_chunks=1):
+def cpu_baseline(S, nx, n_sample, as_written_chunks=4):
     """Oracle port (the reference algorithm restated in torch CPU ops, oracle/oracle.py) timed on
     this host's cores: (a) decoder only with the planes computed once; (b) as the reference's
     Generator3D.eval_points runs it: U-Net + VGG19 loss + decoder for every 3000-point chunk."""
