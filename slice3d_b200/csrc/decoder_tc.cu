@@ -258,6 +258,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
 
   constexpr int NPART = (NPASS == 3) ? 2 : 1;  // ring parts per weight unit (hi [, lo])
 
+  // Single-pass mode only (there the gather warps bind: 36 of 149 kcycles per tile were token waits): register
+  // re-budgeting inside the CTA's launch allocation (640 threads x 96) -- the four compute warpgroups give up 8 registers
+  // per thread, the service warpgroup (producer, MMA issuer, two gather warps) takes 128, enough for the gather warps
+  // to keep all 20 tap loads of a step in flight (one L2 round trip per step instead of two): 149 -> 130 kcycles.
+  // In the three-pass mode the compute warps need their 96 registers more (measured 189.7 vs 183.3 kcycles).
+  constexpr bool REGSPLIT = (NPASS == 1);
+  if (REGSPLIT) {
+    if (warp >= NCW) reg_alloc<128>();
+    else reg_dealloc<88>();
+  }
   if (warp >= NCW + 2) {
     // ===================================================================== gather warps
     // They run up to two tiles ahead of the compute warps (double-buffered token scratch), so the L2 latency
@@ -306,6 +316,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
       };
       // plane of scale s for slice k starts at P + (12 * sum_{i<s} R_i^2 + k * (R_s^2 - R_0^2)) * 128
       const size_t r2 = (size_t)R0 * R0;
+      if (REGSPLIT) {  // all 20 tap loads in flight: one L2 round trip per step
+        float4 v0[4], v1[4], v2[4], v3[4], v4[4];
+        const Taps t0 = make_taps(gu, gv, R0), t1 = make_taps(gu, gv, 2 * R0), t2 = make_taps(gu, gv, 4 * R0);
+        const Taps t3 = make_taps(gu, gv, 8 * R0), t4 = make_taps(gu, gv, 16 * R0);
+        issue(v0, t0, P);
+        issue(v1, t1, P + (12 * r2 + (size_t)k * 3 * r2) * 128);
+        issue(v2, t2, P + (12 * 5 * r2 + (size_t)k * 15 * r2) * 128);
+        issue(v3, t3, P + (12 * 21 * r2 + (size_t)k * 63 * r2) * 128);
+        issue(v4, t4, P + (12 * 85 * r2 + (size_t)k * 255 * r2) * 128);
+        fold(v0, t0);
+        fold(v1, t1);
+        fold(v2, t2);
+        fold(v3, t3);
+        fold(v4, t4);
+      } else {
       {  // 12 + 8 loads in flight per lane: two L2 round trips per step
         float4 v0[4], v1[4], v2[4];
         const Taps t0 = make_taps(gu, gv, R0), t1 = make_taps(gu, gv, 2 * R0), t2 = make_taps(gu, gv, 4 * R0);
@@ -323,6 +348,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
         issue(v4, t4, P + (12 * 85 * r2 + (size_t)k * 255 * r2) * 128);
         fold(v3, t3);
         fold(v4, t4);
+      }
       }
       __stcg(reinterpret_cast<float4*>(tokbuf + (size_t)(NTOK * q + 1 + k) * 128 + ch), acc);
     };
