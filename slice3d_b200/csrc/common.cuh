@@ -93,7 +93,6 @@ struct DecF32 {
 struct DecTC {
   __nv_bfloat16* wimg = nullptr;
   float* vec = nullptr;
-  uint32_t* order = nullptr;
   size_t wimg_elems = 0;
 };
 

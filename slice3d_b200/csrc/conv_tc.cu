@@ -180,13 +180,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
           for (int ks = 0; ks < 4; ++ks) {
             const uint64_t o = (uint64_t)((ks * 32) >> 4);
             // correction terms first: they are ~2^-11 of the leading term
-            umma_bf16(d, a_lo + o, b_hi + o, IDESC, ks == 0 ? 0u : 1u);
-            umma_bf16(d, a_hi + o, b_lo + o, IDESC, 1u);
+            umma_f16kind(d, a_lo + o, b_hi + o, IDESC, ks == 0 ? 0u : 1u);
+            umma_f16kind(d, a_hi + o, b_lo + o, IDESC, 1u);
           }
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) {
             const uint64_t o = (uint64_t)((ks * 32) >> 4);
-            umma_bf16(d, a_hi + o, b_hi + o, IDESC, 1u);
+            umma_f16kind(d, a_hi + o, b_hi + o, IDESC, 1u);
           }
           umma_commit(empty(s));
           umma_commit(acc_full(buf));

@@ -69,7 +69,7 @@ constexpr int ST_PITCH = 132;
 // shared memory map (bytes from the 1024-aligned base)
 constexpr uint32_t OFF_AX_HI = 0;                 // [2 k-blocks][128 rows][64] bf16 = 32 KB
 constexpr uint32_t OFF_AX_LO = 32768;             // 32 KB
-constexpr uint32_t OFF_H = 65536;                 // 2 x (H chunk hi 16 KB + lo 16 KB) | K/V staging [128][128] fp32 | gather scratch
+constexpr uint32_t OFF_H = 65536;                 // attention staging: K, then V, of all heads as fp32 [117][ST_PITCH] (+ last-layer scores)
 constexpr uint32_t H_BUF_BYTES = 32768;
 constexpr uint32_t OFF_RING = OFF_H + 2 * H_BUF_BYTES;  // 131072
 constexpr uint32_t OFF_SC = OFF_H + TILE_Q * NTOK * ST_PITCH * 4;

@@ -216,7 +216,8 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int n, int m = 128) {
          (static_cast<uint32_t>(m >> 4) << 24);
 }
 
-// D[tmem] (+)= A[smem] * B[smem]^T ; one thread issues for the CTA.
+// D[tmem] (+)= A[smem] * B[smem]^T ; one thread issues for the CTA.  kind::f16 covers bf16 AND fp16 operands: the
+// instruction descriptor (make_idesc_bf16 / make_idesc_f16) names the formats.
 __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                           uint32_t accumulate) {
   asm volatile(
@@ -225,6 +226,10 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint6
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
+}
+
+__device__ __forceinline__ void umma_f16kind(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  umma_bf16(d_tmem, adesc, bdesc, idesc, accumulate);
 }
 
 // Same with the A operand in tensor memory (lane = row, two bf16 per 32-bit column, K = 16 -> 8 columns):
