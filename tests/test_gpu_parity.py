@@ -338,3 +338,27 @@ def test_vgg_perceptual_loss_matches_oracle(S, N):
     print(f"vgg loss S={S} N={N}: native {got:.7f} oracle {want:.7f}")
     assert abs(got - want) <= 1e-4 * abs(want)
     assert float(m.native().vgg_loss(a.to(DEV), a.to(DEV))) == 0.0
+
+
+def test_decoder_border_and_clamp_cases_match_oracle():
+    """grid_sample edge cases (models.py:28-46): projections exactly on the image border, beyond it (clamped to +-1),
+    exactly on texel centres of every plane resolution, and the image centre -- with an orthographic camera so that the
+    coordinates are exact.  fp32 and bf16x3 paths against the CPU oracle on the same planes."""
+    case = helpers.load_case("k12_s128_g128")
+    m, sd = _model(case)
+    feed = _feed(case)
+    nat = m.native()
+    planes, feats = nat.encode(feed["img_input"], want_feats=True)
+    T = torch.tensor([[1.0, 0.0, 0.0], [0.0, 1.0, 0.0], [0.0, 0.0, 0.0], [0.5, 0.5, 1.0]])  # u = x + .5, v = y + .5, w = 1
+    xs = [-0.5, 0.5, -0.75, 0.75, 0.0, -0.5 + 1.0 / 7, -0.5 + 3.0 / 15, -0.5 + 17.0 / 31, -0.5 + 40.0 / 63, -0.5 + 100.0 / 127,
+          0.4999999, -0.4999999, 0.25]
+    pts = torch.tensor([[x, y, z] for x in xs for y in xs for z in (-0.3, 0.2)], dtype=torch.float32)
+    # test mode negates y (and z) before the projection: models.py:55
+    q = oracle.prepare_queries(pts.unsqueeze(0), None, "test")
+    with torch.no_grad():
+        want = oracle.decode(sd, [f.cpu() for f in feats], q, T.unsqueeze(0), 12)[0]
+    for prec in ("fp32", "bf16x3"):
+        got = nat.decode(planes, 0, pts.to(DEV), T.to(DEV), precision=prec)
+        err = helpers.maxabs(got.cpu(), want)
+        print(f"border/clamp cases, {prec}: max-abs {err:.3e} over {pts.shape[0]} points")
+        assert err < TOL
