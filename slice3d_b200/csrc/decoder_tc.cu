@@ -555,33 +555,36 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
             release();
           }
         };
-        issue1(0);
-        issue1(1);
+        // one call site per unit kind (the unrolled issue sequences are large: instruction-cache footprint):
+        // c = -2, -1 only issue MMA1 of chunks 0, 1; then MMA2(c), MMA1(c + 2)
 #pragma unroll 1
-        for (int c = 0; c < NCHUNK; ++c) {
-          // h_ready(c): the compute warps have drained D1[c&1] and written the H operand of chunk c
-          const uint32_t t0 = (uint32_t)clock();
-          wait_lead(B_HREADY, ph_hr);
-          ph_hr ^= 1u;
-          w_h += (uint32_t)clock() - t0;
-          tc_fence_after();
-          issue2(c);
-          if (c + 1 < NCHUNK) commit(B_HFREE);  // H may be rewritten once MMA2 of chunk c has completed
+        for (int c = -2; c < NCHUNK; ++c) {
+          if (c >= 0) {
+            // h_ready(c): the compute warps have drained D1[c&1] and written the H operand of chunk c
+            const uint32_t t0 = (uint32_t)clock();
+            wait_lead(B_HREADY, ph_hr);
+            ph_hr ^= 1u;
+            w_h += (uint32_t)clock() - t0;
+            tc_fence_after();
+            issue2(c);
+            if (c + 1 < NCHUNK) commit(B_HFREE);  // H may be rewritten once MMA2 of chunk c has completed
+          }
           if (c + 2 < NCHUNK) issue1(c + 2);
         }
         commit(B_DDONE);
       };
       int pending = 0;
       for (long long base = base_first; base < p.num_tiles; base += gridDim.x) {
-        for (int layer = 0; layer < 2; ++layer) {
+#pragma unroll 1
+        for (int layer = 0; layer < 3; ++layer) {  // (one call site for each of the two issue sequences)
           mma_qkv();
-          mma_out_ffn();
-        }
-        mma_qkv();  // last layer: only token 0 of every query is consumed downstream -> batched tail pass
-        ++pending;
-        if (pending == TAIL_SLOTS || base + gridDim.x >= p.num_tiles) {
-          mma_out_ffn();
-          pending = 0;
+          bool ffn = true;
+          if (layer == 2) {  // last layer: only token 0 of every query is consumed downstream -> batched tail pass
+            ++pending;
+            ffn = (pending == TAIL_SLOTS || base + gridDim.x >= p.num_tiles);
+            if (ffn) pending = 0;
+          }
+          if (ffn) mma_out_ffn();
         }
       }
       if (lane == 0) {
@@ -1037,45 +1040,49 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
         mbar_wait(bar(B_KDONE), ph_kq);  // K projected (Q and V follow, see mma_qkv)
         tc_fence_after();
         lap(PF_WAIT_QKV)
+        // (post_attn has ONE call site: the unrolled FFN epilogue is large and the kernel's code already exceeds the
+        // instruction cache)
+        bool post = true, head_valid = false;
+        long long head_q = 0;
         if (layer < 2) {
           attention(layer, valid);
-          post_attn(layer, false, 0);
         } else {
           attention_tok0(tile, pending);
-        }
-      }
-      if (pending == 0) batch_tile0 = tile;
-      ++pending;
-      if (pending == TAIL_SLOTS || tile - rank + gridDim.x >= p.num_tiles) {
-        // ---------------------------------------------------------------- tail pass: token 0 of up to 126 queries
-        named_bar_sync(1, NCT);  // scratch rows written by other threads are visible after the CTA barrier
-        {
-          const int k = r / TILE_Q, qq = r - k * TILE_Q;
-          const long long tq = (batch_tile0 + (long long)k * gridDim.x) * TILE_Q + qq;
-          const bool tvalid = (r < pending * TILE_Q) && (tq < p.n);
-          const float* row = p.scratch + ((size_t)blockIdx.x * (TAIL_SLOTS * TILE_Q) + (r < TAIL_SLOTS * TILE_Q ? r : 0)) * 256;
-          float v[32];
+          if (pending == 0) batch_tile0 = tile;
+          ++pending;
+          post = (pending == TAIL_SLOTS || tile - rank + gridDim.x >= p.num_tiles);
+          if (post) {
+            // -------------------------------------------------------------- tail pass: token 0 of up to 126 queries
+            named_bar_sync(1, NCT);  // scratch rows written by other threads are visible after the CTA barrier
+            const int k = r / TILE_Q, qq = r - k * TILE_Q;
+            const long long tq = (batch_tile0 + (long long)k * gridDim.x) * TILE_Q + qq;
+            const bool tvalid = (r < pending * TILE_Q) && (tq < p.n);
+            const float* row = p.scratch + ((size_t)blockIdx.x * (TAIL_SLOTS * TILE_Q) + (r < TAIL_SLOTS * TILE_Q ? r : 0)) * 256;
+            float v[32];
 #pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            float4 t4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (tvalid) t4 = __ldcg(reinterpret_cast<const float4*>(row + 32 * g) + c);
-            v[4 * c] = t4.x; v[4 * c + 1] = t4.y; v[4 * c + 2] = t4.z; v[4 * c + 3] = t4.w;
-          }
-          store_ax(v);  // attention output -> operand A of out-proj
+            for (int c = 0; c < 8; ++c) {
+              float4 t4 = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (tvalid) t4 = __ldcg(reinterpret_cast<const float4*>(row + 32 * g) + c);
+              v[4 * c] = t4.x; v[4 * c + 1] = t4.y; v[4 * c + 2] = t4.z; v[4 * c + 3] = t4.w;
+            }
+            store_ax(v);  // attention output -> operand A of out-proj
 #pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            float4 t4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (tvalid) t4 = __ldcg(reinterpret_cast<const float4*>(row + 128 + 32 * g) + c);
-            v[4 * c] = t4.x; v[4 * c + 1] = t4.y; v[4 * c + 2] = t4.z; v[4 * c + 3] = t4.w;
+            for (int c = 0; c < 8; ++c) {
+              float4 t4 = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (tvalid) t4 = __ldcg(reinterpret_cast<const float4*>(row + 128 + 32 * g) + c);
+              v[4 * c] = t4.x; v[4 * c + 1] = t4.y; v[4 * c + 2] = t4.z; v[4 * c + 3] = t4.w;
+            }
+            tmem_st32(trow + TM_R + 32 * g, v);  // x + b_o -> accumulator of out-proj
+            tmem_st_wait();
+            tc_fence_before();
+            fence_proxy_async_smem();
+            arrive_lead(B_AREADY);
+            head_valid = (g == 0) && tvalid;
+            head_q = tq;
+            pending = 0;
           }
-          tmem_st32(trow + TM_R + 32 * g, v);  // x + b_o -> accumulator of out-proj
-          tmem_st_wait();
-          tc_fence_before();
-          fence_proxy_async_smem();
-          arrive_lead(B_AREADY);
-          post_attn(2, g == 0 && tvalid, tq);
         }
-        pending = 0;
+        if (post) post_attn(layer, head_valid, head_q);
       }
       ++tiles_done;
     }
