@@ -6,7 +6,8 @@ C ABI declared in ``include/slice3d_b200.h``.
 """
 from .models import Slices3DRegModel  # noqa: F401
 from .generator import Generator3D  # noqa: F401
+from .mcubes import Mesh, marching_cubes  # noqa: F401
 from .mise import MISE  # noqa: F401
 from .synth import make_3d_grid  # noqa: F401
 
-__all__ = ["Slices3DRegModel", "Generator3D", "MISE", "make_3d_grid"]
+__all__ = ["Slices3DRegModel", "Generator3D", "MISE", "Mesh", "marching_cubes", "make_3d_grid"]

@@ -16,7 +16,10 @@
   query points never leave the GPU, and every refinement round is ONE decoder launch instead of
   ceil(n / 3000) model calls; the resulting (R+1)^3 volume equals the reference's.
 
-Mesh extraction (marching cubes, reconstruct.py:175-243) is outside the hot path.
+* ``extract_mesh(value_grid)`` is reconstruct.py:175-243 without the dead branches: pad with -1e6, marching cubes
+  (``slice3d_b200.mcubes``: same vertex array as libmcubes bit for bit, same oriented polygons, its own fan
+  triangulation), undo the padding / cell-centre shift, normalise to the unit box.  Returns a minimal ``Mesh``
+  (vertices, faces, ``export``) in place of the trimesh object.
 """
 import math
 
@@ -24,6 +27,7 @@ import numpy as np
 import torch
 
 from . import dist as s3d_dist
+from .mcubes import Mesh, marching_cubes
 from .mise import MISE
 from .synth import make_3d_grid  # noqa: F401  (re-exported: reference src_convonet/common.py:145)
 
@@ -82,8 +86,27 @@ class Generator3D(object):
         return self.extract_mesh(value_grid, c, stats_dict=stats_dict if stats_dict is not None else {})
 
     def extract_mesh(self, occ_hat, c=None, stats_dict=None):
-        raise NotImplementedError("marching cubes / mesh export (reconstruct.py:175-243) is outside the hot path "
-                                  "(SURVEY.md section 8f-2); generate_grid() returns the value volume")
+        """reconstruct.py:175-243.  ``occ_hat``: (nx,ny,nz) value grid (numpy or tensor; evaluated in float64 like the
+        reference's np.pad + libmcubes path)."""
+        if self.with_normals or self.refinement_step > 0:
+            # the reference's estimate_normals / refine_mesh call a model.decode() that does not exist (SURVEY.md 8b)
+            raise NotImplementedError("with_normals / refinement_step > 0 are dead code in the reference (model.decode)")
+        if self.simplify_nfaces is not None or self.vol_bound is not None:
+            raise NotImplementedError("simplify_nfaces / vol_bound are not supported (trimesh / crop pipeline)")
+        dev = next(self.model.parameters()).device if self.model is not None else "cpu"
+        vol = torch.as_tensor(occ_hat).to(device=dev, dtype=torch.float64)
+        n_x, n_y, n_z = vol.shape
+        box_size = 1 + self.padding
+        threshold = self.threshold_logit()
+        padded = torch.nn.functional.pad(vol, (1, 1, 1, 1, 1, 1), value=-1e6)  # make sure that the mesh is watertight
+        vertices, triangles = marching_cubes(padded, threshold)
+        vertices = vertices - 0.5  # libmcubes' cell-centre shift (reconstruct.py:193-194)
+        vertices = vertices - 1    # undo padding
+        vertices = vertices / torch.tensor([n_x - 1, n_y - 1, n_z - 1], dtype=torch.float64, device=vertices.device)
+        vertices = box_size * (vertices - 0.5)
+        if stats_dict is not None:
+            stats_dict["n_vertices"], stats_dict["n_faces"] = int(vertices.shape[0]), int(triangles.shape[0])
+        return Mesh(vertices.cpu().numpy(), triangles.cpu().numpy())
 
     # ------------------------------------------------------------------ dense hot path
     def grid_axes(self, nx, device):
