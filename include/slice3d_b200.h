@@ -20,6 +20,8 @@
  *   s3d_decoder_grid_fwd  <- the same over a make_3d_grid slab without materialising
  *                            the (nx*ny*nz,3) point tensor (src_convonet/common.py:145-164,
  *                            reconstruct.py:137-146).
+ *   s3d_vgg_loss_fwd      <- self.vggptlossfunc(slices_rec, img_slices) (models.py:90-92,
+ *                            vgg_perceptual_loss.py:51-71), evaluated in every forward.
  *
  * Conventions
  *   - plain C types only; every pointer named *_dev is a CUDA device pointer on the
