@@ -150,6 +150,20 @@ size_t s3d_vgg_loss_workspace_bytes(int32_t N, int32_t S);
 int s3d_vgg_loss_fwd(const s3d_model* m, const float* a_dev, const float* b_dev, int32_t N, int32_t S, float* loss_dev,
                      void* workspace_dev, size_t workspace_bytes, void* stream);
 
+/* Marching cubes over a float64 volume (nx,ny,nz), replacing libmcubes.marching_cubes (reg_slices/reconstruct.py:190;
+ * src_convonet/utils/libmcubes/marchingcubes.h:22-196, pywrapper.cpp:90-128) in two passes around the caller's
+ * exclusive prefix sums (the running vertex / triangle counters of the sequential reference):
+ *   s3d_mc_count  per cell (x-major, (nx-1)(ny-1)(nz-1) of them): vcount = vertices the cell creates, tcount =
+ *                 tri_count_dev[configuration] (256 entries), owned = which of its edges 6, 5, 10 are crossed.
+ *   s3d_mc_emit   vbase / tbase = exclusive prefix sums of vcount / tcount; table_dev = 256 x 15 edge ids per
+ *                 configuration (5 triangles, unused entries ignored); writes verts (n,3) float64 -- the reference's
+ *                 vertex array bit for bit, in its order -- and tris (m,3) int64. */
+int s3d_mc_count(const double* vol_dev, int32_t nx, int32_t ny, int32_t nz, double isovalue, const int32_t* tri_count_dev,
+                 int32_t* vcount_dev, int32_t* tcount_dev, uint8_t* owned_dev, void* stream);
+int s3d_mc_emit(const double* vol_dev, int32_t nx, int32_t ny, int32_t nz, double isovalue, const int8_t* table_dev,
+                const int64_t* vbase_dev, const int64_t* tbase_dev, const int32_t* tcount_dev, const uint8_t* owned_dev,
+                double* verts_dev, int64_t* tris_dev, void* stream);
+
 /* Instrumentation of the tensor-core decoder: 32 cycle counters (clock64 deltas summed over CTAs since the
  * last reset; index meaning in slice3d_b200/_native.py PROFILE_FIELDS).  Synchronises the device. */
 int s3d_debug_profile(int64_t* out32, int32_t reset);

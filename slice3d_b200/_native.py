@@ -21,7 +21,7 @@ SYMBOLS = [
     "s3d_abi_version", "s3d_last_error", "s3d_model_create", "s3d_model_destroy", "s3d_model_n_slices",
     "s3d_planes_bytes", "s3d_encoder_workspace_bytes", "s3d_encoder_fwd", "s3d_decoder_workspace_bytes",
     "s3d_decoder_fwd", "s3d_decoder_grid_fwd", "s3d_decoder_debug_tokens", "s3d_vgg_loss_workspace_bytes",
-    "s3d_vgg_loss_fwd", "s3d_selftest_umma", "s3d_debug_profile", "s3d_launch_count",
+    "s3d_vgg_loss_fwd", "s3d_mc_count", "s3d_mc_emit", "s3d_selftest_umma", "s3d_debug_profile", "s3d_launch_count",
 ]
 
 
@@ -84,6 +84,12 @@ def lib():
     L.s3d_vgg_loss_fwd.restype = C.c_int
     L.s3d_vgg_loss_fwd.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
                                    C.c_size_t, C.c_void_p]
+    L.s3d_mc_count.restype = C.c_int
+    L.s3d_mc_count.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p,
+                               C.c_void_p, C.c_void_p]
+    L.s3d_mc_emit.restype = C.c_int
+    L.s3d_mc_emit.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p,
+                              C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.s3d_selftest_umma.restype = C.c_int
     L.s3d_selftest_umma.argtypes = [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.s3d_debug_profile.restype = C.c_int
@@ -111,6 +117,33 @@ def selftest_umma(mode, passes, a, w):
     with torch.cuda.device(a.device):
         _check(lib().s3d_selftest_umma(mode, passes, a.data_ptr(), w.data_ptr(), d.data_ptr(), _stream(a.device)))
     return d
+
+
+def marching_cubes(vol, isovalue, tri_table, tri_count):
+    """vol (nx,ny,nz) float64 CUDA tensor; tri_table (256,15) int8 and tri_count (256,) int32 on the same device.
+    -> (vertices (n,3) float64, triangles (m,3) int64): two kernels around torch.cumsum."""
+    if not vol.is_cuda or vol.dtype != torch.float64 or not vol.is_contiguous():
+        raise NativeError("marching_cubes needs a contiguous float64 CUDA volume")
+    nx, ny, nz = vol.shape
+    dev, L = vol.device, lib()
+    cells = (nx - 1) * (ny - 1) * (nz - 1)
+    with torch.cuda.device(dev):
+        vcount = torch.empty(cells, dtype=torch.int32, device=dev)
+        tcount = torch.empty(cells, dtype=torch.int32, device=dev)
+        owned = torch.empty(cells, dtype=torch.uint8, device=dev)
+        _check(L.s3d_mc_count(vol.data_ptr(), nx, ny, nz, float(isovalue), tri_count.data_ptr(), vcount.data_ptr(),
+                              tcount.data_ptr(), owned.data_ptr(), _stream(dev)))
+        vsum = torch.cumsum(vcount, 0, dtype=torch.int64)
+        tsum = torch.cumsum(tcount, 0, dtype=torch.int64)
+        n_v, n_t = int(vsum[-1]), int(tsum[-1])
+        verts = torch.empty((n_v, 3), dtype=torch.float64, device=dev)
+        tris = torch.empty((n_t, 3), dtype=torch.int64, device=dev)
+        if n_v:
+            vbase, tbase = vsum - vcount, tsum - tcount
+            _check(L.s3d_mc_emit(vol.data_ptr(), nx, ny, nz, float(isovalue), tri_table.data_ptr(), vbase.data_ptr(),
+                                 tbase.data_ptr(), tcount.data_ptr(), owned.data_ptr(), verts.data_ptr(), tris.data_ptr(),
+                                 _stream(dev)))
+    return verts, tris
 
 
 PROFILE_FIELDS = ["token", "vec", "wait_qkv", "attn", "wait_out", "ln1", "ffn_wait_d1", "ffn_math", "ffn_wait_hfree",

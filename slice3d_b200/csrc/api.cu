@@ -420,6 +420,20 @@ int s3d_vgg_loss_fwd(const s3d_model* m, const float* a_dev, const float* b_dev,
   return vgg_loss_fwd(m, a_dev, b_dev, N, S, loss_dev, workspace_dev, workspace_bytes, static_cast<cudaStream_t>(stream));
 }
 
+int s3d_mc_count(const double* vol_dev, int32_t nx, int32_t ny, int32_t nz, double isovalue, const int32_t* tri_count_dev,
+                 int32_t* vcount_dev, int32_t* tcount_dev, uint8_t* owned_dev, void* stream) {
+  return mc_count(vol_dev, nx, ny, nz, isovalue, tri_count_dev, vcount_dev, tcount_dev, owned_dev,
+                  static_cast<cudaStream_t>(stream));
+}
+
+int s3d_mc_emit(const double* vol_dev, int32_t nx, int32_t ny, int32_t nz, double isovalue, const int8_t* table_dev,
+                const int64_t* vbase_dev, const int64_t* tbase_dev, const int32_t* tcount_dev, const uint8_t* owned_dev,
+                double* verts_dev, int64_t* tris_dev, void* stream) {
+  return mc_emit(vol_dev, nx, ny, nz, isovalue, reinterpret_cast<const signed char*>(table_dev),
+                 reinterpret_cast<const long long*>(vbase_dev), reinterpret_cast<const long long*>(tbase_dev), tcount_dev,
+                 owned_dev, verts_dev, reinterpret_cast<long long*>(tris_dev), static_cast<cudaStream_t>(stream));
+}
+
 int s3d_debug_profile(int64_t* out32, int32_t reset) { return debug_profile(reinterpret_cast<long long*>(out32), reset); }
 
 int s3d_selftest_umma(int32_t mode, int32_t passes, const float* a_dev, const float* w_dev, float* d_dev,

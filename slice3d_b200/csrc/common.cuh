@@ -157,6 +157,13 @@ int conv_tc(const ConvTC& w, const __half* in_hi, const __half* in_lo, int NI, i
             int shuffle_c = 0);
 int enctc_pack(s3d_model* m, cudaStream_t st);
 
+// mcubes.cu
+int mc_count(const double* vol, int nx, int ny, int nz, double iso, const int* tri_count, int* vcount, int* tcount,
+             unsigned char* owned, cudaStream_t st);
+int mc_emit(const double* vol, int nx, int ny, int nz, double iso, const signed char* table, const long long* vbase,
+            const long long* tbase, const int* tcount, const unsigned char* owned, double* verts, long long* tris,
+            cudaStream_t st);
+
 // perceptual.cu
 size_t vgg_loss_workspace_bytes(int N, int S);
 int vgg_loss_fwd(const s3d_model* m, const float* a, const float* b, int N, int S, float* loss, void* ws, size_t ws_bytes,

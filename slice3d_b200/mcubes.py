@@ -96,6 +96,7 @@ def _build_tables():
 
 
 _TABLE, _COUNT = _build_tables()
+_DEV_TABLES = {}
 
 
 def marching_cubes(volume, isovalue):
@@ -107,6 +108,17 @@ def marching_cubes(volume, isovalue):
     cx, cy, cz = nx - 1, ny - 1, nz - 1
     if min(cx, cy, cz) <= 0:
         return torch.zeros((0, 3), dtype=torch.float64, device=dev), torch.zeros((0, 3), dtype=torch.int64, device=dev)
+    if vol.is_cuda:
+        # on the device: two hand-written kernels around the prefix sums (csrc/mcubes.cu, s3d_mc_count / s3d_mc_emit);
+        # the tensor program below is the same algorithm for host tensors (what the CPU tests run)
+        from . import _native
+        key = str(dev)
+        if key not in _DEV_TABLES:
+            t15 = np.where(_TABLE.reshape(256, 15) < 0, 0, _TABLE.reshape(256, 15)).astype(np.int8)
+            _DEV_TABLES[key] = (torch.as_tensor(t15, device=dev).contiguous(),
+                                torch.as_tensor(_COUNT.astype(np.int32), device=dev).contiguous())
+        tab, cnt = _DEV_TABLES[key]
+        return _native.marching_cubes(vol.contiguous(), isovalue, tab, cnt)
     iso = float(isovalue)
     v = [vol[a:a + cx, b:b + cy, c:c + cz] for a, b, c in _CORNERS]  # corner values per cell
     inside = [x <= iso for x in v]
