@@ -150,6 +150,16 @@ size_t s3d_vgg_loss_workspace_bytes(int32_t N, int32_t S);
 int s3d_vgg_loss_fwd(const s3d_model* m, const float* a_dev, const float* b_dev, int32_t N, int32_t S, float* loss_dev,
                      void* workspace_dev, size_t workspace_bytes, void* stream);
 
+/* One MISE refinement step on dense device state, replacing MISE.subdivide_voxels (reg_slices/src_convonet/utils/
+ * libmise/mise.pyx:184-283) after the caller has stored the new values: R = resolution0 << depth; value_dev / known_dev /
+ * exists_dev are (R+1)^3 lattice arrays (float64 / bytes), cell_level_dev is the R^3 int8 array "level of the leaf voxel
+ * containing this unit cell" (the octree), flags_dev a scratch of s3d_mise_scratch_ints() int32 that is zero on entry and
+ * zero again on return.  Every leaf voxel below `depth` that is next to a known value >= threshold AND a known value <=
+ * threshold is split (its cells move one level down, the 27 lattice points of its children start to exist). */
+size_t s3d_mise_scratch_ints(int32_t resolution0, int32_t depth);
+int s3d_mise_subdivide(int32_t resolution0, int32_t depth, double threshold, const double* value_dev, const uint8_t* known_dev,
+                       int8_t* cell_level_dev, uint8_t* exists_dev, int32_t* flags_dev, void* stream);
+
 /* Marching cubes over a float64 volume (nx,ny,nz), replacing libmcubes.marching_cubes (reg_slices/reconstruct.py:190;
  * src_convonet/utils/libmcubes/marchingcubes.h:22-196, pywrapper.cpp:90-128) in two passes around the caller's
  * exclusive prefix sums (the running vertex / triangle counters of the sequential reference):

@@ -21,7 +21,8 @@ SYMBOLS = [
     "s3d_abi_version", "s3d_last_error", "s3d_model_create", "s3d_model_destroy", "s3d_model_n_slices",
     "s3d_planes_bytes", "s3d_encoder_workspace_bytes", "s3d_encoder_fwd", "s3d_decoder_workspace_bytes",
     "s3d_decoder_fwd", "s3d_decoder_grid_fwd", "s3d_decoder_debug_tokens", "s3d_vgg_loss_workspace_bytes",
-    "s3d_vgg_loss_fwd", "s3d_mc_count", "s3d_mc_emit", "s3d_selftest_umma", "s3d_debug_profile", "s3d_launch_count",
+    "s3d_vgg_loss_fwd", "s3d_mc_count", "s3d_mc_emit", "s3d_mise_scratch_ints",
+    "s3d_mise_subdivide", "s3d_selftest_umma", "s3d_debug_profile", "s3d_launch_count",
 ]
 
 
@@ -90,6 +91,11 @@ def lib():
     L.s3d_mc_emit.restype = C.c_int
     L.s3d_mc_emit.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p,
                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.s3d_mise_scratch_ints.restype = C.c_size_t
+    L.s3d_mise_scratch_ints.argtypes = [C.c_int32, C.c_int32]
+    L.s3d_mise_subdivide.restype = C.c_int
+    L.s3d_mise_subdivide.argtypes = [C.c_int32, C.c_int32, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                     C.c_void_p, C.c_void_p]
     L.s3d_selftest_umma.restype = C.c_int
     L.s3d_selftest_umma.argtypes = [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.s3d_debug_profile.restype = C.c_int
@@ -117,6 +123,18 @@ def selftest_umma(mode, passes, a, w):
     with torch.cuda.device(a.device):
         _check(lib().s3d_selftest_umma(mode, passes, a.data_ptr(), w.data_ptr(), d.data_ptr(), _stream(a.device)))
     return d
+
+
+def mise_subdivide(res0, depth, threshold, value, known, cell_level, exists, flags):
+    """One refinement step on the dense MISE state tensors (all on one CUDA device; flags int32 zeros, left zeroed)."""
+    dev = value.device
+    with torch.cuda.device(dev):
+        _check(lib().s3d_mise_subdivide(res0, depth, float(threshold), value.data_ptr(), known.data_ptr(),
+                                        cell_level.data_ptr(), exists.data_ptr(), flags.data_ptr(), _stream(dev)))
+
+
+def mise_scratch_ints(res0, depth):
+    return int(lib().s3d_mise_scratch_ints(res0, depth))
 
 
 def marching_cubes(vol, isovalue, tri_table, tri_count):

@@ -434,6 +434,14 @@ int s3d_mc_emit(const double* vol_dev, int32_t nx, int32_t ny, int32_t nz, doubl
                  owned_dev, verts_dev, reinterpret_cast<long long*>(tris_dev), static_cast<cudaStream_t>(stream));
 }
 
+size_t s3d_mise_scratch_ints(int32_t resolution0, int32_t depth) { return mise_scratch_ints(resolution0, depth); }
+
+int s3d_mise_subdivide(int32_t resolution0, int32_t depth, double threshold, const double* value_dev, const uint8_t* known_dev,
+                       int8_t* cell_level_dev, uint8_t* exists_dev, int32_t* flags_dev, void* stream) {
+  return mise_subdivide(resolution0, depth, threshold, value_dev, known_dev, reinterpret_cast<signed char*>(cell_level_dev),
+                        exists_dev, flags_dev, static_cast<cudaStream_t>(stream));
+}
+
 int s3d_debug_profile(int64_t* out32, int32_t reset) { return debug_profile(reinterpret_cast<long long*>(out32), reset); }
 
 int s3d_selftest_umma(int32_t mode, int32_t passes, const float* a_dev, const float* w_dev, float* d_dev,

@@ -164,6 +164,11 @@ int mc_emit(const double* vol, int nx, int ny, int nz, double iso, const signed 
             const long long* tbase, const int* tcount, const unsigned char* owned, double* verts, long long* tris,
             cudaStream_t st);
 
+// mise.cu
+size_t mise_scratch_ints(int res0, int depth);
+int mise_subdivide(int res0, int depth, double thr, const double* value, const unsigned char* known, signed char* cell_level,
+                   unsigned char* exists, int* flags_zeroed, cudaStream_t st);
+
 // perceptual.cu
 size_t vgg_loss_workspace_bytes(int N, int S);
 int vgg_loss_fwd(const s3d_model* m, const float* a, const float* b, int N, int S, float* loss, void* ws, size_t ws_bytes,

@@ -43,6 +43,7 @@ class MISE(object):
         self._adj = torch.stack(torch.meshgrid(o, o, o, indexing="ij"), -1).reshape(8, 3)
         t = torch.arange(3, device=self.device)
         self._child_pts = torch.stack(torch.meshgrid(t, t, t, indexing="ij"), -1).reshape(27, 3)
+        self._flags = None
 
     # ------------------------------------------------------------------ reference API
     def query(self):
@@ -79,6 +80,16 @@ class MISE(object):
     def _subdivide_voxels(self):
         R, depth = self.resolution, self.depth
         if depth == 0:
+            return
+        if self.device.type == "cuda":
+            # on the device: two hand-written kernels (csrc/mise.cu, s3d_mise_subdivide); the tensor program below is
+            # the same step for host tensors (what the CPU tests run against the reference)
+            from . import _native
+            if self._flags is None:
+                self._flags = torch.zeros(_native.mise_scratch_ints(self.resolution_0, depth), dtype=torch.int32,
+                                          device=self.device)
+            _native.mise_subdivide(self.resolution_0, depth, self.threshold, self.value, self.known, self.cell_level,
+                                   self.exists, self._flags)
             return
         pts = torch.nonzero(self.known)
         val = self.value[pts[:, 0], pts[:, 1], pts[:, 2]]
