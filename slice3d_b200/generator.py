@@ -182,7 +182,7 @@ class Generator3D(object):
                 nat.decode(planes, 0, pointsf[lo:hi].contiguous(), T[0], None, True, -1.0, precision, out=vals[lo:hi])
             if world > 1:
                 s3d_dist.all_gather_ranges(vals, n, group)
-            ext.update(points, vals.double())
+            ext.update(points, vals.double(), validate=False)
             rounds.append(n)
             points = ext.query()
         if stats is not None:

@@ -50,14 +50,15 @@ class MISE(object):
         """(n, 3) int64 lattice coordinates of the grid points whose value is still unknown."""
         return torch.nonzero(self.exists & ~self.known)
 
-    def update(self, points, values):
-        """Set ``values`` (n,) at ``points`` (n, 3) and split every active voxel."""
+    def update(self, points, values, validate=True):
+        """Set ``values`` (n,) at ``points`` (n, 3) and split every active voxel.  ``validate=False`` skips the
+        "Point not in grid!" check (one device synchronisation) when the points come straight from ``query()``."""
         points = torch.as_tensor(points, device=self.device).long()
         values = torch.as_tensor(values, device=self.device).double()
         if points.shape[0] != values.shape[0] or points.shape[1] != 3:
             raise ValueError("points must be (n, 3) and values (n,)")
         px, py, pz = points.unbind(1)
-        if points.numel() and not bool(self.exists[px, py, pz].all()):
+        if validate and points.numel() and not bool(self.exists[px, py, pz].all()):
             raise ValueError("Point not in grid!")
         self.value[px, py, pz] = values
         self.known[px, py, pz] = True
