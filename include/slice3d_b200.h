@@ -56,7 +56,9 @@ extern "C" {
 /* Decoder arithmetic.  All modes accumulate in fp32. */
 #define S3D_PREC_FP32 0   /* CUDA-core fp32 (validation grade, slow)                     */
 #define S3D_PREC_BF16X3 1 /* tcgen05, operands split into bf16 hi+lo, 3 MMA passes (<=1e-4) */
-#define S3D_PREC_BF16 2   /* tcgen05, single bf16 pass (fast, ~5e-3)                      */
+#define S3D_PREC_BF16 2   /* tcgen05, single bf16 pass (fast; measured 1.8e-2 max-abs)    */
+#define S3D_PREC_FP16X3 3 /* tcgen05, operands split into fp16 hi+lo, 3 MMA passes: same speed as BF16X3, ~10x
+                             smaller error (22 instead of 16 mantissa bits); activations saturate at 65504 */
 
 typedef struct s3d_model s3d_model;
 
@@ -117,6 +119,14 @@ int s3d_decoder_fwd(const s3d_model* m, const void* planes_dev, int32_t S, float
                     float* out_dev, int32_t precision, void* workspace_dev, size_t workspace_bytes,
                     void* stream);
 
+/* The same for a batch: B images whose planes lie back to back in planes_dev (the encoder's batch layout), qry_dev
+ * (B, n_per_image, 3), T_dev (B,4,3), rot_dev (B,3,3) or NULL, out_dev (B, n_per_image): ONE launch for the whole
+ * feed_dict of Slices3DRegModel.forward (models.py:48-94 with n_bs > 1, e.g. train.py:val_step). */
+int s3d_decoder_batch_fwd(const s3d_model* m, const void* planes_dev, int32_t S, float* qry_dev, int32_t B,
+                          int64_t n_per_image, const float* T_dev, const float* rot_dev, int32_t flip_in_place,
+                          float out_scale, float* out_dev, int32_t precision, void* workspace_dev,
+                          size_t workspace_bytes, void* stream);
+
 /* Decoder over grid points [first, first+count) of `grid` (test-mode y,z flip applied
  * on the fly).  out_dev receives `count` values. */
 int s3d_decoder_grid_fwd(const s3d_model* m, const void* planes_dev, int32_t S, const s3d_grid* grid,
@@ -133,7 +143,8 @@ int s3d_decoder_debug_tokens(const s3d_model* m, const void* planes_dev, int32_t
 
 /* Hardware self-test of the tensor-core plumbing the decoder relies on (UMMA shared-memory and
  * instruction descriptors, 128-byte-swizzled operand tiles, bulk async copy, TMEM load): one
- * 128-row tile against one weight unit, passes = 1 (bf16) or 3 (bf16 hi/lo split).
+ * 128-row tile against one weight unit, passes = 1 (bf16), 3 (bf16 hi/lo split) or 4 (= three passes over
+ * fp16 hi/lo pairs, the S3D_PREC_FP16X3 operands).
  *   d[128][128] = a[128][128] . w[128][128]^T;  mode 0: A operand in shared memory, mode 1: A operand in
  *   tensor memory (the two operand paths of the decoder).
  * a_dev, w_dev, d_dev are fp32 row-major device arrays.  Synchronises the stream. */

@@ -12,15 +12,15 @@ import torch
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("S3D_LIB") or os.path.join(HERE, "_lib", "libslice3d_b200.so")  # S3D_LIB: kernel experiments
 
-PREC_FP32, PREC_BF16X3, PREC_BF16 = 0, 1, 2
-PRECISIONS = {"fp32": PREC_FP32, "bf16x3": PREC_BF16X3, "bf16": PREC_BF16}
+PREC_FP32, PREC_BF16X3, PREC_BF16, PREC_FP16X3 = 0, 1, 2, 3
+PRECISIONS = {"fp32": PREC_FP32, "bf16x3": PREC_BF16X3, "bf16": PREC_BF16, "fp16x3": PREC_FP16X3}
 ABI_VERSION = 1
 
 # every symbol include/slice3d_b200.h declares (tests check the library exports all of them)
 SYMBOLS = [
     "s3d_abi_version", "s3d_last_error", "s3d_model_create", "s3d_model_destroy", "s3d_model_n_slices",
     "s3d_planes_bytes", "s3d_encoder_workspace_bytes", "s3d_encoder_fwd", "s3d_decoder_workspace_bytes",
-    "s3d_decoder_fwd", "s3d_decoder_grid_fwd", "s3d_decoder_debug_tokens", "s3d_vgg_loss_workspace_bytes",
+    "s3d_decoder_fwd", "s3d_decoder_batch_fwd", "s3d_decoder_grid_fwd", "s3d_decoder_debug_tokens", "s3d_vgg_loss_workspace_bytes",
     "s3d_vgg_loss_fwd", "s3d_mc_count", "s3d_mc_emit", "s3d_mise_scratch_ints",
     "s3d_mise_subdivide", "s3d_selftest_umma", "s3d_debug_profile", "s3d_launch_count",
 ]
@@ -73,6 +73,10 @@ def lib():
     L.s3d_decoder_fwd.restype = C.c_int
     L.s3d_decoder_fwd.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
                                   C.c_int32, C.c_float, C.c_void_p, C.c_int32, C.c_void_p, C.c_size_t, C.c_void_p]
+    L.s3d_decoder_batch_fwd.restype = C.c_int
+    L.s3d_decoder_batch_fwd.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p,
+                                        C.c_void_p, C.c_int32, C.c_float, C.c_void_p, C.c_int32, C.c_void_p, C.c_size_t,
+                                        C.c_void_p]
     L.s3d_decoder_grid_fwd.restype = C.c_int
     L.s3d_decoder_grid_fwd.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(S3DGrid), C.c_int64, C.c_int64,
                                        C.c_void_p, C.c_float, C.c_void_p, C.c_int32, C.c_void_p, C.c_size_t,
@@ -113,7 +117,7 @@ def _check(rc):
 
 def available_precisions():
     """Decoder arithmetic modes built into this revision of the library."""
-    return ("fp32", "bf16x3", "bf16")
+    return ("fp32", "fp16x3", "bf16x3", "bf16")
 
 
 def selftest_umma(mode, passes, a, w):
@@ -285,7 +289,7 @@ class NativeModel:
         return out
 
     # ---- decoder ----------------------------------------------------------------
-    def decode(self, planes, b, qry, T, rot=None, flip_in_place=False, out_scale=1.0, precision="bf16x3", out=None):
+    def decode(self, planes, b, qry, T, rot=None, flip_in_place=False, out_scale=1.0, precision="fp16x3", out=None):
         """qry (n,3) of image b -> (n,) = out_scale * sdf_pred.  rot None = test mode (y,z negated)."""
         if not qry.is_cuda or qry.dtype != torch.float32 or not qry.is_contiguous():
             raise NativeError("qry must be a contiguous float32 CUDA tensor")
@@ -303,7 +307,27 @@ class NativeModel:
                                      _stream(self.device)))
         return out
 
-    def decode_grid(self, planes, b, axes, first, count, T, out_scale=1.0, precision="bf16x3", out=None):
+    def decode_batch(self, planes, qry, T, rot=None, flip_in_place=False, out_scale=1.0, precision="fp16x3", out=None):
+        """All images of an encoder batch in ONE launch: qry (B,n,3), T (B,4,3), rot (B,3,3) or None -> (B,n)."""
+        if not qry.is_cuda or qry.dtype != torch.float32 or not qry.is_contiguous() or qry.dim() != 3:
+            raise NativeError("qry must be a contiguous float32 CUDA tensor (B,n,3)")
+        B, n = qry.shape[0], qry.shape[1]
+        if B != planes.B:
+            raise NativeError("qry batch does not match the encoder batch")
+        T = _f32c(T, "trans_mat_wo_rot_tp")
+        rot = _f32c(rot, "obj_rot_mat") if rot is not None else None
+        L, prec = lib(), PRECISIONS[precision]
+        with torch.cuda.device(self.device):
+            if out is None:
+                out = torch.empty(B, n, dtype=torch.float32, device=self.device)
+            ws = self._workspace("dec", L.s3d_decoder_workspace_bytes(B * n, prec))
+            _check(L.s3d_decoder_batch_fwd(self._h, planes.image_ptr(0), planes.S, qry.data_ptr(), B, n, T.data_ptr(),
+                                           rot.data_ptr() if rot is not None else None, 1 if flip_in_place else 0,
+                                           out_scale, out.data_ptr(), prec, ws.data_ptr(), ws.numel(),
+                                           _stream(self.device)))
+        return out
+
+    def decode_grid(self, planes, b, axes, first, count, T, out_scale=1.0, precision="fp16x3", out=None):
         """Grid points [first, first+count) of the (nx,ny,nz) grid given by the three per-axis
         coordinate tensors ``axes`` (x slowest, z fastest), test-mode flip applied on the fly."""
         px, py, pz = (_f32c(a, "grid axis") for a in axes)

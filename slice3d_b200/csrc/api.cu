@@ -263,23 +263,45 @@ __global__ void k_flip_yz(float* q, long long n) {
   q[3 * i + 2] = -q[3 * i + 2];
 }
 
-int run_decoder(const s3d_model* m, const void* planes, int S, const QueryCtx& q, int64_t n, float out_scale,
-                float* out, int precision, float* debug_tokens, void* ws, size_t ws_bytes, cudaStream_t st) {
-  if (!m || !planes || !out || !q.T || n < 0 || S < 32 || S % 16) {
+// Argument / capability / workspace validation of a decoder call, separate from the launch so that entry points with
+// side effects on the caller's buffers (the in-place y,z flip) can validate first.
+int check_decoder(const s3d_model* m, const void* planes, int S, const float* T, int64_t n, const float* out, int precision,
+                  const float* debug_tokens, const void* ws, size_t ws_bytes) {
+  if (!m || !planes || !out || !T || n < 0 || S < 32 || S % 16) {
     set_error("decoder: bad argument");
     return S3D_ERR_BAD_ARG;
   }
-  if (precision == S3D_PREC_FP32)
-    return decoder_simt(m, static_cast<const float*>(planes), S, q, n, out_scale, out, debug_tokens, ws, ws_bytes, st);
-  if (precision == S3D_PREC_BF16X3 || precision == S3D_PREC_BF16) {
+  if (precision != S3D_PREC_FP32 && precision != S3D_PREC_BF16X3 && precision != S3D_PREC_BF16 &&
+      precision != S3D_PREC_FP16X3) {
+    set_error("decoder: unknown precision mode");
+    return S3D_ERR_BAD_ARG;
+  }
+  if (precision != S3D_PREC_FP32) {
     if (debug_tokens) {
       set_error("decoder: token dump is only available with S3D_PREC_FP32");
       return S3D_ERR_UNSUPPORTED;
     }
-    return decoder_tc(m, static_cast<const float*>(planes), S, q, n, out_scale, out, precision, ws, ws_bytes, st);
+    if (!decoder_tc_supported(m)) {
+      set_error("decoder: this n_slices has no tensor-core instantiation (use S3D_PREC_FP32)");
+      return S3D_ERR_UNSUPPORTED;
+    }
+  } else if (m->K > 12) {
+    set_error("decoder(fp32): n_slices > 12 unsupported");
+    return S3D_ERR_UNSUPPORTED;
   }
-  set_error("decoder: unknown precision mode");
-  return S3D_ERR_BAD_ARG;
+  if (n > 0 && (ws == nullptr || ws_bytes < s3d_decoder_workspace_bytes(n, precision))) {
+    set_error("decoder: workspace too small");
+    return S3D_ERR_WORKSPACE;
+  }
+  return S3D_OK;
+}
+
+int run_decoder(const s3d_model* m, const void* planes, int S, const QueryCtx& q, int64_t n, float out_scale,
+                float* out, int precision, float* debug_tokens, void* ws, size_t ws_bytes, cudaStream_t st) {
+  S3D_TRY(check_decoder(m, planes, S, q.T, n, out, precision, debug_tokens, ws, ws_bytes));
+  if (precision == S3D_PREC_FP32)
+    return decoder_simt(m, static_cast<const float*>(planes), S, q, n, out_scale, out, debug_tokens, ws, ws_bytes, st);
+  return decoder_tc(m, static_cast<const float*>(planes), S, q, n, out_scale, out, precision, ws, ws_bytes, st);
 }
 
 }  // namespace
@@ -368,9 +390,15 @@ size_t s3d_decoder_workspace_bytes(int64_t n, int32_t precision) {
   return decoder_tc_workspace_bytes(n);
 }
 
-int s3d_decoder_fwd(const s3d_model* m, const void* planes_dev, int32_t S, float* qry_dev, int64_t n,
-                    const float* T_dev, const float* rot_dev, int32_t flip_in_place, float out_scale, float* out_dev,
-                    int32_t precision, void* workspace_dev, size_t workspace_bytes, void* stream) {
+int s3d_decoder_batch_fwd(const s3d_model* m, const void* planes_dev, int32_t S, float* qry_dev, int32_t B,
+                          int64_t n_per_image, const float* T_dev, const float* rot_dev, int32_t flip_in_place,
+                          float out_scale, float* out_dev, int32_t precision, void* workspace_dev, size_t workspace_bytes,
+                          void* stream) {
+  if (B < 1 || n_per_image < 0) {
+    set_error("decoder: bad batch");
+    return S3D_ERR_BAD_ARG;
+  }
+  const int64_t n = (int64_t)B * n_per_image;
   if (n == 0) return S3D_OK;  /* empty query set (a zero-element tensor has a null data pointer) */
   if (!qry_dev) {
     set_error("decoder: null query pointer");
@@ -381,12 +409,25 @@ int s3d_decoder_fwd(const s3d_model* m, const void* planes_dev, int32_t S, float
   q.qry = qry_dev;
   q.T = T_dev;
   q.rot = rot_dev;
+  if (B > 1) {
+    q.per_img = n_per_image;
+    q.plane_stride = plane_offset_floats(m ? m->K : 0, S, 5);
+  }
+  // validate everything before touching the caller's query tensor: a failing call must leave it unflipped
+  S3D_TRY(check_decoder(m, planes_dev, S, T_dev, n, out_dev, precision, nullptr, workspace_dev, workspace_bytes));
   if (!rot_dev && flip_in_place && n > 0) {
     k_flip_yz<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(qry_dev, n);
     S3D_LAUNCH_CHECK();
     q.preflipped = 1;
   }
   return run_decoder(m, planes_dev, S, q, n, out_scale, out_dev, precision, nullptr, workspace_dev, workspace_bytes, st);
+}
+
+int s3d_decoder_fwd(const s3d_model* m, const void* planes_dev, int32_t S, float* qry_dev, int64_t n,
+                    const float* T_dev, const float* rot_dev, int32_t flip_in_place, float out_scale, float* out_dev,
+                    int32_t precision, void* workspace_dev, size_t workspace_bytes, void* stream) {
+  return s3d_decoder_batch_fwd(m, planes_dev, S, qry_dev, 1, n, T_dev, rot_dev, flip_in_place, out_scale, out_dev,
+                               precision, workspace_dev, workspace_bytes, stream);
 }
 
 int s3d_decoder_grid_fwd(const s3d_model* m, const void* planes_dev, int32_t S, const s3d_grid* grid, int64_t first,
@@ -402,6 +443,12 @@ int s3d_decoder_grid_fwd(const s3d_model* m, const void* planes_dev, int32_t S, 
   q.px = grid->px_dev; q.py = grid->py_dev; q.pz = grid->pz_dev;
   q.first = first;
   q.T = T_dev;
+  const int64_t plane = (int64_t)grid->ny * grid->nz;
+  if (precision != S3D_PREC_FP32 && first % plane == 0 && count % plane == 0 && count > 0) {
+    q.blk = 1;  // whole x-planes: evaluate in the locality order of common.cuh (the output layout is unchanged)
+    q.x0 = (int)(first / plane);
+    q.nxs = (int)(count / plane);
+  }
   return run_decoder(m, planes_dev, S, q, count, out_scale, out_dev, precision, nullptr, workspace_dev,
                      workspace_bytes, static_cast<cudaStream_t>(stream));
 }

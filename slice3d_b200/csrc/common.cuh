@@ -91,7 +91,8 @@ struct DecF32 {
 // tcgen05 decoder weights (decoder_tc.cu): bf16 hi/lo operand images in the canonical
 // K-major 128B-swizzled shared-memory layout, plus packed fp32 vectors.
 struct DecTC {
-  __nv_bfloat16* wimg = nullptr;
+  __nv_bfloat16* wimg = nullptr;  // bf16 hi/lo pairs
+  __half* wimg_h = nullptr;        // fp16 hi/lo pairs (S3D_PREC_FP16X3)
   float* vec = nullptr;
   size_t wimg_elems = 0;
 };
@@ -184,7 +185,17 @@ struct QueryCtx {
   long long first;
   const float* T;       // (4,3)
   const float* rot;     // (3,3) or null
+  // Locality order of a grid range made of whole x-planes [x0, x0 + nxs) (blk = 1): the i-th query of the launch is
+  // not flat index first + i but the i-th point of a walk over GRID_BX x GRID_BY blocks of (x, y) columns, z fastest
+  // inside a column.  The columns of a block project to neighbouring rays of every plane, so the texels a wave of CTAs
+  // gathers stay in L2 until the neighbouring columns need them (the flat order re-read ~260 MB per x-plane).
+  int blk, x0, nxs;
+  // Batched explicit points (per_img > 0): query i belongs to image i / per_img, whose camera is T + 12 b, rotation
+  // rot + 9 b and projected planes planes + b * plane_stride floats (the encoder's batch layout).
+  long long per_img;
+  size_t plane_stride;
 };
+constexpr int GRID_BX = 16, GRID_BY = 16;
 
 // decoder_simt.cu
 size_t decoder_simt_workspace_bytes(int64_t n);
@@ -193,6 +204,7 @@ int decoder_simt(const s3d_model* m, const float* planes, int S, const QueryCtx&
 
 // decoder_tc.cu
 int dectc_pack(s3d_model* m, cudaStream_t st);
+bool decoder_tc_supported(const s3d_model* m);
 size_t decoder_tc_workspace_bytes(int64_t n);
 int decoder_tc(const s3d_model* m, const float* planes, int S, const QueryCtx& q, int64_t n, float out_scale,
                float* out, int precision, void* ws, size_t ws_bytes, cudaStream_t st);
@@ -201,26 +213,58 @@ int debug_profile(long long* out32, int reset);
 int umma_selftest(int mode, int passes, const float* a_dev, const float* w_dev, float* d_dev, cudaStream_t st);
 
 #ifdef __CUDACC__
+// i-th query of a grid launch -> (ix, iy, iz) and its position in the launch's output range.
+__device__ __forceinline__ long long grid_point(const QueryCtx& c, long long i, int& ix, int& iy, int& iz) {
+  if (c.blk) {
+    const long long colq = c.nz, rowq = (long long)GRID_BX * c.ny * colq;  // queries per column / per row of blocks
+    const int bx = (int)(i / rowq);
+    long long r = i - bx * rowq;
+    const int wx = min(GRID_BX, c.nxs - GRID_BX * bx);
+    const long long blkq = (long long)wx * GRID_BY * colq;
+    const int by = (int)(r / blkq);
+    r -= by * blkq;
+    const int wy = min(GRID_BY, c.ny - GRID_BY * by);
+    const int rem = (int)r;  // < 16 * 16 * nz
+    const int lx = rem / (wy * c.nz);
+    const int r3 = rem - lx * (wy * c.nz);
+    const int ly = r3 / c.nz;
+    iz = r3 - ly * c.nz;
+    ix = c.x0 + GRID_BX * bx + lx;
+    iy = GRID_BY * by + ly;
+    return ((long long)(ix - c.x0) * c.ny + iy) * c.nz + iz;
+  }
+  const long long g = c.first + i;
+  iz = (int)(g % c.nz);
+  const long long t = g / c.nz;
+  iy = (int)(t % c.ny);
+  ix = (int)(t / c.ny);
+  return i;
+}
+// where the value of the i-th query of the launch goes in the caller's output
+__device__ __forceinline__ long long out_index(const QueryCtx& c, long long i) {
+  if (c.qry || !c.blk) return i;
+  int ix, iy, iz;
+  return grid_point(c, i, ix, iy, iz);
+}
+
 // Query i -> model-space point (after the test-mode y,z flip or the train-mode rotation)
 // and the clamped grid_sample coordinates (reference models.py:53-60, 28-36).
-__device__ __forceinline__ void load_query(const QueryCtx& c, long long i, float& x, float& y, float& z, float& gu,
-                                           float& gv) {
+__device__ __forceinline__ int load_query(const QueryCtx& c, long long i, float& x, float& y, float& z, float& gu,
+                                          float& gv) {
+  const int b = c.per_img > 0 ? (int)(i / c.per_img) : 0;  // image of the batch this query belongs to
   if (c.qry) {
     x = c.qry[3 * i + 0];
     y = c.qry[3 * i + 1];
     z = c.qry[3 * i + 2];
   } else {
-    long long g = c.first + i;
-    int iz = (int)(g % c.nz);
-    long long t = g / c.nz;
-    int iy = (int)(t % c.ny);
-    int ix = (int)(t / c.ny);
+    int ix, iy, iz;
+    grid_point(c, i, ix, iy, iz);
     x = c.px[ix];
     y = c.py[iy];
     z = c.pz[iz];
   }
   if (c.rot) {
-    const float* R = c.rot;  // qry_rot = qry (1x3) . R (3x3)
+    const float* R = c.rot + 9 * b;  // qry_rot = qry (1x3) . R (3x3)
     float rx = __fmaf_rn(z, R[6], __fmaf_rn(y, R[3], __fmul_rn(x, R[0])));
     float ry = __fmaf_rn(z, R[7], __fmaf_rn(y, R[4], __fmul_rn(x, R[1])));
     float rz = __fmaf_rn(z, R[8], __fmaf_rn(y, R[5], __fmul_rn(x, R[2])));
@@ -229,12 +273,13 @@ __device__ __forceinline__ void load_query(const QueryCtx& c, long long i, float
     y = -y;
     z = -z;
   }
-  const float* T = c.T;
+  const float* T = c.T + 12 * b;
   float pu = x * T[0] + y * T[3] + z * T[6] + T[9];
   float pv = x * T[1] + y * T[4] + z * T[7] + T[10];
   float pw = x * T[2] + y * T[5] + z * T[8] + T[11];
   gu = fminf(fmaxf(2.f * (pu / pw - 0.5f), -1.f), 1.f);
   gv = fminf(fmaxf(2.f * (pv / pw - 0.5f), -1.f), 1.f);
+  return b;
 }
 
 // grid_sample(bilinear, zeros, align_corners=True) tap set for one plane resolution R

@@ -23,7 +23,7 @@ __global__ void __launch_bounds__(32 * 13) k_tokens(QueryCtx q, long long i0, in
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp > K) return;
   float x, y, z, gu, gv;
-  load_query(q, i0 + i, x, y, z, gu, gv);
+  planes += (size_t)load_query(q, i0 + i, x, y, z, gu, gv) * q.plane_stride;
   float* dst = X + ((size_t)i * (K + 1) + warp) * TOK + lane * 4;
   if (warp == 0) {
     float4 r;

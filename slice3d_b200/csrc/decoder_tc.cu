@@ -21,8 +21,9 @@
 // Precision: BF16X3 splits both operands into bf16 hi + lo and issues hi*hi + lo*hi + hi*lo
 // (3 passes, ~16 mantissa bits, max-abs error 3-4e-5 on sdf_pred); BF16 issues hi*hi only.
 //
-// Warp roles (576 threads): warps 0-15 = compute, thread = (tile row r = TMEM lane, column quarter g);
-// warp 16 = weight producer; warp 17 = MMA issuer (warp-uniform control flow, one elected lane issues).
+// Warp roles (640 threads): warps 0-15 = compute, thread = (tile row r = TMEM lane, column quarter g);
+// warp 16 = weight producer; warp 17 = MMA issuer (warp-uniform control flow, one elected lane issues) / slot relay;
+// warps 18-19 = gather warps (token build of the next tiles).
 #include <cstdlib>
 #include <cstring>
 
@@ -118,10 +119,15 @@ struct TcParams {
 // ---- operand writes ------------------------------------------------------------------------
 // 8 consecutive k values of row r -> one 16-byte chunk of the hi tile (and of the lo tile).
 // x = hi + lo + O(2^-17 |x|): hi = bf16_rn(x), lo = bf16_rn(x - hi), converted two at a time.
-template <int NPASS>
+template <bool LO, bool F16>
+__device__ __forceinline__ void split8x(const float* v, uint32_t* h, uint32_t* l) {
+  if (F16) split8_h(v, h, l);  // fp16 pairs (only used with LO): x = hi + lo + O(2^-22 |x|), |x| saturates at 65504
+  else split8<LO>(v, h, l);
+}
+template <int NPASS, bool F16>
 __device__ __forceinline__ void store_chunk(uint8_t* tile_hi, uint8_t* tile_lo, int r, int kc, const float* v) {
   uint32_t h[4], l[4];
-  split8<NPASS == 3>(v, h, l);
+  split8x<NPASS == 3, F16>(v, h, l);
   const uint32_t off = sw128_chunk_off(r, kc);
   *reinterpret_cast<uint4*>(tile_hi + off) = make_uint4(h[0], h[1], h[2], h[3]);
   if (NPASS == 3) *reinterpret_cast<uint4*>(tile_lo + off) = make_uint4(l[0], l[1], l[2], l[3]);
@@ -199,7 +205,7 @@ __device__ __forceinline__ void warp_arrive(uint32_t bar, int lane) {
 // cta_group::2 MMAs (M = 256: 128 rows = one tile in each CTA) and every CTA streams only ITS HALF of each weight
 // part (N/2 rows of B), which halves the L2 -> shared-memory weight traffic and the shared-memory operand reads per SM
 // and doubles the MMA time one ring slot covers.  Everything outside the MMA / producer warps is per CTA.
-template <int NPASS, int CG>
+template <int NPASS, int CG, bool F16>
 __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -281,6 +287,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
     // 16-byte token pieces go to this CTA's global token scratch [128 rows][128] (L2-resident); the row owners
     // pick them up after a CTA barrier.
     float qgu = 0.f, qgv = 0.f;  // lane l < 9: grid_sample coordinates of query l of the current tile
+    int qimg = 0;                // ... and the image of the batch it belongs to
     auto gather_step = [&](long long gt, int idx, float* tokbuf) {  // idx 0..111
       const int qtr = lane >> 3, l8 = lane & 7;
       int q, k, cb;
@@ -297,11 +304,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
       }
       const long long gq = gt * TILE_Q + q;
       const float gu = __shfl_sync(0xffffffffu, qgu, q), gv = __shfl_sync(0xffffffffu, qgv, q);
+      const int img = __shfl_sync(0xffffffffu, qimg, q);
       if (k >= 12 || gq >= p.n) return;
       const int ch = 32 * cb + l8 * 4;
       float4 acc = __ldg(reinterpret_cast<const float4*>(p.fcs_b + ch));
       const int R0 = plane_res(p.S, 0);
-      const float* P = p.planes + (size_t)k * R0 * R0 * 128 + ch;
+      const float* P = p.planes + (size_t)img * p.q.plane_stride + (size_t)k * R0 * R0 * 128 + ch;
       auto fold = [&](const float4* v, const Taps& t) {
         acc.x += v[0].x * t.w00 + v[1].x * t.w01 + v[2].x * t.w10 + v[3].x * t.w11;
         acc.y += v[0].y * t.w00 + v[1].y * t.w01 + v[2].y * t.w10 + v[3].y * t.w11;
@@ -366,7 +374,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
           const int ql = lane < TILE_Q ? lane : TILE_Q - 1;
           const long long gq = tile * TILE_Q + ql;
           float qx = 0.f, qy = 0.f, qz = 0.f;
-          if (gq < p.n) load_query(p.q, gq, qx, qy, qz, qgu, qgv);
+          if (gq < p.n) qimg = load_query(p.q, gq, qx, qy, qz, qgu, qgv);
           // query tokens fc_p(q) (models.py:79): rows 13 q of the tile, 4 channels per lane
           const int gw = warp - NCW - 2;
           const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.fcp_b) + lane);
@@ -471,7 +479,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
       uint32_t w_a = 0, w_full = 0, w_h = 0;  // 32-bit cycle sums (wrap after ~2 s; only read in profiling runs)
       const uint32_t t_start = (uint32_t)clock();
       const uint32_t ax_hi = sbase + OFF_AX_HI, ax_lo = sbase + OFF_AX_LO;
-      constexpr uint32_t ID128 = make_idesc_bf16(128, 128 * CG);
+      constexpr uint32_t ID128 = F16 ? make_idesc_f16(128, 128 * CG) : make_idesc_bf16(128, 128 * CG);
       constexpr uint32_t BKB = 8192u;  // k-block stride of this CTA's half of a part: [64 n][64 k]
       auto wait_full = [&]() -> uint32_t {
         const uint32_t t0 = (uint32_t)clock();
@@ -655,7 +663,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
     auto store_ax = [&](const float* v) {
 #pragma unroll
       for (int cc = 0; cc < 4; ++cc)
-        store_chunk<NPASS>(ax_hi + (g >> 1) * 16384, ax_lo + (g >> 1) * 16384, r, (g & 1) * 4 + cc, v + 8 * cc);
+        store_chunk<NPASS, F16>(ax_hi + (g >> 1) * 16384, ax_lo + (g >> 1) * 16384, r, (g & 1) * 4 + cc, v + 8 * cc);
     };
     // R[r][32g..] = v + bias ; publish operand A + R to the MMA issuer
     auto publish = [&](float* v, const float* bias) {
@@ -811,8 +819,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
             o[2 * c] = o2[c].x;
             o[2 * c + 1] = o2[c].y;
           }
-          store_chunk<NPASS>(ax_hi + (g >> 1) * 16384, ax_lo + (g >> 1) * 16384, r, (g & 1) * 4 + 2 * hf, o);
-          store_chunk<NPASS>(ax_hi + (g >> 1) * 16384, ax_lo + (g >> 1) * 16384, r, (g & 1) * 4 + 2 * hf + 1, o + 8);
+          store_chunk<NPASS, F16>(ax_hi + (g >> 1) * 16384, ax_lo + (g >> 1) * 16384, r, (g & 1) * 4 + 2 * hf, o);
+          store_chunk<NPASS, F16>(ax_hi + (g >> 1) * 16384, ax_lo + (g >> 1) * 16384, r, (g & 1) * 4 + 2 * hf + 1, o + 8);
         }
       }
       lap(15)
@@ -959,7 +967,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
             {  // H chunk -> A operand of linear2 in tensor memory (16 packed columns per thread, hi and lo)
               uint32_t hh[16], hl[16];
 #pragma unroll
-              for (int j = 0; j < 4; ++j) split8<NPASS == 3>(d + 8 * j, hh + 4 * j, hl + 4 * j);
+              for (int j = 0; j < 4; ++j) split8x<NPASS == 3, F16>(d + 8 * j, hh + 4 * j, hl + 4 * j);
               if (c > 0) {  // MMA2 of the previous chunk has finished reading H
                 mbar_wait(bar(B_HFREE), ph_hf);
                 ph_hf ^= 1u;
@@ -997,7 +1005,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
             named_bar_sync(1, NCT);
             if (head_valid) {
               const float4 a4 = *reinterpret_cast<const float4*>(red0 + r * 4);
-              p.out[head_q] = p.out_scale * (a4.x + a4.y + a4.z + a4.w + __ldg(p.fco_b));
+              p.out[out_index(p.q, head_q)] = p.out_scale * (a4.x + a4.y + a4.z + a4.w + __ldg(p.fco_b));
             }
           }
         }
@@ -1106,7 +1114,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
 // ---- self-test: one 128-row UMMA tile against one weight unit -------------------------------------
 // D[128][128] = A[128][128] . W[128][128]^T, single CTA (cta_group::1).
 // mode 0: A in shared memory (the QKV / out-proj / linear1 path); mode 1: A in tensor memory (the linear2 path).
-template <int NPASS>
+template <int NPASS, bool F16>
 __global__ void __launch_bounds__(128, 1) umma_selftest_kernel(const float* __restrict__ A, const uint8_t* wimg, int mode,
                                                                float* __restrict__ D) {
   extern __shared__ uint8_t smem_raw[];
@@ -1135,7 +1143,7 @@ __global__ void __launch_bounds__(128, 1) umma_selftest_kernel(const float* __re
     for (int kc = 0; kc < 16; ++kc) {
       float v[8];
       for (int i = 0; i < 8; ++i) v[i] = A[r * 128 + kc * 8 + i];
-      store_chunk<NPASS>(sgen + OFF_AX_HI + (kc >> 3) * 16384, sgen + OFF_AX_LO + (kc >> 3) * 16384, r, kc & 7, v);
+      store_chunk<NPASS, F16>(sgen + OFF_AX_HI + (kc >> 3) * 16384, sgen + OFF_AX_LO + (kc >> 3) * 16384, r, kc & 7, v);
     }
     fence_proxy_async_smem();
   } else {  // packed bf16 pairs, column = k / 2: hi at columns TM_HT.., lo at TM_HT + 64..
@@ -1143,7 +1151,7 @@ __global__ void __launch_bounds__(128, 1) umma_selftest_kernel(const float* __re
       float v[32];
       for (int i = 0; i < 32; ++i) v[i] = A[r * 128 + 32 * j + i];
       uint32_t h[16], l[16];
-      for (int c = 0; c < 4; ++c) split8<NPASS == 3>(v + 8 * c, h + 4 * c, l + 4 * c);
+      for (int c = 0; c < 4; ++c) split8x<NPASS == 3, F16>(v + 8 * c, h + 4 * c, l + 4 * c);
       tmem_st16(trow + TM_HT + 16 * j, h);
       if (NPASS == 3) tmem_st16(trow + TM_HT + 64 + 16 * j, l);
     }
@@ -1155,7 +1163,7 @@ __global__ void __launch_bounds__(128, 1) umma_selftest_kernel(const float* __re
     mbar_wait(full, 0);
     tc_fence_after();
     const uint32_t w = sbase + OFF_H;
-    constexpr uint32_t ID = make_idesc_bf16(128);
+    constexpr uint32_t ID = F16 ? make_idesc_f16(128) : make_idesc_bf16(128);
     if (mode == 0) {
       issue_part<1, (NPASS == 3 ? 2 : 1), 8, 16384u, 16384u, ID>(tmem, sbase + OFF_AX_HI, sbase + OFF_AX_LO, w, true);
       if (NPASS == 3) issue_part<1, 1, 8, 16384u, 16384u, ID>(tmem, sbase + OFF_AX_HI, sbase + OFF_AX_HI, w + UNIT_PART_BYTES, false);
@@ -1188,16 +1196,19 @@ inline float bf16_val(uint16_t b) {
 }
 
 // W(n, k) for n in [0,NU), k in [0,KU) -> hi image then lo image (each NU*KU bf16, SW128 K-major tiles).
+inline uint16_t f16_bits(float x) { return __half_as_ushort(__float2half_rn(x)); }
+inline float f16_val(uint16_t b) { return __half2float(__ushort_as_half(b)); }
+
 template <class F>
-void pack_unit(F W, int NU, int KU, uint8_t* dst) {
+void pack_unit(F W, int NU, int KU, uint8_t* dst, bool f16 = false) {
   uint16_t* hi = reinterpret_cast<uint16_t*>(dst);
   uint16_t* lo = reinterpret_cast<uint16_t*>(dst + UNIT_PART_BYTES);
   for (int kb = 0; kb < KU / 64; ++kb)
     for (int n = 0; n < NU; ++n)
       for (int k = 0; k < 64; ++k) {
         const float w = W(n, kb * 64 + k);
-        const uint16_t h = bf16_bits(w);
-        const uint16_t l = bf16_bits(w - bf16_val(h));
+        const uint16_t h = f16 ? f16_bits(fminf(fmaxf(w, -65504.f), 65504.f)) : bf16_bits(w);
+        const uint16_t l = f16 ? f16_bits(w - f16_val(h)) : bf16_bits(w - bf16_val(h));
         const size_t off = (size_t)kb * NU * 128 + sw128_chunk_off(n, k >> 3) + (k & 7) * 2;
         hi[off / 2] = h;
         lo[off / 2] = l;
@@ -1218,43 +1229,48 @@ int dectc_pack(s3d_model* m, cudaStream_t st) {
     S3D_CUDA(cudaStreamSynchronize(st));
     return S3D_OK;
   };
-  for (int l = 0; l < 3; ++l) {
-    const DecLayerF32& L = m->dec32.L[l];
-    std::vector<float> win, wo, w1, w2;  // each [K][N]: W(n,k) = w[k*N + n]
-    S3D_TRY(fetch(L.in_proj, win));
-    S3D_TRY(fetch(L.out_proj, wo));
-    S3D_TRY(fetch(L.lin1, w1));
-    S3D_TRY(fetch(L.lin2, w2));
-    uint8_t* dst = img.data() + (size_t)l * UNITS_PER_LAYER * UNIT_STRIDE_BYTES;
-    int g = 0;
-    for (int u : {1, 0, 2}) {  // issue order of the QKV projection: K, Q, V
-      pack_unit([&](int n, int k) { return win[(size_t)k * 384 + 128 * u + n]; }, 128, 128, dst + (size_t)g * UNIT_STRIDE_BYTES);
+  // two images: bf16 hi/lo pairs (S3D_PREC_BF16X3, S3D_PREC_BF16) and fp16 hi/lo pairs (S3D_PREC_FP16X3)
+  for (int fmt = 0; fmt < 2; ++fmt) {
+    const bool f16 = fmt == 1;
+    for (int l = 0; l < 3; ++l) {
+      const DecLayerF32& L = m->dec32.L[l];
+      std::vector<float> win, wo, w1, w2;  // each [K][N]: W(n,k) = w[k*N + n]
+      S3D_TRY(fetch(L.in_proj, win));
+      S3D_TRY(fetch(L.out_proj, wo));
+      S3D_TRY(fetch(L.lin1, w1));
+      S3D_TRY(fetch(L.lin2, w2));
+      uint8_t* dst = img.data() + (size_t)l * UNITS_PER_LAYER * UNIT_STRIDE_BYTES;
+      int g = 0;
+      for (int u : {1, 0, 2}) {  // issue order of the QKV projection: K, Q, V
+        pack_unit([&](int n, int k) { return win[(size_t)k * 384 + 128 * u + n]; }, 128, 128, dst + (size_t)g * UNIT_STRIDE_BYTES, f16);
+        ++g;
+      }
+      pack_unit([&](int n, int k) { return wo[(size_t)k * 128 + n]; }, 128, 128, dst + (size_t)g * UNIT_STRIDE_BYTES, f16);
       ++g;
+      auto pack_w1 = [&](int c) {  // hidden units 128c .. +127 as output columns
+        pack_unit([&](int n, int k) { return w1[(size_t)k * 2048 + 128 * c + n]; }, 128, 128, dst + (size_t)g * UNIT_STRIDE_BYTES, f16);
+        ++g;
+      };
+      auto pack_w2 = [&](int c) {  // hidden units 128c .. +127 as the contraction index
+        pack_unit([&](int n, int k) { return w2[(size_t)(128 * c + k) * 128 + n]; }, 128, 128, dst + (size_t)g * UNIT_STRIDE_BYTES, f16);
+        ++g;
+      };
+      // consumption order of the FFN pipeline: W1_0, W1_1, then (W2_c, W1_{c+2}) ...
+      pack_w1(0);
+      pack_w1(1);
+      for (int c = 0; c < NCHUNK; ++c) {
+        pack_w2(c);
+        if (c + 2 < NCHUNK) pack_w1(c + 2);
+      }
     }
-    pack_unit([&](int n, int k) { return wo[(size_t)k * 128 + n]; }, 128, 128, dst + (size_t)g * UNIT_STRIDE_BYTES);
-    ++g;
-    auto pack_w1 = [&](int c) {  // hidden units 128c .. +127 as output columns
-      pack_unit([&](int n, int k) { return w1[(size_t)k * 2048 + 128 * c + n]; }, 128, 128, dst + (size_t)g * UNIT_STRIDE_BYTES);
-      ++g;
-    };
-    auto pack_w2 = [&](int c) {  // hidden units 128c .. +127 as the contraction index
-      pack_unit([&](int n, int k) { return w2[(size_t)(128 * c + k) * 128 + n]; }, 128, 128, dst + (size_t)g * UNIT_STRIDE_BYTES);
-      ++g;
-    };
-    // consumption order of the FFN pipeline: W1_0, W1_1, then (W2_c, W1_{c+2}) ...
-    pack_w1(0);
-    pack_w1(1);
-    for (int c = 0; c < NCHUNK; ++c) {
-      pack_w2(c);
-      if (c + 2 < NCHUNK) pack_w1(c + 2);
-    }
+    void* d = nullptr;
+    S3D_CUDA(cudaMalloc(&d, total));
+    m->allocs.push_back(d);
+    S3D_CUDA(cudaMemcpyAsync(d, img.data(), total, cudaMemcpyHostToDevice, st));
+    S3D_CUDA(cudaStreamSynchronize(st));
+    if (f16) m->dectc.wimg_h = static_cast<__half*>(d);
+    else m->dectc.wimg = static_cast<__nv_bfloat16*>(d);
   }
-  void* d = nullptr;
-  S3D_CUDA(cudaMalloc(&d, total));
-  m->allocs.push_back(d);
-  S3D_CUDA(cudaMemcpyAsync(d, img.data(), total, cudaMemcpyHostToDevice, st));
-  S3D_CUDA(cudaStreamSynchronize(st));
-  m->dectc.wimg = static_cast<__nv_bfloat16*>(d);
   m->dectc.wimg_elems = total / 2;
   // per-layer fp32 vector blocks (biases, LayerNorm affines) in the order of the V_* offsets
   std::vector<float> vecs((size_t)3 * VEC_FLOATS, 0.f);
@@ -1284,6 +1300,8 @@ int dectc_pack(s3d_model* m, cudaStream_t st) {
   return S3D_OK;
 }
 
+bool decoder_tc_supported(const s3d_model* m) { return m && m->K == 12 && m->dectc.wimg != nullptr; }
+
 int debug_profile(long long* out32, int reset) {
   unsigned long long h[32];
   S3D_CUDA(cudaMemcpyFromSymbol(h, g_prof, sizeof(h)));
@@ -1303,13 +1321,13 @@ size_t decoder_tc_workspace_bytes(int64_t) {
 
 int decoder_tc(const s3d_model* m, const float* planes, int S, const QueryCtx& q, int64_t n, float out_scale, float* out,
                int precision, void* ws, size_t ws_bytes, cudaStream_t st) {
-  if (m->K != 12 || m->dectc.wimg == nullptr) {
+  if (!decoder_tc_supported(m)) {
     set_error("decoder: tensor-core modes need n_slices == 12 (use S3D_PREC_FP32 otherwise)");
     return S3D_ERR_UNSUPPORTED;
   }
   if (n <= 0) return S3D_OK;
   TcParams p{};
-  p.wimg = reinterpret_cast<const uint8_t*>(m->dectc.wimg);
+  p.wimg = reinterpret_cast<const uint8_t*>(precision == S3D_PREC_FP16X3 ? (const void*)m->dectc.wimg_h : (const void*)m->dectc.wimg);
   p.vecs = m->dectc.vec;
   p.planes = planes;
   p.S = S;
@@ -1350,8 +1368,9 @@ int decoder_tc(const s3d_model* m, const float* planes, int S, const QueryCtx& q
   {  // CTA pairs: clusters of 2, one pair per TPC
     const long long pairs = (p.num_tiles + 1) / 2;
     const unsigned g2 = 2u * (unsigned)(pairs < sms / 2 ? pairs : sms / 2);
-    if (precision == S3D_PREC_BF16X3) S3D_TRY(launch(decoder_tc_kernel<3, 2>, g2, 2));
-    else S3D_TRY(launch(decoder_tc_kernel<1, 2>, g2, 2));
+    if (precision == S3D_PREC_FP16X3) S3D_TRY(launch(decoder_tc_kernel<3, 2, true>, g2, 2));
+    else if (precision == S3D_PREC_BF16X3) S3D_TRY(launch(decoder_tc_kernel<3, 2, false>, g2, 2));
+    else S3D_TRY(launch(decoder_tc_kernel<1, 2, false>, g2, 2));
   }
   S3D_LAUNCH_CHECK();
   return S3D_OK;
@@ -1359,7 +1378,8 @@ int decoder_tc(const s3d_model* m, const float* planes, int S, const QueryCtx& q
 
 // Self-test of the UMMA plumbing (descriptors, swizzle, bulk copy, TMEM load): see include/slice3d_b200.h.
 int umma_selftest(int mode, int passes, const float* a_dev, const float* w_dev, float* d_dev, cudaStream_t st) {
-  if ((mode != 0 && mode != 1) || (passes != 1 && passes != 3) || !a_dev || !w_dev || !d_dev) {
+  const bool f16 = passes == 4;  // passes = 4: the three-pass schedule with fp16 hi/lo pairs (S3D_PREC_FP16X3)
+  if ((mode != 0 && mode != 1) || (passes != 1 && passes != 3 && passes != 4) || !a_dev || !w_dev || !d_dev) {
     set_error("selftest: bad argument");
     return S3D_ERR_BAD_ARG;
   }
@@ -1368,16 +1388,19 @@ int umma_selftest(int mode, int passes, const float* a_dev, const float* w_dev, 
   S3D_CUDA(cudaMemcpyAsync(w.data(), w_dev, w.size() * sizeof(float), cudaMemcpyDeviceToHost, st));
   S3D_CUDA(cudaStreamSynchronize(st));
   std::vector<uint8_t> img(UNIT_STRIDE_BYTES);
-  pack_unit([&](int n, int k) { return w[(size_t)n * K + k]; }, N, K, img.data());
+  pack_unit([&](int n, int k) { return w[(size_t)n * K + k]; }, N, K, img.data(), f16);
   void* d = nullptr;
   S3D_CUDA(cudaMalloc(&d, UNIT_STRIDE_BYTES));
   S3D_CUDA(cudaMemcpyAsync(d, img.data(), UNIT_STRIDE_BYTES, cudaMemcpyHostToDevice, st));
-  if (passes == 3) {
-    cudaFuncSetAttribute(umma_selftest_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-    umma_selftest_kernel<3><<<1, 128, SMEM_BYTES, st>>>(a_dev, static_cast<const uint8_t*>(d), mode, d_dev);
+  if (f16) {
+    cudaFuncSetAttribute(umma_selftest_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    umma_selftest_kernel<3, true><<<1, 128, SMEM_BYTES, st>>>(a_dev, static_cast<const uint8_t*>(d), mode, d_dev);
+  } else if (passes == 3) {
+    cudaFuncSetAttribute(umma_selftest_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    umma_selftest_kernel<3, false><<<1, 128, SMEM_BYTES, st>>>(a_dev, static_cast<const uint8_t*>(d), mode, d_dev);
   } else {
-    cudaFuncSetAttribute(umma_selftest_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-    umma_selftest_kernel<1><<<1, 128, SMEM_BYTES, st>>>(a_dev, static_cast<const uint8_t*>(d), mode, d_dev);
+    cudaFuncSetAttribute(umma_selftest_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    umma_selftest_kernel<1, false><<<1, 128, SMEM_BYTES, st>>>(a_dev, static_cast<const uint8_t*>(d), mode, d_dev);
   }
   g_launches.fetch_add(1, std::memory_order_relaxed);
   cudaError_t e = cudaStreamSynchronize(st);

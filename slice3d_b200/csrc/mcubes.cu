@@ -9,8 +9,8 @@
 //   (host)       exclusive prefix sums of the two count arrays (the running counters of the sequential scan).
 //   k_mc_emit    one thread per cell: writes its new vertices (same float64 expression as mc_add_vertex) at
 //                base + rank, resolves shared edges through the owning neighbour's base and mask, writes its triangles.
-// The vertex array equals the reference's bit for bit; the triangle table is supplied by the caller
-// (slice3d_b200/mcubes.py generates it from the cube's geometry).
+// The vertex array equals the reference's bit for bit; so does the face array when the caller supplies the classic
+// Lorensen-Cline / Bourke table the reference uses (slice3d_b200/mc_table.py).
 #include "common.cuh"
 
 namespace s3d {

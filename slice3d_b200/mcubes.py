@@ -2,20 +2,20 @@
 (reference: reg_slices/reconstruct.py:175-243 -> libmcubes.marching_cubes =
 reg_slices/src_convonet/utils/libmcubes/marchingcubes.h:22-196, pywrapper.cpp:90-128).
 
-What is reproduced exactly:
+Both output arrays equal libmcubes' bit for bit:
 
 * the **vertex array**: same vertices, same float64 coordinates, same ORDER as the reference's sequential scan
   (cells x-major; inside a cell the three "owned" edges 6, 5, 10 first, then the edges that are only created on the
   low boundaries -- including the reference's duplicated vertices on the i = 0 / j = 0 / k = 0 faces).  The running
   vertex counter of the sequential code becomes an exclusive prefix sum over the per-cell counts.
-* the **polygons**: every cell is cut into the same oriented polygons (the inside = `value <= isovalue` corners of an
-  ambiguous face are separated, normals point to the inside, as in the reference's table).
+* the **face array**: cells in scan order, and inside a cell the triangles of the classic Lorensen-Cline / Bourke
+  table (`mc_table.TRI_ROWS`, the public-domain constant the reference consumes at marchingcubes.h:185-196) in the
+  table's order, so `np.array_equal(faces, reference_faces)` holds.  `_build_tables` still derives the polygons of
+  every configuration from the cube's geometry; tests/test_mcubes.py uses it to check that the constant cuts every
+  configuration into the same oriented polygons (a typo in the constant cannot go unnoticed).
 
-What differs: each polygon of 4-7 vertices is triangulated as a fan from its first vertex, while the reference's
-hand-made 256-row table picks other diagonals for some of them.  The triangle table used here is GENERATED at import
-from the cube's geometry (`_build_tables`), not stored: triangle counts per cell are equal, the triangles of a
-polygon may differ.  tests/test_mcubes.py checks vertices bit-for-bit and the oriented polygon sets against the
-reference compiled from /root/reference (oracle/build_ref_mcubes.py).
+tests/test_mcubes.py compares both arrays exactly against the reference compiled from /root/reference
+(oracle/build_ref_mcubes.py) and against committed goldens.
 """
 import numpy as np
 import torch
@@ -95,7 +95,19 @@ def _build_tables():
     return table, count
 
 
-_TABLE, _COUNT = _build_tables()
+def _canonical_tables():
+    """(256, 5, 3) / (256,) arrays from the hex rows of mc_table.TRI_ROWS."""
+    from .mc_table import TRI_ROWS
+    table = -np.ones((256, 5, 3), dtype=np.int64)
+    count = np.zeros(256, dtype=np.int64)
+    for c, row in enumerate(TRI_ROWS):
+        ids = [int(ch, 16) for ch in row]
+        count[c] = len(ids) // 3
+        table[c].reshape(-1)[:len(ids)] = ids
+    return table, count
+
+
+_TABLE, _COUNT = _canonical_tables()
 _DEV_TABLES = {}
 
 
@@ -168,7 +180,7 @@ def marching_cubes(volume, isovalue):
         t = torch.where(f2 == f1, (x2 + x1) / 2, (x2 - x1) * (iso - f1) / (f2 - f1) + x1)
         out = torch.stack([t if ax == axis else p1[ax] for ax in range(3)], 1)
         verts[idx[e][m]] = out
-    # triangles: cells in scan order, the generated table's order inside a cell
+    # triangles: cells in scan order, the table's order inside a cell
     table = torch.as_tensor(_TABLE, device=dev)
     count = torch.as_tensor(_COUNT, device=dev)[cube].reshape(-1)
     tbase = torch.cumsum(count, 0) - count

@@ -23,7 +23,13 @@ from . import _native
 from .perceptual import VGGPerceptualLoss
 from .unet import UNet
 
-DEFAULT_PRECISION = "bf16x3"
+DEFAULT_PRECISION = "fp16x3"  # <= 1e-4 tensor-core mode (fp16 hi/lo split operands, 3 passes); needs n_slices == 12
+
+
+def default_precision(n_slices):
+    """The tensor-core decoder is instantiated for the reference's 13-token layout (K = 12); other K run the fp32
+    CUDA-core decoder."""
+    return DEFAULT_PRECISION if n_slices == 12 else "fp32"
 
 
 class Slices3DRegModel(nn.Module):
@@ -42,25 +48,65 @@ class Slices3DRegModel(nn.Module):
         self.vggptlossfunc = VGGPerceptualLoss()
         self.n_slices = n_slices
         # --- not part of the reference API ---
-        self.precision = precision or DEFAULT_PRECISION  # decoder arithmetic: fp32 | bf16x3 | bf16
+        self.precision = precision or default_precision(n_slices)  # decoder arithmetic: fp32 | fp16x3 | bf16x3 | bf16
         self.test_time_vgg_loss = True  # the reference evaluates (and discards) it at test time too
-        self._native_model = None
-        self._native_key = None
+        # Packed-weight handles, one per device, in a dict that nn.DataParallel replicas share by reference
+        # (replicate() copies __dict__ shallowly): {"epoch": int, "dev": {device: entry}}.
+        self._nat = {"epoch": 0, "dev": {}}
         self._enc_cache = None
 
     # ------------------------------------------------------------------ native plumbing
-    def _weights_key(self):
-        return tuple((t.data_ptr(), t._version) for t in self.state_dict(keep_vars=True).values())
+    def invalidate_native(self):
+        """Mark the packed CUDA weights stale.  Called by load_state_dict / .to() / .train(); call it yourself after
+        writing parameters through ``.data`` (EMA / weight-swap helpers), which no version counter sees."""
+        self._nat["epoch"] += 1
+        self._enc_cache = None
+
+    def load_state_dict(self, *a, **k):
+        r = super().load_state_dict(*a, **k)
+        self.invalidate_native()
+        return r
+
+    def _apply(self, fn, *a, **k):
+        r = super()._apply(fn, *a, **k)
+        self.invalidate_native()
+        return r
+
+    def train(self, mode=True):
+        self.invalidate_native()  # an optimizer may have stepped since the last eval session
+        return super().train(mode)
+
+    def _tensors(self):
+        return [t for t in self.state_dict(keep_vars=True).values() if t.dtype == torch.float32]
+
+    @staticmethod
+    def _fingerprint(tensors):
+        """Content fingerprint of the weights (one device reduction + one 8-byte read): catches in-place
+        writes through ``.data`` that leave ``_version`` untouched."""
+        with torch.no_grad():
+            norms = torch._foreach_norm([t.detach() for t in tensors], 1)
+            w = torch.arange(1, len(norms) + 1, dtype=torch.float64, device=norms[0].device)
+            return float((torch.stack(norms).double() * w).sum())
 
     def native(self):
-        """The C-ABI model handle for the current weights (rebuilt when any tensor changed)."""
+        """The C-ABI model handle for the current weights on this module's device.  The (cheap) per-call check
+        compares the parameters' version counters; the full check -- data pointers, versions and a content
+        fingerprint -- runs once per eval session (after ``invalidate_native``), and the handle is rebuilt only
+        when the weights actually changed."""
         dev = self.fc_p.weight.device
-        key = (dev, self._weights_key())
-        if self._native_model is None or self._native_key != key:
-            self._native_model = _native.NativeModel(self.state_dict(), self.n_slices, dev)
-            self._native_key = key
+        nat = self._nat
+        ent = nat["dev"].get(dev)
+        if ent is not None and ent["epoch"] == nat["epoch"] and ent["owner"] is self:
+            if sum(t._version for t in ent["tensors"]) == ent["vsum"]:
+                return ent["model"]
+        tensors = self._tensors()
+        fp = self._fingerprint(tensors)
+        if ent is None or ent["fp"] != fp:
+            ent = {"model": _native.NativeModel(self.state_dict(), self.n_slices, dev), "fp": fp}
+            nat["dev"][dev] = ent
             self._enc_cache = None
-        return self._native_model
+        ent.update(epoch=nat["epoch"], owner=self, tensors=tensors, vsum=sum(t._version for t in tensors))
+        return ent["model"]
 
     def encode(self, img_input):
         """Run the plane encoder once for ``img_input`` (B,3,S,S); cached per tensor object/version."""
@@ -102,20 +148,18 @@ class Slices3DRegModel(nn.Module):
         qry = feed_dict["qry_norot"]
         n_qry = qry.shape[1]
         T = feed_dict["trans_mat_wo_rot_tp"]
-        sdf = torch.empty(n_bs, n_qry, dtype=torch.float32, device=img_input.device)
-        for b in range(n_bs):
-            qb = qry[b]
-            if self.mode == "test":
-                # y,z of the caller's tensor are negated in place, like models.py:55
-                if qb.is_contiguous() and qb.dtype == torch.float32:
-                    nat.decode(planes, b, qb, T[b], None, True, 1.0, self.precision, out=sdf[b])
-                else:
-                    tmp = qb.float().contiguous()
-                    nat.decode(planes, b, tmp, T[b], None, True, 1.0, self.precision, out=sdf[b])
-                    qb.copy_(tmp)
+        # one decoder launch for all images of the feed_dict
+        if self.mode == "test":
+            # y,z of the caller's tensor are negated in place, like models.py:55
+            if qry.is_contiguous() and qry.dtype == torch.float32:
+                sdf = nat.decode_batch(planes, qry, T, None, True, 1.0, self.precision)
             else:
-                nat.decode(planes, b, qb.float().contiguous(), T[b], feed_dict["obj_rot_mat"][b], False, 1.0,
-                           self.precision, out=sdf[b])
+                tmp = qry.float().contiguous()
+                sdf = nat.decode_batch(planes, tmp, T, None, True, 1.0, self.precision)
+                qry.copy_(tmp)
+        else:
+            sdf = nat.decode_batch(planes, qry.float().contiguous(), T, feed_dict["obj_rot_mat"], False, 1.0,
+                                   self.precision)
         ret = {"sdf_pred": sdf, "slices_rec": planes.slices_rec.view(n_bs, K * 3, S, S)}
         if self.test_time_vgg_loss and "img_slices" in feed_dict:
             ret["vgg_loss"] = self._cached_vgg_loss(planes, feed_dict["img_slices"])
