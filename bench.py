@@ -41,6 +41,8 @@ def parse():
     ap.add_argument("--img", type=int, default=256)
     ap.add_argument("--precision", default=None, help="fp32 | bf16x3 | bf16 (default: best <=1e-4 mode built)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the BASELINE configs[4] training leg")
+    ap.add_argument("--no-extra", action="store_true", help="skip the e2e_api / sparse / parity blocks")
     ap.add_argument("--cpu-sample", type=int, default=60000, help="queries in the bounded CPU sample (decoder-only leg)")
     return ap.parse_args()
 
@@ -210,7 +212,7 @@ def run_native(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     S, nx, K = args.img, args.grid, 12
-    prec = args.precision or [p for p in ("bf16x3", "fp32") if p in _native.available_precisions()][0]
+    prec = args.precision or [p for p in ("fp16x3", "bf16x3", "fp32") if p in _native.available_precisions()][0]
 
     torch.manual_seed(0)
     model = Slices3DRegModel(S, K, "test", precision=prec)
@@ -296,6 +298,7 @@ def run_native(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": {"fp32": "f32", "bf16x3": "bf16x3 (bf16 hi/lo split operands, 3 tcgen05 passes, fp32 accumulate)",
+                  "fp16x3": "fp16x3 (fp16 hi/lo split operands, 3 tcgen05 passes, fp32 accumulate)",
                   "bf16": "bf16"}[prec],
         "data": "synthetic",
         "config": {"workload": f"12 slices {S}x{S} -> {nx}^3 dense occupancy grid (encoder + decoder"
@@ -315,12 +318,73 @@ def run_native(args):
                      "peak_source": how + " sustained bf16"},
         "clocks": clocks,
     }
+    if not args.no_train:
+        line["train"] = train_leg(dev, world, rank, args.steps, args.warmup, max_over_ranks, barrier)
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(S, nx, args.cpu_sample)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def train_leg(dev, world, rank, steps, warmup, max_over_ranks, barrier):
+    """BASELINE configs[4]: reg_slices train.py fwd + bwd + Adam, per-GPU batch 4 (global 4 x N), S = 128, n_qry = 256,
+    DDP gradient all-reduce over NCCL when N > 1.  (1) parity: three optimizer steps with dropout 0 from the seeded
+    weights of tests/golden/train_traj_b4_s128.npz, the per-step loss terms (mean over ranks) next to the reference's
+    (generated by oracle/make_golden_train.py from the unmodified reference, DDP semantics emulated on the CPU);
+    (2) timing: W warm-up + K timed steps with the product's dropout (0.1), host batches (pinned) copied inside the
+    step, losses read back every step as train_step does, CUDA events, max over ranks."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from slice3d_b200 import Slices3DRegModel, _native, synth
+    from slice3d_b200 import train as s3d_train
+    S, K, B, NQ = 128, 12, 4, 256
+    torch.manual_seed(0)
+    m = Slices3DRegModel(S, K, "train")
+    m.load_state_dict(synth.synthetic_state_dict(m.state_dict(), 8))
+    m = synth.set_dropout(m.to(dev).train(), 0.0)
+    net = s3d_train.wrap_ddp(m, dev) if world > 1 else m
+    opt = torch.optim.Adam(m.parameters(), lr=3e-4)
+    host = {k: v.pin_memory() for k, v in synth.synthetic_train_batch(S, K, B, NQ, seed=100 + rank).items()}
+    h2d = int(sum(v.numel() * v.element_size() for v in host.values()))
+    losses = []
+    for _ in range(3):
+        lp, li, lv, _acc = s3d_train.train_step(dict(host), net, opt)
+        t = torch.tensor([lp, li, lv], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t)
+            t /= world
+        losses.append([float(x) for x in t.tolist()])
+    ref, rel = None, None
+    gpath = os.path.join(ROOT, "tests", "golden", "train_traj_b4_s128.npz")
+    if os.path.exists(gpath):
+        z = np.load(gpath)
+        if f"loss_w{world}" in z.files:
+            ref = z[f"loss_w{world}"].tolist()
+            rel = float(np.max(np.abs(np.array(losses) - np.array(ref)) / np.abs(np.array(ref))))
+    synth.set_dropout(m, 0.1)
+    for _ in range(warmup):
+        s3d_train.train_step(dict(host), net, opt)
+    barrier()
+    l0 = _native.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        s3d_train.train_step(dict(host), net, opt)
+    e1.record()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1)) / steps
+    return {"config": f"reg_slices train.py fwd+bwd+Adam, batch {B}/GPU x {world} GPU(s), S={S}, n_qry={NQ}, fp32"
+                      + (", DDP (NCCL gradient all-reduce, find_unused_parameters)" if world > 1 else ""),
+            "ms_per_step": ms, "samples_per_s": B * world / (ms / 1e3), "steps": steps, "warmup": warmup,
+            "h2d_bytes_per_step": h2d, "gpu_launches_per_step": (_native.launch_count() - l0) / steps,
+            "loss": losses, "loss_ref": ref, "loss_max_rel_diff": rel,
+            "loss_note": "3 Adam steps, dropout 0 on both sides; [L1(sdf), L1(slices), 0.001 * VGG19 perceptual] mean over ranks",
+            "native_ops": "decoder forward + backward (projection, grid_sample, fc_s/fc_p, transformer, fc_out): "
+                          "csrc/train_decoder.cu",
+            "torch_ops": "U-Net and VGG19 convolutions / BatchNorm (cuDNN through torch autograd), Adam"}
 
 
 def nat_planes_mb(K, S):

@@ -58,7 +58,7 @@ extern "C" {
 #define S3D_PREC_BF16X3 1 /* tcgen05, operands split into bf16 hi+lo, 3 MMA passes (<=1e-4) */
 #define S3D_PREC_BF16 2   /* tcgen05, single bf16 pass (fast; measured 1.8e-2 max-abs)    */
 #define S3D_PREC_FP16X3 3 /* tcgen05, operands split into fp16 hi+lo, 3 MMA passes: same speed as BF16X3, ~10x
-                             smaller error (22 instead of 16 mantissa bits); activations saturate at 65504 */
+                             smaller error (22 instead of 16 mantissa bits); decoder activations must stay below 65504 */
 
 typedef struct s3d_model s3d_model;
 
@@ -160,6 +160,35 @@ int s3d_selftest_umma(int32_t mode, int32_t passes, const float* a_dev, const fl
 size_t s3d_vgg_loss_workspace_bytes(int32_t N, int32_t S);
 int s3d_vgg_loss_fwd(const s3d_model* m, const float* a_dev, const float* b_dev, int32_t N, int32_t S, float* loss_dev,
                      void* workspace_dev, size_t workspace_bytes, void* stream);
+
+/* ---- Training (reg_slices/train.py:41-53: model(batch) under model.train(), loss.backward()) ----------------------
+ * Forward and backward of the per-query half of Slices3DRegModel.forward in TRAIN mode (reg_slices/src/models.py:57-84):
+ * project_coord, 5 x grid_sample of the NCHW feature planes the U-Net produced, fc_s / fc_p, the 3-layer
+ * nn.TransformerEncoder WITH dropout (p = dropout_p on the attention weights, after the attention block, inside the FFN
+ * and after it), fc_out on token 0 -- exact fp32, PyTorch parameter layouts used in place (no packing: the optimizer
+ * rewrites them every step).  The U-Net / VGG19 convolutions keep their autograd on the caller's side.
+ *   feats_dev[5]   (B*K, C_s, R_s, R_s) fp32 NCHW, C = 512,256,128,64,32, R_s = S/16 * 2^s.
+ *   qry_dev        (B, n_qry, 3) fp32, already rotated (bmm with obj_rot_mat, models.py:60) or flipped.
+ *   T_dev          (B, 4, 3) fp32.
+ *   params_dev[42] fc_p.weight, fc_p.bias, fc_s.weight, fc_s.bias, then for each layer l = 0..2 of att_decoder.layers:
+ *                  self_attn.in_proj_weight, in_proj_bias, out_proj.weight, out_proj.bias, linear1.weight, linear1.bias,
+ *                  linear2.weight, linear2.bias, norm1.weight, norm1.bias, norm2.weight, norm2.bias; fc_out.0.weight, bias.
+ *   saved_dev      s3d_train_decoder_saved_bytes(): activations kept for the backward pass (caller-owned).
+ *   bwd: dsdf_dev (B, n_qry); dfeats_dev[5] ZERO-INITIALISED gradients of the feature planes (accumulated with
+ *        atomics: queries share texels); dparams_dev[42] gradients, overwritten; workspace of
+ *        s3d_train_decoder_bwd_workspace_bytes().  Dropout masks are regenerated from (seed, site, element). */
+typedef struct {
+  int32_t B, n_qry, K, S;
+  float dropout_p;
+  uint64_t seed;
+} s3d_train_cfg;
+size_t s3d_train_decoder_saved_bytes(const s3d_train_cfg* cfg);
+size_t s3d_train_decoder_bwd_workspace_bytes(const s3d_train_cfg* cfg);
+int s3d_train_decoder_fwd(const s3d_train_cfg* cfg, const float* const* feats_dev, const float* qry_dev, const float* T_dev,
+                          const float* const* params_dev, float* sdf_dev, void* saved_dev, size_t saved_bytes, void* stream);
+int s3d_train_decoder_bwd(const s3d_train_cfg* cfg, const float* qry_dev, const float* T_dev, const float* const* params_dev,
+                          const float* dsdf_dev, void* saved_dev, size_t saved_bytes, float* const* dfeats_dev,
+                          float* const* dparams_dev, void* workspace_dev, size_t workspace_bytes, void* stream);
 
 /* One MISE refinement step on dense device state, replacing MISE.subdivide_voxels (reg_slices/src_convonet/utils/
  * libmise/mise.pyx:184-283) after the caller has stored the new values: R = resolution0 << depth; value_dev / known_dev /

@@ -9,5 +9,7 @@ from .generator import Generator3D  # noqa: F401
 from .mcubes import Mesh, marching_cubes  # noqa: F401
 from .mise import MISE  # noqa: F401
 from .synth import make_3d_grid  # noqa: F401
+from .train import cal_acc, cal_loss_pred, train_step, val_step, wrap_ddp  # noqa: F401
 
-__all__ = ["Slices3DRegModel", "Generator3D", "MISE", "Mesh", "marching_cubes", "make_3d_grid"]
+__all__ = ["Slices3DRegModel", "Generator3D", "MISE", "Mesh", "marching_cubes", "make_3d_grid", "train_step", "val_step",
+           "cal_loss_pred", "cal_acc", "wrap_ddp"]

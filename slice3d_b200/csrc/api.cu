@@ -481,6 +481,20 @@ int s3d_mc_emit(const double* vol_dev, int32_t nx, int32_t ny, int32_t nz, doubl
                  owned_dev, verts_dev, reinterpret_cast<long long*>(tris_dev), static_cast<cudaStream_t>(stream));
 }
 
+size_t s3d_train_decoder_saved_bytes(const s3d_train_cfg* cfg) { return train_decoder_saved_bytes(cfg); }
+size_t s3d_train_decoder_bwd_workspace_bytes(const s3d_train_cfg* cfg) { return train_decoder_bwd_workspace_bytes(cfg); }
+int s3d_train_decoder_fwd(const s3d_train_cfg* cfg, const float* const* feats_dev, const float* qry_dev, const float* T_dev,
+                          const float* const* params_dev, float* sdf_dev, void* saved_dev, size_t saved_bytes, void* stream) {
+  return train_decoder_fwd(cfg, feats_dev, qry_dev, T_dev, params_dev, sdf_dev, saved_dev, saved_bytes,
+                           static_cast<cudaStream_t>(stream));
+}
+int s3d_train_decoder_bwd(const s3d_train_cfg* cfg, const float* qry_dev, const float* T_dev, const float* const* params_dev,
+                          const float* dsdf_dev, void* saved_dev, size_t saved_bytes, float* const* dfeats_dev,
+                          float* const* dparams_dev, void* workspace_dev, size_t workspace_bytes, void* stream) {
+  return train_decoder_bwd(cfg, qry_dev, T_dev, params_dev, dsdf_dev, saved_dev, saved_bytes, dfeats_dev, dparams_dev,
+                           workspace_dev, workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+
 size_t s3d_mise_scratch_ints(int32_t resolution0, int32_t depth) { return mise_scratch_ints(resolution0, depth); }
 
 int s3d_mise_subdivide(int32_t resolution0, int32_t depth, double threshold, const double* value_dev, const uint8_t* known_dev,

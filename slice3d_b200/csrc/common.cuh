@@ -175,6 +175,15 @@ size_t vgg_loss_workspace_bytes(int N, int S);
 int vgg_loss_fwd(const s3d_model* m, const float* a, const float* b, int N, int S, float* loss, void* ws, size_t ws_bytes,
                  cudaStream_t st);
 
+// train_decoder.cu
+size_t train_decoder_saved_bytes(const s3d_train_cfg* c);
+size_t train_decoder_bwd_workspace_bytes(const s3d_train_cfg* c);
+int train_decoder_fwd(const s3d_train_cfg* c, const float* const* feats, const float* qry, const float* T,
+                      const float* const* params, float* sdf, void* saved, size_t saved_bytes, cudaStream_t st);
+int train_decoder_bwd(const s3d_train_cfg* c, const float* qry, const float* T, const float* const* params, const float* dsdf,
+                      void* saved, size_t saved_bytes, float* const* dfeats, float* const* dparams, void* ws, size_t ws_bytes,
+                      cudaStream_t st);
+
 // ---- queries ----------------------------------------------------------------------
 struct QueryCtx {
   const float* qry;     // explicit points (n,3) or null

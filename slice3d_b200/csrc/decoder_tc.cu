@@ -121,7 +121,7 @@ struct TcParams {
 // x = hi + lo + O(2^-17 |x|): hi = bf16_rn(x), lo = bf16_rn(x - hi), converted two at a time.
 template <bool LO, bool F16>
 __device__ __forceinline__ void split8x(const float* v, uint32_t* h, uint32_t* l) {
-  if (F16) split8_h(v, h, l);  // fp16 pairs (only used with LO): x = hi + lo + O(2^-22 |x|), |x| saturates at 65504
+  if (F16) split8_hn(v, h, l);  // fp16 pairs (only used with LO): x = hi + lo + O(2^-22 |x|) for |x| < 65504
   else split8<LO>(v, h, l);
 }
 template <int NPASS, bool F16>

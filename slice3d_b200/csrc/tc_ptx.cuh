@@ -349,6 +349,19 @@ __device__ __forceinline__ void split8_h(const float* v, uint32_t* h, uint32_t* 
     l[i] = *reinterpret_cast<const uint32_t*>(&l2);
   }
 }
+// The same without the clamp (the decoder's fp16x3 mode: its activations are LayerNorm outputs, attention outputs and
+// FFN hidden values, orders of magnitude below 65504; a value beyond the fp16 range would become inf and the result NaN --
+// loud, not silent).  lo parts below 2^-14 are fp16 subnormals (the tensor core does not flush them): the split then
+// carries an ABSOLUTE error <= 2^-25 instead of a relative one.
+__device__ __forceinline__ void split8_hn(const float* v, uint32_t* h, uint32_t* l) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const __half2 h2 = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+    h[i] = *reinterpret_cast<const uint32_t*>(&h2);
+    const __half2 l2 = __floats2half2_rn(v[2 * i] - __low2float(h2), v[2 * i + 1] - __high2float(h2));
+    l[i] = *reinterpret_cast<const uint32_t*>(&l2);
+  }
+}
 // Instruction descriptor, kind::f16 with fp16 operands (both K-major), fp32 accumulate.
 __host__ __device__ constexpr uint32_t make_idesc_f16(int n, int m = 128) {
   return (1u << 4) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);

@@ -19,7 +19,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import _native
+from . import _native, train_ops
 from .perceptual import VGGPerceptualLoss
 from .unet import UNet
 
@@ -50,6 +50,7 @@ class Slices3DRegModel(nn.Module):
         # --- not part of the reference API ---
         self.precision = precision or default_precision(n_slices)  # decoder arithmetic: fp32 | fp16x3 | bf16x3 | bf16
         self.test_time_vgg_loss = True  # the reference evaluates (and discards) it at test time too
+        self.native_train = True  # CUDA tensors: train-mode decoder forward + backward in the CUDA library
         # Packed-weight handles, one per device, in a dict that nn.DataParallel replicas share by reference
         # (replicate() copies __dict__ shallowly): {"epoch": int, "dev": {device: entry}}.
         self._nat = {"epoch": 0, "dev": {}}
@@ -188,6 +189,16 @@ class Slices3DRegModel(nn.Module):
             qry = torch.bmm(qry, feed_dict["obj_rot_mat"])
         n_qry = qry.shape[1]
         feats, slices_rec = self.slices_generator.forward_train(img_input)
+        if img_input.is_cuda and self.native_train:
+            # a3-a9 in train mode: forward AND backward in the CUDA library (csrc/train_decoder.cu)
+            p = float(self.att_decoder.layers[0].dropout.p) if self.training else 0.0
+            seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if p > 0 else 0
+            sdf = train_ops.decoder_train(feats, qry, feed_dict["trans_mat_wo_rot_tp"], train_ops.param_list(self), K, S,
+                                          p, seed)
+            ret = {"sdf_pred": sdf, "slices_rec": slices_rec.view(n_bs, K * 3, S, S)}
+            tgt = feed_dict["img_slices"].view(n_bs, K, 3, S, S).view(n_bs * K, 3, S, S)
+            ret["vgg_loss"] = self.vggptlossfunc(slices_rec, tgt)["pt_c_loss"] * 0.001
+            return ret
         uv = self.project_coord(qry, feed_dict["trans_mat_wo_rot_tp"])
         grid = uv.view(n_bs, 1, 1, n_qry, 2).expand(-1, K, -1, -1, -1).reshape(n_bs * K, 1, n_qry, 2)
         sampled = [F.grid_sample(f, grid, mode="bilinear", padding_mode="zeros", align_corners=True)

@@ -115,3 +115,27 @@ def sample_grid_indices(nx, n, seed=0):
     face = [((i * 37) % nx * nx + (i * 53) % nx) * nx + (0 if i % 2 else m) for i in range(64)]
     idx = torch.tensor(sorted(set(corners + rnd + face)), dtype=torch.int64)
     return idx
+
+
+def synthetic_train_batch(img_size, n_slices=12, batch=4, n_qry=256, seed=0):
+    """One training batch of BASELINE configs[4]: the dataset's keys (reference datasets.py:169-177)
+    with random rotations, queries in the unit box and sdf = randn * 0.1; everything from one seeded CPU generator."""
+    feed = synthetic_inputs(img_size, n_slices, seed=seed, batch=batch)
+    g = torch.Generator(device="cpu")
+    g.manual_seed(5000 + seed)
+    feed["qry_norot"] = torch.rand(batch, n_qry, 3, generator=g) - 0.5
+    feed["obj_rot_mat"] = torch.linalg.qr(torch.randn(batch, 3, 3, generator=g))[0].contiguous()
+    feed["sdf"] = torch.randn(batch, n_qry, generator=g) * 0.1
+    feed["occ"] = (feed["sdf"] < 0).float()
+    return feed
+
+
+def set_dropout(model, p):
+    """Set every dropout probability of a Slices3DRegModel-shaped module (the transformer's nn.Dropout modules and the
+    attention-weight dropout of nn.MultiheadAttention).  Gradient parity tests use p = 0 on both sides."""
+    for m in model.modules():
+        if isinstance(m, torch.nn.Dropout):
+            m.p = p
+        if isinstance(m, torch.nn.MultiheadAttention):
+            m.dropout = p
+    return model

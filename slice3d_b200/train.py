@@ -1,0 +1,73 @@
+"""Training-loop pieces of the reference's ``train.py`` for ``Slices3DRegModel`` (reference: reg_slices/train.py:21-53,
+70-93, 131-136), plus the one-process-per-GPU wrapper BASELINE configs[4] asks for.
+
+``train_step`` keeps the reference's signature and return values (the three loss terms and the sign accuracy as Python
+floats).  With CUDA tensors the decoder's forward and backward run in the CUDA library (``slice3d_b200.train_ops``);
+the U-Net / VGG19 convolutions run through torch autograd.  ``wrap_ddp`` replaces the reference's
+``torch.nn.DataParallel`` (train.py:131-132) by DistributedDataParallel: per-replica BatchNorm statistics exactly like
+DataParallel, gradients averaged over ranks with bucketed NCCL all-reduces.  14 parameters never receive a gradient
+(``att_layer.*`` is the unused original of the deep-copied encoder layers, ``down5_.41.*`` feeds a discarded tensor;
+SURVEY.md section 3.3), hence ``find_unused_parameters``.
+"""
+import torch
+import torch.nn.functional as F
+
+
+def cal_acc(x, gt, pred_type="sdf"):
+    """train.py:21-27."""
+    if pred_type == "occ":
+        acc = ((x["occ_pred"].sigmoid() > 0.5) == (gt["occ"] > 0.5)).float().sum(dim=-1) / x["occ_pred"].shape[1]
+    else:
+        acc = ((x["sdf_pred"] >= 0) == (gt["sdf"] >= 0)).float().sum(dim=-1) / x["sdf_pred"].shape[1]
+    return acc.mean(-1)
+
+
+def cal_loss_pred(x, gt, pred_type="sdf"):
+    """train.py:29-39."""
+    if pred_type == "occ":
+        loss_pred = F.binary_cross_entropy_with_logits(x["occ_pred"], gt["occ"])
+    else:
+        loss_pred = F.l1_loss(x["sdf_pred"], gt["sdf"])
+    return loss_pred, F.l1_loss(x["slices_rec"], gt["img_slices"]), x["vgg_loss"]
+
+
+def train_step(batch, model, opt, args=None, device=None):
+    """train.py:41-53.  ``args`` only needs ``pred_type``; ``device`` defaults to the model's."""
+    pred_type = getattr(args, "pred_type", "sdf")
+    device = device or next(model.parameters()).device
+    for key in batch:
+        batch[key] = batch[key].to(device, non_blocking=True)
+    opt.zero_grad()
+    x = model(batch)
+    loss_pred, loss_img, loss_img_vgg = cal_loss_pred(x, batch, pred_type)
+    loss = loss_pred + loss_img + loss_img_vgg
+    loss.backward()
+    opt.step()
+    with torch.no_grad():
+        acc = cal_acc(x, batch, pred_type)
+    return loss_pred.item(), loss_img.item(), loss_img_vgg.item(), acc.item()
+
+
+@torch.no_grad()
+def val_step(model, val_loader, pred_type="sdf", device=None):
+    """train.py:70-93 without the PNG contact sheet: average L1(sdf) and sign accuracy over the loader, plus the last
+    batch's image loss (what the reference returns and writes into the checkpoint name)."""
+    device = device or next(model.parameters()).device
+    avg_loss_pred, avg_acc, ni, loss_img = 0.0, 0.0, 0, None
+    for batch in val_loader:
+        for key in batch:
+            batch[key] = batch[key].to(device, non_blocking=True)
+        x = model(batch)
+        loss_pred, loss_img, _ = cal_loss_pred(x, batch, pred_type)
+        avg_loss_pred += loss_pred.item()
+        avg_acc += cal_acc(x, batch, pred_type).item()
+        ni += 1
+    return avg_loss_pred / max(ni, 1), avg_acc / max(ni, 1), loss_img
+
+
+def wrap_ddp(model, device=None):
+    """One process per GPU (torchrun): DistributedDataParallel in place of train.py:131-132's DataParallel."""
+    from torch.nn.parallel import DistributedDataParallel as DDP
+    if device is not None and torch.device(device).type == "cuda":
+        return DDP(model, device_ids=[torch.device(device).index], find_unused_parameters=True)
+    return DDP(model, find_unused_parameters=True)

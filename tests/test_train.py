@@ -1,0 +1,196 @@
+"""Training path (reference reg_slices/train.py:21-53) against goldens produced by the
+UNMODIFIED reference in train mode (oracle/make_golden_train.py): loss terms, sdf_pred and autograd gradients of tensors
+spanning the graph from fc_out back to the first trunk convolution.  Dropout is p = 0 on both sides (deterministic).
+
+CPU: the torch restatement of the train-mode forward (models.py:_forward_autograd).  GPU: the same with the decoder's
+forward AND backward in the CUDA library (csrc/train_decoder.cu behind s3d_train_decoder_fwd / _bwd)."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from slice3d_b200 import Slices3DRegModel, synth
+from tests import helpers
+
+
+def _setup(case, device):
+    # the goldens are fp32 CPU arithmetic: keep cuDNN / cuBLAS from switching the torch-side convolutions to TF32
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    S, K, seed, B = int(case["img_size"]), int(case["n_slices"]), int(case["seed"]), int(case["batch"])
+    torch.manual_seed(0)
+    m = Slices3DRegModel(S, K, "train")
+    m.load_state_dict(synth.synthetic_state_dict(m.state_dict(), seed))
+    m = synth.set_dropout(m.to(device).train(), 0.0)
+    feed = {k: v.to(device) for k, v in synth.synthetic_train_batch(S, K, batch=B, n_qry=256, seed=seed).items()}
+    return m, feed
+
+
+def _step(m, feed):
+    ret = m(feed)
+    lp = F.l1_loss(ret["sdf_pred"], feed["sdf"])
+    li = F.l1_loss(ret["slices_rec"], feed["img_slices"])
+    lv = ret["vgg_loss"]
+    (lp + li + lv).backward()
+    return ret, [lp.item(), li.item(), lv.item()]
+
+
+def _check_against_golden(m, ret, losses, case, rtol, tag, loss_rtol=2e-5):
+    """Forward: loss terms and sdf_pred.  Backward: per tensor, |g - g_ref|_2 / |g_ref|_2 over the stored subset."""
+    err = helpers.maxabs(ret["sdf_pred"].detach().cpu(), case["sdf_pred"])
+    print(f"train forward ({tag}): losses {losses} vs reference {case['loss'].tolist()}, sdf_pred max-abs {err:.3e}")
+    assert np.allclose(losses, case["loss"], rtol=loss_rtol, atol=1e-6), (losses, case["loss"])
+    assert err < 1e-4, err
+    named = dict(m.named_parameters())
+    rels = {}
+    for key in [k[5:] for k in case if k.startswith("grad:")]:
+        g = named[key].grad.detach().cpu().reshape(-1)[::int(case["stride:" + key])].double().numpy()
+        ref = case["grad:" + key].astype(np.float64)
+        rels[key] = float(np.linalg.norm(g - ref) / max(np.linalg.norm(ref), 1e-30))
+    worst = max(rels.values())
+    print(f"  gradient errors ({tag}), |g - ref| / |ref|: " + ", ".join(f"{k} {v:.1e}" for k, v in rels.items()))
+    helpers.record(f"train_grads_{tag}_worst_rel_err", worst)
+    assert worst < rtol, rels
+    unused = sorted(k for k, p in named.items() if p.requires_grad and p.grad is None)
+    assert unused == sorted(str(x) for x in case["unused"])  # the 14 tensors DDP must not wait for
+    return rels
+
+
+def test_train_step_cpu_matches_reference_gradients():
+    case = helpers.load_case("train_grads_b2_s128")
+    m, feed = _setup(case, "cpu")
+    ret, losses = _step(m, feed)
+    _check_against_golden(m, ret, losses, case, 2e-4, "cpu_torch")
+
+
+@pytest.mark.gpu
+def test_train_decoder_kernels_match_torch_ops_on_identical_inputs():
+    """The kernels of csrc/train_decoder.cu against the torch-op restatement of the same arithmetic (which the CPU test
+    above pins to the reference bit for bit) ON THE SAME DEVICE AND INPUTS, both measured against a float64 evaluation:
+    sdf_pred and the gradients of all five feature planes and all 42 decoder parameters.  This isolates the hand-written
+    forward/backward from the chaotic part of an end-to-end comparison (ReLU gates / max-pool winners of the U-Net flipping
+    between CPU and GPU arithmetic)."""
+    from slice3d_b200 import train_ops
+    case = helpers.load_case("train_grads_b2_s128")
+    m, feed = _setup(case, "cuda:0")
+    with torch.no_grad():
+        feats, _ = m.slices_generator.forward_train(feed["img_input"])
+    qry = torch.bmm(feed["qry_norot"], feed["obj_rot_mat"])
+    T = feed["trans_mat_wo_rot_tp"]
+    params = train_ops.param_list(m)
+    g = torch.Generator().manual_seed(3)
+    dsdf = torch.randn(2, 256, generator=g).to("cuda:0")
+    import copy
+
+    def torch_decoder(fs, mod, q, Tm):
+        K, n_bs, n_qry = 12, 2, 256
+        uv = mod.project_coord(q, Tm)
+        grid = uv.view(n_bs, 1, 1, n_qry, 2).expand(-1, K, -1, -1, -1).reshape(n_bs * K, 1, n_qry, 2)
+        sampled = [F.grid_sample(f, grid, mode="bilinear", padding_mode="zeros", align_corners=True)
+                   .permute(0, 3, 2, 1).reshape(n_bs * K, n_qry, f.shape[1]) for f in fs]
+        agg = torch.cat(sampled, dim=2).view(n_bs, K, n_qry, 992).permute(0, 2, 1, 3).reshape(n_bs * n_qry, K, 992)
+        tok = torch.cat([mod.fc_p(q).view(n_bs * n_qry, 1, 128), mod.fc_s(agg)], 1)
+        att = mod.att_decoder(tok).view(n_bs, n_qry, K + 1, 128)[:, :, 0, :]
+        return mod.fc_out(att).squeeze(-1)
+
+    class Dec(torch.nn.Module):  # the decoder's modules only (a float64 copy serves as the exact reference)
+        project_coord = staticmethod(Slices3DRegModel.project_coord)
+
+        def __init__(self, src):
+            super().__init__()
+            self.fc_p, self.fc_s, self.fc_out = copy.deepcopy(src.fc_p), copy.deepcopy(src.fc_s), copy.deepcopy(src.fc_out)
+            self.att_decoder = copy.deepcopy(src.att_decoder)
+
+    m64 = Dec(m).double().train()
+    synth.set_dropout(m64, 0.0)
+    params64 = train_ops.param_list(m64)
+
+    def run(kind):
+        ps = params64 if kind == "fp64" else params
+        for q in ps:
+            q.grad = None
+        dt = torch.float64 if kind == "fp64" else torch.float32
+        fs = [f.clone().to(dt).requires_grad_(True) for f in feats]
+        if kind == "native":
+            out = train_ops.decoder_train(fs, qry, T, params, 12, 128, 0.0, 0)
+        elif kind == "torch":
+            out = torch_decoder(fs, m, qry, T)
+        else:
+            out = torch_decoder(fs, m64, qry.double(), T.double())
+        (out * dsdf.to(dt)).sum().backward()
+        return out.detach().double(), [f.grad.double() for f in fs], [q.grad.double().clone() for q in ps]
+
+    ref, nat, tch = run("fp64"), run("native"), run("torch")
+    rel = lambda a, b: float((a - b).norm() / b.norm())
+    e_nat = [rel(a, b) for a, b in zip(nat[1] + nat[2], ref[1] + ref[2])]
+    e_tch = [rel(a, b) for a, b in zip(tch[1] + tch[2], ref[1] + ref[2])]
+    o_nat, o_tch = helpers.maxabs(nat[0].cpu(), ref[0].cpu()), helpers.maxabs(tch[0].cpu(), ref[0].cpu())
+    print(f"decoder fwd+bwd vs a float64 reference: sdf max-abs native {o_nat:.2e} / torch fp32 {o_tch:.2e}; worst gradient "
+          f"|g - ref| / |ref| over 5 planes + 42 parameters: native {max(e_nat):.1e} / torch fp32 {max(e_tch):.1e}")
+    helpers.record("train_decoder_native_vs_fp64_worst_grad_rel_err", max(e_nat))
+    helpers.record("train_decoder_torchfp32_vs_fp64_worst_grad_rel_err", max(e_tch))
+    # fp32 arithmetic flips a few ReLU gates of the 3 x 2048-wide FFN against the exact reference: both fp32
+    # implementations sit at the same distance from it
+    assert o_nat < 2e-5
+    assert max(e_nat) < 1e-2
+    for a, b in zip(e_nat, e_tch):
+        assert a <= 3 * b + 2e-5, (e_nat, e_tch)
+
+
+@pytest.mark.gpu
+def test_train_step_gpu_native_decoder_matches_reference_gradients():
+    """End to end on the GPU against the reference's CPU gradients.  The forward agrees to the usual 1e-4; the gradients
+    only to ~1e-2 of each tensor's norm FOR ANY GPU ARITHMETIC, torch's own included: CPU and GPU convolutions differ by
+    ~1e-6, which flips ReLU gates / max-pool winners / L1 signs of activations that sit on zero, and every flip is a
+    finite jump of the gradient.  So the bar is: native-decoder run within 3e-2 and not worse than the all-torch GPU
+    run by more than a factor 2 (+1e-4)."""
+    from slice3d_b200 import _native
+    case = helpers.load_case("train_grads_b2_s128")
+    m, feed = _setup(case, "cuda:0")
+    assert m.native_train
+    n0 = _native.launch_count()
+    ret, losses = _step(m, feed)
+    torch.cuda.synchronize()
+    assert _native.launch_count() - n0 > 100  # the decoder's forward and backward ran in the library
+    m2, feed2 = _setup(case, "cuda:0")
+    m2.native_train = False
+    ret2, losses2 = _step(m2, feed2)
+    r_torch = _check_against_golden(m2, ret2, losses2, case, 3e-2, "gpu_torch")
+    r_native = _check_against_golden(m, ret, losses, case, 3e-2, "gpu_native")
+    for k in r_native:
+        assert r_native[k] <= 2 * r_torch[k] + 1e-4, (k, r_native[k], r_torch[k])
+
+
+@pytest.mark.gpu
+def test_train_decoder_dropout_statistics_and_determinism():
+    """p = 0.1 (the reference's default): same seed -> identical output and gradients (the masks are regenerated in the
+    backward pass from the same counter-based hash); different seeds differ; kept activations are scaled by 1/(1-p)
+    (the mean over seeds moves back towards the p = 0 output)."""
+    from slice3d_b200 import train_ops
+    case = helpers.load_case("train_grads_b2_s128")
+    m, feed = _setup(case, "cuda:0")
+    with torch.no_grad():
+        feats, _ = m.slices_generator.forward_train(feed["img_input"])
+    qry = torch.bmm(feed["qry_norot"], feed["obj_rot_mat"])
+    params = train_ops.param_list(m)
+    T = feed["trans_mat_wo_rot_tp"]
+
+    def run(p, seed):
+        fs = [f.clone().requires_grad_(True) for f in feats]
+        out = train_ops.decoder_train(fs, qry, T, params, 12, 128, p, seed)
+        out.sum().backward()
+        return out.detach(), fs[4].grad.clone(), params[2].grad.clone()
+
+    for q in params:
+        q.grad = None
+    a = run(0.1, 7)
+    for q in params:
+        q.grad = None
+    b = run(0.1, 7)
+    assert torch.equal(a[0], b[0]) and torch.equal(a[2], b[2])
+    assert helpers.maxabs(a[1].cpu(), b[1].cpu()) < 1e-5  # atomics: order-dependent rounding only
+    base = run(0.0, 0)[0]
+    outs = torch.stack([run(0.1, s)[0] for s in range(8)])
+    assert not torch.equal(outs[0], outs[1])
+    # dropout noise is (to first order) zero-mean around the p = 0 output: averaging 8 seeds shrinks the deviation ~ 1/sqrt(8)
+    assert float((outs.mean(0) - base).abs().mean()) < 0.6 * float((outs[0] - base).abs().mean()) + 1e-3
