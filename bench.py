@@ -24,11 +24,18 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 FLOP_PER_QUERY = 32.82e6  # minimal exact algorithm (contract figure)
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE decoder launch from `ncu --set full` captures of the same
-# configuration (profiles/r1_e_summary.md); keyed by (grid, precision, queries in the launch).  Not measured -> null.
-DECODER_DRAM_BYTES = {(256, "bf16x3", 256 ** 3): 67.477e9 + 18.064e9}
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE decoder launch from ncu captures of the same configuration
+# (profiles/r2_summary.md; round 1 measured 85.5 GB before the locality order of the grid walk); keyed by
+# (grid, precision, queries in the launch).  Not measured -> null.
+DECODER_DRAM_BYTES = {(256, "fp16x3", 256 ** 3): 4.956e9 + 2.926e9}
 METRIC = "occupancy_queries_per_sec"
 UNIT = "queries/s"
+
+
+def bench_config(S, nx):
+    """The workload description BOTH arms print (the driver compares the two dicts)."""
+    return {"workload": f"12 slices {S}x{S} -> {nx}^3 dense occupancy grid", "grid": nx, "img_size": S, "n_slices": 12,
+            "l2": "inputs larger than L2 (projected planes %.0f MB; a fresh view is encoded every step)" % nat_planes_mb(12, S)}
 
 
 def parse():
@@ -187,8 +194,7 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"12 slices {S}x{S} -> {nx}^3 dense occupancy grid", "grid": nx, "img_size": S,
-                       "n_slices": 12},
+            "config": bench_config(S, nx),
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": "each step = one 3000-point chunk of the grid through U-Net + VGG19 loss + "
                                        "decoder, as Generator3D.eval_points (reconstruct.py:74-102) runs it"},
@@ -301,11 +307,9 @@ def run_native(args):
                   "fp16x3": "fp16x3 (fp16 hi/lo split operands, 3 tcgen05 passes, fp32 accumulate)",
                   "bf16": "bf16"}[prec],
         "data": "synthetic",
-        "config": {"workload": f"12 slices {S}x{S} -> {nx}^3 dense occupancy grid (encoder + decoder"
-                               + (" + slab all-gather" if world > 1 else "") + ")",
-                   "grid": nx, "img_size": S, "n_slices": K, "precision": prec,
-                   "parallelism": f"axis-0 slabs x{world}" if world > 1 else "single GPU",
-                   "l2": "inputs larger than L2 (projected planes %.0f MB)" % (nat_planes_mb(K, S))},
+        "config": bench_config(S, nx),
+        "variant": {"step": "plane encoder + decoder over the grid" + (" + slab all-gather" if world > 1 else ""),
+                    "precision": prec, "parallelism": f"axis-0 slabs x{world}" if world > 1 else "single GPU"},
         "e2e": {"value": nx ** 3 * args.steps / (e2e_ms / 1e3), "unit": UNIT,
                 "h2d_bytes_per_step": int(feed["img_input"].numel() * 4 + feed["trans_mat_wo_rot_tp"].numel() * 4),
                 "d2h_bytes_per_step": int(nx ** 3 * 4), "ms_per_step": e2e_ms / args.steps},
@@ -318,6 +322,13 @@ def run_native(args):
                      "peak_source": how + " sustained bf16"},
         "clocks": clocks,
     }
+    if not args.no_extra:
+        with torch.no_grad():
+            line["parity"] = parity_block(dev, prec)
+            if world == 1:
+                line["e2e_api"] = e2e_api_block(model, gen, feed, nx, dev, args.steps)
+                line["sparse"] = sparse_block(dev, prec)
+                line["configs1_128"] = small_grid_block(nat, img_d, T_d, gen, dev, prec)
     if not args.no_train:
         line["train"] = train_leg(dev, world, rank, args.steps, args.warmup, max_over_ranks, barrier)
     if rank == 0:
@@ -326,6 +337,118 @@ def run_native(args):
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def parity_block(dev, prec):
+    """Max-abs error of this build against the reference's own outputs (tests/golden, made by the unmodified reference):
+    the 2071 golden points of the 256^3 grid of the K=12 / S=256 case, through the explicit-point decoder entry."""
+    import numpy as np
+    import torch
+    from slice3d_b200 import Slices3DRegModel, synth
+    z = np.load(os.path.join(ROOT, "tests", "golden", "k12_s256_g128_g256.npz"))
+    S, K, seed = int(z["img_size"]), int(z["n_slices"]), int(z["seed"])
+    m = Slices3DRegModel(S, K, "test", precision=prec)
+    m.load_state_dict(synth.synthetic_state_dict(m.state_dict(), seed))
+    m = m.to(dev).eval()
+    feed = {k: v.to(dev) for k, v in synth.synthetic_inputs(S, K, seed).items()}
+    out = {}
+    for nx in (128, 256):
+        feed["qry_norot"] = torch.from_numpy(z[f"pts_g{nx}"]).unsqueeze(0).to(dev)
+        sdf = m(feed)["sdf_pred"][0].cpu().numpy()
+        out[f"max_abs_vs_golden_g{nx}"] = float(np.abs(sdf - z[f"sdf_g{nx}"]).max())
+    out["max_abs_vs_golden"] = max(out.values())
+    out["golden"] = "tests/golden/k12_s256_g128_g256.npz (unmodified reference, oracle/make_golden.py)"
+    out["precision"] = prec
+    return out
+
+
+def e2e_api_block(model, gen, feed, nx, dev, steps):
+    """The reference-shaped call chain of reconstruct.py:137-146 through this package's Generator3D.eval_points with HOST
+    buffers: make_3d_grid points (nx^3 x 3 fp32, pinned) -> device, eval_points, values -> host.  `value`: eval_points'
+    default here (one model call); `chunked_value`: the reference's literal loop at chunk_size 3000 (5593 model calls for
+    256^3, each a decoder launch of 334 tiles on 148 CTAs: the per-launch floor)."""
+    import torch
+    from slice3d_b200 import synth
+    pts = synth.make_3d_grid((-0.5,) * 3, (0.5,) * 3, (nx,) * 3).pin_memory()
+    host = {k: v.pin_memory() for k, v in feed.items()}
+    out_host = torch.empty(nx ** 3, dtype=torch.float32, pin_memory=True)
+
+    def once(chunked):
+        model._enc_cache = None
+        data = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+        data["qry_norot"] = pts.unsqueeze(0).to(dev, non_blocking=True)
+        vals = gen.eval_points(data, chunked=chunked)
+        out_host.copy_(vals, non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+
+    res = {}
+    for name, chunked, reps in (("value", False, steps), ("chunked_value", True, 1)):
+        once(chunked)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            once(chunked)
+        dt = (time.perf_counter() - t0) / reps
+        res[name] = nx ** 3 / dt
+        res[name.replace("value", "ms_per_step")] = 1e3 * dt
+    res.update({"unit": UNIT, "h2d_bytes_per_step": int(pts.numel() * 4 + sum(v.numel() * 4 for v in host.values())),
+                "d2h_bytes_per_step": int(nx ** 3 * 4), "chunk_size": gen.chunk_size,
+                "call": "Generator3D.eval_points(data) with data['qry_norot'] = make_3d_grid points (reconstruct.py:137-146)"})
+    return res
+
+
+def sparse_block(dev, prec):
+    """The reference's DEFAULT extraction path (reconstruct.py:147-167 + 175-243): MISE 32 x 2^3 -> 257^3 value grid and
+    marching cubes, S = 256.  Two fields: the noisy field of random weights (many refinement rounds) and a smooth field
+    (out-proj / linear2 zeroed: a few rounds, like a real shape)."""
+    import torch
+    from slice3d_b200 import Generator3D, Slices3DRegModel, synth
+    S, K = 256, 12
+    res = {"config": "MISE resolution0 32, 3 upsampling steps -> 257^3, S=256, K=12", "precision": prec}
+    for name in ("noisy", "smooth"):
+        m = Slices3DRegModel(S, K, "test", precision=prec)
+        sd = synth.synthetic_state_dict(m.state_dict(), 0)
+        if name == "smooth":
+            for k in sd:
+                if "att_decoder" in k and ("out_proj" in k or "linear2" in k):
+                    sd[k] = torch.zeros_like(sd[k])
+        m.load_state_dict(sd)
+        m = m.to(dev).eval()
+        feed = synth.synthetic_inputs(S, K, 0)
+        gen = Generator3D(m, resolution0=32, upsampling_steps=3, pred_type="sdf")
+        for _ in range(2):
+            stats = {}
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            grid = gen.generate_sparse_grid(feed, stats=stats, as_numpy=False)
+            torch.cuda.synchronize()
+            t1 = time.perf_counter()
+            mesh = gen.extract_mesh(grid)
+            t2 = time.perf_counter()
+        res[name] = {"rounds": len(stats["points_per_round"]), "points_evaluated": stats["points_evaluated"],
+                     "value_grid_ms": 1e3 * (t1 - t0), "marching_cubes_ms": 1e3 * (t2 - t1),
+                     "generate_mesh_ms": 1e3 * (t2 - t0), "faces": int(len(mesh.faces))}
+    return res
+
+
+def small_grid_block(nat, img_d, T_d, gen, dev, prec):
+    """BASELINE configs[1]: 12 slices 256x256 -> 128^3 (encoder + decoder, inputs resident), same kernels."""
+    import torch
+    nx = 128
+    ax = gen.grid_axes(nx, dev)
+    out = torch.empty(nx ** 3, dtype=torch.float32, device=dev)
+    ts = []
+    for i in range(4):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        planes = nat.encode(img_d, want_slices_rec=True)
+        nat.decode_grid(planes, 0, (ax, ax, ax), 0, nx ** 3, T_d[0], out_scale=-1.0, precision=prec, out=out)
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ms = sum(ts[1:]) / 3
+    return {"workload": "12 slices 256x256 -> 128^3 dense occupancy grid", "ms_per_step": ms, "value": nx ** 3 / (ms / 1e3),
+            "unit": UNIT, "precision": prec}
 
 
 def train_leg(dev, world, rank, steps, warmup, max_over_ranks, barrier):
@@ -341,6 +464,9 @@ def train_leg(dev, world, rank, steps, warmup, max_over_ranks, barrier):
     from slice3d_b200 import Slices3DRegModel, _native, synth
     from slice3d_b200 import train as s3d_train
     S, K, B, NQ = 128, 12, 4, 256
+    # true fp32 on the torch side too (cuDNN would otherwise run the convolutions in TF32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
     torch.manual_seed(0)
     m = Slices3DRegModel(S, K, "train")
     m.load_state_dict(synth.synthetic_state_dict(m.state_dict(), 8))

@@ -200,6 +200,22 @@ size_t s3d_mise_scratch_ints(int32_t resolution0, int32_t depth);
 int s3d_mise_subdivide(int32_t resolution0, int32_t depth, double threshold, const double* value_dev, const uint8_t* known_dev,
                        int8_t* cell_level_dev, uint8_t* exists_dev, int32_t* flags_dev, void* stream);
 
+/* `n_rounds` whole MISE rounds enqueued back to back with NO host round trip, replacing the loop of reconstruct.py:147-167
+ * (query -> points to the device -> eval_points -> values to the host -> update): per round a deterministic compaction of
+ * the lattice points that exist without a value (flat-index order), ONE tensor-core decoder launch whose query count is
+ * read from device memory, the value store and s3d_mise_subdivide.  State arrays as for s3d_mise_subdivide.
+ *   scratch_dev   s3d_sparse_scratch_bytes(resolution0, depth, capacity) bytes: block counts, point indices, points, values.
+ *   counts_dev    int32 [n_rounds + 2]: entry r receives the number of points round r asked for (0 = the refinement had
+ *                 already converged: the round was a no-op); [n_rounds] = live count, [n_rounds + 1] = overflow flag (a
+ *                 round asked for more than `capacity` points: the state is then incomplete and the caller must re-run).
+ * precision must be a tensor-core mode; decoder workspace as for s3d_decoder_fwd with n = capacity. */
+size_t s3d_sparse_scratch_bytes(int32_t resolution0, int32_t depth, int64_t capacity);
+int s3d_sparse_rounds(const s3d_model* m, const void* planes_dev, int32_t S, const float* T_dev, double box_size,
+                      float out_scale, int32_t resolution0, int32_t depth, double threshold, double* value_dev,
+                      uint8_t* known_dev, int8_t* cell_level_dev, uint8_t* exists_dev, int32_t* flags_dev, void* scratch_dev,
+                      int64_t capacity, int32_t* counts_dev, int32_t n_rounds, int32_t precision, void* workspace_dev,
+                      size_t workspace_bytes, void* stream);
+
 /* Marching cubes over a float64 volume (nx,ny,nz), replacing libmcubes.marching_cubes (reg_slices/reconstruct.py:190;
  * src_convonet/utils/libmcubes/marchingcubes.h:22-196, pywrapper.cpp:90-128) in two passes around the caller's
  * exclusive prefix sums (the running vertex / triangle counters of the sequential reference):

@@ -22,7 +22,7 @@ SYMBOLS = [
     "s3d_planes_bytes", "s3d_encoder_workspace_bytes", "s3d_encoder_fwd", "s3d_decoder_workspace_bytes",
     "s3d_decoder_fwd", "s3d_decoder_batch_fwd", "s3d_decoder_grid_fwd", "s3d_decoder_debug_tokens", "s3d_vgg_loss_workspace_bytes",
     "s3d_vgg_loss_fwd", "s3d_mc_count", "s3d_mc_emit", "s3d_mise_scratch_ints",
-    "s3d_mise_subdivide", "s3d_train_decoder_saved_bytes", "s3d_train_decoder_bwd_workspace_bytes",
+    "s3d_mise_subdivide", "s3d_sparse_scratch_bytes", "s3d_sparse_rounds", "s3d_train_decoder_saved_bytes", "s3d_train_decoder_bwd_workspace_bytes",
     "s3d_train_decoder_fwd", "s3d_train_decoder_bwd", "s3d_selftest_umma", "s3d_debug_profile", "s3d_launch_count",
 ]
 
@@ -101,6 +101,12 @@ def lib():
     L.s3d_mise_subdivide.restype = C.c_int
     L.s3d_mise_subdivide.argtypes = [C.c_int32, C.c_int32, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                      C.c_void_p, C.c_void_p]
+    L.s3d_sparse_scratch_bytes.restype = C.c_size_t
+    L.s3d_sparse_scratch_bytes.argtypes = [C.c_int32, C.c_int32, C.c_int64]
+    L.s3d_sparse_rounds.restype = C.c_int
+    L.s3d_sparse_rounds.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_double, C.c_float, C.c_int32, C.c_int32,
+                                    C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                    C.c_int64, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_size_t, C.c_void_p]
     L.s3d_train_decoder_saved_bytes.restype = C.c_size_t
     L.s3d_train_decoder_saved_bytes.argtypes = [C.c_void_p]
     L.s3d_train_decoder_bwd_workspace_bytes.restype = C.c_size_t
@@ -353,6 +359,18 @@ class NativeModel:
                                           T.data_ptr(), out_scale, out.data_ptr(), prec, ws.data_ptr(), ws.numel(),
                                           _stream(self.device)))
         return out
+
+    def sparse_rounds(self, planes, b, T, box_size, out_scale, mise, scratch, capacity, counts, n_rounds, precision):
+        """Enqueue ``n_rounds`` device-resident MISE rounds (s3d_sparse_rounds) on the state tensors of ``mise``."""
+        T = _f32c(T, "trans_mat_wo_rot_tp")
+        L, prec = lib(), PRECISIONS[precision]
+        with torch.cuda.device(self.device):
+            ws = self._workspace("dec", L.s3d_decoder_workspace_bytes(capacity, prec))
+            _check(L.s3d_sparse_rounds(self._h, planes.image_ptr(b), planes.S, T.data_ptr(), float(box_size), out_scale,
+                                       mise.resolution_0, mise.depth, mise.threshold, mise.value.data_ptr(),
+                                       mise.known.data_ptr(), mise.cell_level.data_ptr(), mise.exists.data_ptr(),
+                                       mise.flags().data_ptr(), scratch.data_ptr(), capacity, counts.data_ptr(), n_rounds,
+                                       prec, ws.data_ptr(), ws.numel(), _stream(self.device)))
 
     def debug_tokens(self, planes, b, qry, T, rot=None):
         """fp32 validation path: returns (sdf (n,), tokens (4,n,K+1,128))."""

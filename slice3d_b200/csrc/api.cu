@@ -503,6 +503,52 @@ int s3d_mise_subdivide(int32_t resolution0, int32_t depth, double threshold, con
                         exists_dev, flags_dev, static_cast<cudaStream_t>(stream));
 }
 
+size_t s3d_sparse_scratch_bytes(int32_t resolution0, int32_t depth, int64_t capacity) {
+  if (resolution0 < 1 || depth < 0 || depth > 15 || capacity < 1) return 0;
+  const size_t nblk = mise_query_blocks(resolution0 << depth);
+  return (nblk + 64) * sizeof(int) + (size_t)capacity * (sizeof(int) + 4 * sizeof(float)) + 256;
+}
+
+int s3d_sparse_rounds(const s3d_model* m, const void* planes_dev, int32_t S, const float* T_dev, double box_size,
+                      float out_scale, int32_t resolution0, int32_t depth, double threshold, double* value_dev,
+                      uint8_t* known_dev, int8_t* cell_level_dev, uint8_t* exists_dev, int32_t* flags_dev, void* scratch_dev,
+                      int64_t capacity, int32_t* counts_dev, int32_t n_rounds, int32_t precision, void* workspace_dev,
+                      size_t workspace_bytes, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (!value_dev || !known_dev || !cell_level_dev || !exists_dev || !flags_dev || !scratch_dev || !counts_dev ||
+      n_rounds < 1 || capacity < 1 || capacity > 0x7fffffff || resolution0 < 1 || depth < 0 || depth > 15) {
+    set_error("sparse_rounds: bad argument");
+    return S3D_ERR_BAD_ARG;
+  }
+  if (precision == S3D_PREC_FP32) {
+    set_error("sparse_rounds: needs a tensor-core precision mode (the fp32 decoder keeps the host loop)");
+    return S3D_ERR_UNSUPPORTED;
+  }
+  float* out_probe = reinterpret_cast<float*>(scratch_dev);
+  S3D_TRY(check_decoder(m, planes_dev, S, T_dev, capacity, out_probe, precision, nullptr, workspace_dev, workspace_bytes));
+  const int R = resolution0 << depth;
+  const size_t nblk = mise_query_blocks(R);
+  int* blk = static_cast<int*>(scratch_dev);
+  int* pt_idx = blk + nblk + 64;
+  float* pts = reinterpret_cast<float*>(pt_idx + capacity);
+  float* vals = pts + 3 * (size_t)capacity;
+  int* live = counts_dev + n_rounds;
+  int* overflow = counts_dev + n_rounds + 1;
+  for (int r = 0; r < n_rounds; ++r) {
+    S3D_TRY(mise_query_device(R, box_size, exists_dev, known_dev, blk, live, (int)capacity, counts_dev + r, overflow, pt_idx,
+                              pts, st));
+    QueryCtx q{};
+    q.qry = pts;  // test mode: y,z negated on the fly (our own buffer: nothing to write back)
+    q.T = T_dev;
+    S3D_TRY(decoder_tc(m, static_cast<const float*>(planes_dev), S, q, capacity, out_scale, vals, precision, workspace_dev,
+                       workspace_bytes, st, live));
+    S3D_TRY(mise_apply_device(live, pt_idx, vals, value_dev, known_dev, st));
+    S3D_TRY(mise_subdivide(resolution0, depth, threshold, value_dev, known_dev, reinterpret_cast<signed char*>(cell_level_dev),
+                           exists_dev, flags_dev, st));
+  }
+  return S3D_OK;
+}
+
 int s3d_debug_profile(int64_t* out32, int32_t reset) { return debug_profile(reinterpret_cast<long long*>(out32), reset); }
 
 int s3d_selftest_umma(int32_t mode, int32_t passes, const float* a_dev, const float* w_dev, float* d_dev,

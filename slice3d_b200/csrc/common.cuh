@@ -170,6 +170,12 @@ size_t mise_scratch_ints(int res0, int depth);
 int mise_subdivide(int res0, int depth, double thr, const double* value, const unsigned char* known, signed char* cell_level,
                    unsigned char* exists, int* flags_zeroed, cudaStream_t st);
 
+int mise_query_device(int R, double box, const unsigned char* exists, const unsigned char* known, int* blk, int* count, int cap,
+                      int* round_count, int* overflow, int* pt_idx, float* pts, cudaStream_t st);
+size_t mise_query_blocks(int R);
+int mise_apply_device(const int* count, const int* pt_idx, const float* vals, double* value, unsigned char* known,
+                      cudaStream_t st);
+
 // perceptual.cu
 size_t vgg_loss_workspace_bytes(int N, int S);
 int vgg_loss_fwd(const s3d_model* m, const float* a, const float* b, int N, int S, float* loss, void* ws, size_t ws_bytes,
@@ -216,7 +222,7 @@ int dectc_pack(s3d_model* m, cudaStream_t st);
 bool decoder_tc_supported(const s3d_model* m);
 size_t decoder_tc_workspace_bytes(int64_t n);
 int decoder_tc(const s3d_model* m, const float* planes, int S, const QueryCtx& q, int64_t n, float out_scale,
-               float* out, int precision, void* ws, size_t ws_bytes, cudaStream_t st);
+               float* out, int precision, void* ws, size_t ws_bytes, cudaStream_t st, const int* n_dev = nullptr);
 
 int debug_profile(long long* out32, int reset);
 int umma_selftest(int mode, int passes, const float* a_dev, const float* w_dev, float* d_dev, cudaStream_t st);

@@ -109,6 +109,7 @@ struct TcParams {
   int S;
   QueryCtx q;
   long long n;
+  const int* n_dev;  // when set: the query count lives in device memory (n is then only the capacity)
   float out_scale;
   float* out;
   const float *fcp_wt, *fcp_b, *fcs_b, *fco_w, *fco_b, *b_o0;
@@ -261,6 +262,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
   else __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(sgen + OFF_TMEMPTR);
+  // number of queries: a launch parameter, or read from device memory (device-resident MISE rounds: the count is
+  // produced by the compaction kernel that precedes this launch in the stream; the grid is then launched full)
+  const long long n_q = p.n_dev ? (long long)__ldg(p.n_dev) : p.n;
+  const long long n_tiles = (n_q + TILE_Q - 1) / TILE_Q;
 
   constexpr int NPART = (NPASS == 3) ? 2 : 1;  // ring parts per weight unit (hi [, lo])
 
@@ -305,7 +310,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
       const long long gq = gt * TILE_Q + q;
       const float gu = __shfl_sync(0xffffffffu, qgu, q), gv = __shfl_sync(0xffffffffu, qgv, q);
       const int img = __shfl_sync(0xffffffffu, qimg, q);
-      if (k >= 12 || gq >= p.n) return;
+      if (k >= 12 || gq >= n_q) return;
       const int ch = 32 * cb + l8 * 4;
       float4 acc = __ldg(reinterpret_cast<const float4*>(p.fcs_b + ch));
       const int R0 = plane_res(p.S, 0);
@@ -365,7 +370,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
       float* const tokbase = p.scratch + (size_t)gridDim.x * (TAIL_SLOTS * TILE_Q) * 256 + (size_t)blockIdx.x * (2 * 128 * 128);
       uint32_t ph_te = 3u;  // "empty"-type: the first wait on each buffer passes
       int it = 0;
-      for (long long tile = tile_first; tile - rank < p.num_tiles; tile += gridDim.x, ++it) {
+      for (long long tile = tile_first; tile - rank < n_tiles; tile += gridDim.x, ++it) {
         const int buf = it & 1;
         mbar_wait(bar(B_TOKEMPTY0 + buf), (ph_te >> buf) & 1u);
         ph_te ^= 1u << buf;
@@ -374,7 +379,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
           const int ql = lane < TILE_Q ? lane : TILE_Q - 1;
           const long long gq = tile * TILE_Q + ql;
           float qx = 0.f, qy = 0.f, qz = 0.f;
-          if (gq < p.n) qimg = load_query(p.q, gq, qx, qy, qz, qgu, qgv);
+          if (gq < n_q) qimg = load_query(p.q, gq, qx, qy, qz, qgu, qgv);
           // query tokens fc_p(q) (models.py:79): rows 13 q of the tile, 4 channels per lane
           const int gw = warp - NCW - 2;
           const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.fcp_b) + lane);
@@ -385,7 +390,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
           for (int q = gw; q < TILE_Q; q += NGW) {
             const float px = __shfl_sync(0xffffffffu, qx, q), py = __shfl_sync(0xffffffffu, qy, q),
                         pz = __shfl_sync(0xffffffffu, qz, q);
-            if (tile * TILE_Q + q < p.n)
+            if (tile * TILE_Q + q < n_q)
               __stcg(reinterpret_cast<float4*>(tokbuf + (size_t)(NTOK * q) * 128) + lane,
                      make_float4(b4.x + px * w0.x + py * w1.x + pz * w2.x, b4.y + px * w0.y + py * w1.y + pz * w2.y,
                                  b4.z + px * w0.z + py * w1.z + pz * w2.z, b4.w + px * w0.w + py * w1.w + pz * w2.w));
@@ -432,10 +437,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
         }
       };
       int pending = 0;
-      for (long long base = base_first; base < p.num_tiles; base += gridDim.x) {
+      for (long long base = base_first; base < n_tiles; base += gridDim.x) {
         stream(0, TAIL_UNIT0 * NPART);  // layers 0,1 and the in_proj of layer 2
         ++pending;
-        if (pending == TAIL_SLOTS || base + gridDim.x >= p.num_tiles) {
+        if (pending == TAIL_SLOTS || base + gridDim.x >= n_tiles) {
           stream(TAIL_UNIT0 * NPART, 3 * UNITS_PER_LAYER * NPART);  // tail pass: out_proj + FFN of layer 2
           pending = 0;
         }
@@ -462,10 +467,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
       }
     };
     int pending = 0;
-    for (long long base = base_first; base < p.num_tiles; base += gridDim.x) {
+    for (long long base = base_first; base < n_tiles; base += gridDim.x) {
       relay(TAIL_UNIT0 * NPART);
       ++pending;
-      if (pending == TAIL_SLOTS || base + gridDim.x >= p.num_tiles) {
+      if (pending == TAIL_SLOTS || base + gridDim.x >= n_tiles) {
         relay((3 * UNITS_PER_LAYER - TAIL_UNIT0) * NPART);
         pending = 0;
       }
@@ -582,14 +587,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
         commit(B_DDONE);
       };
       int pending = 0;
-      for (long long base = base_first; base < p.num_tiles; base += gridDim.x) {
+      for (long long base = base_first; base < n_tiles; base += gridDim.x) {
 #pragma unroll 1
         for (int layer = 0; layer < 3; ++layer) {  // (one call site for each of the two issue sequences)
           mma_qkv();
           bool ffn = true;
           if (layer == 2) {  // last layer: only token 0 of every query is consumed downstream -> batched tail pass
             ++pending;
-            ffn = (pending == TAIL_SLOTS || base + gridDim.x >= p.num_tiles);
+            ffn = (pending == TAIL_SLOTS || base + gridDim.x >= n_tiles);
             if (ffn) pending = 0;
           }
           if (ffn) mma_out_ffn();
@@ -921,7 +926,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
           o.z = fmaf(pj[j], v4.z, o.z);
           o.w = fmaf(pj[j], v4.w, o.w);
         }
-        if (tile * TILE_Q + q < p.n)
+        if (tile * TILE_Q + q < n_q)
           *reinterpret_cast<float4*>(tail0 + (size_t)q * 256 + 4 * c4) = make_float4(o.x * inv, o.y * inv, o.z * inv, o.w * inv);
       }
       lap(15)
@@ -1017,9 +1022,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
     int pending = 0, tile_it = 0, tiles_done = 0;
     uint32_t ph_tf = 0;
     long long batch_tile0 = 0;
-    for (long long tile = tile_first; tile - rank < p.num_tiles; tile += gridDim.x) {
+    for (long long tile = tile_first; tile - rank < n_tiles; tile += gridDim.x) {
       const long long q_idx = tile * TILE_Q + qi;
-      const bool valid = (qi < TILE_Q) && (q_idx < p.n);
+      const bool valid = (qi < TILE_Q) && (q_idx < n_q);
       // ------------------------------------------------------------------ token build
       const int tbuf = tile_it & 1;
       const float* tokbuf = tokbase + (size_t)tbuf * (128 * 128);
@@ -1058,13 +1063,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
           attention_tok0(tile, pending);
           if (pending == 0) batch_tile0 = tile;
           ++pending;
-          post = (pending == TAIL_SLOTS || tile - rank + gridDim.x >= p.num_tiles);
+          post = (pending == TAIL_SLOTS || tile - rank + gridDim.x >= n_tiles);
           if (post) {
             // -------------------------------------------------------------- tail pass: token 0 of up to 126 queries
             named_bar_sync(1, NCT);  // scratch rows written by other threads are visible after the CTA barrier
             const int k = r / TILE_Q, qq = r - k * TILE_Q;
             const long long tq = (batch_tile0 + (long long)k * gridDim.x) * TILE_Q + qq;
-            const bool tvalid = (r < pending * TILE_Q) && (tq < p.n);
+            const bool tvalid = (r < pending * TILE_Q) && (tq < n_q);
             const float* row = p.scratch + ((size_t)blockIdx.x * (TAIL_SLOTS * TILE_Q) + (r < TAIL_SLOTS * TILE_Q ? r : 0)) * 256;
             float v[32];
 #pragma unroll
@@ -1320,7 +1325,7 @@ size_t decoder_tc_workspace_bytes(int64_t) {
 }
 
 int decoder_tc(const s3d_model* m, const float* planes, int S, const QueryCtx& q, int64_t n, float out_scale, float* out,
-               int precision, void* ws, size_t ws_bytes, cudaStream_t st) {
+               int precision, void* ws, size_t ws_bytes, cudaStream_t st, const int* n_dev) {
   if (!decoder_tc_supported(m)) {
     set_error("decoder: tensor-core modes need n_slices == 12 (use S3D_PREC_FP32 otherwise)");
     return S3D_ERR_UNSUPPORTED;
@@ -1333,6 +1338,7 @@ int decoder_tc(const s3d_model* m, const float* planes, int S, const QueryCtx& q
   p.S = S;
   p.q = q;
   p.n = n;
+  p.n_dev = n_dev;
   p.out_scale = out_scale;
   p.out = out;
   const DecF32& d = m->dec32;
@@ -1367,7 +1373,7 @@ int decoder_tc(const s3d_model* m, const float* planes, int S, const QueryCtx& q
   };
   {  // CTA pairs: clusters of 2, one pair per TPC
     const long long pairs = (p.num_tiles + 1) / 2;
-    const unsigned g2 = 2u * (unsigned)(pairs < sms / 2 ? pairs : sms / 2);
+    const unsigned g2 = 2u * (unsigned)((pairs < sms / 2 && !n_dev) ? pairs : sms / 2);
     if (precision == S3D_PREC_FP16X3) S3D_TRY(launch(decoder_tc_kernel<3, 2, true>, g2, 2));
     else if (precision == S3D_PREC_BF16X3) S3D_TRY(launch(decoder_tc_kernel<3, 2, false>, g2, 2));
     else S3D_TRY(launch(decoder_tc_kernel<1, 2, false>, g2, 2));

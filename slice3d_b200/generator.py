@@ -26,6 +26,7 @@ import math
 import numpy as np
 import torch
 
+from . import _native
 from . import dist as s3d_dist
 from .mcubes import Mesh, marching_cubes
 from .mise import MISE
@@ -33,6 +34,8 @@ from .synth import make_3d_grid  # noqa: F401  (re-exported: reference src_convo
 
 
 class Generator3D(object):
+    ROUNDS_PER_SYNC = 6
+
     def __init__(self, model, points_batch_size=100000, threshold=0.5, refinement_step=0, device=None,
                  resolution0=64, upsampling_steps=2, chunk_size=3000, with_normals=False, padding=0.0, sample=False,
                  input_type=None, vol_info=None, vol_bound=None, simplify_nfaces=None, pred_type="occ"):
@@ -51,13 +54,30 @@ class Generator3D(object):
         self.chunk_size = chunk_size
         self.pred_type = pred_type
         self.vol_bound = vol_bound
+        # --- not part of the reference API: MISE rounds enqueued per host synchronisation, lattice points a round may ask for
+        self.device_rounds = True
+        self.sparse_capacity = None
         if vol_info is not None:
             self.input_vol, _, _ = vol_info
 
     # ------------------------------------------------------------------ reference-shaped API
-    def eval_points(self, data):
-        """reconstruct.py:74-102.  ``data['qry_norot']`` is (1, n_qry, 3); returns (n_qry,)."""
+    def eval_points(self, data, chunked=None):
+        """reconstruct.py:74-102.  ``data['qry_norot']`` is (1, n_qry, 3); returns (n_qry,).
+
+        The reference chunks the queries (``chunk_size`` 3000) because every model call re-runs the U-Net and holds
+        (n_qry x 12 x 992) activations.  With this package's model the planes are cached and the decoder is one fused
+        kernel, so by default the whole query set goes through ONE model call -- same values (queries are independent),
+        same in-place y,z flip of ``data['qry_norot']`` as the chunk views would leave behind.  ``chunked=True`` (or a
+        model without ``fused_eval_points``) runs the reference's loop literally."""
         n_qry = data["qry_norot"].shape[1]
+        if chunked is None:
+            chunked = not (getattr(self.model, "fused_eval_points", False) and not self.model.training
+                           and not torch.is_grad_enabled())
+        if not chunked:
+            ret_dict = self.model(data)
+            if self.pred_type == "occ":
+                return ret_dict["occ_pred"].squeeze(0)  # KeyError, like the reference (SURVEY.md section 0)
+            return (-ret_dict["sdf_pred"]).squeeze(0)
         chunk_size = self.chunk_size
         n_chunk = math.ceil(n_qry / chunk_size)
         ret = []
@@ -170,7 +190,33 @@ class Generator3D(object):
         ext = MISE(self.resolution0, self.upsampling_steps, self.threshold_logit(), device=dev)
         rank, world = s3d_dist.rank_world(group)
         rounds = []
-        points = ext.query()
+        if world == 1 and precision != "fp32" and dev.type == "cuda" and self.upsampling_steps > 0 and self.device_rounds:
+            # Device-resident rounds: compaction of the unknown lattice points, ONE decoder launch that reads its query
+            # count from device memory, value store and octree split -- enqueued ROUNDS_PER_SYNC rounds at a time; the
+            # only host round trip is the read of the per-round counts after each batch (a round that finds no unknown
+            # point is a no-op, so running past the last round is harmless).
+            n_lattice = (ext.resolution + 1) ** 3
+            capacity = min(n_lattice, self.sparse_capacity or (1 << 25))
+            scratch = torch.empty(_native.lib().s3d_sparse_scratch_bytes(ext.resolution_0, ext.depth, capacity),
+                                  dtype=torch.uint8, device=dev)
+            nr = self.ROUNDS_PER_SYNC
+            while True:
+                counts = torch.zeros(nr + 2, dtype=torch.int32, device=dev)
+                nat.sparse_rounds(planes, 0, T[0], box_size, -1.0, ext, scratch, capacity, counts, nr, precision)
+                c = counts.cpu().tolist()
+                if c[nr + 1]:
+                    raise _native.NativeError(f"MISE round asked for more than sparse_capacity={capacity} points")
+                done = False
+                for n in c[:nr]:
+                    if n == 0:
+                        done = True
+                        break
+                    rounds.append(n)
+                if done:
+                    break
+            points = torch.empty(0, 3, dtype=torch.long, device=dev)
+        else:
+            points = ext.query()
         while points.shape[0] != 0:
             n = points.shape[0]
             # float64 like numpy's int64 / int, then the reference's torch.FloatTensor rounding

@@ -77,6 +77,14 @@ class MISE(object):
         pts = torch.nonzero(self.exists)
         return pts, self.value[pts[:, 0], pts[:, 1], pts[:, 2]]
 
+    def flags(self):
+        """Zeroed int32 scratch of the CUDA refinement step (one word per voxel of every level below the maximum depth)."""
+        if self._flags is None:
+            from . import _native
+            self._flags = torch.zeros(_native.mise_scratch_ints(self.resolution_0, self.depth), dtype=torch.int32,
+                                      device=self.device)
+        return self._flags
+
     # ------------------------------------------------------------------ internals
     def _subdivide_voxels(self):
         R, depth = self.resolution, self.depth
@@ -86,11 +94,8 @@ class MISE(object):
             # on the device: two hand-written kernels (csrc/mise.cu, s3d_mise_subdivide); the tensor program below is
             # the same step for host tensors (what the CPU tests run against the reference)
             from . import _native
-            if self._flags is None:
-                self._flags = torch.zeros(_native.mise_scratch_ints(self.resolution_0, depth), dtype=torch.int32,
-                                          device=self.device)
             _native.mise_subdivide(self.resolution_0, depth, self.threshold, self.value, self.known, self.cell_level,
-                                   self.exists, self._flags)
+                                   self.exists, self.flags())
             return
         pts = torch.nonzero(self.known)
         val = self.value[pts[:, 0], pts[:, 1], pts[:, 2]]

@@ -50,6 +50,7 @@ class Slices3DRegModel(nn.Module):
         # --- not part of the reference API ---
         self.precision = precision or default_precision(n_slices)  # decoder arithmetic: fp32 | fp16x3 | bf16x3 | bf16
         self.test_time_vgg_loss = True  # the reference evaluates (and discards) it at test time too
+        self.fused_eval_points = True  # Generator3D.eval_points may pass all queries in one call (no 3000-point chunks)
         self.native_train = True  # CUDA tensors: train-mode decoder forward + backward in the CUDA library
         # Packed-weight handles, one per device, in a dict that nn.DataParallel replicas share by reference
         # (replicate() copies __dict__ shallowly): {"epoch": int, "dev": {device: entry}}.

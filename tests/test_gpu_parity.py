@@ -156,10 +156,15 @@ def test_eval_points_chunked_driver_matches_reference():
     feed["qry_norot"] = torch.from_numpy(pts).unsqueeze(0).to(DEV)
     gen = Generator3D(m, upsampling_steps=0, chunk_size=3000, pred_type="sdf")
     with torch.no_grad():
-        vals = gen.eval_points(feed)
+        vals = gen.eval_points(feed, chunked=True)  # the reference's loop, literally
+        feed["qry_norot"] = torch.from_numpy(pts).unsqueeze(0).to(DEV)
+        fused = gen.eval_points(feed)  # one model call over all queries
     want = -np.concatenate([case["sdf_g128"], case["sdf_g256"]])
     assert vals.shape == (pts.shape[0],)
     assert helpers.maxabs(vals.cpu(), want) < TOL
+    assert helpers.maxabs(fused.cpu(), vals.cpu()) < 1e-6
+    # both leave the caller's queries flipped in y,z (models.py:55 applied to every chunk view)
+    assert torch.equal(feed["qry_norot"][0, :, 1:].cpu(), -torch.from_numpy(pts)[:, 1:])
     launches = _native.launch_count()
     assert launches > 0
 

@@ -155,6 +155,20 @@ def test_generate_sparse_grid_matches_reference_loop():
     assert (diff < 1e-4).mean() > 0.999
     if stats["points_per_round"] == gold["rounds"].tolist():
         assert diff.max() < 1e-4
+    # device-resident rounds (s3d_sparse_rounds: compaction + decoder with a device-side query count + update, several
+    # rounds per host synchronisation) against the host-driven loop with the same decoder arithmetic: identical volume
+    # and identical points per round
+    with torch.no_grad():
+        for rounds_per_sync in (6, 1, 40):
+            gen.ROUNDS_PER_SYNC = rounds_per_sync
+            s_dev, s_host = {}, {}
+            gen.device_rounds = True
+            g_dev = gen.generate_sparse_grid(feed, precision="fp16x3", stats=s_dev)
+            gen.device_rounds = False
+            g_host = gen.generate_sparse_grid(feed, precision="fp16x3", stats=s_host)
+            assert s_dev["points_per_round"] == s_host["points_per_round"], rounds_per_sync
+            assert np.array_equal(g_dev, g_host)
+    gen.device_rounds = True
     # every lattice value of the sparse volume is the model's value at that point or a forward fill of one:
     # re-evaluate the whole lattice densely with the same kernels and compare at the evaluated points
     R = grid.shape[0] - 1
