@@ -728,104 +728,166 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
             __ldg(reinterpret_cast<const float4*>(p.vecs + (size_t)nl * VEC_FLOATS) + tid);
       }
     };
+    // ---- attention of the full layers on the warp-level tensor-core path (mma.sync m16n8k16, fp16 hi/lo pairs, 3 passes)
+    // Q (scaled), K, V (+ biases) are staged as fp16 hi / lo matrices [120 rows][128 channels] with rows of 256 bytes
+    // whose 16-byte chunks are XOR-swizzled with (row & 7): the staging stores (one row per lane) and the ldmatrix
+    // reads (8 consecutive rows per 8x8 matrix) are both conflict free.  K / V live in the H region, Q in the activation
+    // operand region (free once the V projection has completed).  The 36 (query, head) problems of a tile are dealt to
+    // the 16 compute warps; a problem is one 16-row tile (13 token rows + 3 rows of the next query, discarded):
+    //   S = Q K^T   m16 n16 k32: 2 n-tiles x 2 k-steps x 3 passes = 12 MMAs; masked softmax on the accumulator fragments
+    //   O = P V     m16 n32 k16: 4 n-tiles x 3 passes = 12 MMAs (P is re-used from the S fragments: the accumulator
+    //               layout of two n-tiles IS the A layout of one k16 step), V through ldmatrix.trans
+    // and O goes straight into the out-proj A operand.  (The CUDA-core version spent 15 kcycles per layer in LDS-bound
+    // FMAs: every key / value row was re-read by the 13 row owners of its query.)
+    constexpr uint32_t ATT_ARR = 120u * 256u;  // one staged matrix (hi or lo)
+    auto att_off = [](int row, int chunk) -> uint32_t { return (uint32_t)(row * 256 + ((chunk ^ (row & 7)) << 4)); };
+    auto stage_att = [&](uint32_t col, const float* bias, float scale, uint8_t* dst) {
+      const float live = r < TILE_Q * NTOK ? scale : 0.f;  // rows 117..119 are read as padding: exact zeros
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {  // two halves of 16 columns: small live state next to the P fragments
+        float v[16];
+        tmem_ld16(trow + col + 32 * g + 16 * hf, v);
+        tmem_ld_wait();
+        if (r < 120) {
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            const float4 b0 = *reinterpret_cast<const float4*>(bias + 32 * g + 16 * hf + 8 * c);
+            const float4 b1 = *reinterpret_cast<const float4*>(bias + 32 * g + 16 * hf + 8 * c + 4);
+            const float w[8] = {(v[8 * c] + b0.x) * live,     (v[8 * c + 1] + b0.y) * live, (v[8 * c + 2] + b0.z) * live,
+                                (v[8 * c + 3] + b0.w) * live, (v[8 * c + 4] + b1.x) * live, (v[8 * c + 5] + b1.y) * live,
+                                (v[8 * c + 6] + b1.z) * live, (v[8 * c + 7] + b1.w) * live};
+            uint32_t h[4], l[4];
+            split8_hn(w, h, l);
+            const uint32_t off = att_off(r, 4 * g + 2 * hf + c);
+            *reinterpret_cast<uint4*>(dst + off) = make_uint4(h[0], h[1], h[2], h[3]);
+            *reinterpret_cast<uint4*>(dst + ATT_ARR + off) = make_uint4(l[0], l[1], l[2], l[3]);
+          }
+        }
+      }
+    };
     auto attention = [&](int layer, bool valid) {
+      (void)valid;  // rows of queries beyond n carry zero tokens: finite everywhere, their outputs are never stored
       const float* b_in = vec + V_BIN;
-      float sc[NTOK];
+      constexpr int NPROB = TILE_Q * 4, PPW = (NPROB + NCW - 1) / NCW;  // 36 problems, at most 3 per warp
+      const uint32_t kv_s = sbase + OFF_H, q_s = sbase + OFF_AX_HI;
+      const int l8 = lane & 7, mi = lane >> 3, tq = lane & 3, rq = lane >> 2;
+      uint32_t phi[PPW][4], plo[PPW][4];
       {
         float4 vb[2];
         vecB_fetch(layer, vb);
-        stage_kv(TM_S + 128, b_in + 128);
+        stage_att(TM_S + 128, b_in + 128, 1.f, sgen + OFF_H);  // K
+        lap(12)
+        mbar_wait(bar(B_QDONE), ph_kq);
+        ph_kq ^= 1u;
+        mbar_wait(bar(B_DDONE), ph_d);  // V projected: every MMA that reads the activation operand has completed
+        ph_d ^= 1;
+        tc_fence_after();
+        stage_att(TM_S, b_in, 0.17677669529663687f, sgen + OFF_AX_HI);  // Q / sqrt(32)
         named_bar_sync(1, NCT);
         vecB_store(vb);
       }
-      mbar_wait(bar(B_QDONE), ph_kq);
-      ph_kq ^= 1u;
-      tc_fence_after();
-      lap(12)
-      {
 #pragma unroll
-        for (int j = 0; j < NTOK; ++j) sc[j] = 0.f;
-        // head dim in two halves of 16: small live state lets the compiler keep several key rows in flight
+      for (int i = 0; i < PPW; ++i) {
+        const int pr = warp + NCW * i;
+        if (pr < NPROB) {  // warp-uniform
+          const int R0 = NTOK * (pr >> 2), hh = pr & 3;
+          float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};  // n-tiles: keys 0-7, keys 8-15
 #pragma unroll
-        for (int hf = 0; hf < 2; ++hf) {
-          float qq[16];
-          tmem_ld16(trow + TM_S + 32 * g + 16 * hf, qq);
-          tmem_ld_wait();
-#pragma unroll
-          for (int c = 0; c < 16; c += 4) {
-            const float4 b4 = *reinterpret_cast<const float4*>(b_in + 32 * g + 16 * hf + c);
-            qq[c] = (qq[c] + b4.x) * 0.17677669529663687f;
-            qq[c + 1] = (qq[c + 1] + b4.y) * 0.17677669529663687f;
-            qq[c + 2] = (qq[c + 2] + b4.z) * 0.17677669529663687f;
-            qq[c + 3] = (qq[c + 3] + b4.w) * 0.17677669529663687f;
+          for (int ks = 0; ks < 2; ++ks) {
+            const int c0 = 4 * hh + 2 * ks;  // first 16-byte chunk of this k-step
+            uint32_t qh[4], ql[4], kh[4], kl[4];
+            const uint32_t qa = q_s + att_off(R0 + l8 + 8 * (mi & 1), c0 + (mi >> 1));
+            ldsm_x4(qa, qh[0], qh[1], qh[2], qh[3]);
+            ldsm_x4(qa + ATT_ARR, ql[0], ql[1], ql[2], ql[3]);
+            const uint32_t ka = kv_s + att_off(R0 + l8 + 8 * (mi >> 1), c0 + (mi & 1));
+            ldsm_x4(ka, kh[0], kh[1], kh[2], kh[3]);
+            ldsm_x4(ka + ATT_ARR, kl[0], kl[1], kl[2], kl[3]);
+            mma_f16_16816(s0, ql, kh[0], kh[1]);
+            mma_f16_16816(s1, ql, kh[2], kh[3]);
+            mma_f16_16816(s0, qh, kl[0], kl[1]);
+            mma_f16_16816(s1, qh, kl[2], kl[3]);
+            mma_f16_16816(s0, qh, kh[0], kh[1]);
+            mma_f16_16816(s1, qh, kh[2], kh[3]);
           }
-          if (valid) {
+          // fragment: s0[0,1] / s1[0,1] = row rq, keys 2 tq + {0,1} / 8 + 2 tq + {0,1};  [2,3] = row rq + 8.  Keys >= 13 masked.
+          const bool m0 = (8 + 2 * tq) < NTOK, m1 = (9 + 2 * tq) < NTOK;
 #pragma unroll
-            for (int j = 0; j < NTOK; ++j) {
-              const float4* kb = reinterpret_cast<const float4*>(qrows + j * ST_PITCH + 16 * hf);
-              float2 a0 = make_float2(0.f, 0.f), a1 = make_float2(0.f, 0.f);
-#pragma unroll
-              for (int c = 0; c < 4; ++c) {
-                const float4 k4 = kb[c];
-                ffma2(a0, make_float2(qq[4 * c], qq[4 * c + 1]), make_float2(k4.x, k4.y));
-                ffma2(a1, make_float2(qq[4 * c + 2], qq[4 * c + 3]), make_float2(k4.z, k4.w));
-              }
-              sc[j] += (a0.x + a0.y) + (a1.x + a1.y);
-            }
+          for (int hr = 0; hr < 2; ++hr) {
+            float a0 = s0[2 * hr], a1 = s0[2 * hr + 1], a2 = m0 ? s1[2 * hr] : -INFINITY, a3 = m1 ? s1[2 * hr + 1] : -INFINITY;
+            float mx = fmaxf(fmaxf(a0, a1), fmaxf(a2, a3));
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+            a0 = __expf(a0 - mx); a1 = __expf(a1 - mx);
+            a2 = m0 ? __expf(a2 - mx) : 0.f;
+            a3 = m1 ? __expf(a3 - mx) : 0.f;
+            float sum = (a0 + a1) + (a2 + a3);
+            sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+            sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+            const float inv = 1.f / sum;
+            // A fragment of P: a0a1 (row, keys 0-7), a2a3 (row + 8, keys 0-7), a4a5 (row, keys 8-15), a6a7 (row + 8, keys 8-15)
+            split2_h(a0 * inv, a1 * inv, phi[i][hr], plo[i][hr]);
+            split2_h(a2 * inv, a3 * inv, phi[i][2 + hr], plo[i][2 + hr]);
           }
-        }
-        if (valid) {
-          float mx = sc[0];
-#pragma unroll
-          for (int j = 1; j < NTOK; ++j) mx = fmaxf(mx, sc[j]);
-          float sum = 0.f;
-#pragma unroll
-          for (int j = 0; j < NTOK; ++j) {
-            sc[j] = __expf(sc[j] - mx);
-            sum += sc[j];
-          }
-          const float inv = 1.f / sum;
-#pragma unroll
-          for (int j = 0; j < NTOK; ++j) sc[j] *= inv;
         }
       }
       lap(13)
-      named_bar_sync(1, NCT);  // everyone has read K
-      mbar_wait(bar(B_DDONE), ph_d);  // V projected
-      ph_d ^= 1;
-      tc_fence_after();
-      stage_kv(TM_S + 256, b_in + 256);
+      named_bar_sync(1, NCT);  // everyone has read K and Q
+      stage_att(TM_S + 256, b_in + 256, 1.f, sgen + OFF_H);  // V over K
+      if (r >= TILE_Q * NTOK) {  // padding rows of the out-proj operand (the region held Q until now): zeros
+        const float z[32] = {};
+        store_ax(z);
+      }
       named_bar_sync(1, NCT);
       vecA_next(layer);
       lap(14)
-      {
-        // O[:, 32g:32g+32] in two halves of 16 -> operand A chunks (k-block g/2, chunks 4*(g&1) + 2*hf ..+1)
 #pragma unroll
-        for (int hf = 0; hf < 2; ++hf) {
-          float2 o2[8];
+      for (int i = 0; i < PPW; ++i) {
+        const int pr = warp + NCW * i;
+        if (pr < NPROB) {
+          const int R0 = NTOK * (pr >> 2), hh = pr & 3;
+          float o[4][4];
 #pragma unroll
-          for (int c = 0; c < 8; ++c) o2[c] = make_float2(0.f, 0.f);
-          if (valid) {
+          for (int jn = 0; jn < 4; ++jn)
 #pragma unroll
-            for (int j = 0; j < NTOK; ++j) {
-              const float4* vb = reinterpret_cast<const float4*>(qrows + j * ST_PITCH + 16 * hf);
-              const float2 p2 = make_float2(sc[j], sc[j]);
+            for (int e = 0; e < 4; ++e) o[jn][e] = 0.f;
 #pragma unroll
-              for (int c = 0; c < 4; ++c) {
-                const float4 v4 = vb[c];
-                ffma2(o2[2 * c], p2, make_float2(v4.x, v4.y));
-                ffma2(o2[2 * c + 1], p2, make_float2(v4.z, v4.w));
+          for (int jp = 0; jp < 2; ++jp) {  // channel n-tiles 2 jp, 2 jp + 1 of head hh
+            uint32_t vh[4], vl[4];
+            const uint32_t va = kv_s + att_off(R0 + l8 + 8 * (mi & 1), 4 * hh + 2 * jp + (mi >> 1));
+            ldsm_x4_t(va, vh[0], vh[1], vh[2], vh[3]);
+            ldsm_x4_t(va + ATT_ARR, vl[0], vl[1], vl[2], vl[3]);
+            mma_f16_16816(o[2 * jp], plo[i], vh[0], vh[1]);
+            mma_f16_16816(o[2 * jp + 1], plo[i], vh[2], vh[3]);
+            mma_f16_16816(o[2 * jp], phi[i], vl[0], vl[1]);
+            mma_f16_16816(o[2 * jp + 1], phi[i], vl[2], vl[3]);
+            mma_f16_16816(o[2 * jp], phi[i], vh[0], vh[1]);
+            mma_f16_16816(o[2 * jp + 1], phi[i], vh[2], vh[3]);
+          }
+          // O[row][32 hh + 8 jn + 2 tq + {0,1}] -> out-proj A operand (k-block hh / 2, chunk 4 (hh & 1) + jn, element pair tq)
+          uint8_t* const thi = ax_hi + (hh >> 1) * 16384;
+          uint8_t* const tlo = ax_lo + (hh >> 1) * 16384;
+#pragma unroll
+          for (int hr = 0; hr < 2; ++hr) {
+            const int row = rq + 8 * hr;
+            if (row < NTOK) {
+#pragma unroll
+              for (int jn = 0; jn < 4; ++jn) {
+                const uint32_t off = sw128_chunk_off(R0 + row, 4 * (hh & 1) + jn) + 4 * tq;
+                uint32_t hv, lv;
+                if (F16) {
+                  split2_h(o[jn][2 * hr], o[jn][2 * hr + 1], hv, lv);
+                } else {
+                  const __nv_bfloat162 h2 = __floats2bfloat162_rn(o[jn][2 * hr], o[jn][2 * hr + 1]);
+                  hv = *reinterpret_cast<const uint32_t*>(&h2);
+                  const __nv_bfloat162 l2 = __floats2bfloat162_rn(o[jn][2 * hr] - __uint_as_float(hv << 16),
+                                                                  o[jn][2 * hr + 1] - __uint_as_float(hv & 0xffff0000u));
+                  lv = *reinterpret_cast<const uint32_t*>(&l2);
+                }
+                *reinterpret_cast<uint32_t*>(thi + off) = hv;
+                if (NPASS == 3) *reinterpret_cast<uint32_t*>(tlo + off) = lv;
               }
             }
           }
-          float o[16];
-#pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            o[2 * c] = o2[c].x;
-            o[2 * c + 1] = o2[c].y;
-          }
-          store_chunk<NPASS, F16>(ax_hi + (g >> 1) * 16384, ax_lo + (g >> 1) * 16384, r, (g & 1) * 4 + 2 * hf, o);
-          store_chunk<NPASS, F16>(ax_hi + (g >> 1) * 16384, ax_lo + (g >> 1) * 16384, r, (g & 1) * 4 + 2 * hf + 1, o + 8);
         }
       }
       lap(15)

@@ -317,6 +317,30 @@ __device__ __forceinline__ void ffma2(float2& d, const float2 a, const float2 b)
   asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(dd));
 }
 
+// ---------------------------------------------------------------- warp-level MMA (the decoder's 13 x 13 attention)
+// Four 8x8 b16 matrices from shared memory: lane l supplies the address of row l % 8 of matrix l / 8.
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+// d (16x8 fp32) += a (16x16 f16, row) * b (16x8 f16, col)
+__device__ __forceinline__ void mma_f16_16816(float* d, const uint32_t* a, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// two floats -> packed fp16 pair hi and the packed fp16 pair of the remainders
+__device__ __forceinline__ void split2_h(float x, float y, uint32_t& hi, uint32_t& lo) {
+  const __half2 h2 = __floats2half2_rn(x, y);
+  const __half2 l2 = __floats2half2_rn(x - __low2float(h2), y - __high2float(h2));
+  hi = *reinterpret_cast<const uint32_t*>(&h2);
+  lo = *reinterpret_cast<const uint32_t*>(&l2);
+}
+
 // ---------------------------------------------------------------- bf16 split helpers
 // x = hi + lo + O(2^-17 |x|): hi = bf16_rn(x), lo = bf16_rn(x - hi).
 __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
