@@ -229,23 +229,16 @@ def run_native(args):
     nat = model.native()
     img_d = feed["img_input"].to(dev)
     T_d = feed["trans_mat_wo_rot_tp"].to(dev)
-    ax = gen.grid_axes(nx, dev)
-    lo, hi = s3d_dist.slab_range(nx, rank, world)
-    first, count = lo * nx * nx, (hi - lo) * nx * nx
-    vol = torch.empty(nx ** 3, dtype=torch.float32, device=dev)
+    dfeed = {"img_input": img_d, "trans_mat_wo_rot_tp": T_d}
     dec_ev = []
 
     def step(timed):
-        planes = nat.encode(img_d, want_slices_rec=True)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        nat.decode_grid(planes, 0, (ax, ax, ax), first, count, T_d[0], out_scale=-1.0, precision=prec,
-                        out=vol[first:first + count])
-        e1.record()
+        # the product path with device-resident inputs: encoder (cache dropped: a new view every step), decoder over this
+        # rank's slab (slab widths follow the ranks' measured rates), slab all-gather
+        model._enc_cache = None
+        gen.generate_grid(dfeed, resolution=nx, precision=prec, as_numpy=False)
         if timed:
-            dec_ev.append((e0, e1))
-        if world > 1:
-            s3d_dist.all_gather_slabs(vol, nx)
+            dec_ev.append(gen._last_dec[:3])
 
     def barrier():
         if world > 1:
@@ -275,18 +268,27 @@ def run_native(args):
         barrier()
         launches = _native.launch_count() - l0
         ms = max_over_ranks(s0.elapsed_time(s1))
-        dec_ms = sum(a.elapsed_time(b) for a, b in dec_ev) / len(dec_ev)
+        dec_ms = sum(a.elapsed_time(b) for a, b, _ in dec_ev) / len(dec_ev)
+        count = int(sum(p for _, _, p in dec_ev) / len(dec_ev)) * nx * nx  # queries of this rank's launch (mean over steps)
         dec_ms_max = max_over_ranks(dec_ms)  # slowest rank's decoder launch (power-capped clocks differ per GPU)
+        per_rank = None
+        if world > 1:
+            mine = torch.tensor([dec_ms, float(dec_ev[-1][2])], dtype=torch.float64, device=dev)
+            allr = torch.empty(world, 2, dtype=torch.float64, device=dev)
+            dist.all_gather_into_tensor(allr, mine)
+            allr = allr.cpu()
+            per_rank = {"decoder_ms": [round(float(x), 3) for x in allr[:, 0]], "slab_planes": [int(x) for x in allr[:, 1]],
+                        "decoder_ms_min_mean_max": [float(allr[:, 0].min()), float(allr[:, 0].mean()), float(allr[:, 0].max())]}
         clocks = sampler.stop() if rank == 0 else None
 
         # ---- end to end through the public API with host buffers
         host_feed = {"img_input": feed["img_input"].pin_memory(),
                      "trans_mat_wo_rot_tp": feed["trans_mat_wo_rot_tp"].pin_memory()}
-        out_host = torch.empty(nx, nx, nx, dtype=torch.float32, pin_memory=True)
+        out_host = torch.empty(nx, nx, nx, dtype=torch.float32, pin_memory=True) if rank == 0 else None
 
         def e2e_step():
             model._enc_cache = None  # a new view every step: nothing cached across steps
-            gen.generate_grid(host_feed, resolution=nx, precision=prec, out_host=out_host)
+            gen.generate_grid(host_feed, resolution=nx, precision=prec, out_host=out_host, host_rank=0)
 
         for _ in range(max(1, min(args.warmup, 2))):
             e2e_step()
@@ -318,7 +320,8 @@ def run_native(args):
                      "frac": dec_tflops / sustained,
                      "traffic": DECODER_DRAM_BYTES.get((nx, prec, count)), "traffic_unit": "bytes per launch (ncu dram read+write)",
                      "kernel": "decoder (all launches of one decode_grid call)", "kernel_ms": dec_ms,
-                     "kernel_ms_max_over_ranks": dec_ms_max, "flop_per_query": FLOP_PER_QUERY, "queries_per_launch": count,
+                     "kernel_ms_max_over_ranks": dec_ms_max, "per_rank": per_rank, "flop_per_query": FLOP_PER_QUERY,
+                     "queries_per_launch": count,
                      "peak_source": how + " sustained bf16"},
         "clocks": clocks,
     }
@@ -491,21 +494,32 @@ def train_leg(dev, world, rank, steps, warmup, max_over_ranks, barrier):
             ref = z[f"loss_w{world}"].tolist()
             rel = float(np.max(np.abs(np.array(losses) - np.array(ref)) / np.abs(np.array(ref))))
     synth.set_dropout(m, 0.1)
-    for _ in range(warmup):
-        s3d_train.train_step(dict(host), net, opt)
-    barrier()
-    l0 = _native.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(steps):
-        s3d_train.train_step(dict(host), net, opt)
-    e1.record()
-    barrier()
-    ms = max_over_ranks(e0.elapsed_time(e1)) / steps
+
+    def timed(n_warm, n_steps):
+        for _ in range(n_warm):
+            s3d_train.train_step(dict(host), net, opt)
+        barrier()
+        l0 = _native.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n_steps):
+            s3d_train.train_step(dict(host), net, opt)
+        e1.record()
+        barrier()
+        return max_over_ranks(e0.elapsed_time(e1)) / n_steps, (_native.launch_count() - l0) / n_steps
+
+    ms, launches = timed(warmup, steps)
+    # the reference's own precision on this hardware: torch's default lets cuDNN run the convolutions in TF32
+    torch.backends.cudnn.allow_tf32 = True
+    ms_tf32, _ = timed(warmup, steps)
+    torch.backends.cudnn.allow_tf32 = False
     return {"config": f"reg_slices train.py fwd+bwd+Adam, batch {B}/GPU x {world} GPU(s), S={S}, n_qry={NQ}, fp32"
                       + (", DDP (NCCL gradient all-reduce, find_unused_parameters)" if world > 1 else ""),
             "ms_per_step": ms, "samples_per_s": B * world / (ms / 1e3), "steps": steps, "warmup": warmup,
-            "h2d_bytes_per_step": h2d, "gpu_launches_per_step": (_native.launch_count() - l0) / steps,
+            "ms_per_step_tf32_convs": ms_tf32, "samples_per_s_tf32_convs": B * world / (ms_tf32 / 1e3),
+            "precision_note": "ms_per_step: strict fp32 everywhere (cudnn.allow_tf32 = False); *_tf32_convs: torch's default, "
+                              "which is what the reference's train.py runs with on this GPU",
+            "h2d_bytes_per_step": h2d, "gpu_launches_per_step": launches,
             "loss": losses, "loss_ref": ref, "loss_max_rel_diff": rel,
             "loss_note": "3 Adam steps, dropout 0 on both sides; [L1(sdf), L1(slices), 0.001 * VGG19 perceptual] mean over ranks",
             "native_ops": "decoder forward + backward (projection, grid_sample, fc_s/fc_p, transformer, fc_out): "

@@ -30,18 +30,45 @@ def slab_range(nx, rank, world):
     return b[rank], b[rank + 1]
 
 
-def all_gather_slabs(vol_flat, nx, group=None):
-    """In place: every rank has filled its own slab of ``vol_flat`` (nx^3 values, flat);
-    afterwards every rank holds the whole volume."""
+def proportional_bounds(nx, rates):
+    """Axis-0 boundaries with slab widths proportional to ``rates`` (planes per unit time of each rank), every rank
+    keeping at least one plane; largest-remainder rounding, deterministic for identical input on every rank."""
+    world = len(rates)
+    if nx < world:
+        return slab_bounds(nx, world)
+    total = float(sum(rates))
+    ideal = [max(1.0, nx * float(r) / total) for r in rates]
+    scale = nx / sum(ideal)
+    ideal = [x * scale for x in ideal]
+    w = [max(1, int(x)) for x in ideal]
+    order = sorted(range(world), key=lambda i: (-(ideal[i] - int(ideal[i])), i))
+    k = 0
+    while sum(w) < nx:
+        w[order[k % world]] += 1
+        k += 1
+    while sum(w) > nx:
+        i = max(range(world), key=lambda j: (w[j], -j))
+        w[i] -= 1
+    b = [0]
+    for x in w:
+        b.append(b[-1] + x)
+    return b
+
+
+def all_gather_slabs(vol_flat, nx, group=None, bounds=None):
+    """In place: every rank has filled its own slab of ``vol_flat`` (nx^3 values, flat; slab r = planes
+    [bounds[r], bounds[r+1]), equal slabs by default); afterwards every rank holds the whole volume."""
     rank, world = rank_world(group)
     if world == 1:
         return vol_flat
     plane = vol_flat.numel() // nx
-    b = slab_bounds(nx, world)
-    if nx % world == 0:
+    b = list(bounds) if bounds is not None else slab_bounds(nx, world)
+    if all(b[r + 1] - b[r] == b[1] - b[0] for r in range(world)):
         lo, hi = b[rank], b[rank + 1]
-        # equal slabs: a single in-place all-gather straight into the volume
-        dist.all_gather_into_tensor(vol_flat, vol_flat[lo * plane:hi * plane].clone(), group=group)
+        # equal slabs: a single all-gather straight into the volume.  NCCL gathers in place when the input IS the
+        # rank's slot of the output (no staging copy); the gloo backend of the CPU tests needs a separate input.
+        mine = vol_flat[lo * plane:hi * plane]
+        dist.all_gather_into_tensor(vol_flat, mine if vol_flat.is_cuda else mine.clone(), group=group)
     else:
         outs = [vol_flat[b[r] * plane:b[r + 1] * plane] for r in range(world)]
         if hasattr(dist, "all_gather") and all(o.numel() == outs[0].numel() for o in outs):

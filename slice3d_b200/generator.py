@@ -57,6 +57,8 @@ class Generator3D(object):
         # --- not part of the reference API: MISE rounds enqueued per host synchronisation, lattice points a round may ask for
         self.device_rounds = True
         self.sparse_capacity = None
+        self.balance_slabs = True   # multi-GPU dense grid: slab widths follow the ranks' measured decoder rates
+        self._last_dec = None
         if vol_info is not None:
             self.input_vol, _, _ = vol_info
 
@@ -135,13 +137,30 @@ class Generator3D(object):
         ax = box_size * torch.linspace(-0.5, 0.5, nx)
         return ax.to(device)
 
-    def generate_grid(self, data, resolution=None, precision=None, group=None, as_numpy=True, out_host=None):
+    def _slab_plan(self, nx, rank, world, group, dev):
+        """Axis-0 slab boundaries of this call.  With ``balance_slabs`` the widths follow the ranks' measured decoder
+        rates of the previous call at the same size (GPUs of one box differ by a few per cent under the power cap;
+        the step ends when the slowest rank does): one tiny all-gather of (planes, milliseconds) per call."""
+        prev = self._last_dec
+        if not (self.balance_slabs and world > 1 and prev is not None and prev[3:] == (nx, world)):
+            return s3d_dist.slab_bounds(nx, world)
+        e0, e1, planes = prev[:3]
+        e1.synchronize()
+        mine = torch.tensor([float(planes), max(e0.elapsed_time(e1), 1e-3)], dtype=torch.float64, device=dev)
+        allr = torch.empty(world, 2, dtype=torch.float64, device=dev)
+        torch.distributed.all_gather_into_tensor(allr, mine, group=group)
+        allr = allr.cpu()
+        return s3d_dist.proportional_bounds(nx, [float(p / t) for p, t in allr.tolist()])
+
+    def generate_grid(self, data, resolution=None, precision=None, group=None, as_numpy=True, out_host=None,
+                      host_rank=None):
         """Dense ``-sdf_pred`` volume (nx,nx,nx) for one input view.
 
         ``data`` holds ``img_input`` (1,3,S,S) and ``trans_mat_wo_rot_tp`` (1,4,3) on the host or
         on the device.  Host tensors are copied to the model's device here and the volume is
         copied back (into ``out_host`` when given), so timing this call measures the end-to-end
-        path.  Under torch.distributed each rank evaluates one axis-0 slab.
+        path.  Under torch.distributed each rank evaluates one axis-0 slab; ``host_rank`` = r makes
+        only rank r copy the gathered volume to the host (the others return None).
         """
         model = self.model
         nx = int(resolution or self.resolution0)
@@ -155,15 +174,22 @@ class Generator3D(object):
         planes = model.encode(img)
         ax = self.grid_axes(nx, dev)
         rank, world = s3d_dist.rank_world(group)
-        lo, hi = s3d_dist.slab_range(nx, rank, world)
+        bounds = self._slab_plan(nx, rank, world, group, dev)
+        lo, hi = bounds[rank], bounds[rank + 1]
         vol = torch.empty(nx * nx * nx, dtype=torch.float32, device=dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
         if hi > lo:
             first, count = lo * nx * nx, (hi - lo) * nx * nx
             nat.decode_grid(planes, 0, (ax, ax, ax), first, count, T[0], out_scale=-1.0, precision=precision,
                             out=vol[first:first + count])
+        e1.record()
+        self._last_dec = (e0, e1, hi - lo, nx, world)
         if world > 1:
-            s3d_dist.all_gather_slabs(vol, nx, group)
+            s3d_dist.all_gather_slabs(vol, nx, group, bounds)
         vol = vol.view(nx, nx, nx)
+        if host_rank is not None and rank != host_rank:
+            return None
         if not as_numpy and out_host is None:
             return vol
         if out_host is None:
