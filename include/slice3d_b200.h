@@ -190,6 +190,19 @@ int s3d_train_decoder_bwd(const s3d_train_cfg* cfg, const float* qry_dev, const 
                           const float* dsdf_dev, void* saved_dev, size_t saved_bytes, float* const* dfeats_dev,
                           float* const* dparams_dev, void* workspace_dev, size_t workspace_bytes, void* stream);
 
+/* ---- Input pipeline (reg_slices/src/datasets.py:37,75-118) ----------------------------------------------------------
+ * A batch of decoded RGBA images (N, H, W, 4) uint8 -> (N, 3, S, S) fp32 exactly as Slice3DDataset prepares them:
+ * alpha compositing (png_2_whitebg when white_bg != 0, else png_2_rgb), Pillow's antialiased bilinear resize of the
+ * 8-bit image to S x S (T.Resize on a PIL image) bit for bit, T.ToTensor, T.Normalize(0.5, 0.5).
+ *   bounds_*_dev  int32 [S][2] = (first input index, tap count) per output column (h) / row (v);
+ *   kk_*_dev      int32 [S][ksize] fixed-point (22-bit) filter coefficients -- Pillow's precompute_coeffs +
+ *                 normalize_coeffs_8bpc, evaluated in float64 on the host (slice3d_b200/inputs.py:resample_tables). */
+size_t s3d_preprocess_workspace_bytes(int32_t N, int32_t H, int32_t S);
+int s3d_preprocess_rgba(const uint8_t* rgba_dev, int32_t N, int32_t H, int32_t W, int32_t S, int32_t white_bg,
+                        const int32_t* bounds_h_dev, const int32_t* kk_h_dev, int32_t ksize_h, const int32_t* bounds_v_dev,
+                        const int32_t* kk_v_dev, int32_t ksize_v, float* out_dev, void* workspace_dev, size_t workspace_bytes,
+                        void* stream);
+
 /* One MISE refinement step on dense device state, replacing MISE.subdivide_voxels (reg_slices/src_convonet/utils/
  * libmise/mise.pyx:184-283) after the caller has stored the new values: R = resolution0 << depth; value_dev / known_dev /
  * exists_dev are (R+1)^3 lattice arrays (float64 / bytes), cell_level_dev is the R^3 int8 array "level of the leaf voxel

@@ -8,6 +8,7 @@ from .models import Slices3DRegModel  # noqa: F401
 from .generator import Generator3D  # noqa: F401
 from .mcubes import Mesh, marching_cubes  # noqa: F401
 from .mise import MISE  # noqa: F401
+from . import inputs  # noqa: F401
 from .synth import make_3d_grid  # noqa: F401
 from .train import cal_acc, cal_loss_pred, train_step, val_step, wrap_ddp  # noqa: F401
 

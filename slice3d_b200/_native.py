@@ -22,7 +22,7 @@ SYMBOLS = [
     "s3d_planes_bytes", "s3d_encoder_workspace_bytes", "s3d_encoder_fwd", "s3d_decoder_workspace_bytes",
     "s3d_decoder_fwd", "s3d_decoder_batch_fwd", "s3d_decoder_grid_fwd", "s3d_decoder_debug_tokens", "s3d_vgg_loss_workspace_bytes",
     "s3d_vgg_loss_fwd", "s3d_mc_count", "s3d_mc_emit", "s3d_mise_scratch_ints",
-    "s3d_mise_subdivide", "s3d_sparse_scratch_bytes", "s3d_sparse_rounds", "s3d_train_decoder_saved_bytes", "s3d_train_decoder_bwd_workspace_bytes",
+    "s3d_mise_subdivide", "s3d_sparse_scratch_bytes", "s3d_sparse_rounds", "s3d_preprocess_workspace_bytes", "s3d_preprocess_rgba", "s3d_train_decoder_saved_bytes", "s3d_train_decoder_bwd_workspace_bytes",
     "s3d_train_decoder_fwd", "s3d_train_decoder_bwd", "s3d_selftest_umma", "s3d_debug_profile", "s3d_launch_count",
 ]
 
@@ -101,6 +101,12 @@ def lib():
     L.s3d_mise_subdivide.restype = C.c_int
     L.s3d_mise_subdivide.argtypes = [C.c_int32, C.c_int32, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                      C.c_void_p, C.c_void_p]
+    L.s3d_preprocess_workspace_bytes.restype = C.c_size_t
+    L.s3d_preprocess_workspace_bytes.argtypes = [C.c_int32, C.c_int32, C.c_int32]
+    L.s3d_preprocess_rgba.restype = C.c_int
+    L.s3d_preprocess_rgba.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
+                                      C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_size_t,
+                                      C.c_void_p]
     L.s3d_sparse_scratch_bytes.restype = C.c_size_t
     L.s3d_sparse_scratch_bytes.argtypes = [C.c_int32, C.c_int32, C.c_int64]
     L.s3d_sparse_rounds.restype = C.c_int

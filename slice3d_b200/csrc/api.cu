@@ -503,6 +503,18 @@ int s3d_mise_subdivide(int32_t resolution0, int32_t depth, double threshold, con
                         exists_dev, flags_dev, static_cast<cudaStream_t>(stream));
 }
 
+size_t s3d_preprocess_workspace_bytes(int32_t N, int32_t H, int32_t S) {
+  if (N < 1 || H < 1 || S < 1) return 0;
+  return preprocess_workspace_bytes(N, H, S);
+}
+int s3d_preprocess_rgba(const uint8_t* rgba_dev, int32_t N, int32_t H, int32_t W, int32_t S, int32_t white_bg,
+                        const int32_t* bounds_h_dev, const int32_t* kk_h_dev, int32_t ksize_h, const int32_t* bounds_v_dev,
+                        const int32_t* kk_v_dev, int32_t ksize_v, float* out_dev, void* workspace_dev, size_t workspace_bytes,
+                        void* stream) {
+  return preprocess_rgba(rgba_dev, N, H, W, S, white_bg, bounds_h_dev, kk_h_dev, ksize_h, bounds_v_dev, kk_v_dev, ksize_v,
+                         out_dev, workspace_dev, workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+
 size_t s3d_sparse_scratch_bytes(int32_t resolution0, int32_t depth, int64_t capacity) {
   if (resolution0 < 1 || depth < 0 || depth > 15 || capacity < 1) return 0;
   const size_t nblk = mise_query_blocks(resolution0 << depth);

@@ -176,6 +176,12 @@ size_t mise_query_blocks(int R);
 int mise_apply_device(const int* count, const int* pt_idx, const float* vals, double* value, unsigned char* known,
                       cudaStream_t st);
 
+// inputs.cu
+size_t preprocess_workspace_bytes(int N, int H, int S);
+int preprocess_rgba(const unsigned char* rgba, int N, int H, int W, int S, int white_bg, const int* bounds_h, const int* kk_h,
+                    int ksize_h, const int* bounds_v, const int* kk_v, int ksize_v, float* out, void* ws, size_t ws_bytes,
+                    cudaStream_t st);
+
 // perceptual.cu
 size_t vgg_loss_workspace_bytes(int N, int S);
 int vgg_loss_fwd(const s3d_model* m, const float* a, const float* b, int N, int S, float* loss, void* ws, size_t ws_bytes,
