@@ -84,8 +84,8 @@ int s3d_abi_version(void);
 const char* s3d_last_error(void);
 
 /* Create / destroy.  `tensors` must contain every key under slices_generator.*,
- * att_decoder.*, fc_p.*, fc_s.*, fc_out.* (att_layer.*, vggptlossfunc.* and
- * num_batches_tracked are not read).  n_slices = K (12 in the reference). */
+ * att_decoder.*, fc_p.*, fc_s.*, fc_out.* (att_layer.* and num_batches_tracked are not read; vggptlossfunc.* is
+ * optional) -- or the keys of a Slices3DGTModel checkpoint, see s3d_gt_encoder_fwd.  n_slices = K (12 in the reference). */
 int s3d_model_create(s3d_model** out, const s3d_tensor* tensors, int32_t n_tensors, int32_t n_slices,
                      int32_t device, void* stream);
 void s3d_model_destroy(s3d_model* m);
@@ -189,6 +189,23 @@ int s3d_train_decoder_fwd(const s3d_train_cfg* cfg, const float* const* feats_de
 int s3d_train_decoder_bwd(const s3d_train_cfg* cfg, const float* qry_dev, const float* T_dev, const float* const* params_dev,
                           const float* dsdf_dev, void* saved_dev, size_t saved_bytes, float* const* dfeats_dev,
                           float* const* dparams_dev, void* workspace_dev, size_t workspace_bytes, void* stream);
+
+/* ---- Slices3DGTModel (reg_slices/src/model_gt.py:12-111) ---------------------------------------------------------------
+ * s3d_model_create recognises a GT checkpoint by its keys (img_encoder.*, fc_local.*, pts_feat_extractor.*, att_decoder.*,
+ * fc_out.*) and returns a handle for the two entry points below; the regression entry points refuse it.
+ *   s3d_gt_encoder_fwd   <- self.img_encoder(img_slices) (model_gt.py:81-84, vgg16bn_feats.py:44-58) + the first Linear of
+ *                           fc_local hoisted onto the five taps (model_gt.py:97): img_slices_dev (B*K,3,S,S) fp32 NCHW ->
+ *                           planes_dev in the layout of s3d_encoder_fwd (scale s holds tap 4 - s); taps_nchw_dev optional:
+ *                           the raw taps conv1_2 .. conv5_3 (B*K, 64..512, S..S/16) for validation.
+ *   s3d_gt_decoder_fwd   <- model_gt.py:69-79 (flip / rotation), :86-104 (projection, 5 x grid_sample, fc_local,
+ *                           pts_feat_extractor, att_decoder, fc_out); arguments as s3d_decoder_batch_fwd. */
+size_t s3d_gt_encoder_workspace_bytes(int32_t B, int32_t K, int32_t S);
+int s3d_gt_encoder_fwd(const s3d_model* m, const float* img_slices_dev, int32_t B, int32_t S, void* planes_dev,
+                       float* const* taps_nchw_dev, void* workspace_dev, size_t workspace_bytes, void* stream);
+size_t s3d_gt_decoder_workspace_bytes(int64_t n, int32_t precision);
+int s3d_gt_decoder_fwd(const s3d_model* m, const void* planes_dev, int32_t S, float* qry_dev, int32_t B, int64_t n_per_image,
+                       const float* T_dev, const float* rot_dev, int32_t flip_in_place, float out_scale, float* out_dev,
+                       int32_t precision, void* workspace_dev, size_t workspace_bytes, void* stream);
 
 /* ---- Input pipeline (reg_slices/src/datasets.py:37,75-118) ----------------------------------------------------------
  * A batch of decoded RGBA images (N, H, W, 4) uint8 -> (N, 3, S, S) fp32 exactly as Slice3DDataset prepares them:

@@ -44,8 +44,8 @@ def _bn(sd, prefix, x):
                         sd[prefix + ".bias"], training=False, eps=EPS_BN)
 
 
-def _down(sd, name, x):
-    p = "slices_generator." + name + "."
+def _down(sd, name, x, prefix=None):
+    p = prefix if prefix is not None else "slices_generator." + name + "."
     for op in _DOWN_BLOCKS[name]:
         if op[0] == "conv":
             x = F.conv2d(x, sd[f"{p}{op[1]}.weight"], sd[f"{p}{op[1]}.bias"], padding=1)
@@ -270,3 +270,52 @@ def dense_grid_values(sd, feed, nx, n_slices=12, box_size=1.0):
     f = dict(feed)
     f["qry_norot"] = pts.unsqueeze(0)
     return eval_points(sd, f, 32768, n_slices).reshape(nx, nx, nx)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Slices3DGTModel (src/model_gt.py:12-111, src/vgg16bn_feats.py:5-58): the 3-D stage of the generation-based pipeline
+_GT_BLOCKS = [("conv1_2", "down1"), ("conv2_2", "down2"), ("conv3_3", "down3"), ("conv4_3", "down4"), ("conv5_3", "down5")]
+
+
+def gt_encoder(sd, img_slices):
+    """VGG16BNFeats.forward (vgg16bn_feats.py:44-58), eval mode: the five pre-BatchNorm taps of the trunk run on the
+    (B*K,3,S,S) slice images (same cut points as the U-Net trunk; conv_last / classifier are computed by the reference
+    but never used)."""
+    x, feats = img_slices, []
+    for name, block in _GT_BLOCKS:
+        x = _down(sd, block, x, prefix=f"img_encoder.{name}.")
+        feats.append(x)
+    return feats
+
+
+def gt_decode(sd, feats, qry, T, n_slices=12, chunk=8192):
+    """model_gt.py:84-104 given the taps and the (already flipped / rotated) queries."""
+    B, M, _ = qry.shape
+    K = n_slices
+    lin = lambda x, p: x @ sd[p + ".weight"].t() + sd[p + ".bias"]
+    outs = []
+    for s in range(0, M, chunk):
+        q = qry[:, s:s + chunk]
+        m = q.shape[1]
+        uv = project_coord(q, T)
+        uvk = uv.view(B, 1, m, 2).expand(-1, K, -1, -1).reshape(B * K, m, 2)
+        sampled = torch.cat([sample_plane(f, uvk) for f in feats], dim=2)  # (B*K, m, 1472)
+        sampled = sampled.view(B, K, m, 1472).permute(0, 2, 1, 3).reshape(B * m, K, 1472)
+        tok_s = F.relu(lin(F.relu(lin(sampled, "fc_local.0")), "fc_local.2"))
+        tq = q
+        for i in (0, 2, 4):
+            tq = F.relu(lin(tq, f"pts_feat_extractor.{i}"))
+        x = torch.cat([tq.reshape(B * m, 1, 128), tok_s], 1)
+        for l in range(3):
+            x = transformer_layer(sd, f"att_decoder.layers.{l}", x)
+        t0 = x.view(B, m, K + 1, 128)[:, :, 0, :]
+        outs.append((t0 @ sd["fc_out.0.weight"].t() + sd["fc_out.0.bias"]).squeeze(-1))
+    return torch.cat(outs, 1)
+
+
+def gt_model_forward(sd, feed, mode="test", n_slices=12):
+    """Slices3DGTModel.forward (model_gt.py:69-111), eval-mode arithmetic."""
+    B, _, S, _ = feed["img_input"].shape
+    q = prepare_queries(feed["qry_norot"], feed.get("obj_rot_mat"), mode)
+    feats = gt_encoder(sd, feed["img_slices"].view(B * n_slices, 3, S, S))
+    return {"sdf_pred": gt_decode(sd, feats, q, feed["trans_mat_wo_rot_tp"], n_slices), "feats": feats}

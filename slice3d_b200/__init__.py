@@ -5,6 +5,7 @@ Public surface mirrors the reference (reg_slices/src/models.py, reg_slices/recon
 C ABI declared in ``include/slice3d_b200.h``.
 """
 from .models import Slices3DRegModel  # noqa: F401
+from .model_gt import Slices3DGTModel  # noqa: F401
 from .generator import Generator3D  # noqa: F401
 from .mcubes import Mesh, marching_cubes  # noqa: F401
 from .mise import MISE  # noqa: F401
@@ -12,5 +13,5 @@ from . import inputs  # noqa: F401
 from .synth import make_3d_grid  # noqa: F401
 from .train import cal_acc, cal_loss_pred, train_step, val_step, wrap_ddp  # noqa: F401
 
-__all__ = ["Slices3DRegModel", "Generator3D", "MISE", "Mesh", "marching_cubes", "make_3d_grid", "train_step", "val_step",
+__all__ = ["Slices3DRegModel", "Slices3DGTModel", "Generator3D", "MISE", "Mesh", "marching_cubes", "make_3d_grid", "train_step", "val_step",
            "cal_loss_pred", "cal_acc", "wrap_ddp"]

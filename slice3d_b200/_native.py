@@ -22,7 +22,8 @@ SYMBOLS = [
     "s3d_planes_bytes", "s3d_encoder_workspace_bytes", "s3d_encoder_fwd", "s3d_decoder_workspace_bytes",
     "s3d_decoder_fwd", "s3d_decoder_batch_fwd", "s3d_decoder_grid_fwd", "s3d_decoder_debug_tokens", "s3d_vgg_loss_workspace_bytes",
     "s3d_vgg_loss_fwd", "s3d_mc_count", "s3d_mc_emit", "s3d_mise_scratch_ints",
-    "s3d_mise_subdivide", "s3d_sparse_scratch_bytes", "s3d_sparse_rounds", "s3d_preprocess_workspace_bytes", "s3d_preprocess_rgba", "s3d_train_decoder_saved_bytes", "s3d_train_decoder_bwd_workspace_bytes",
+    "s3d_mise_subdivide", "s3d_sparse_scratch_bytes", "s3d_sparse_rounds", "s3d_preprocess_workspace_bytes", "s3d_preprocess_rgba",
+    "s3d_gt_encoder_workspace_bytes", "s3d_gt_encoder_fwd", "s3d_gt_decoder_workspace_bytes", "s3d_gt_decoder_fwd", "s3d_train_decoder_saved_bytes", "s3d_train_decoder_bwd_workspace_bytes",
     "s3d_train_decoder_fwd", "s3d_train_decoder_bwd", "s3d_selftest_umma", "s3d_debug_profile", "s3d_launch_count",
 ]
 
@@ -101,6 +102,17 @@ def lib():
     L.s3d_mise_subdivide.restype = C.c_int
     L.s3d_mise_subdivide.argtypes = [C.c_int32, C.c_int32, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                      C.c_void_p, C.c_void_p]
+    L.s3d_gt_encoder_workspace_bytes.restype = C.c_size_t
+    L.s3d_gt_encoder_workspace_bytes.argtypes = [C.c_int32, C.c_int32, C.c_int32]
+    L.s3d_gt_encoder_fwd.restype = C.c_int
+    L.s3d_gt_encoder_fwd.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.POINTER(C.c_void_p),
+                                     C.c_void_p, C.c_size_t, C.c_void_p]
+    L.s3d_gt_decoder_workspace_bytes.restype = C.c_size_t
+    L.s3d_gt_decoder_workspace_bytes.argtypes = [C.c_int64, C.c_int32]
+    L.s3d_gt_decoder_fwd.restype = C.c_int
+    L.s3d_gt_decoder_fwd.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p,
+                                     C.c_void_p, C.c_int32, C.c_float, C.c_void_p, C.c_int32, C.c_void_p, C.c_size_t,
+                                     C.c_void_p]
     L.s3d_preprocess_workspace_bytes.restype = C.c_size_t
     L.s3d_preprocess_workspace_bytes.argtypes = [C.c_int32, C.c_int32, C.c_int32]
     L.s3d_preprocess_rgba.restype = C.c_int
@@ -348,6 +360,47 @@ class NativeModel:
                                            rot.data_ptr() if rot is not None else None, 1 if flip_in_place else 0,
                                            out_scale, out.data_ptr(), prec, ws.data_ptr(), ws.numel(),
                                            _stream(self.device)))
+        return out
+
+    # ---- Slices3DGTModel --------------------------------------------------------
+    def encode_gt(self, img_slices, B, want_taps=False):
+        """img_slices (B*K,3,S,S) -> Planes (fc_local's first Linear applied to the five trunk taps)."""
+        img = _f32c(img_slices, "img_slices")
+        N, c, S, S2 = img.shape
+        K = self.K
+        if c != 3 or S != S2 or N != B * K:
+            raise NativeError("img_slices must be (B*K,3,S,S)")
+        L = lib()
+        with torch.cuda.device(self.device):
+            blob = torch.empty(L.s3d_planes_bytes(B, K, S) // 4, dtype=torch.float32, device=self.device)
+            taps, tptr = None, None
+            if want_taps:
+                chans = [64, 128, 256, 512, 512]
+                taps = [torch.empty(N, chans[i], S >> i, S >> i, dtype=torch.float32, device=self.device) for i in range(5)]
+                tptr = (C.c_void_p * 5)(*[t.data_ptr() for t in taps])
+            ws = self._workspace("enc", L.s3d_gt_encoder_workspace_bytes(B, K, S))
+            _check(L.s3d_gt_encoder_fwd(self._h, img.data_ptr(), B, S, blob.data_ptr(), tptr, ws.data_ptr(), ws.numel(),
+                                        _stream(self.device)))
+        planes = Planes(blob, B, K, S, None)
+        return (planes, taps) if want_taps else planes
+
+    def decode_gt(self, planes, qry, T, rot=None, flip_in_place=False, out_scale=1.0, precision="fp16x3", out=None):
+        """qry (B,n,3), T (B,4,3), rot (B,3,3) or None -> (B,n): the GT model's per-query path in the library."""
+        if not qry.is_cuda or qry.dtype != torch.float32 or not qry.is_contiguous() or qry.dim() != 3:
+            raise NativeError("qry must be a contiguous float32 CUDA tensor (B,n,3)")
+        B, n = qry.shape[0], qry.shape[1]
+        if B != planes.B:
+            raise NativeError("qry batch does not match the encoder batch")
+        T = _f32c(T, "trans_mat_wo_rot_tp")
+        rot = _f32c(rot, "obj_rot_mat") if rot is not None else None
+        L, prec = lib(), PRECISIONS[precision]
+        with torch.cuda.device(self.device):
+            if out is None:
+                out = torch.empty(B, n, dtype=torch.float32, device=self.device)
+            ws = self._workspace("dec", L.s3d_gt_decoder_workspace_bytes(B * n, prec))
+            _check(L.s3d_gt_decoder_fwd(self._h, planes.image_ptr(0), planes.S, qry.data_ptr(), B, n, T.data_ptr(),
+                                        rot.data_ptr() if rot is not None else None, 1 if flip_in_place else 0, out_scale,
+                                        out.data_ptr(), prec, ws.data_ptr(), ws.numel(), _stream(self.device)))
         return out
 
     def decode_grid(self, planes, b, axes, first, count, T, out_scale=1.0, precision="fp16x3", out=None):

@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "_lib")
 LIB = os.path.join(OUT_DIR, "libslice3d_b200.so")
-SOURCES = ["api.cu", "encoder.cu", "conv_tc.cu", "perceptual.cu", "mcubes.cu", "mise.cu", "decoder_simt.cu", "decoder_tc.cu", "train_decoder.cu", "inputs.cu"]
+SOURCES = ["api.cu", "encoder.cu", "conv_tc.cu", "perceptual.cu", "mcubes.cu", "mise.cu", "decoder_simt.cu", "decoder_tc.cu", "train_decoder.cu", "inputs.cu", "gt.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
               "--expt-relaxed-constexpr", "-Xptxas", "-v"]
 

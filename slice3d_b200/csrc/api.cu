@@ -120,7 +120,17 @@ struct Packer {
   }
 
   bool build() {
-    const std::string g = "slices_generator.";
+    // Slices3DGTModel checkpoints (reg_slices/src/model_gt.py) are recognised by their encoder keys: the same VGG16-BN
+    // trunk under img_encoder.conv1_2 .. conv5_3 (vgg16bn_feats.py:27-32: same cut points as down1 .. down5)
+    const bool gt = by_name.count("img_encoder.conv1_2.0.weight") != 0;
+    m->kind = gt ? 1 : 0;
+    const std::string g = gt ? "img_encoder." : "slices_generator.";
+    auto blk_name = [&](const char* down) -> std::string {
+      if (!gt) return down;
+      static const std::map<std::string, std::string> mp = {{"down1", "conv1_2"}, {"down2", "conv2_2"}, {"down3", "conv3_3"},
+                                                            {"down4", "conv4_3"}, {"down5", "conv5_3"}};
+      return mp.at(down);
+    };
     // ---- VGG16-BN trunk (unet_custom.py:15-19; torchvision feature indices)
     struct VC {
       const char* blk;
@@ -132,25 +142,44 @@ struct Packer {
                        {"down4", 30, 512, 512, -1}, {"down5", 34, 512, 512, 35}, {"down5", 37, 512, 512, 38},
                        {"down5", 40, 512, 512, -1}};
     for (int i = 0; i < 13; ++i) {
-      std::string p = g + vc[i].blk + "." + std::to_string(vc[i].idx);
+      std::string p = g + blk_name(vc[i].blk) + "." + std::to_string(vc[i].idx);
       if (!pack_conv(p + ".weight", vc[i].cout, vc[i].cin, 3, m->vgg[i])) return false;
       std::vector<float> bias;
       if (!fetch(p + ".bias", vc[i].cout, bias)) return false;
       if (vc[i].bn >= 0) {
         std::vector<float> sc, sh;
-        if (!bn_fold(g + vc[i].blk + "." + std::to_string(vc[i].bn), vc[i].cout, bias, sc, sh)) return false;
+        if (!bn_fold(g + blk_name(vc[i].blk) + "." + std::to_string(vc[i].bn), vc[i].cout, bias, sc, sh)) return false;
         if (!(m->vgg[i].scale = upload(sc)) || !(m->vgg[i].shift = upload(sh))) return false;
       } else {
         if (!(m->vgg[i].shift = upload(bias))) return false;
       }
     }
-    const char* lead[4] = {"down2.4", "down3.11", "down4.21", "down5.31"};
+    const char* leadb[4] = {"down2", "down3", "down4", "down5"};
+    const char* leadi[4] = {".4", ".11", ".21", ".31"};
     const int leadc[4] = {64, 128, 256, 512};
     for (int i = 0; i < 4; ++i) {
       std::vector<float> sc, sh;
-      if (!bn_fold(g + lead[i], leadc[i], {}, sc, sh)) return false;
+      if (!bn_fold(g + blk_name(leadb[i]) + leadi[i], leadc[i], {}, sc, sh)) return false;
       if (!(m->bn_scale[i] = upload(sc)) || !(m->bn_shift[i] = upload(sh))) return false;
     }
+    DecF32& d = m->dec32;
+    if (gt) {
+      // ---- fc_local (model_gt.py:33-38): the first Linear(1472, 128) hoisted onto the taps.  Its input channels follow the
+      //      concatenation order conv1_2 (64) .. conv5_3 (512); tap i has resolution S / 2^i = plane scale 4 - i of the blob.
+      const int tapc[5] = {64, 128, 256, 512, 512};
+      int c0 = 0;
+      for (int i = 0; i < 5; ++i) {
+        if (!pack_linear("fc_local.0.weight", 128, 1472, c0, tapc[i], m->fcs[4 - i])) return false;
+        c0 += tapc[i];
+      }
+      if (!vec("fc_local.0.bias", 128, d.fcs_b)) return false;
+      if (!pack_linear("fc_local.2.weight", 128, 128, 0, 128, m->fcl2) || !vec("fc_local.2.bias", 128, m->fcl2.shift)) return false;
+      // ---- pts_feat_extractor (model_gt.py:24-31): raw PyTorch (out, in) matrices, evaluated per query by one warp
+      if (!vec("pts_feat_extractor.0.weight", 32 * 3, m->pts_w[0]) || !vec("pts_feat_extractor.0.bias", 32, m->pts_b[0]) ||
+          !vec("pts_feat_extractor.2.weight", 64 * 32, m->pts_w[1]) || !vec("pts_feat_extractor.2.bias", 64, m->pts_b[1]) ||
+          !vec("pts_feat_extractor.4.weight", 128 * 64, m->pts_w[2]) || !vec("pts_feat_extractor.4.bias", 128, m->pts_b[2]))
+        return false;
+    } else {
     // ---- trans_c: 1x1 conv over cat[x5 (512), slice embedding (128)] (unet_custom.py:52-57)
     {
       const int K = m->K;
@@ -227,7 +256,6 @@ struct Packer {
       m->has_pvgg = 1;
     }
     // ---- decoder
-    DecF32& d = m->dec32;
     {
       std::vector<float> w;
       if (!fetch("fc_p.weight", 128 * 3, w)) return false;
@@ -236,9 +264,9 @@ struct Packer {
         for (int j = 0; j < 3; ++j) t[j * 128 + c] = w[c * 3 + j];
       if (!(d.fcp_wt = upload(t))) return false;
     }
-    if (!vec("fc_p.bias", 128, d.fcp_b) || !vec("fc_s.bias", 128, d.fcs_b) || !vec("fc_out.0.weight", 128, d.fco_w) ||
-        !vec("fc_out.0.bias", 1, d.fco_b))
-      return false;
+    if (!vec("fc_p.bias", 128, d.fcp_b) || !vec("fc_s.bias", 128, d.fcs_b)) return false;
+    }  // !gt
+    if (!vec("fc_out.0.weight", 128, d.fco_w) || !vec("fc_out.0.bias", 1, d.fco_b)) return false;
     for (int l = 0; l < 3; ++l) {
       std::string p = "att_decoder.layers." + std::to_string(l);
       DecLayerF32& L = d.L[l];
@@ -266,9 +294,13 @@ __global__ void k_flip_yz(float* q, long long n) {
 // Argument / capability / workspace validation of a decoder call, separate from the launch so that entry points with
 // side effects on the caller's buffers (the in-place y,z flip) can validate first.
 int check_decoder(const s3d_model* m, const void* planes, int S, const float* T, int64_t n, const float* out, int precision,
-                  const float* debug_tokens, const void* ws, size_t ws_bytes) {
+                  const float* debug_tokens, const void* ws, size_t ws_bytes, bool gt_tokens = false) {
   if (!m || !planes || !out || !T || n < 0 || S < 32 || S % 16) {
     set_error("decoder: bad argument");
+    return S3D_ERR_BAD_ARG;
+  }
+  if (m->kind != 0 && !gt_tokens) {
+    set_error("decoder: this handle holds a Slices3DGTModel (use s3d_gt_decoder_fwd)");
     return S3D_ERR_BAD_ARG;
   }
   if (precision != S3D_PREC_FP32 && precision != S3D_PREC_BF16X3 && precision != S3D_PREC_BF16 &&
@@ -289,7 +321,8 @@ int check_decoder(const s3d_model* m, const void* planes, int S, const float* T,
     set_error("decoder(fp32): n_slices > 12 unsupported");
     return S3D_ERR_UNSUPPORTED;
   }
-  if (n > 0 && (ws == nullptr || ws_bytes < s3d_decoder_workspace_bytes(n, precision))) {
+  const size_t need = gt_tokens ? gt_decoder_workspace_bytes(n, precision) : s3d_decoder_workspace_bytes(n, precision);
+  if (n > 0 && (ws == nullptr || ws_bytes < need)) {
     set_error("decoder: workspace too small");
     return S3D_ERR_WORKSPACE;
   }
@@ -501,6 +534,47 @@ int s3d_mise_subdivide(int32_t resolution0, int32_t depth, double threshold, con
                        int8_t* cell_level_dev, uint8_t* exists_dev, int32_t* flags_dev, void* stream) {
   return mise_subdivide(resolution0, depth, threshold, value_dev, known_dev, reinterpret_cast<signed char*>(cell_level_dev),
                         exists_dev, flags_dev, static_cast<cudaStream_t>(stream));
+}
+
+size_t s3d_gt_encoder_workspace_bytes(int32_t B, int32_t K, int32_t S) {
+  if (B <= 0 || K <= 0 || S <= 0) return 0;
+  return gt_encoder_workspace_bytes(B * K, S);
+}
+int s3d_gt_encoder_fwd(const s3d_model* m, const float* img_slices_dev, int32_t B, int32_t S, void* planes_dev,
+                       float* const* taps_nchw_dev, void* workspace_dev, size_t workspace_bytes, void* stream) {
+  return gt_encoder_fwd(m, img_slices_dev, B, S, planes_dev, taps_nchw_dev, workspace_dev, workspace_bytes,
+                        static_cast<cudaStream_t>(stream));
+}
+size_t s3d_gt_decoder_workspace_bytes(int64_t n, int32_t precision) { return gt_decoder_workspace_bytes(n, precision); }
+int s3d_gt_decoder_fwd(const s3d_model* m, const void* planes_dev, int32_t S, float* qry_dev, int32_t B, int64_t n_per_image,
+                       const float* T_dev, const float* rot_dev, int32_t flip_in_place, float out_scale, float* out_dev,
+                       int32_t precision, void* workspace_dev, size_t workspace_bytes, void* stream) {
+  if (B < 1 || n_per_image < 0) {
+    set_error("gt_decoder: bad batch");
+    return S3D_ERR_BAD_ARG;
+  }
+  const int64_t n = (int64_t)B * n_per_image;
+  if (n == 0) return S3D_OK;
+  if (!qry_dev) {
+    set_error("gt_decoder: null query pointer");
+    return S3D_ERR_BAD_ARG;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  QueryCtx q{};
+  q.qry = qry_dev;
+  q.T = T_dev;
+  q.rot = rot_dev;
+  if (B > 1) {
+    q.per_img = n_per_image;
+    q.plane_stride = plane_offset_floats(m ? m->K : 0, S, 5);
+  }
+  S3D_TRY(check_decoder(m, planes_dev, S, T_dev, n, out_dev, precision, nullptr, workspace_dev, workspace_bytes, true));
+  if (!rot_dev && flip_in_place) {
+    k_flip_yz<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(qry_dev, n);
+    S3D_LAUNCH_CHECK();
+    q.preflipped = 1;
+  }
+  return gt_decoder_fwd(m, planes_dev, S, q, n, out_scale, out_dev, precision, workspace_dev, workspace_bytes, st);
 }
 
 size_t s3d_preprocess_workspace_bytes(int32_t N, int32_t H, int32_t S) {

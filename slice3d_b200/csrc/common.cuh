@@ -102,6 +102,12 @@ struct DecTC {
 struct s3d_model {
   int device = 0;
   int K = 12;
+  int kind = 0;                // 0 = Slices3DRegModel, 1 = Slices3DGTModel (model_gt.py)
+  // GT model only: second Linear of fc_local (128 -> 128, shift = bias) and the query MLP (PyTorch (out, in) layouts)
+  s3d::ConvW fcl2;
+  s3d::ConvTC tfcl2;
+  float* pts_w[3] = {};
+  float* pts_b[3] = {};
   // encoder (all BatchNorms are eval-mode and folded)
   s3d::ConvW vgg[13];          // conv idx 0,3 | 7,10 | 14,17,20 | 24,27,30 | 34,37,40
   float* bn_scale[4] = {};     // block-leading BNs (features idx 4, 11, 21, 31) applied to the raw taps
@@ -211,12 +217,26 @@ struct QueryCtx {
   // inside a column.  The columns of a block project to neighbouring rays of every plane, so the texels a wave of CTAs
   // gathers stay in L2 until the neighbouring columns need them (the flat order re-read ~260 MB per x-plane).
   int blk, x0, nxs;
+  // Ready tokens (Slices3DGTModel: built by gt.cu before the decoder launch): query token [n][128] and slice tokens
+  // [n][K][128]; the decoders then skip their own token build.
+  const float* tok_query;
+  const float* tok_slice;
   // Batched explicit points (per_img > 0): query i belongs to image i / per_img, whose camera is T + 12 b, rotation
   // rot + 9 b and projected planes planes + b * plane_stride floats (the encoder's batch layout).
   long long per_img;
   size_t plane_stride;
 };
 constexpr int GRID_BX = 16, GRID_BY = 16;
+
+// gt.cu (Slices3DGTModel)
+size_t gt_encoder_workspace_bytes(int N, int S);
+int gt_encoder_fwd(const s3d_model* m, const float* img_slices, int B, int S, void* planes, float* const* taps_nchw, void* ws,
+                   size_t ws_bytes, cudaStream_t st);
+size_t gt_decoder_workspace_bytes(int64_t n, int precision);
+int gt_decoder_fwd(const s3d_model* m, const void* planes, int S, QueryCtx q, int64_t n, float out_scale, float* out,
+                   int precision, void* ws, size_t ws_bytes, cudaStream_t st);
+int trunk_tc(const s3d_model* m, const float* img, int B, int S, float* x0, float* ta, float* tb, float* const* x,
+             float* const* xs, cudaStream_t st);
 
 // decoder_simt.cu
 size_t decoder_simt_workspace_bytes(int64_t n);

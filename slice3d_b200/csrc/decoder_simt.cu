@@ -56,6 +56,14 @@ __global__ void __launch_bounds__(32 * 13) k_tokens(QueryCtx q, long long i0, in
   *reinterpret_cast<float4*>(dst) = acc;
 }
 
+// Ready tokens (Slices3DGTModel, gt.cu): X[i][0] = tok_query[i], X[i][1 + k] = tok_slice[i][k].
+__global__ void __launch_bounds__(128) k_assemble_tokens(const float* __restrict__ tq, const float* __restrict__ ts, int K,
+                                                         float* __restrict__ X) {
+  const int i = blockIdx.x, c = threadIdx.x, L = K + 1;
+  X[((size_t)i * L) * TOK + c] = tq[(size_t)i * TOK + c];
+  for (int k = 0; k < K; ++k) X[((size_t)i * L + 1 + k) * TOK + c] = ts[((size_t)i * K + k) * TOK + c];
+}
+
 // Self-attention of one query's L = K+1 tokens, 4 heads of 32 (nn.MultiheadAttention inside
 // nn.TransformerEncoderLayer, models.py:18).  One block (128 threads) per query.
 __global__ void __launch_bounds__(128) k_attention(const float* __restrict__ QKV, float* __restrict__ O, int n, int L) {
@@ -191,7 +199,10 @@ int decoder_simt(const s3d_model* m, const float* planes, int S, const QueryCtx&
   for (int64_t i0 = 0; i0 < n; i0 += QCHUNK) {
     const int c = (int)((n - i0) < QCHUNK ? (n - i0) : QCHUNK);
     const long long rows = (long long)c * L;
-    k_tokens<<<c, 32 * 13, 0, st>>>(q, i0, c, planes, S, K, d.fcp_wt, d.fcp_b, d.fcs_b, X);
+    if (q.tok_slice)
+      k_assemble_tokens<<<c, 128, 0, st>>>(q.tok_query + (size_t)i0 * TOK, q.tok_slice + (size_t)i0 * K * TOK, K, X);
+    else
+      k_tokens<<<c, 32 * 13, 0, st>>>(q, i0, c, planes, S, K, d.fcp_wt, d.fcp_b, d.fcs_b, X);
     S3D_LAUNCH_CHECK();
     if (debug_tokens)
       S3D_CUDA(cudaMemcpyAsync(debug_tokens + (size_t)i0 * L * 128, X, rows * 128 * sizeof(float),

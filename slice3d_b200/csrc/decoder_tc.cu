@@ -366,7 +366,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
       __stcg(reinterpret_cast<float4*>(tokbuf + (size_t)(NTOK * q + 1 + k) * 128 + ch), acc);
     };
 
-    {
+    if (p.q.tok_slice == nullptr) {  // (ready tokens -- Slices3DGTModel, gt.cu -- need no gather)
       float* const tokbase = p.scratch + (size_t)gridDim.x * (TAIL_SLOTS * TILE_Q) * 256 + (size_t)blockIdx.x * (2 * 128 * 128);
       uint32_t ph_te = 3u;  // "empty"-type: the first wait on each buffer passes
       int it = 0;
@@ -1089,15 +1089,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
       const bool valid = (qi < TILE_Q) && (q_idx < n_q);
       // ------------------------------------------------------------------ token build
       const int tbuf = tile_it & 1;
-      const float* tokbuf = tokbase + (size_t)tbuf * (128 * 128);
-      mbar_wait(bar(B_TOKFULL0 + tbuf), (ph_tf >> tbuf) & 1u);  // slice tokens of this tile gathered
-      ph_tf ^= 1u << tbuf;
+      const float* tokrow;
+      if (p.q.tok_slice) {  // ready tokens in global memory: query token [n][128], slice tokens [n][12][128]
+        tokrow = tk == 0 ? p.q.tok_query + (size_t)(valid ? q_idx : 0) * 128
+                         : p.q.tok_slice + ((size_t)(valid ? q_idx : 0) * (NTOK - 1) + (tk - 1)) * 128;
+      } else {
+        tokrow = tokbase + (size_t)tbuf * (128 * 128) + (size_t)r * 128;
+        mbar_wait(bar(B_TOKFULL0 + tbuf), (ph_tf >> tbuf) & 1u);  // slice tokens of this tile gathered
+        ph_tf ^= 1u << tbuf;
+      }
       {
         float v[32];
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
           float4 t4 = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (valid) t4 = __ldcg(reinterpret_cast<const float4*>(tokbuf + (size_t)r * 128 + 32 * g) + c);
+          if (valid) t4 = __ldcg(reinterpret_cast<const float4*>(tokrow + 32 * g) + c);
           v[4 * c] = t4.x; v[4 * c + 1] = t4.y; v[4 * c + 2] = t4.z; v[4 * c + 3] = t4.w;
         }
         warp_arrive(bar(B_TOKEMPTY0 + tbuf), lane);  // this warp has read its tokens: the buffer may be refilled

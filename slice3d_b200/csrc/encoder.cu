@@ -209,29 +209,26 @@ int dense(const ConvW& w, const float* a, long long M, float* out, int relu, cud
 inline unsigned blocks_for(long long n, int t) { return (unsigned)((n + t - 1) / t); }
 
 
-// The encoder on the tensor cores (conv_tc.cu): every convolution except the first (3 input channels), the
-// transposed convolutions, the 1x1 adapters and the hoisted fc_s projection.  Activations that feed a tensor-core
-// GEMM are written in the split-fp16 format by their producer; taps and feature planes are also kept in fp32 for
-// their fp32 consumers (BatchNorm+pool, tanh head, export).  DoubleConv's first convolution over cat([skip, up])
-// (unet_parts.py:73) is split by input-channel half: the skip half does not depend on the slice, so it is evaluated
-// once per view (B images) and added in the epilogue of the per-slice half (B*K images) -- half of that
-// convolution's work, 12x less of it, same result.
-int trunk_and_up_tc(const s3d_model* m, const float* img, int B, int S, EncBufs& e, cudaStream_t st) {
-  const int K = m->K;
+}  // namespace
+
+// VGG16-BN trunk on B images on the tensor cores (unet_custom.py:42-48 / vgg16bn_feats.py:44-52): taps x[1..5] = the
+// pre-BatchNorm outputs of the last convolution of each block, fp32 NHWC, and their split-fp16 copies xs[1..5].
+int trunk_tc(const s3d_model* m, const float* img, int B, int S, float* x0, float* ta, float* tb, float* const* x,
+             float* const* xs, cudaStream_t st) {
   const size_t S2 = (size_t)S * S;
-  k_nchw3_to_nhwc4<<<blocks_for((long long)B * S * S, 256), 256, 0, st>>>(img, e.x0, B, S * S);
+  k_nchw3_to_nhwc4<<<blocks_for((long long)B * S * S, 256), 256, 0, st>>>(img, x0, B, S * S);
   S3D_LAUNCH_CHECK();
   int H = S;
   const int xc[6] = {0, 64, 128, 256, 512, 512};
-  auto xs_of = [&](int i) { return split_of(e.xs[i], B * (S2 >> (2 * (i - 1))) * xc[i]); };
-  Split sa = split_of(e.ta, B * S2 * 64);
+  auto xs_of = [&](int i) { return split_of(xs[i], B * (S2 >> (2 * (i - 1))) * xc[i]); };
+  Split sa = split_of(ta, B * S2 * 64);
   {  // down1: conv0 on the fp32 path (K = 27), written split; conv1 -> tap x1 (pre-BN)
     const ConvW& w = m->vgg[0];
-    LoadConv L{e.x0, nullptr, B * H * H, w.k, H, H, 4, 0, 1, w.ks};
+    LoadConv L{x0, nullptr, B * H * H, w.k, H, H, 4, 0, 1, w.ks};
     EpiAffineSplit E{sa.hi, sa.lo, w.scale, w.shift, w.ncols, 1};
     S3D_TRY(launch_gemm(L, w.w, w.ncols, w.kpad, E, st));
     Split x1 = xs_of(1);
-    S3D_TRY(conv_tc(m->tvgg[1], sa.hi, sa.lo, B, H, H, nullptr, 1, 0, e.x[1], 64, x1.hi, x1.lo, 64, st));
+    S3D_TRY(conv_tc(m->tvgg[1], sa.hi, sa.lo, B, H, H, nullptr, 1, 0, x[1], 64, x1.hi, x1.lo, 64, st));
   }
   const int first_conv[4] = {2, 4, 7, 10};
   const int n_conv[4] = {2, 3, 3, 3};
@@ -239,18 +236,18 @@ int trunk_and_up_tc(const s3d_model* m, const float* img, int B, int S, EncBufs&
   for (int b = 0; b < 4; ++b) {
     long long tot = (long long)B * (H / 2) * (H / 2) * (cprev[b] / 4);
     H /= 2;
-    Split cur = split_of(e.ta, (size_t)B * H * H * cprev[b]);
-    k_bn_relu_pool_split<<<blocks_for(tot, 256), 256, 0, st>>>(e.x[b + 1], cur.hi, cur.lo, m->bn_scale[b], m->bn_shift[b], B,
+    Split cur = split_of(ta, (size_t)B * H * H * cprev[b]);
+    k_bn_relu_pool_split<<<blocks_for(tot, 256), 256, 0, st>>>(x[b + 1], cur.hi, cur.lo, m->bn_scale[b], m->bn_shift[b], B,
                                                                2 * H, 2 * H, cprev[b]);
     S3D_LAUNCH_CHECK();
-    float* nxt_base = e.tb;
-    float* cur_base = e.ta;
+    float* nxt_base = tb;
+    float* cur_base = ta;
     for (int j = 0; j < n_conv[b]; ++j) {
       const ConvTC& w = m->tvgg[first_conv[b] + j];
       const bool last = (j == n_conv[b] - 1);
       if (last) {
         Split xo = xs_of(b + 2);
-        S3D_TRY(conv_tc(w, cur.hi, cur.lo, B, H, H, nullptr, 1, 0, e.x[b + 2], w.cout, xo.hi, xo.lo, w.cout, st));
+        S3D_TRY(conv_tc(w, cur.hi, cur.lo, B, H, H, nullptr, 1, 0, x[b + 2], w.cout, xo.hi, xo.lo, w.cout, st));
       } else {
         Split nxt = split_of(nxt_base, (size_t)B * H * H * w.cout);
         S3D_TRY(conv_tc(w, cur.hi, cur.lo, B, H, H, nullptr, 1, 1, nullptr, 0, nxt.hi, nxt.lo, w.cout, st));
@@ -261,6 +258,24 @@ int trunk_and_up_tc(const s3d_model* m, const float* img, int B, int S, EncBufs&
       }
     }
   }
+  return S3D_OK;
+}
+
+namespace {
+
+// The encoder on the tensor cores (conv_tc.cu): every convolution except the first (3 input channels), the
+// transposed convolutions, the 1x1 adapters and the hoisted fc_s projection.  Activations that feed a tensor-core
+// GEMM are written in the split-fp16 format by their producer; taps and feature planes are also kept in fp32 for
+// their fp32 consumers (BatchNorm+pool, tanh head, export).  DoubleConv's first convolution over cat([skip, up])
+// (unet_parts.py:73) is split by input-channel half: the skip half does not depend on the slice, so it is evaluated
+// once per view (B images) and added in the epilogue of the per-slice half (B*K images) -- half of that
+// convolution's work, 12x less of it, same result.
+int trunk_and_up_tc(const s3d_model* m, const float* img, int B, int S, EncBufs& e, cudaStream_t st) {
+  const int K = m->K;
+  const size_t S2 = (size_t)S * S;
+  const int xc[6] = {0, 64, 128, 256, 512, 512};
+  auto xs_of = [&](int i) { return split_of(e.xs[i], B * (S2 >> (2 * (i - 1))) * xc[i]); };
+  S3D_TRY(trunk_tc(m, img, B, S, e.x0, e.ta, e.tb, e.x, e.xs, st));
   // latent = trans_c(cat[x5 tiled, slice embedding]) (unet_custom.py:52-57) -> feat[0]
   const int R0 = S / 16;
   auto fs_of = [&](int s) {
@@ -317,6 +332,12 @@ int enctc_pack(s3d_model* m, cudaStream_t st) {
   const char* env = getenv("S3D_ENCODER");
   m->enc_simt = (env && std::string(env) == "simt") ? 1 : 0;
   for (int i = 1; i < 13; ++i) S3D_TRY(convtc_pack(m, m->vgg[i], m->vgg[i].cin, 0, m->vgg[i].cin, m->tvgg[i], st));
+  if (m->kind == 1) {  // Slices3DGTModel: trunk + hoisted fc_local.0 per tap + fc_local.2
+    const int sc[5] = {512, 512, 256, 128, 64};  // channels of the tap behind plane scale s (tap 4 - s)
+    for (int s = 0; s < 5; ++s) S3D_TRY(convtc_pack(m, m->fcs[s], sc[s], 0, sc[s], m->tfcs[s], st));
+    S3D_TRY(convtc_pack(m, m->fcl2, 128, 0, 128, m->tfcl2, st));
+    return S3D_OK;
+  }
   for (int n = 0; n < 4; ++n) {
     const int C = kPlaneC[n + 1];
     const ConvW& d1 = m->dc1[n];
@@ -361,6 +382,10 @@ size_t encoder_workspace_bytes(int B, int K, int S) {
 int encoder_fwd(const s3d_model* m, const float* img, int B, int S, void* planes, float* const* feats_nchw,
                 float* slices_rec, void* ws, size_t ws_bytes, cudaStream_t st) {
   const int K = m->K;
+  if (m->kind != 0) {
+    set_error("encoder: this handle holds a Slices3DGTModel (use s3d_gt_encoder_fwd)");
+    return S3D_ERR_BAD_ARG;
+  }
   if (B <= 0 || S < 32 || (S % 16) != 0) {
     set_error("encoder: S must be a multiple of 16 (>= 32) and B positive");
     return S3D_ERR_BAD_ARG;
@@ -464,6 +489,51 @@ int encoder_fwd(const s3d_model* m, const float* img, int B, int S, void* planes
       const int R = plane_res(S, s), C = kPlaneC[s];
       dim3 grid((R * R + 31) / 32, (C + 31) / 32, B * K), blk(32, 8);
       k_nhwc_to_nchw<<<grid, blk, 0, st>>>(e.feat[s], feats_nchw[s], R * R, C);
+      S3D_LAUNCH_CHECK();
+    }
+  }
+  return S3D_OK;
+}
+
+// ---- Slices3DGTModel (reg_slices/src/model_gt.py:81-96, src/vgg16bn_feats.py:44-58) --------------------------------
+// The trunk runs on the B*K GIVEN slice images; tap i (conv1_2 .. conv5_3: 64 @ S ... 512 @ S/16) is projected by its
+// column block of fc_local's first Linear (hoisted: bilinear sampling is linear) into plane scale 4 - i of the same
+// (K, R_s, R_s, 128) fp32 channels-last blob the regression model's decoder samples.
+size_t gt_encoder_workspace_bytes(int N, int S) { return encoder_workspace_bytes(N, 1, S); }
+
+int gt_encoder_fwd(const s3d_model* m, const float* img_slices, int B, int S, void* planes, float* const* taps_nchw, void* ws,
+                   size_t ws_bytes, cudaStream_t st) {
+  if (!m || m->kind != 1) {
+    set_error("gt_encoder: the handle does not hold a Slices3DGTModel");
+    return S3D_ERR_BAD_ARG;
+  }
+  const int K = m->K, N = B * K;
+  if (!img_slices || !planes || B <= 0 || S < 32 || (S % 16) != 0) {
+    set_error("gt_encoder: bad argument (S must be a multiple of 16, >= 32)");
+    return S3D_ERR_BAD_ARG;
+  }
+  if (ws == nullptr || ws_bytes < gt_encoder_workspace_bytes(N, S)) {
+    set_error("gt_encoder: workspace too small");
+    return S3D_ERR_WORKSPACE;
+  }
+  Bump bp{static_cast<char*>(ws), 0, ws_bytes};
+  EncBufs e;
+  carve(bp, e, N, 1, S);
+  S3D_TRY(trunk_tc(m, img_slices, N, S, e.x0, e.ta, e.tb, e.x, e.xs, st));
+  const int xc[6] = {0, 64, 128, 256, 512, 512};
+  const size_t per_img = s3d_planes_bytes(1, K, S) / sizeof(float);
+  float* pl = static_cast<float*>(planes);
+  for (int i = 1; i <= 5; ++i) {
+    const int s = 5 - i, R = plane_res(S, s), C = xc[i];
+    Split x = split_of(e.xs[i], (size_t)N * R * R * C);
+    for (int b = 0; b < B; ++b) {
+      const size_t o = (size_t)b * K * R * R * C;
+      S3D_TRY(conv_tc(m->tfcs[s], x.hi + o, x.lo + o, K, R, R, nullptr, 1, 0, pl + b * per_img + plane_offset_floats(K, S, s), 128,
+                      nullptr, nullptr, 0, st));
+    }
+    if (taps_nchw && taps_nchw[i - 1]) {
+      dim3 grid((R * R + 31) / 32, (C + 31) / 32, N), blk(32, 8);
+      k_nhwc_to_nchw<<<grid, blk, 0, st>>>(e.x[i], taps_nchw[i - 1], R * R, C);
       S3D_LAUNCH_CHECK();
     }
   }

@@ -165,6 +165,14 @@ class Generator3D(object):
         model = self.model
         nx = int(resolution or self.resolution0)
         dev = next(model.parameters()).device
+        if not hasattr(model, "slices_generator"):
+            # Slices3DGTModel: the reference's own formulation (reconstruct.py:137-146): explicit make_3d_grid points
+            # through eval_points (one fused model call)
+            pts = (1 + self.padding) * make_3d_grid((-0.5,) * 3, (0.5,) * 3, (nx,) * 3)
+            d = {k: v.to(dev, non_blocking=True) for k, v in data.items()}
+            d["qry_norot"] = pts.unsqueeze(0).to(dev)
+            vol = self.eval_points(d).view(nx, nx, nx)
+            return vol.cpu().numpy() if as_numpy else vol
         precision = precision or model.precision
         img = data["img_input"].to(dev, non_blocking=True)
         T = data["trans_mat_wo_rot_tp"].to(dev, non_blocking=True)
@@ -208,6 +216,8 @@ class Generator3D(object):
         precision = precision or model.precision
         if self.pred_type == "occ":
             raise KeyError("occ_pred")  # same failure as the reference (reconstruct.py:95)
+        if not hasattr(model, "slices_generator"):
+            return self._sparse_grid_via_eval_points(data, dev, as_numpy, stats)
         img = data["img_input"].to(dev, non_blocking=True)
         T = data["trans_mat_wo_rot_tp"].to(dev, non_blocking=True)
         nat = model.native()
@@ -260,6 +270,25 @@ class Generator3D(object):
         if stats is not None:
             stats["points_per_round"] = rounds
             stats["points_evaluated"] = int(sum(rounds))
+        grid = ext.to_dense()
+        return grid.cpu().numpy() if as_numpy else grid
+
+    def _sparse_grid_via_eval_points(self, data, dev, as_numpy, stats):
+        """reconstruct.py:147-167 literally (for models without the regression model's grid entry points, i.e.
+        Slices3DGTModel): MISE on the device, one eval_points call per round."""
+        box_size = 1 + self.padding
+        ext = MISE(self.resolution0, self.upsampling_steps, self.threshold_logit(), device=dev)
+        d = {k: v.to(dev, non_blocking=True) for k, v in data.items()}
+        rounds = []
+        points = ext.query()
+        while points.shape[0] != 0:
+            pointsf = (box_size * (points.double() / ext.resolution - 0.5)).float()
+            d["qry_norot"] = pointsf.unsqueeze(0).contiguous()
+            ext.update(points, self.eval_points(d).double(), validate=False)
+            rounds.append(int(points.shape[0]))
+            points = ext.query()
+        if stats is not None:
+            stats["points_per_round"], stats["points_evaluated"] = rounds, int(sum(rounds))
         grid = ext.to_dense()
         return grid.cpu().numpy() if as_numpy else grid
 

@@ -32,30 +32,10 @@ def default_precision(n_slices):
     return DEFAULT_PRECISION if n_slices == 12 else "fp32"
 
 
-class Slices3DRegModel(nn.Module):
-    def __init__(self, img_size=128, n_slices=12, mode="train", precision=None):
-        super().__init__()
-        self.mode = mode
-        self.slices_generator = UNet(n_channels=3, n_slices=n_slices)
-        self.img_size = img_size
-        # registered-but-unused original layer, exactly like the reference (nn.TransformerEncoder
-        # deep-copies it); keeps the 12 ``att_layer.*`` checkpoint keys (models.py:18-19)
-        self.att_layer = nn.TransformerEncoderLayer(d_model=128, nhead=4, batch_first=True)
-        self.att_decoder = nn.TransformerEncoder(self.att_layer, num_layers=3)
-        self.fc_p = nn.Linear(3, 128)
-        self.fc_s = nn.Linear(992, 128)
-        self.fc_out = nn.Sequential(nn.Linear(128, 1))
-        self.vggptlossfunc = VGGPerceptualLoss()
-        self.n_slices = n_slices
-        # --- not part of the reference API ---
-        self.precision = precision or default_precision(n_slices)  # decoder arithmetic: fp32 | fp16x3 | bf16x3 | bf16
-        self.test_time_vgg_loss = True  # the reference evaluates (and discards) it at test time too
-        self.fused_eval_points = True  # Generator3D.eval_points may pass all queries in one call (no 3000-point chunks)
-        self.native_train = True  # CUDA tensors: train-mode decoder forward + backward in the CUDA library
-        # Packed-weight handles, one per device, in a dict that nn.DataParallel replicas share by reference
-        # (replicate() copies __dict__ shallowly): {"epoch": int, "dev": {device: entry}}.
-        self._nat = {"epoch": 0, "dev": {}}
-        self._enc_cache = None
+class NativeHandleMixin:
+    """Packed-weight handles of the CUDA library for an nn.Module whose state_dict the library understands (shared by
+    Slices3DRegModel and Slices3DGTModel).  Needs ``self._nat = {"epoch": 0, "dev": {}}``, ``self._enc_cache`` and
+    ``self.n_slices``."""
 
     # ------------------------------------------------------------------ native plumbing
     def invalidate_native(self):
@@ -95,7 +75,7 @@ class Slices3DRegModel(nn.Module):
         compares the parameters' version counters; the full check -- data pointers, versions and a content
         fingerprint -- runs once per eval session (after ``invalidate_native``), and the handle is rebuilt only
         when the weights actually changed."""
-        dev = self.fc_p.weight.device
+        dev = self.fc_out[0].weight.device
         nat = self._nat
         ent = nat["dev"].get(dev)
         if ent is not None and ent["epoch"] == nat["epoch"] and ent["owner"] is self:
@@ -109,6 +89,33 @@ class Slices3DRegModel(nn.Module):
             self._enc_cache = None
         ent.update(epoch=nat["epoch"], owner=self, tensors=tensors, vsum=sum(t._version for t in tensors))
         return ent["model"]
+
+
+
+class Slices3DRegModel(NativeHandleMixin, nn.Module):
+    def __init__(self, img_size=128, n_slices=12, mode="train", precision=None):
+        super().__init__()
+        self.mode = mode
+        self.slices_generator = UNet(n_channels=3, n_slices=n_slices)
+        self.img_size = img_size
+        # registered-but-unused original layer, exactly like the reference (nn.TransformerEncoder
+        # deep-copies it); keeps the 12 ``att_layer.*`` checkpoint keys (models.py:18-19)
+        self.att_layer = nn.TransformerEncoderLayer(d_model=128, nhead=4, batch_first=True)
+        self.att_decoder = nn.TransformerEncoder(self.att_layer, num_layers=3)
+        self.fc_p = nn.Linear(3, 128)
+        self.fc_s = nn.Linear(992, 128)
+        self.fc_out = nn.Sequential(nn.Linear(128, 1))
+        self.vggptlossfunc = VGGPerceptualLoss()
+        self.n_slices = n_slices
+        # --- not part of the reference API ---
+        self.precision = precision or default_precision(n_slices)  # decoder arithmetic: fp32 | fp16x3 | bf16x3 | bf16
+        self.test_time_vgg_loss = True  # the reference evaluates (and discards) it at test time too
+        self.fused_eval_points = True  # Generator3D.eval_points may pass all queries in one call (no 3000-point chunks)
+        self.native_train = True  # CUDA tensors: train-mode decoder forward + backward in the CUDA library
+        # Packed-weight handles, one per device, in a dict that nn.DataParallel replicas share by reference
+        # (replicate() copies __dict__ shallowly): {"epoch": int, "dev": {device: entry}}.
+        self._nat = {"epoch": 0, "dev": {}}
+        self._enc_cache = None
 
     def encode(self, img_input):
         """Run the plane encoder once for ``img_input`` (B,3,S,S); cached per tensor object/version."""
