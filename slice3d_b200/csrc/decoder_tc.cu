@@ -109,6 +109,7 @@ struct TcParams {
   int S;
   QueryCtx q;
   long long n;
+  int K;             // slices of the model (<= 12): token rows K + 1 .. 12 of every query are dead (zero tokens, masked keys)
   const int* n_dev;  // when set: the query count lives in device memory (n is then only the capacity)
   float out_scale;
   float* out;
@@ -310,7 +311,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
       const long long gq = gt * TILE_Q + q;
       const float gu = __shfl_sync(0xffffffffu, qgu, q), gv = __shfl_sync(0xffffffffu, qgv, q);
       const int img = __shfl_sync(0xffffffffu, qimg, q);
-      if (k >= 12 || gq >= n_q) return;
+      if (k >= p.K || gq >= n_q) return;
       const int ch = 32 * cb + l8 * 4;
       float4 acc = __ldg(reinterpret_cast<const float4*>(p.fcs_b + ch));
       const int R0 = plane_res(p.S, 0);
@@ -327,17 +328,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
         v[2] = __ldg(reinterpret_cast<const float4*>(base + (size_t)t.o10 * 128));
         v[3] = __ldg(reinterpret_cast<const float4*>(base + (size_t)t.o11 * 128));
       };
-      // plane of scale s for slice k starts at P + (12 * sum_{i<s} R_i^2 + k * (R_s^2 - R_0^2)) * 128
+      // plane of scale s for slice k starts at P + (K * sum_{i<s} R_i^2 + k * (R_s^2 - R_0^2)) * 128
       const size_t r2 = (size_t)R0 * R0;
       if (REGSPLIT) {  // all 20 tap loads in flight: one L2 round trip per step
         float4 v0[4], v1[4], v2[4], v3[4], v4[4];
         const Taps t0 = make_taps(gu, gv, R0), t1 = make_taps(gu, gv, 2 * R0), t2 = make_taps(gu, gv, 4 * R0);
         const Taps t3 = make_taps(gu, gv, 8 * R0), t4 = make_taps(gu, gv, 16 * R0);
         issue(v0, t0, P);
-        issue(v1, t1, P + (12 * r2 + (size_t)k * 3 * r2) * 128);
-        issue(v2, t2, P + (12 * 5 * r2 + (size_t)k * 15 * r2) * 128);
-        issue(v3, t3, P + (12 * 21 * r2 + (size_t)k * 63 * r2) * 128);
-        issue(v4, t4, P + (12 * 85 * r2 + (size_t)k * 255 * r2) * 128);
+        issue(v1, t1, P + ((size_t)p.K * r2 + (size_t)k * 3 * r2) * 128);
+        issue(v2, t2, P + ((size_t)p.K * 5 * r2 + (size_t)k * 15 * r2) * 128);
+        issue(v3, t3, P + ((size_t)p.K * 21 * r2 + (size_t)k * 63 * r2) * 128);
+        issue(v4, t4, P + ((size_t)p.K * 85 * r2 + (size_t)k * 255 * r2) * 128);
         fold(v0, t0);
         fold(v1, t1);
         fold(v2, t2);
@@ -348,8 +349,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
         float4 v0[4], v1[4], v2[4];
         const Taps t0 = make_taps(gu, gv, R0), t1 = make_taps(gu, gv, 2 * R0), t2 = make_taps(gu, gv, 4 * R0);
         issue(v0, t0, P);
-        issue(v1, t1, P + (12 * r2 + (size_t)k * 3 * r2) * 128);
-        issue(v2, t2, P + (12 * 5 * r2 + (size_t)k * 15 * r2) * 128);
+        issue(v1, t1, P + ((size_t)p.K * r2 + (size_t)k * 3 * r2) * 128);
+        issue(v2, t2, P + ((size_t)p.K * 5 * r2 + (size_t)k * 15 * r2) * 128);
         fold(v0, t0);
         fold(v1, t1);
         fold(v2, t2);
@@ -357,8 +358,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
       {
         float4 v3[4], v4[4];
         const Taps t3 = make_taps(gu, gv, 8 * R0), t4 = make_taps(gu, gv, 16 * R0);
-        issue(v3, t3, P + (12 * 21 * r2 + (size_t)k * 63 * r2) * 128);
-        issue(v4, t4, P + (12 * 85 * r2 + (size_t)k * 255 * r2) * 128);
+        issue(v3, t3, P + ((size_t)p.K * 21 * r2 + (size_t)k * 63 * r2) * 128);
+        issue(v4, t4, P + ((size_t)p.K * 85 * r2 + (size_t)k * 255 * r2) * 128);
         fold(v3, t3);
         fold(v4, t4);
       }
@@ -810,14 +811,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
             mma_f16_16816(s1, qh, kh[2], kh[3]);
           }
           // fragment: s0[0,1] / s1[0,1] = row rq, keys 2 tq + {0,1} / 8 + 2 tq + {0,1};  [2,3] = row rq + 8.  Keys >= 13 masked.
-          const bool m0 = (8 + 2 * tq) < NTOK, m1 = (9 + 2 * tq) < NTOK;
+          // (keys >= K + 1: the rows of the next query, or the dead rows of a model with fewer than 12 slices)
+          const int Lk = p.K + 1;
+          const bool k0 = 2 * tq < Lk, k1 = 2 * tq + 1 < Lk, m0 = (8 + 2 * tq) < Lk, m1 = (9 + 2 * tq) < Lk;
 #pragma unroll
           for (int hr = 0; hr < 2; ++hr) {
-            float a0 = s0[2 * hr], a1 = s0[2 * hr + 1], a2 = m0 ? s1[2 * hr] : -INFINITY, a3 = m1 ? s1[2 * hr + 1] : -INFINITY;
+            float a0 = k0 ? s0[2 * hr] : -INFINITY, a1 = k1 ? s0[2 * hr + 1] : -INFINITY;
+            float a2 = m0 ? s1[2 * hr] : -INFINITY, a3 = m1 ? s1[2 * hr + 1] : -INFINITY;
             float mx = fmaxf(fmaxf(a0, a1), fmaxf(a2, a3));
             mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
             mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
-            a0 = __expf(a0 - mx); a1 = __expf(a1 - mx);
+            a0 = k0 ? __expf(a0 - mx) : 0.f;
+            a1 = k1 ? __expf(a1 - mx) : 0.f;
             a2 = m0 ? __expf(a2 - mx) : 0.f;
             a3 = m1 ? __expf(a3 - mx) : 0.f;
             float sum = (a0 + a1) + (a2 + a3);
@@ -968,13 +973,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
         float mx = sp[0];
 #pragma unroll
         for (int j = 0; j < NTOK; ++j) {
-          pj[j] = sp[j];
+          pj[j] = j <= p.K ? sp[j] : -INFINITY;  // keys beyond the model's K + 1 tokens are dead rows
           mx = fmaxf(mx, pj[j]);
         }
         float sum = 0.f;
 #pragma unroll
         for (int j = 0; j < NTOK; ++j) {
-          pj[j] = __expf(pj[j] - mx);
+          pj[j] = j <= p.K ? __expf(pj[j] - mx) : 0.f;
           sum += pj[j];
         }
         const float inv = 1.f / sum;
@@ -1092,7 +1097,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
       const float* tokrow;
       if (p.q.tok_slice) {  // ready tokens in global memory: query token [n][128], slice tokens [n][12][128]
         tokrow = tk == 0 ? p.q.tok_query + (size_t)(valid ? q_idx : 0) * 128
-                         : p.q.tok_slice + ((size_t)(valid ? q_idx : 0) * (NTOK - 1) + (tk - 1)) * 128;
+                         : p.q.tok_slice + ((size_t)(valid ? q_idx : 0) * p.K + (tk <= p.K ? tk - 1 : 0)) * 128;
       } else {
         tokrow = tokbase + (size_t)tbuf * (128 * 128) + (size_t)r * 128;
         mbar_wait(bar(B_TOKFULL0 + tbuf), (ph_tf >> tbuf) & 1u);  // slice tokens of this tile gathered
@@ -1103,7 +1108,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
           float4 t4 = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (valid) t4 = __ldcg(reinterpret_cast<const float4*>(tokrow + 32 * g) + c);
+          if (valid && tk <= p.K) t4 = __ldcg(reinterpret_cast<const float4*>(tokrow + 32 * g) + c);  // dead rows: zero tokens
           v[4 * c] = t4.x; v[4 * c + 1] = t4.y; v[4 * c + 2] = t4.z; v[4 * c + 3] = t4.w;
         }
         warp_arrive(bar(B_TOKEMPTY0 + tbuf), lane);  // this warp has read its tokens: the buffer may be refilled
@@ -1293,7 +1298,6 @@ void pack_unit(F W, int NU, int KU, uint8_t* dst, bool f16 = false) {
 // Build the operand images of the three attention layers from the fp32 [K][N] matrices already
 // packed for the fp32 path (DecF32), in the order the MMA issuer consumes them.
 int dectc_pack(s3d_model* m, cudaStream_t st) {
-  if (m->K != 12) return S3D_OK;  // the tensor-core tile layout is specialised for 13 tokens; fp32 path serves other K
   const size_t total = (size_t)3 * UNITS_PER_LAYER * UNIT_STRIDE_BYTES;
   std::vector<uint8_t> img(total);
   auto fetch = [&](const ConvW& cw, std::vector<float>& h) -> int {
@@ -1373,7 +1377,7 @@ int dectc_pack(s3d_model* m, cudaStream_t st) {
   return S3D_OK;
 }
 
-bool decoder_tc_supported(const s3d_model* m) { return m && m->K == 12 && m->dectc.wimg != nullptr; }
+bool decoder_tc_supported(const s3d_model* m) { return m && m->K >= 1 && m->K <= 12 && m->dectc.wimg != nullptr; }
 
 int debug_profile(long long* out32, int reset) {
   unsigned long long h[32];
@@ -1395,7 +1399,7 @@ size_t decoder_tc_workspace_bytes(int64_t) {
 int decoder_tc(const s3d_model* m, const float* planes, int S, const QueryCtx& q, int64_t n, float out_scale, float* out,
                int precision, void* ws, size_t ws_bytes, cudaStream_t st, const int* n_dev) {
   if (!decoder_tc_supported(m)) {
-    set_error("decoder: tensor-core modes need n_slices == 12 (use S3D_PREC_FP32 otherwise)");
+    set_error("decoder: tensor-core modes need 1 <= n_slices <= 12");
     return S3D_ERR_UNSUPPORTED;
   }
   if (n <= 0) return S3D_OK;
@@ -1406,6 +1410,7 @@ int decoder_tc(const s3d_model* m, const float* planes, int S, const QueryCtx& q
   p.S = S;
   p.q = q;
   p.n = n;
+  p.K = m->K;
   p.n_dev = n_dev;
   p.out_scale = out_scale;
   p.out = out;

@@ -81,7 +81,7 @@ size_t padded_rows(int64_t c, int K) { return ((size_t)c * K + 127) / 128 * 128;
 
 size_t gt_decoder_workspace_bytes(int64_t n, int precision) {
   const int64_t c = n < GT_CHUNK ? (n < 1 ? 1 : n) : GT_CHUNK;
-  const size_t rows = padded_rows(c, 12);
+  const size_t rows = padded_rows(c, 12);  // K <= 12
   const size_t tok = rows * TOK * (2 * sizeof(__half) + sizeof(float)) + (size_t)c * TOK * sizeof(float) + 1024;
   const size_t dec = precision == S3D_PREC_FP32 ? decoder_simt_workspace_bytes(c) : decoder_tc_workspace_bytes(c);
   return tok + ((dec + 255) / 256) * 256;

@@ -23,13 +23,13 @@ from . import _native, train_ops
 from .perceptual import VGGPerceptualLoss
 from .unet import UNet
 
-DEFAULT_PRECISION = "fp16x3"  # <= 1e-4 tensor-core mode (fp16 hi/lo split operands, 3 passes); needs n_slices == 12
+DEFAULT_PRECISION = "fp16x3"  # <= 1e-4 tensor-core mode (fp16 hi/lo split operands, 3 passes)
 
 
 def default_precision(n_slices):
-    """The tensor-core decoder is instantiated for the reference's 13-token layout (K = 12); other K run the fp32
-    CUDA-core decoder."""
-    return DEFAULT_PRECISION if n_slices == 12 else "fp32"
+    """The tensor-core decoder keeps the reference's 13-token tile layout; models with fewer than 12 slices run on it
+    with the unused token rows dead (zero tokens, masked as attention keys)."""
+    return DEFAULT_PRECISION if 1 <= n_slices <= 12 else "fp32"
 
 
 class NativeHandleMixin:
@@ -46,6 +46,7 @@ class NativeHandleMixin:
 
     def load_state_dict(self, *a, **k):
         r = super().load_state_dict(*a, **k)
+        self._pretrained_loaded = True  # a checkpoint carries its own trunk / perceptual weights
         self.invalidate_native()
         return r
 
@@ -110,6 +111,8 @@ class Slices3DRegModel(NativeHandleMixin, nn.Module):
         # --- not part of the reference API ---
         self.precision = precision or default_precision(n_slices)  # decoder arithmetic: fp32 | fp16x3 | bf16x3 | bf16
         self.test_time_vgg_loss = True  # the reference evaluates (and discards) it at test time too
+        self._pretrained_loaded = False  # set by load_pretrained_vgg / load_state_dict
+        self._warned_init = False
         self.fused_eval_points = True  # Generator3D.eval_points may pass all queries in one call (no 3000-point chunks)
         self.native_train = True  # CUDA tensors: train-mode decoder forward + backward in the CUDA library
         # Packed-weight handles, one per device, in a dict that nn.DataParallel replicas share by reference
@@ -140,9 +143,47 @@ class Slices3DRegModel(NativeHandleMixin, nn.Module):
             c["vgg"] = (key, loss * 0.001, img_slices)
         return c["vgg"][1]
 
+    # ------------------------------------------------------------------ pretrained initialisation
+    def load_pretrained_vgg(self, vgg16_bn_state_dict=None, vgg19_state_dict=None):
+        """The reference builds its U-Net trunk from ``torchvision.models.vgg16_bn(pretrained=True)`` and the frozen
+        perceptual network from ``vgg19(pretrained=True)`` (unet_custom.py:12, vgg_perceptual_loss.py:9).  This package
+        never downloads anything: pass the two torchvision state_dicts (``features.<i>.*`` keys; e.g. loaded from the
+        files torchvision caches under ~/.cache/torch/hub/checkpoints) before training from scratch.  Checkpoints
+        written by ``train.py`` already contain both networks and need nothing."""
+        own = self.state_dict()
+        loaded = 0
+        if vgg16_bn_state_dict is not None:
+            blocks = {"down1": range(0, 4), "down2": range(4, 11), "down3": range(11, 21), "down4": range(21, 31),
+                      "down5": range(31, 41), "down5_": range(41, 44)}
+            for name, idxs in blocks.items():
+                for i in idxs:
+                    for leaf in ("weight", "bias", "running_mean", "running_var", "num_batches_tracked"):
+                        src, dst = f"features.{i}.{leaf}", f"slices_generator.{name}.{i}.{leaf}"
+                        if src in vgg16_bn_state_dict and dst in own:
+                            own[dst].copy_(vgg16_bn_state_dict[src])
+                            loaded += 1
+        if vgg19_state_dict is not None:
+            from .perceptual import _SLICE_RANGES
+            for n, (a, b) in enumerate(_SLICE_RANGES, start=1):
+                for i in range(a, b):
+                    for leaf in ("weight", "bias"):
+                        src, dst = f"features.{i}.{leaf}", f"vggptlossfunc.vgg.slice{n}.{i}.{leaf}"
+                        if src in vgg19_state_dict and dst in own:
+                            own[dst].copy_(vgg19_state_dict[src])
+                            loaded += 1
+        self._pretrained_loaded = True
+        self.invalidate_native()
+        return loaded
+
     # ------------------------------------------------------------------ forward
     def forward(self, feed_dict):
         if self.training or torch.is_grad_enabled():
+            if self.training and not self._pretrained_loaded and not self._warned_init:
+                import warnings
+                warnings.warn("Slices3DRegModel is training from randomly initialised VGG16-BN / VGG19 weights: the "
+                              "reference starts from torchvision's pretrained ones (call load_pretrained_vgg or "
+                              "load_state_dict first)", stacklevel=2)
+                self._warned_init = True
             return self._forward_autograd(feed_dict)
         return self._forward_native(feed_dict)
 

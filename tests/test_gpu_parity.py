@@ -326,7 +326,7 @@ def test_full_size_dense_grid_256():
 
 def test_tc_decoder_ragged_empty_and_unsupported():
     """Edge cases of the tensor-core path: empty query set, fewer queries than one tile (9), ragged last tile, a
-    count that leaves one CTA of a pair without work, and K != 12 (served by the fp32 path only: loud error)."""
+    count that leaves one CTA of a pair without work, K != 12 (dead token rows), and a refused call."""
     case = helpers.load_case("k12_s128_g128")
     m, _ = _model(case)
     feed = _feed(case)
@@ -347,14 +347,42 @@ def test_tc_decoder_ragged_empty_and_unsupported():
     f4 = _feed(case4)
     p4 = m4.encode(f4["img_input"])
     q4 = torch.from_numpy(case4["pts_g64"]).to(DEV)
-    assert m4.precision == "fp32"  # the module picks the fp32 decoder for K != 12 by itself
+    # K = 4 (BASELINE configs[0]) on the tensor-core path: 5 live token rows per query, the other 8 dead and masked
+    assert m4.precision == "fp16x3"
+    for prec in ("fp16x3", "bf16x3"):
+        got = m4.native().decode(p4, 0, q4, f4["trans_mat_wo_rot_tp"][0], precision=prec)
+        err = helpers.maxabs(got.cpu(), case4["sdf_g64"])
+        print(f"K=4 model on the tensor-core decoder, {prec}: max-abs vs reference {err:.3e}")
+        helpers.record(f"decoder_{prec}_cfg0_k4_max_abs_vs_reference", err)
+        assert err < TOL
     before = q4.clone()
-    with pytest.raises(_native.NativeError):
-        m4.native().decode(p4, 0, q4, f4["trans_mat_wo_rot_tp"][0], None, True, precision="bf16x3")
-    assert torch.equal(q4, before)  # a refused call leaves the caller's queries unflipped
+    with pytest.raises(_native.NativeError):  # a refused call (unknown precision) leaves the caller's queries unflipped
+        _native.PRECISIONS["bogus"] = 9
+        try:
+            m4.native().decode(p4, 0, q4, f4["trans_mat_wo_rot_tp"][0], None, True, precision="bogus")
+        finally:
+            del _native.PRECISIONS["bogus"]
+    assert torch.equal(q4, before)
     with torch.no_grad():
         ret = m4({**f4, "qry_norot": q4.clone().unsqueeze(0)})
     assert helpers.maxabs(ret["sdf_pred"][0].cpu(), case4["sdf_g64"]) < TOL
+    # other slice counts (1, 5, 11) against the fp32 CUDA path on the same planes, incl. the dense-grid entry point
+    from slice3d_b200 import Slices3DRegModel
+    for K in (1, 5, 11):
+        mk = Slices3DRegModel(64, K, "test")
+        mk.load_state_dict(synth.synthetic_state_dict(mk.state_dict(), seed=20 + K))
+        mk = mk.to(DEV).eval()
+        fk = {k: v.to(DEV) for k, v in synth.synthetic_inputs(64, K, seed=K).items()}
+        pk = mk.encode(fk["img_input"])
+        qk = (torch.rand(777, 3, generator=torch.Generator().manual_seed(K)) - 0.5).to(DEV)
+        Tk = fk["trans_mat_wo_rot_tp"][0]
+        a = mk.native().decode(pk, 0, qk, Tk, precision="fp16x3")
+        b = mk.native().decode(pk, 0, qk, Tk, precision="fp32")
+        assert helpers.maxabs(a.cpu(), b.cpu()) < TOL, K
+        ax = torch.linspace(-0.5, 0.5, 17).to(DEV)
+        ga = mk.native().decode_grid(pk, 0, (ax, ax, ax), 0, 17 ** 3, Tk, precision="fp16x3")
+        gb = mk.native().decode_grid(pk, 0, (ax, ax, ax), 0, 17 ** 3, Tk, precision="fp32")
+        assert helpers.maxabs(ga.cpu(), gb.cpu()) < TOL, K
 
 
 def test_batched_decoder_one_launch_equals_per_image_launches():

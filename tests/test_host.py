@@ -182,3 +182,26 @@ def test_ddp_gradient_allreduce_world2_gloo(tmp_path):
     procs = [subprocess.Popen([sys.executable, str(script), ROOT, port, str(r)]) for r in range(2)]
     codes = [p.wait(timeout=600) for p in procs]
     assert codes == [0, 0]
+
+
+def test_load_pretrained_vgg_maps_torchvision_keys():
+    """the reference starts from torchvision's pretrained VGG16-BN / VGG19; this package takes their
+    state_dicts explicitly (no download) and maps features.<i>.* into the trunk blocks / perceptual slices."""
+    import warnings
+    import torch
+    from slice3d_b200 import Slices3DRegModel, synth
+    torchvision = pytest.importorskip("torchvision")
+    m = Slices3DRegModel(32, 12, "train")
+    v16 = torchvision.models.vgg16_bn(weights=None).state_dict()
+    v19 = torchvision.models.vgg19(weights=None).state_dict()
+    assert m.load_pretrained_vgg(v16, v19) == 13 * 2 + 13 * 5 + 14 * 2
+    sd = m.state_dict()
+    assert torch.equal(sd["slices_generator.down1.0.weight"], v16["features.0.weight"])
+    assert torch.equal(sd["slices_generator.down5_.41.running_var"], v16["features.41.running_var"])
+    assert torch.equal(sd["vggptlossfunc.vgg.slice5.30.bias"], v19["features.30.bias"])
+    fresh = Slices3DRegModel(32, 12, "train").train()
+    feed = synth.synthetic_train_batch(32, 12, batch=1, n_qry=8, seed=0)
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        fresh(feed)
+    assert any("pretrained" in str(x.message) for x in w)
