@@ -523,8 +523,9 @@ def train_leg(dev, world, rank, steps, warmup, max_over_ranks, barrier):
             "loss": losses, "loss_ref": ref, "loss_max_rel_diff": rel,
             "loss_note": "3 Adam steps, dropout 0 on both sides; [L1(sdf), L1(slices), 0.001 * VGG19 perceptual] mean over ranks",
             "native_ops": "decoder forward + backward (projection, grid_sample, fc_s/fc_p, transformer, fc_out): "
-                          "csrc/train_decoder.cu",
-            "torch_ops": "U-Net and VGG19 convolutions / BatchNorm (cuDNN through torch autograd), Adam"}
+                          "csrc/train_decoder.cu; VGG19 perceptual loss forward + data-gradient backward on the tcgen05 "
+                          "convolution kernel: csrc/perceptual.cu",
+            "torch_ops": "U-Net convolutions / BatchNorm forward + backward (cuDNN through torch autograd), Adam"}
 
 
 def nat_planes_mb(K, S):

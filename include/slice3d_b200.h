@@ -220,6 +220,19 @@ int s3d_preprocess_rgba(const uint8_t* rgba_dev, int32_t N, int32_t H, int32_t W
                         const int32_t* kk_v_dev, int32_t ksize_v, float* out_dev, void* workspace_dev, size_t workspace_bytes,
                         void* stream);
 
+/* The same loss in TRAINING (reg_slices/train.py:41-53 back-propagates through ret['vgg_loss']): forward keeping the
+ * activations, and the gradient with respect to the FIRST batch a (the network is frozen: data gradients only, each a
+ * 3x3 convolution with the rotated / transposed weights on the same tcgen05 kernel).  A handle created from the
+ * vggptlossfunc.* tensors ALONE is enough (and is what training uses: those weights never change).
+ *   saved_dev   s3d_vgg_loss_train_bytes(N, S) bytes, kept by the caller between forward and backward.
+ *   gout_dev    one float: the upstream gradient of the loss value (e.g. 0.001 from models.py:92, times d(total)/d(term)).
+ *   grad_a_dev  (N,3,S,S) fp32 NCHW, overwritten. */
+size_t s3d_vgg_loss_train_bytes(int32_t N, int32_t S);
+int s3d_vgg_loss_train_fwd(const s3d_model* m, const float* a_dev, const float* b_dev, int32_t N, int32_t S, float* loss_dev,
+                           void* saved_dev, size_t saved_bytes, void* stream);
+int s3d_vgg_loss_train_bwd(const s3d_model* m, int32_t N, int32_t S, const float* gout_dev, void* saved_dev, size_t saved_bytes,
+                           float* grad_a_dev, void* stream);
+
 /* One MISE refinement step on dense device state, replacing MISE.subdivide_voxels (reg_slices/src_convonet/utils/
  * libmise/mise.pyx:184-283) after the caller has stored the new values: R = resolution0 << depth; value_dev / known_dev /
  * exists_dev are (R+1)^3 lattice arrays (float64 / bytes), cell_level_dev is the R^3 int8 array "level of the leaf voxel

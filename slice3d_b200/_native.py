@@ -21,7 +21,7 @@ SYMBOLS = [
     "s3d_abi_version", "s3d_last_error", "s3d_model_create", "s3d_model_destroy", "s3d_model_n_slices",
     "s3d_planes_bytes", "s3d_encoder_workspace_bytes", "s3d_encoder_fwd", "s3d_decoder_workspace_bytes",
     "s3d_decoder_fwd", "s3d_decoder_batch_fwd", "s3d_decoder_grid_fwd", "s3d_decoder_debug_tokens", "s3d_vgg_loss_workspace_bytes",
-    "s3d_vgg_loss_fwd", "s3d_mc_count", "s3d_mc_emit", "s3d_mise_scratch_ints",
+    "s3d_vgg_loss_fwd", "s3d_vgg_loss_train_bytes", "s3d_vgg_loss_train_fwd", "s3d_vgg_loss_train_bwd", "s3d_mc_count", "s3d_mc_emit", "s3d_mise_scratch_ints",
     "s3d_mise_subdivide", "s3d_sparse_scratch_bytes", "s3d_sparse_rounds", "s3d_preprocess_workspace_bytes", "s3d_preprocess_rgba",
     "s3d_gt_encoder_workspace_bytes", "s3d_gt_encoder_fwd", "s3d_gt_decoder_workspace_bytes", "s3d_gt_decoder_fwd", "s3d_train_decoder_saved_bytes", "s3d_train_decoder_bwd_workspace_bytes",
     "s3d_train_decoder_fwd", "s3d_train_decoder_bwd", "s3d_selftest_umma", "s3d_debug_profile", "s3d_launch_count",
@@ -91,6 +91,14 @@ def lib():
     L.s3d_vgg_loss_fwd.restype = C.c_int
     L.s3d_vgg_loss_fwd.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
                                    C.c_size_t, C.c_void_p]
+    L.s3d_vgg_loss_train_bytes.restype = C.c_size_t
+    L.s3d_vgg_loss_train_bytes.argtypes = [C.c_int32, C.c_int32]
+    L.s3d_vgg_loss_train_fwd.restype = C.c_int
+    L.s3d_vgg_loss_train_fwd.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
+                                         C.c_size_t, C.c_void_p]
+    L.s3d_vgg_loss_train_bwd.restype = C.c_int
+    L.s3d_vgg_loss_train_bwd.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p,
+                                         C.c_void_p]
     L.s3d_mc_count.restype = C.c_int
     L.s3d_mc_count.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p,
                                C.c_void_p, C.c_void_p]

@@ -119,7 +119,42 @@ struct Packer {
     return dst != nullptr;
   }
 
+  // ---- VGG19 perceptual loss (optional; vgg_perceptual_loss.py:6-40: torchvision feature indices per slice), plus the
+  //      weights of the data-gradient convolutions of its backward pass: dX = conv3x3(dY, W') with
+  //      W'[ci][co][ky][kx] = W[co][ci][2-ky][2-kx] (the network is frozen: no weight gradients)
+  bool build_pvgg() {
+    struct PC {
+      int slice, idx, cin, cout;
+    };
+    const PC pc[14] = {{1, 0, 3, 64},     {1, 2, 64, 64},    {2, 5, 64, 128},   {2, 7, 128, 128},  {3, 10, 128, 256},
+                       {3, 12, 256, 256}, {4, 14, 256, 256}, {4, 16, 256, 256}, {4, 19, 256, 512}, {4, 21, 512, 512},
+                       {5, 23, 512, 512}, {5, 25, 512, 512}, {5, 28, 512, 512}, {5, 30, 512, 512}};
+    for (int i = 0; i < 14; ++i) {
+      std::string p = "vggptlossfunc.vgg.slice" + std::to_string(pc[i].slice) + "." + std::to_string(pc[i].idx);
+      if (!pack_conv(p + ".weight", pc[i].cout, pc[i].cin, 3, m->pvgg[i])) return false;
+      if (!vec(p + ".bias", pc[i].cout, m->pvgg[i].shift)) return false;
+      std::vector<float> w;
+      const int Cout = pc[i].cout, Cin = pc[i].cin, CinP = (Cin + 3) / 4 * 4;
+      if (!fetch(p + ".weight", (int64_t)Cout * Cin * 9, w)) return false;
+      ConvW& d = m->pvgg_d[i];
+      d.cin = Cout; d.ncols = CinP; d.ks = 3; d.k = 9 * Cout; d.kpad = (d.k + 15) / 16 * 16;
+      std::vector<float> t((size_t)d.kpad * CinP, 0.f);
+      for (int co = 0; co < Cout; ++co)
+        for (int ci = 0; ci < Cin; ++ci)
+          for (int tp = 0; tp < 9; ++tp) t[((size_t)tp * Cout + co) * CinP + ci] = w[((size_t)co * Cin + ci) * 9 + (8 - tp)];
+      if (!(d.w = upload(t))) return false;
+    }
+    if (!vec("vggptlossfunc.mean", 3, m->pvgg_mean) || !vec("vggptlossfunc.std", 3, m->pvgg_std)) return false;
+    m->has_pvgg = 1;
+    return true;
+  }
+
   bool build() {
+    if (!by_name.count("slices_generator.down1.0.weight") && !by_name.count("img_encoder.conv1_2.0.weight") &&
+        by_name.count("vggptlossfunc.vgg.slice1.0.weight")) {
+      m->kind = 2;  // the frozen perceptual network alone (training: its weights never change, the model's do every step)
+      return build_pvgg();
+    }
     // Slices3DGTModel checkpoints (reg_slices/src/model_gt.py) are recognised by their encoder keys: the same VGG16-BN
     // trunk under img_encoder.conv1_2 .. conv5_3 (vgg16bn_feats.py:27-32: same cut points as down1 .. down5)
     const bool gt = by_name.count("img_encoder.conv1_2.0.weight") != 0;
@@ -239,22 +274,7 @@ struct Packer {
         c0 += kPlaneC[s];
       }
     }
-    // ---- VGG19 perceptual loss (optional; vgg_perceptual_loss.py:6-40: torchvision feature indices per slice)
-    if (by_name.count("vggptlossfunc.vgg.slice1.0.weight")) {
-      struct PC {
-        int slice, idx, cin, cout;
-      };
-      const PC pc[14] = {{1, 0, 3, 64},     {1, 2, 64, 64},    {2, 5, 64, 128},   {2, 7, 128, 128},  {3, 10, 128, 256},
-                         {3, 12, 256, 256}, {4, 14, 256, 256}, {4, 16, 256, 256}, {4, 19, 256, 512}, {4, 21, 512, 512},
-                         {5, 23, 512, 512}, {5, 25, 512, 512}, {5, 28, 512, 512}, {5, 30, 512, 512}};
-      for (int i = 0; i < 14; ++i) {
-        std::string p = "vggptlossfunc.vgg.slice" + std::to_string(pc[i].slice) + "." + std::to_string(pc[i].idx);
-        if (!pack_conv(p + ".weight", pc[i].cout, pc[i].cin, 3, m->pvgg[i])) return false;
-        if (!vec(p + ".bias", pc[i].cout, m->pvgg[i].shift)) return false;
-      }
-      if (!vec("vggptlossfunc.mean", 3, m->pvgg_mean) || !vec("vggptlossfunc.std", 3, m->pvgg_std)) return false;
-      m->has_pvgg = 1;
-    }
+    if (by_name.count("vggptlossfunc.vgg.slice1.0.weight") && !build_pvgg()) return false;
     // ---- decoder
     {
       std::vector<float> w;
@@ -299,8 +319,8 @@ int check_decoder(const s3d_model* m, const void* planes, int S, const float* T,
     set_error("decoder: bad argument");
     return S3D_ERR_BAD_ARG;
   }
-  if (m->kind != 0 && !gt_tokens) {
-    set_error("decoder: this handle holds a Slices3DGTModel (use s3d_gt_decoder_fwd)");
+  if ((m->kind != 0 && !gt_tokens) || m->kind == 2) {
+    set_error("decoder: this handle holds a Slices3DGTModel (use s3d_gt_decoder_fwd) or only the perceptual network");
     return S3D_ERR_BAD_ARG;
   }
   if (precision != S3D_PREC_FP32 && precision != S3D_PREC_BF16X3 && precision != S3D_PREC_BF16 &&
@@ -380,7 +400,7 @@ int s3d_model_create(s3d_model** out, const s3d_tensor* tensors, int32_t n_tenso
     return missing ? S3D_ERR_MISSING_TENSOR : S3D_ERR_BAD_ARG;
   }
   int r = enctc_pack(m, static_cast<cudaStream_t>(stream));
-  if (r == S3D_OK) r = dectc_pack(m, static_cast<cudaStream_t>(stream));
+  if (r == S3D_OK && m->kind != 2) r = dectc_pack(m, static_cast<cudaStream_t>(stream));
   if (r != S3D_OK) {
     s3d_model_destroy(m);
     return r;
@@ -534,6 +554,27 @@ int s3d_mise_subdivide(int32_t resolution0, int32_t depth, double threshold, con
                        int8_t* cell_level_dev, uint8_t* exists_dev, int32_t* flags_dev, void* stream) {
   return mise_subdivide(resolution0, depth, threshold, value_dev, known_dev, reinterpret_cast<signed char*>(cell_level_dev),
                         exists_dev, flags_dev, static_cast<cudaStream_t>(stream));
+}
+
+size_t s3d_vgg_loss_train_bytes(int32_t N, int32_t S) {
+  if (N <= 0 || S <= 0) return 0;
+  return vgg_loss_train_bytes(N, S);
+}
+int s3d_vgg_loss_train_fwd(const s3d_model* m, const float* a_dev, const float* b_dev, int32_t N, int32_t S, float* loss_dev,
+                           void* saved_dev, size_t saved_bytes, void* stream) {
+  if (!m) {
+    set_error("vgg_loss_train: null model");
+    return S3D_ERR_BAD_ARG;
+  }
+  return vgg_loss_train_fwd(m, a_dev, b_dev, N, S, loss_dev, saved_dev, saved_bytes, static_cast<cudaStream_t>(stream));
+}
+int s3d_vgg_loss_train_bwd(const s3d_model* m, int32_t N, int32_t S, const float* gout_dev, void* saved_dev, size_t saved_bytes,
+                           float* grad_a_dev, void* stream) {
+  if (!m) {
+    set_error("vgg_loss_train: null model");
+    return S3D_ERR_BAD_ARG;
+  }
+  return vgg_loss_train_bwd(m, N, S, gout_dev, saved_dev, saved_bytes, grad_a_dev, static_cast<cudaStream_t>(stream));
 }
 
 size_t s3d_gt_encoder_workspace_bytes(int32_t B, int32_t K, int32_t S) {

@@ -130,6 +130,8 @@ struct s3d_model {
   int has_pvgg = 0;
   s3d::ConvW pvgg[14];         // conv1_1 .. conv5_2 (shift = bias)
   s3d::ConvTC tpvgg[14];       // [0] unused
+  s3d::ConvW pvgg_d[14];       // data-gradient convolutions of the backward pass (rotated, transposed weights)
+  s3d::ConvTC tpvgg_d[14];     // [0] unused (3 output channels: fp32 path)
   float* pvgg_mean = nullptr;
   float* pvgg_std = nullptr;
   int enc_simt = 0;            // S3D_ENCODER=simt: whole encoder on the fp32 CUDA-core path (debugging)
@@ -192,6 +194,11 @@ int preprocess_rgba(const unsigned char* rgba, int N, int H, int W, int S, int w
 size_t vgg_loss_workspace_bytes(int N, int S);
 int vgg_loss_fwd(const s3d_model* m, const float* a, const float* b, int N, int S, float* loss, void* ws, size_t ws_bytes,
                  cudaStream_t st);
+size_t vgg_loss_train_bytes(int N, int S);
+int vgg_loss_train_fwd(const s3d_model* m, const float* a, const float* b, int N, int S, float* loss, void* saved,
+                       size_t saved_bytes, cudaStream_t st);
+int vgg_loss_train_bwd(const s3d_model* m, int N, int S, const float* gout, void* saved, size_t saved_bytes, float* grad_a,
+                       cudaStream_t st);
 
 // train_decoder.cu
 size_t train_decoder_saved_bytes(const s3d_train_cfg* c);

@@ -331,6 +331,14 @@ int project_planes_tc(const s3d_model* m, int B, int S, EncBufs& e, float* pl, c
 int enctc_pack(s3d_model* m, cudaStream_t st) {
   const char* env = getenv("S3D_ENCODER");
   m->enc_simt = (env && std::string(env) == "simt") ? 1 : 0;
+  auto pack_pvgg = [&]() -> int {
+    for (int i = 1; i < 14; ++i) {
+      S3D_TRY(convtc_pack(m, m->pvgg[i], m->pvgg[i].cin, 0, m->pvgg[i].cin, m->tpvgg[i], st));
+      S3D_TRY(convtc_pack(m, m->pvgg_d[i], m->pvgg_d[i].cin, 0, m->pvgg_d[i].cin, m->tpvgg_d[i], st));
+    }
+    return S3D_OK;
+  };
+  if (m->kind == 2) return pack_pvgg();
   for (int i = 1; i < 13; ++i) S3D_TRY(convtc_pack(m, m->vgg[i], m->vgg[i].cin, 0, m->vgg[i].cin, m->tvgg[i], st));
   if (m->kind == 1) {  // Slices3DGTModel: trunk + hoisted fc_local.0 per tap + fc_local.2
     const int sc[5] = {512, 512, 256, 128, 64};  // channels of the tap behind plane scale s (tap 4 - s)
@@ -362,8 +370,7 @@ int enctc_pack(s3d_model* m, cudaStream_t st) {
     S3D_TRY(convtc_pack(m, m->trans_up[n], 2 * C, 0, 2 * C, m->ttrans_up[n], st));
     S3D_TRY(convtc_pack(m, m->up_t[n], m->up_t[n].cin, 0, m->up_t[n].cin, m->tup_t[n], st));
   }
-  if (m->has_pvgg)
-    for (int i = 1; i < 14; ++i) S3D_TRY(convtc_pack(m, m->pvgg[i], m->pvgg[i].cin, 0, m->pvgg[i].cin, m->tpvgg[i], st));
+  if (m->has_pvgg) S3D_TRY(pack_pvgg());
   S3D_TRY(convtc_pack(m, m->trans_c, 512, 0, 512, m->ttrans_c, st));
   for (int s = 0; s < 5; ++s) S3D_TRY(convtc_pack(m, m->fcs[s], kPlaneC[s], 0, kPlaneC[s], m->tfcs[s], st));
   return S3D_OK;

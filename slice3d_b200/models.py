@@ -114,6 +114,7 @@ class Slices3DRegModel(NativeHandleMixin, nn.Module):
         self._pretrained_loaded = False  # set by load_pretrained_vgg / load_state_dict
         self._warned_init = False
         self.fused_eval_points = True  # Generator3D.eval_points may pass all queries in one call (no 3000-point chunks)
+        self.native_vgg_train = True  # ... and the VGG19 perceptual loss's forward + backward
         self.native_train = True  # CUDA tensors: train-mode decoder forward + backward in the CUDA library
         # Packed-weight handles, one per device, in a dict that nn.DataParallel replicas share by reference
         # (replicate() copies __dict__ shallowly): {"epoch": int, "dev": {device: entry}}.
@@ -246,7 +247,11 @@ class Slices3DRegModel(NativeHandleMixin, nn.Module):
                                           p, seed)
             ret = {"sdf_pred": sdf, "slices_rec": slices_rec.view(n_bs, K * 3, S, S)}
             tgt = feed_dict["img_slices"].view(n_bs, K, 3, S, S).view(n_bs * K, 3, S, S)
-            ret["vgg_loss"] = self.vggptlossfunc(slices_rec, tgt)["pt_c_loss"] * 0.001
+            if S % 16 == 0 and self.native_vgg_train:
+                # a10 in train mode: VGG19 forward + data-gradient backward on the tcgen05 convolution kernel
+                ret["vgg_loss"] = train_ops.vgg_loss_train(self.vggptlossfunc, slices_rec, tgt) * 0.001
+            else:
+                ret["vgg_loss"] = self.vggptlossfunc(slices_rec, tgt)["pt_c_loss"] * 0.001
             return ret
         uv = self.project_coord(qry, feed_dict["trans_mat_wo_rot_tp"])
         grid = uv.view(n_bs, 1, 1, n_qry, 2).expand(-1, K, -1, -1, -1).reshape(n_bs * K, 1, n_qry, 2)

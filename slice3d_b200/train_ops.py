@@ -82,3 +82,59 @@ def decoder_train(feats, qry, T, params, n_slices, img_size, dropout_p=0.0, seed
     B, n_qry = qry.shape[0], qry.shape[1]
     cfg = (int(B), int(n_qry), int(n_slices), int(img_size), float(dropout_p), int(seed))
     return _DecoderTrainFn.apply(cfg, qry, T, *feats, *params)
+
+
+# ------------------------------------------------------------------------------------------------ perceptual loss
+class _VGGLossTrainFn(torch.autograd.Function):
+    """VGGPerceptualLoss.forward(a, b)['pt_c_loss'] with its gradient w.r.t. ``a`` in the CUDA library
+    (``s3d_vgg_loss_train_fwd / _bwd``: the forward convolutions and the data-gradient convolutions of the frozen VGG19
+    on the tcgen05 kernel)."""
+
+    @staticmethod
+    def forward(ctx, nat, a, b):
+        a, b = a.detach().float().contiguous(), b.detach().float().contiguous()
+        N, S, dev = a.shape[0], a.shape[2], a.device
+        L = _native.lib()
+        with torch.cuda.device(dev):
+            saved = torch.empty(L.s3d_vgg_loss_train_bytes(N, S) // 4 + 1, dtype=torch.float32, device=dev)
+            loss = torch.empty((), dtype=torch.float32, device=dev)
+            _native._check(L.s3d_vgg_loss_train_fwd(nat._h, a.data_ptr(), b.data_ptr(), N, S, loss.data_ptr(), saved.data_ptr(),
+                                                    saved.numel() * 4, _native._stream(dev)))
+        ctx.nat, ctx.saved, ctx.shape = nat, saved, a.shape
+        return loss
+
+    @staticmethod
+    def backward(ctx, gout):
+        N, _, S, _ = ctx.shape
+        dev = gout.device
+        L = _native.lib()
+        gout = gout.detach().float().contiguous()
+        with torch.cuda.device(dev):
+            grad = torch.empty(ctx.shape, dtype=torch.float32, device=dev)
+            _native._check(L.s3d_vgg_loss_train_bwd(ctx.nat._h, N, S, gout.data_ptr(), ctx.saved.data_ptr(),
+                                                    ctx.saved.numel() * 4, grad.data_ptr(), _native._stream(dev)))
+        ctx.saved = None
+        return None, grad, None
+
+
+_VGG_HANDLES = {}
+
+
+def vgg_handle(vgg_module):
+    """Library handle holding ONLY the frozen perceptual network of ``vgg_module`` (a VGGPerceptualLoss), cached per
+    (device, tensor identities / versions): during training the model's other weights change every step, these never do."""
+    sd = {"vggptlossfunc." + k: v for k, v in vgg_module.state_dict().items()}
+    dev = next(iter(sd.values())).device
+    key = (str(dev),) + tuple((t.data_ptr(), t._version) for t in sd.values())
+    ent = _VGG_HANDLES.get(id(vgg_module))
+    if ent is None or ent[0] != key:
+        ent = (key, _native.NativeModel(sd, 12, dev))
+        _VGG_HANDLES[id(vgg_module)] = ent
+    return ent[1]
+
+
+def vgg_loss_train(vgg_module, a, b):
+    """pt_c_loss of VGGPerceptualLoss (vgg_perceptual_loss.py:51-71), differentiable w.r.t. ``a`` (N,3,S,S)."""
+    if not a.is_cuda:
+        raise _native.NativeError("vgg_loss_train needs CUDA tensors")
+    return _VGGLossTrainFn.apply(vgg_handle(vgg_module), a, b)

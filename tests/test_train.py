@@ -194,3 +194,38 @@ def test_train_decoder_dropout_statistics_and_determinism():
     assert not torch.equal(outs[0], outs[1])
     # dropout noise is (to first order) zero-mean around the p = 0 output: averaging 8 seeds shrinks the deviation ~ 1/sqrt(8)
     assert float((outs.mean(0) - base).abs().mean()) < 0.6 * float((outs[0] - base).abs().mean()) + 1e-3
+
+
+@pytest.mark.gpu
+def test_vgg_loss_training_kernels_match_torch_autograd():
+    """VGGPerceptualLoss forward + backward in the library (tcgen05 convolutions forward, data-gradient convolutions with
+    rotated weights backward) against torch autograd of the same module, both measured against a float64 evaluation."""
+    import copy
+    from slice3d_b200 import train_ops
+    torch.backends.cudnn.allow_tf32 = False
+    m = Slices3DRegModel(64, 12, "train")
+    m.load_state_dict(synth.synthetic_state_dict(m.state_dict(), 3))
+    vgg = m.vggptlossfunc.to("cuda:0")
+    g = torch.Generator().manual_seed(2)
+    a = (torch.rand(6, 3, 64, 64, generator=g) * 2 - 1).to("cuda:0")
+    b = (a.cpu() + 0.3 * torch.randn(6, 3, 64, 64, generator=g)).clamp(-1, 1).to("cuda:0")
+
+    def run(kind):
+        x = a.clone().to(torch.float64 if kind == "fp64" else torch.float32).requires_grad_(True)
+        if kind == "native":
+            loss = train_ops.vgg_loss_train(vgg, x, b)
+        elif kind == "torch":
+            loss = vgg(x, b)["pt_c_loss"]
+        else:
+            loss = copy.deepcopy(vgg).double()(x, b.double())["pt_c_loss"]
+        (loss * 0.001).backward()
+        return float(loss), x.grad.double()
+
+    (l64, g64), (ln, gn), (lt, gt) = run("fp64"), run("native"), run("torch")
+    rel = lambda u, v: float((u - v).norm() / v.norm())
+    print(f"vgg loss train: loss native {ln:.7f} / torch {lt:.7f} / fp64 {l64:.7f}; grad |g - g64| / |g64|: native {rel(gn, g64):.2e}, "
+          f"torch fp32 {rel(gt, g64):.2e}")
+    helpers.record("vgg_train_native_grad_rel_err_vs_fp64", rel(gn, g64))
+    helpers.record("vgg_train_torch_grad_rel_err_vs_fp64", rel(gt, g64))
+    assert abs(ln - l64) <= 1e-4 * abs(l64)
+    assert rel(gn, g64) < 2e-2 and rel(gn, g64) <= 3 * rel(gt, g64) + 1e-4
