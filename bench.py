@@ -332,6 +332,7 @@ def run_native(args):
                 line["e2e_api"] = e2e_api_block(model, gen, feed, nx, dev, args.steps)
                 line["sparse"] = sparse_block(dev, prec)
                 line["configs1_128"] = small_grid_block(nat, img_d, T_d, gen, dev, prec)
+                line["inputs"] = inputs_block(dev)
     if not args.no_train:
         line["train"] = train_leg(dev, world, rank, args.steps, args.warmup, max_over_ranks, barrier)
     if rank == 0:
@@ -452,6 +453,28 @@ def small_grid_block(nat, img_d, T_d, gen, dev, prec):
     ms = sum(ts[1:]) / 3
     return {"workload": "12 slices 256x256 -> 128^3 dense occupancy grid", "ms_per_step": ms, "value": nx ** 3 / (ms / 1e3),
             "unit": UNIT, "precision": prec}
+
+
+def inputs_block(dev):
+    """Input pipeline (datasets.py:37,75-118) for one training batch worth of decoded PNGs: 4 samples x 13 RGBA images,
+    137 x 137 -> 128 x 128 (compositing, Pillow-exact resize, to-tensor, normalise).  HBM-bound byte work: algorithmic
+    bytes = RGBA in + fp32 NCHW out."""
+    import torch
+    from slice3d_b200 import inputs
+    N, H, S = 52, 137, 128
+    rgba = torch.randint(0, 256, (N, H, H, 4), dtype=torch.uint8, device=dev)
+    for _ in range(3):
+        inputs.preprocess_rgba(rgba, S, True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(20):
+        inputs.preprocess_rgba(rgba, S, True)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 20
+    nbytes = N * H * H * 4 + N * 3 * S * S * 4
+    return {"workload": f"{N} RGBA images {H}x{H} -> {S}x{S} fp32 NCHW", "ms": ms, "images_per_s": N / (ms / 1e3),
+            "algorithmic_gb_per_s": nbytes / (ms / 1e3) / 1e9, "note": "two kernels; launch-bound at this size"}
 
 
 def train_leg(dev, world, rank, steps, warmup, max_over_ranks, barrier):

@@ -125,7 +125,9 @@ def vgg_handle(vgg_module):
     (device, tensor identities / versions): during training the model's other weights change every step, these never do."""
     sd = {"vggptlossfunc." + k: v for k, v in vgg_module.state_dict().items()}
     dev = next(iter(sd.values())).device
-    key = (str(dev),) + tuple((t.data_ptr(), t._version) for t in sd.values())
+    # parameters: identity + version (load_state_dict / .to() change them); buffers (mean, std): identity only -- DDP
+    # re-broadcasts buffers before every forward, which bumps their version without changing a bit
+    key = (str(dev),) + tuple(t.data_ptr() for t in sd.values()) + tuple(p._version for p in vgg_module.parameters())
     ent = _VGG_HANDLES.get(id(vgg_module))
     if ent is None or ent[0] != key:
         ent = (key, _native.NativeModel(sd, 12, dev))

@@ -115,9 +115,26 @@ for nx in (8, 7):
     vol[lo * 6:hi * 6] = full[lo * 6:hi * 6]
     sd.all_gather_slabs(vol, nx)
     ok = ok and torch.equal(vol, full)
+# rate-balanced (ragged) slabs: rank 1 is 3x as fast as rank 0
+b = sd.proportional_bounds(8, [1.0, 3.0])
+ok = ok and b == [0, 2, 8]
+full = torch.arange(8 * 6, dtype=torch.float32)
+vol = torch.full_like(full, -1.0)
+r = dist.get_rank()
+vol[b[r] * 6:b[r + 1] * 6] = full[b[r] * 6:b[r + 1] * 6]
+sd.all_gather_slabs(vol, 8, bounds=b)
+ok = ok and torch.equal(vol, full)
 dist.destroy_process_group()
 sys.exit(0 if ok else 3)
 """
+
+
+def test_proportional_bounds():
+    assert s3d_dist.proportional_bounds(256, [1.0] * 8) == s3d_dist.slab_bounds(256, 8)
+    b = s3d_dist.proportional_bounds(256, [1, 1, 1, 1, 1, 1, 1, 0.955])
+    assert b[0] == 0 and b[-1] == 256 and b[8] - b[7] == 31 and all(b[i + 1] - b[i] in (32, 33) for i in range(7))
+    assert s3d_dist.proportional_bounds(3, [1, 100, 1]) == [0, 1, 2, 3]  # every rank keeps a plane
+    assert s3d_dist.proportional_bounds(2, [1, 1, 1]) == s3d_dist.slab_bounds(2, 3)  # fewer planes than ranks
 
 
 def test_slab_all_gather_world2_gloo(tmp_path):
