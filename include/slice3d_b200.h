@@ -273,6 +273,15 @@ int s3d_mc_emit(const double* vol_dev, int32_t nx, int32_t ny, int32_t nz, doubl
                 const int64_t* vbase_dev, const int64_t* tbase_dev, const int32_t* tcount_dev, const uint8_t* owned_dev,
                 double* verts_dev, int64_t* tris_dev, void* stream);
 
+/* Exclusive prefix sum of n int32 counts into int64 offsets (out_dev[i] = in[0] + ... + in[i-1]; *total_dev = the sum): the
+ * running vertex / triangle counters of the sequential marching cubes between s3d_mc_count and s3d_mc_emit.  Three
+ * kernels (block sums, one-block scan of the sums, ranked writes); scratch of s3d_scan_scratch_bytes(n). */
+size_t s3d_scan_scratch_bytes(int64_t n);
+int s3d_exclusive_scan(const int32_t* in_dev, int64_t n, int64_t* out_dev, int64_t* total_dev, void* scratch_dev, void* stream);
+
+/* Debugging aid (tools/enc_check.py): simt != 0 makes s3d_encoder_fwd run the whole encoder on the fp32 CUDA-core GEMM. */
+int s3d_debug_set_encoder(s3d_model* m, int32_t simt);
+
 /* Instrumentation of the tensor-core decoder: 32 cycle counters (clock64 deltas summed over CTAs since the
  * last reset; index meaning in slice3d_b200/_native.py PROFILE_FIELDS).  Synchronises the device. */
 int s3d_debug_profile(int64_t* out32, int32_t reset);

@@ -21,7 +21,7 @@ SYMBOLS = [
     "s3d_abi_version", "s3d_last_error", "s3d_model_create", "s3d_model_destroy", "s3d_model_n_slices",
     "s3d_planes_bytes", "s3d_encoder_workspace_bytes", "s3d_encoder_fwd", "s3d_decoder_workspace_bytes",
     "s3d_decoder_fwd", "s3d_decoder_batch_fwd", "s3d_decoder_grid_fwd", "s3d_decoder_debug_tokens", "s3d_vgg_loss_workspace_bytes",
-    "s3d_vgg_loss_fwd", "s3d_vgg_loss_train_bytes", "s3d_vgg_loss_train_fwd", "s3d_vgg_loss_train_bwd", "s3d_mc_count", "s3d_mc_emit", "s3d_mise_scratch_ints",
+    "s3d_vgg_loss_fwd", "s3d_vgg_loss_train_bytes", "s3d_vgg_loss_train_fwd", "s3d_vgg_loss_train_bwd", "s3d_mc_count", "s3d_mc_emit", "s3d_scan_scratch_bytes", "s3d_exclusive_scan", "s3d_debug_set_encoder", "s3d_mise_scratch_ints",
     "s3d_mise_subdivide", "s3d_sparse_scratch_bytes", "s3d_sparse_rounds", "s3d_preprocess_workspace_bytes", "s3d_preprocess_rgba",
     "s3d_gt_encoder_workspace_bytes", "s3d_gt_encoder_fwd", "s3d_gt_decoder_workspace_bytes", "s3d_gt_decoder_fwd", "s3d_train_decoder_saved_bytes", "s3d_train_decoder_bwd_workspace_bytes",
     "s3d_train_decoder_fwd", "s3d_train_decoder_bwd", "s3d_selftest_umma", "s3d_debug_profile", "s3d_launch_count",
@@ -105,6 +105,12 @@ def lib():
     L.s3d_mc_emit.restype = C.c_int
     L.s3d_mc_emit.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p,
                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.s3d_scan_scratch_bytes.restype = C.c_size_t
+    L.s3d_scan_scratch_bytes.argtypes = [C.c_int64]
+    L.s3d_exclusive_scan.restype = C.c_int
+    L.s3d_exclusive_scan.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.s3d_debug_set_encoder.restype = C.c_int
+    L.s3d_debug_set_encoder.argtypes = [C.c_void_p, C.c_int32]
     L.s3d_mise_scratch_ints.restype = C.c_size_t
     L.s3d_mise_scratch_ints.argtypes = [C.c_int32, C.c_int32]
     L.s3d_mise_subdivide.restype = C.c_int
@@ -186,7 +192,7 @@ def mise_scratch_ints(res0, depth):
 
 def marching_cubes(vol, isovalue, tri_table, tri_count):
     """vol (nx,ny,nz) float64 CUDA tensor; tri_table (256,15) int8 and tri_count (256,) int32 on the same device.
-    -> (vertices (n,3) float64, triangles (m,3) int64): two kernels around torch.cumsum."""
+    -> (vertices (n,3) float64, triangles (m,3) int64): count, prefix sums and emit, all in the library."""
     if not vol.is_cuda or vol.dtype != torch.float64 or not vol.is_contiguous():
         raise NativeError("marching_cubes needs a contiguous float64 CUDA volume")
     nx, ny, nz = vol.shape
@@ -198,13 +204,18 @@ def marching_cubes(vol, isovalue, tri_table, tri_count):
         owned = torch.empty(cells, dtype=torch.uint8, device=dev)
         _check(L.s3d_mc_count(vol.data_ptr(), nx, ny, nz, float(isovalue), tri_count.data_ptr(), vcount.data_ptr(),
                               tcount.data_ptr(), owned.data_ptr(), _stream(dev)))
-        vsum = torch.cumsum(vcount, 0, dtype=torch.int64)
-        tsum = torch.cumsum(tcount, 0, dtype=torch.int64)
-        n_v, n_t = int(vsum[-1]), int(tsum[-1])
+        # the running vertex / triangle counters of the sequential scan: exclusive prefix sums (s3d_exclusive_scan)
+        vbase = torch.empty(cells, dtype=torch.int64, device=dev)
+        tbase = torch.empty(cells, dtype=torch.int64, device=dev)
+        totals = torch.empty(2, dtype=torch.int64, device=dev)
+        scratch = torch.empty(L.s3d_scan_scratch_bytes(cells), dtype=torch.uint8, device=dev)
+        st = _stream(dev)
+        _check(L.s3d_exclusive_scan(vcount.data_ptr(), cells, vbase.data_ptr(), totals.data_ptr(), scratch.data_ptr(), st))
+        _check(L.s3d_exclusive_scan(tcount.data_ptr(), cells, tbase.data_ptr(), totals.data_ptr() + 8, scratch.data_ptr(), st))
+        n_v, n_t = (int(x) for x in totals.tolist())  # the one host read: the output sizes
         verts = torch.empty((n_v, 3), dtype=torch.float64, device=dev)
         tris = torch.empty((n_t, 3), dtype=torch.int64, device=dev)
         if n_v:
-            vbase, tbase = vsum - vcount, tsum - tcount
             _check(L.s3d_mc_emit(vol.data_ptr(), nx, ny, nz, float(isovalue), tri_table.data_ptr(), vbase.data_ptr(),
                                  tbase.data_ptr(), tcount.data_ptr(), owned.data_ptr(), verts.data_ptr(), tris.data_ptr(),
                                  _stream(dev)))

@@ -676,6 +676,22 @@ int s3d_sparse_rounds(const s3d_model* m, const void* planes_dev, int32_t S, con
   return S3D_OK;
 }
 
+int s3d_debug_set_encoder(s3d_model* m, int32_t simt) {
+  if (!m) return S3D_ERR_BAD_ARG;
+  m->enc_simt = simt ? 1 : 0;
+  return S3D_OK;
+}
+
+size_t s3d_scan_scratch_bytes(int64_t n) { return n > 0 ? scan_scratch_bytes(n) : 0; }
+int s3d_exclusive_scan(const int32_t* in_dev, int64_t n, int64_t* out_dev, int64_t* total_dev, void* scratch_dev, void* stream) {
+  if (!in_dev || !out_dev || !total_dev || !scratch_dev || n < 0) {
+    set_error("exclusive_scan: bad argument");
+    return S3D_ERR_BAD_ARG;
+  }
+  return exclusive_scan_i32_i64(in_dev, n, reinterpret_cast<long long*>(out_dev), reinterpret_cast<long long*>(total_dev),
+                                scratch_dev, static_cast<cudaStream_t>(stream));
+}
+
 int s3d_debug_profile(int64_t* out32, int32_t reset) { return debug_profile(reinterpret_cast<long long*>(out32), reset); }
 
 int s3d_selftest_umma(int32_t mode, int32_t passes, const float* a_dev, const float* w_dev, float* d_dev,

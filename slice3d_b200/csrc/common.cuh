@@ -134,7 +134,7 @@ struct s3d_model {
   s3d::ConvTC tpvgg_d[14];     // [0] unused (3 output channels: fp32 path)
   float* pvgg_mean = nullptr;
   float* pvgg_std = nullptr;
-  int enc_simt = 0;            // S3D_ENCODER=simt: whole encoder on the fp32 CUDA-core path (debugging)
+  int enc_simt = 0;            // s3d_debug_set_encoder(m, 1): whole encoder on the fp32 CUDA-core path (debugging)
   // decoder
   s3d::DecF32 dec32;
   s3d::DecTC dectc;
@@ -172,6 +172,8 @@ int mc_count(const double* vol, int nx, int ny, int nz, double iso, const int* t
 int mc_emit(const double* vol, int nx, int ny, int nz, double iso, const signed char* table, const long long* vbase,
             const long long* tbase, const int* tcount, const unsigned char* owned, double* verts, long long* tris,
             cudaStream_t st);
+size_t scan_scratch_bytes(long long n);
+int exclusive_scan_i32_i64(const int* in, long long n, long long* out, long long* total, void* scratch, cudaStream_t st);
 
 // mise.cu
 size_t mise_scratch_ints(int res0, int depth);

@@ -329,8 +329,6 @@ int project_planes_tc(const s3d_model* m, int B, int S, EncBufs& e, float* pl, c
 
 // Weight images of the tensor-core convolutions + the skip half of each DoubleConv (see trunk_and_up_tc).
 int enctc_pack(s3d_model* m, cudaStream_t st) {
-  const char* env = getenv("S3D_ENCODER");
-  m->enc_simt = (env && std::string(env) == "simt") ? 1 : 0;
   auto pack_pvgg = [&]() -> int {
     for (int i = 1; i < 14; ++i) {
       S3D_TRY(convtc_pack(m, m->pvgg[i], m->pvgg[i].cin, 0, m->pvgg[i].cin, m->tpvgg[i], st));

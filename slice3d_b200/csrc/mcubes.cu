@@ -182,4 +182,94 @@ int mc_emit(const double* vol, int nx, int ny, int nz, double iso, const signed 
   return S3D_OK;
 }
 
+// ---- exclusive prefix sum int32 -> int64 (the sequential scan's running counters) --------------------------------------
+namespace {
+constexpr int SCB = 2048;  // elements per block (256 threads x 8)
+
+__global__ void __launch_bounds__(256) k_scan_block_sums(const int* __restrict__ in, long long n, long long* __restrict__ sums) {
+  __shared__ long long w[8];
+  const long long base = (long long)blockIdx.x * SCB + threadIdx.x * 8;
+  long long s = 0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s += base + j < n ? in[base + j] : 0;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) w[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    long long t = 0;
+    for (int i = 0; i < 8; ++i) t += w[i];
+    sums[blockIdx.x] = t;
+  }
+}
+// in place: sums[i] <- sums[0] + ... + sums[i-1]; *total = everything.  One block.
+__global__ void __launch_bounds__(1024) k_scan_sums(long long* __restrict__ sums, int nb, long long* __restrict__ total) {
+  __shared__ long long part[1024];
+  const int t = threadIdx.x, per = (nb + 1023) / 1024, lo = t * per, hi = min(nb, lo + per);
+  long long s = 0;
+  for (int i = lo; i < hi; ++i) s += sums[i];
+  part[t] = s;
+  __syncthreads();
+  for (int o = 1; o < 1024; o <<= 1) {
+    const long long v = t >= o ? part[t - o] : 0;
+    __syncthreads();
+    part[t] += v;
+    __syncthreads();
+  }
+  long long run = t ? part[t - 1] : 0;
+  for (int i = lo; i < hi; ++i) {
+    const long long c = sums[i];
+    sums[i] = run;
+    run += c;
+  }
+  if (t == 1023) *total = part[1023];
+}
+__global__ void __launch_bounds__(256) k_scan_write(const int* __restrict__ in, long long n, const long long* __restrict__ sums,
+                                                    long long* __restrict__ out) {
+  __shared__ long long w[8];
+  const long long base = (long long)blockIdx.x * SCB + threadIdx.x * 8;
+  int v[8];
+  long long s = 0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    v[j] = base + j < n ? in[base + j] : 0;
+    s += v[j];
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  long long incl = s;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const long long u = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += u;
+  }
+  if (lane == 31) w[warp] = incl;
+  __syncthreads();
+  long long run = sums[blockIdx.x] + incl - s;
+  for (int i = 0; i < warp; ++i) run += w[i];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    if (base + j < n) out[base + j] = run;
+    run += v[j];
+  }
+}
+}  // namespace
+
+size_t scan_scratch_bytes(long long n) { return (size_t)((n + SCB - 1) / SCB + 1) * sizeof(long long); }
+
+int exclusive_scan_i32_i64(const int* in, long long n, long long* out, long long* total, void* scratch, cudaStream_t st) {
+  if (n == 0) {
+    S3D_CUDA(cudaMemsetAsync(total, 0, sizeof(long long), st));
+    return S3D_OK;
+  }
+  const int nb = (int)((n + SCB - 1) / SCB);
+  long long* sums = static_cast<long long*>(scratch);
+  k_scan_block_sums<<<nb, 256, 0, st>>>(in, n, sums);
+  S3D_LAUNCH_CHECK();
+  k_scan_sums<<<1, 1024, 0, st>>>(sums, nb, total);
+  S3D_LAUNCH_CHECK();
+  k_scan_write<<<nb, 256, 0, st>>>(in, n, sums, out);
+  S3D_LAUNCH_CHECK();
+  return S3D_OK;
+}
+
 }  // namespace s3d

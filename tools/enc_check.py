@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Encoder check: tensor-core encoder vs the fp32 CUDA-core encoder (S3D_ENCODER=simt) vs the golden planes,
+"""Encoder check: tensor-core encoder vs the fp32 CUDA-core encoder (s3d_debug_set_encoder) vs the golden planes,
 plus timing of both.  Kernel-development tool, not a test."""
 import os
 import sys
@@ -8,7 +8,7 @@ import time
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from slice3d_b200 import synth  # noqa: E402
+from slice3d_b200 import _native, synth  # noqa: E402
 from tests import helpers  # noqa: E402
 
 name = sys.argv[1] if len(sys.argv) > 1 else "k12_s128_g128"
@@ -17,15 +17,12 @@ dev = "cuda:0"
 
 
 def run(simt):
-    if simt:
-        os.environ["S3D_ENCODER"] = "simt"
-    else:
-        os.environ.pop("S3D_ENCODER", None)
     m, sd = helpers.case_weights(case)
     m.load_state_dict(sd, strict=True)
     m = m.to(dev).eval()
     feed = {k: v.to(dev) for k, v in helpers.case_feed(case, 1).items()}
     nat = m.native()
+    _native.lib().s3d_debug_set_encoder(nat._h, 1 if simt else 0)
     planes, feats = nat.encode(feed["img_input"], want_feats=True)
     torch.cuda.synchronize()
     for _ in range(2):
