@@ -59,6 +59,9 @@ extern "C" {
 #define S3D_PREC_BF16 2   /* tcgen05, single bf16 pass (fast; measured 1.8e-2 max-abs)    */
 #define S3D_PREC_FP16X3 3 /* tcgen05, operands split into fp16 hi+lo, 3 MMA passes: same speed as BF16X3, ~10x
                              smaller error (22 instead of 16 mantissa bits); decoder activations must stay below 65504 */
+#define S3D_PREC_FP16F8 4 /* as FP16X3, but the two cross terms (x_lo.w_hi, x_hi.w_lo) of the FFN contractions -- 88 % of the
+                             MMA work -- run as scaled E4M3 products on kind::f8f6f4 at twice the rate; the leading term
+                             stays fp16.  ~5e-5 max-abs; FFN activations must stay below 511 */
 
 typedef struct s3d_model s3d_model;
 
@@ -281,6 +284,9 @@ int s3d_exclusive_scan(const int32_t* in_dev, int64_t n, int64_t* out_dev, int64
 
 /* Debugging aid (tools/enc_check.py): simt != 0 makes s3d_encoder_fwd run the whole encoder on the fp32 CUDA-core GEMM. */
 int s3d_debug_set_encoder(s3d_model* m, int32_t simt);
+/* Timing experiments on the tensor-core decoder (tools/dec_bench.py): bit 0 = the weight producer skips its copies (the
+ * results are garbage; shows what the L2 -> shared-memory weight stream costs).  0 = normal operation. */
+int s3d_debug_set_decoder_flags(int32_t flags);
 
 /* Instrumentation of the tensor-core decoder: 32 cycle counters (clock64 deltas summed over CTAs since the
  * last reset; index meaning in slice3d_b200/_native.py PROFILE_FIELDS).  Synchronises the device. */

@@ -12,8 +12,8 @@ import torch
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("S3D_LIB") or os.path.join(HERE, "_lib", "libslice3d_b200.so")  # S3D_LIB: kernel experiments
 
-PREC_FP32, PREC_BF16X3, PREC_BF16, PREC_FP16X3 = 0, 1, 2, 3
-PRECISIONS = {"fp32": PREC_FP32, "bf16x3": PREC_BF16X3, "bf16": PREC_BF16, "fp16x3": PREC_FP16X3}
+PREC_FP32, PREC_BF16X3, PREC_BF16, PREC_FP16X3, PREC_FP16F8 = 0, 1, 2, 3, 4
+PRECISIONS = {"fp32": PREC_FP32, "bf16x3": PREC_BF16X3, "bf16": PREC_BF16, "fp16x3": PREC_FP16X3, "fp16f8": PREC_FP16F8}
 ABI_VERSION = 1
 
 # every symbol include/slice3d_b200.h declares (tests check the library exports all of them)
@@ -21,7 +21,7 @@ SYMBOLS = [
     "s3d_abi_version", "s3d_last_error", "s3d_model_create", "s3d_model_destroy", "s3d_model_n_slices",
     "s3d_planes_bytes", "s3d_encoder_workspace_bytes", "s3d_encoder_fwd", "s3d_decoder_workspace_bytes",
     "s3d_decoder_fwd", "s3d_decoder_batch_fwd", "s3d_decoder_grid_fwd", "s3d_decoder_debug_tokens", "s3d_vgg_loss_workspace_bytes",
-    "s3d_vgg_loss_fwd", "s3d_vgg_loss_train_bytes", "s3d_vgg_loss_train_fwd", "s3d_vgg_loss_train_bwd", "s3d_mc_count", "s3d_mc_emit", "s3d_scan_scratch_bytes", "s3d_exclusive_scan", "s3d_debug_set_encoder", "s3d_mise_scratch_ints",
+    "s3d_vgg_loss_fwd", "s3d_vgg_loss_train_bytes", "s3d_vgg_loss_train_fwd", "s3d_vgg_loss_train_bwd", "s3d_mc_count", "s3d_mc_emit", "s3d_scan_scratch_bytes", "s3d_exclusive_scan", "s3d_debug_set_encoder", "s3d_debug_set_decoder_flags", "s3d_mise_scratch_ints",
     "s3d_mise_subdivide", "s3d_sparse_scratch_bytes", "s3d_sparse_rounds", "s3d_preprocess_workspace_bytes", "s3d_preprocess_rgba",
     "s3d_gt_encoder_workspace_bytes", "s3d_gt_encoder_fwd", "s3d_gt_decoder_workspace_bytes", "s3d_gt_decoder_fwd", "s3d_train_decoder_saved_bytes", "s3d_train_decoder_bwd_workspace_bytes",
     "s3d_train_decoder_fwd", "s3d_train_decoder_bwd", "s3d_selftest_umma", "s3d_debug_profile", "s3d_launch_count",
@@ -166,7 +166,7 @@ def _check(rc):
 
 def available_precisions():
     """Decoder arithmetic modes built into this revision of the library."""
-    return ("fp32", "fp16x3", "bf16x3", "bf16")
+    return ("fp32", "fp16x3", "fp16f8", "bf16x3", "bf16")
 
 
 def selftest_umma(mode, passes, a, w):

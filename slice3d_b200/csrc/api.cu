@@ -324,7 +324,7 @@ int check_decoder(const s3d_model* m, const void* planes, int S, const float* T,
     return S3D_ERR_BAD_ARG;
   }
   if (precision != S3D_PREC_FP32 && precision != S3D_PREC_BF16X3 && precision != S3D_PREC_BF16 &&
-      precision != S3D_PREC_FP16X3) {
+      precision != S3D_PREC_FP16X3 && precision != S3D_PREC_FP16F8) {
     set_error("decoder: unknown precision mode");
     return S3D_ERR_BAD_ARG;
   }
@@ -673,6 +673,11 @@ int s3d_sparse_rounds(const s3d_model* m, const void* planes_dev, int32_t S, con
     S3D_TRY(mise_subdivide(resolution0, depth, threshold, value_dev, known_dev, reinterpret_cast<signed char*>(cell_level_dev),
                            exists_dev, flags_dev, st));
   }
+  return S3D_OK;
+}
+
+int s3d_debug_set_decoder_flags(int32_t flags) {
+  decoder_tc_set_debug(flags);
   return S3D_OK;
 }
 

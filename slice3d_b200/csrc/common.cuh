@@ -93,6 +93,7 @@ struct DecF32 {
 struct DecTC {
   __nv_bfloat16* wimg = nullptr;  // bf16 hi/lo pairs
   __half* wimg_h = nullptr;        // fp16 hi/lo pairs (S3D_PREC_FP16X3)
+  uint8_t* wimg_f8 = nullptr;      // fp16 pairs (attention) + fp16 / e4m3 / e4m3 (FFN) (S3D_PREC_FP16F8)
   float* vec = nullptr;
   size_t wimg_elems = 0;
 };
@@ -255,6 +256,7 @@ int decoder_simt(const s3d_model* m, const float* planes, int S, const QueryCtx&
 // decoder_tc.cu
 int dectc_pack(s3d_model* m, cudaStream_t st);
 bool decoder_tc_supported(const s3d_model* m);
+void decoder_tc_set_debug(int flags);
 size_t decoder_tc_workspace_bytes(int64_t n);
 int decoder_tc(const s3d_model* m, const float* planes, int S, const QueryCtx& q, int64_t n, float out_scale,
                float* out, int precision, void* ws, size_t ws_bytes, cudaStream_t st, const int* n_dev = nullptr);

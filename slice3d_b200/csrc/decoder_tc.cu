@@ -207,7 +207,7 @@ __device__ __forceinline__ void warp_arrive(uint32_t bar, int lane) {
 // cta_group::2 MMAs (M = 256: 128 rows = one tile in each CTA) and every CTA streams only ITS HALF of each weight
 // part (N/2 rows of B), which halves the L2 -> shared-memory weight traffic and the shared-memory operand reads per SM
 // and doubles the MMA time one ring slot covers.  Everything outside the MMA / producer warps is per CTA.
-template <int NPASS, int CG, bool F16>
+template <int NPASS, int CG, bool F16, bool F8>
 __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -550,14 +550,56 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
         wait_a();
         // D1 is double-buffered, H single: the part of a chunk's epilogue that sits between two MMAs of the pipe
         // is only "h_free -> store H -> h_ready", and it is covered by MMA1 of the chunk after next.
+        // fp16f8 mode (F8): an FFN unit = part A [fp16(w * 2^8)] for the leading term xh.wh on kind::f16, then part B
+        // [e4m3(wh * 2^4) | e4m3(wl * 2^15)] for the two cross terms on kind::f8f6f4 (4 k-steps of 32 each): 16 MMAs per
+        // unit instead of 24, the accumulator carries 2^15 (tc_ptx.cuh).
         auto issue1 = [&](int c) {
-          unit_ss(TM_D1 + 128 * (c & 1), true);
+          if (F8) {
+            const uint32_t d = tmem + TM_D1 + 128 * (c & 1);
+            uint32_t w = wait_full();
+            tc_fence_after();
+            if (elect_one()) issue_part<CG, 1, 8, 16384u, BKB, ID128>(d, ax_hi, ax_hi, w, true);
+            __syncwarp();
+            release();
+            w = wait_full();
+            tc_fence_after();
+            if (elect_one()) {
+              const uint32_t al = make_desc_lo(ax_lo), ah = make_desc_lo(ax_lo + 16384u), bl = make_desc_lo(w), bh = make_desc_lo(w + 8192u);
+#pragma unroll
+              for (uint32_t ks = 0; ks < 4; ++ks) umma_f8_pair_lo(d, al + 2 * ks, bl + 2 * ks, ID128, 1u);
+#pragma unroll
+              for (uint32_t ks = 0; ks < 4; ++ks) umma_f8_pair_lo(d, ah + 2 * ks, bh + 2 * ks, ID128, 1u);
+            }
+            __syncwarp();
+            release();
+          } else {
+            unit_ss(TM_D1 + 128 * (c & 1), true);
+          }
           commit(B_D1READY0 + (c & 1));
         };
         auto issue2 = [&](int c) {
           const uint32_t h_hi = tmem + TM_HT, h_lo = h_hi + 64;
           uint32_t w = wait_full();
           tc_fence_after();
+          if (F8) {  // H in tensor memory: fp16(h * 2^7) 64 columns | e4m3(hl * 2^11) 32 columns | e4m3(hh) 32 columns
+            // (the two e4m3 operands in shared memory instead -- SS mode, H region -- were measured: 169 vs 166 kcycles
+            // per tile pair, no better: profiles/r2_summary.md)
+            if (elect_one()) issue_part_ts<CG, 1, 8, BKB, ID128>(tmem + TM_R, h_hi, h_hi, w, false);
+            __syncwarp();
+            release();
+            w = wait_full();
+            tc_fence_after();
+            if (elect_one()) {
+              const uint32_t bl = make_desc_lo(w), bh = make_desc_lo(w + 8192u);
+#pragma unroll
+              for (uint32_t ks = 0; ks < 4; ++ks) umma_f8_ts_pair_lo(tmem + TM_R, h_hi + 64 + 8 * ks, bl + 2 * ks, ID128, 1u);
+#pragma unroll
+              for (uint32_t ks = 0; ks < 4; ++ks) umma_f8_ts_pair_lo(tmem + TM_R, h_hi + 96 + 8 * ks, bh + 2 * ks, ID128, 1u);
+            }
+            __syncwarp();
+            release();
+            return;
+          }
           if (elect_one()) issue_part_ts<CG, (NPASS == 3 ? 2 : 1), 8, BKB, ID128>(tmem + TM_R, h_hi, h_lo, w, false);
           __syncwarp();
           release();
@@ -671,12 +713,30 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
       for (int cc = 0; cc < 4; ++cc)
         store_chunk<NPASS, F16>(ax_hi + (g >> 1) * 16384, ax_lo + (g >> 1) * 16384, r, (g & 1) * 4 + cc, v + 8 * cc);
     };
-    // R[r][32g..] = v + bias ; publish operand A + R to the MMA issuer
-    auto publish = [&](float* v, const float* bias) {
+    // the same as the A operand of linear1 in fp16f8 mode: fp16(x * 2^7) in the hi tile; e4m3((x - xh) * 2^11) and e4m3(xh)
+    // as two [128 rows][128 B] tiles in the lo region
+    auto store_ax_f8 = [&](const float* v) {
+      uint32_t h[16], l8[8], h8[8];
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) split8_f8(v + 8 * cc, h + 4 * cc, l8 + 2 * cc, h8 + 2 * cc);
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc)
+        *reinterpret_cast<uint4*>(ax_hi + (g >> 1) * 16384 + sw128_chunk_off(r, (g & 1) * 4 + cc)) =
+            make_uint4(h[4 * cc], h[4 * cc + 1], h[4 * cc + 2], h[4 * cc + 3]);
+#pragma unroll
+      for (int c2 = 0; c2 < 2; ++c2) {
+        const uint32_t off = sw128_chunk_off(r, 2 * g + c2);
+        *reinterpret_cast<uint4*>(ax_lo + off) = make_uint4(l8[4 * c2], l8[4 * c2 + 1], l8[4 * c2 + 2], l8[4 * c2 + 3]);
+        *reinterpret_cast<uint4*>(ax_lo + 16384 + off) = make_uint4(h8[4 * c2], h8[4 * c2 + 1], h8[4 * c2 + 2], h8[4 * c2 + 3]);
+      }
+    };
+    // R[r][32g..] = (v + bias) * rscale ; publish operand A + R to the MMA issuer
+    auto publish = [&](float* v, const float* bias, float rscale = 1.f) {
 #pragma unroll
       for (int c = 0; c < 32; c += 4) {
         const float4 b4 = *reinterpret_cast<const float4*>(bias + 32 * g + c);
-        v[c] += b4.x; v[c + 1] += b4.y; v[c + 2] += b4.z; v[c + 3] += b4.w;
+        v[c] = (v[c] + b4.x) * rscale; v[c + 1] = (v[c + 1] + b4.y) * rscale;
+        v[c + 2] = (v[c + 2] + b4.z) * rscale; v[c + 3] = (v[c + 3] + b4.w) * rscale;
       }
       tmem_st32(trow + TM_R + 32 * g, v);
       tmem_st_wait();
@@ -1011,8 +1071,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
           tmem_ld32(trow + TM_R + 32 * g, v);
           tmem_ld_wait();
           layer_norm(v, vec + V_LN1W, vec + V_LN1B);
-          store_ax(v);  // X' -> A operand of linear1 (the activation tile is idle between out-proj and the next layer)
-          publish(v, vec + V_B2);
+          // X' -> A operand of linear1 (the activation tile is idle between out-proj and the next layer)
+          if (F8) {
+            store_ax_f8(v);
+            publish(v, vec + V_B2, 32768.f);  // the FFN accumulates at scale 2^15 on top of the residual
+          } else {
+            store_ax(v);
+            publish(v, vec + V_B2);
+          }
         }
         lap(PF_LN1)
         // -------------------------------------------------------------- FFN hidden chunks (32 columns per thread)
@@ -1030,16 +1096,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               const float4 b4 = *reinterpret_cast<const float4*>(vec + V_B1 + c * 128 + 32 * g + 4 * j);
-              d[4 * j] = fmaxf(d[4 * j] + b4.x, 0.f);
-              d[4 * j + 1] = fmaxf(d[4 * j + 1] + b4.y, 0.f);
-              d[4 * j + 2] = fmaxf(d[4 * j + 2] + b4.z, 0.f);
-              d[4 * j + 3] = fmaxf(d[4 * j + 3] + b4.w, 0.f);
+              const float ds = F8 ? F8_ACC_INV : 1.f;
+              d[4 * j] = fmaxf(fmaf(d[4 * j], ds, b4.x), 0.f);
+              d[4 * j + 1] = fmaxf(fmaf(d[4 * j + 1], ds, b4.y), 0.f);
+              d[4 * j + 2] = fmaxf(fmaf(d[4 * j + 2], ds, b4.z), 0.f);
+              d[4 * j + 3] = fmaxf(fmaf(d[4 * j + 3], ds, b4.w), 0.f);
             }
             lap(PF_FFN_MATH)
             {  // H chunk -> A operand of linear2 in tensor memory (16 packed columns per thread, hi and lo)
-              uint32_t hh[16], hl[16];
+              uint32_t hh[16], hl[16];  // (fp16f8: hl[0..7] = e4m3 lo parts, hl[8..15] = e4m3 hi parts)
 #pragma unroll
-              for (int j = 0; j < 4; ++j) split8x<NPASS == 3, F16>(d + 8 * j, hh + 4 * j, hl + 4 * j);
+              for (int j = 0; j < 4; ++j) {
+                if (F8) split8_f8(d + 8 * j, hh + 4 * j, hl + 2 * j, hl + 8 + 2 * j);
+                else split8x<NPASS == 3, F16>(d + 8 * j, hh + 4 * j, hl + 4 * j);
+              }
               if (c > 0) {  // MMA2 of the previous chunk has finished reading H
                 mbar_wait(bar(B_HFREE), ph_hf);
                 ph_hf ^= 1u;
@@ -1047,7 +1117,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
               }
               lap(PF_FFN_WAIT_HFREE)
               tmem_st16(trow + TM_HT + 16 * g, hh);
-              if (NPASS == 3) tmem_st16(trow + TM_HT + 64 + 16 * g, hl);
+              if (F8) {
+                tmem_st8(trow + TM_HT + 64 + 8 * g, hl);
+                tmem_st8(trow + TM_HT + 96 + 8 * g, hl + 8);
+              } else if (NPASS == 3) {
+                tmem_st16(trow + TM_HT + 64 + 16 * g, hl);
+              }
               tmem_st_wait();
             }
             tc_fence_before();  // orders this thread's D1 load / H store before the MMAs that follow the arrive
@@ -1064,6 +1139,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
           float v[32];
           tmem_ld32(trow + TM_R + 32 * g, v);
           tmem_ld_wait();
+          if (F8) {
+#pragma unroll
+            for (int c = 0; c < 32; ++c) v[c] *= F8_ACC_INV;
+          }
           layer_norm(v, vec + V_LN2W, vec + V_LN2B);
           if (layer < 2) {
             store_ax(v);
@@ -1293,6 +1372,111 @@ void pack_unit(F W, int NU, int KU, uint8_t* dst, bool f16 = false) {
       }
 }
 
+// fp16f8 unit: part A = fp16(w * 2^8) as [2 k-blocks][128 n][64 k]; part B = e4m3(fp16(w) * 2^4) as [128 n][128 k] followed
+// by e4m3((w - fp16(w)) * 2^15) as [128 n][128 k]; all tiles K-major / 128-byte swizzle.
+template <class F>
+void pack_unit_f8(F W, uint8_t* dst) {
+  uint16_t* hi = reinterpret_cast<uint16_t*>(dst);
+  uint8_t* wh8 = dst + UNIT_PART_BYTES;
+  uint8_t* wl8 = dst + UNIT_PART_BYTES + 16384;
+  for (int n = 0; n < 128; ++n)
+    for (int k = 0; k < 128; ++k) {
+      const float w = W(n, k);
+      const float wh = f16_val(f16_bits(w));
+      const int kb = k >> 6, kk = k & 63;
+      hi[((size_t)kb * 128 * 128 + sw128_chunk_off(n, kk >> 3) + (kk & 7) * 2) / 2] = f16_bits(wh * 256.f);
+      const size_t o8 = sw128_chunk_off(n, k >> 4) + (k & 15);
+      wh8[o8] = (uint8_t)__nv_cvt_float_to_fp8(wh * 16.f, __NV_SATFINITE, __NV_E4M3);
+      wl8[o8] = (uint8_t)__nv_cvt_float_to_fp8((w - wh) * 32768.f, __NV_SATFINITE, __NV_E4M3);
+    }
+}
+
+// Self-test of the fp16 + 2 x fp8 unit (the FFN contractions of S3D_PREC_FP16F8): D = A . W^T on one tile, single CTA.
+// mode 0: A in shared memory (linear1's path), mode 1: A in tensor memory (linear2's path).
+__global__ void __launch_bounds__(128, 1) umma_selftest_f8_kernel(const float* __restrict__ A, const uint8_t* wimg, int mode,
+                                                                  float* __restrict__ D) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t sbase = (raw + 1023u) & ~1023u;
+  uint8_t* sgen = smem_raw + (sbase - raw);
+  const int warp = threadIdx.x >> 5;
+  const int r = threadIdx.x;
+  const uint32_t full = sbase + OFF_BAR, done = sbase + OFF_BAR + 8;
+  if (threadIdx.x == 0) {
+    mbar_init(full, 1);
+    mbar_init(done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(sbase + OFF_TMEMPTR, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(sgen + OFF_TMEMPTR);
+  const uint32_t trow = tmem + (static_cast<uint32_t>(warp * 32) << 16);
+  if (threadIdx.x == 0) {
+    mbar_arrive_expect_tx(full, UNIT_STRIDE_BYTES);
+    for (uint32_t o = 0; o < UNIT_STRIDE_BYTES; o += 16384) bulk_g2s(sbase + OFF_H + o, wimg + o, 16384, full);
+  }
+  for (int j = 0; j < 4; ++j) {  // 32 channels at a time, like compute thread (r, g = j)
+    float v[32];
+    for (int i = 0; i < 32; ++i) v[i] = A[r * 128 + 32 * j + i];
+    uint32_t h[16], l8[8], h8[8];
+    for (int c = 0; c < 4; ++c) split8_f8(v + 8 * c, h + 4 * c, l8 + 2 * c, h8 + 2 * c);
+    if (mode == 0) {
+      for (int c = 0; c < 4; ++c)
+        *reinterpret_cast<uint4*>(sgen + OFF_AX_HI + (j >> 1) * 16384 + sw128_chunk_off(r, (j & 1) * 4 + c)) =
+            make_uint4(h[4 * c], h[4 * c + 1], h[4 * c + 2], h[4 * c + 3]);
+      for (int c = 0; c < 2; ++c) {
+        *reinterpret_cast<uint4*>(sgen + OFF_AX_LO + sw128_chunk_off(r, 2 * j + c)) =
+            make_uint4(l8[4 * c], l8[4 * c + 1], l8[4 * c + 2], l8[4 * c + 3]);
+        *reinterpret_cast<uint4*>(sgen + OFF_AX_LO + 16384 + sw128_chunk_off(r, 2 * j + c)) =
+            make_uint4(h8[4 * c], h8[4 * c + 1], h8[4 * c + 2], h8[4 * c + 3]);
+      }
+    } else {
+      tmem_st16(trow + TM_HT + 16 * j, h);
+      tmem_st8(trow + TM_HT + 64 + 8 * j, l8);
+      tmem_st8(trow + TM_HT + 96 + 8 * j, h8);
+    }
+  }
+  if (mode == 0) fence_proxy_async_smem();
+  else {
+    tmem_st_wait();
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    mbar_wait(full, 0);
+    tc_fence_after();
+    const uint32_t w = sbase + OFF_H;
+    constexpr uint32_t ID = make_idesc_f16(128);
+    if (mode == 0) {
+      issue_part<1, 1, 8, 16384u, 16384u, ID>(tmem, sbase + OFF_AX_HI, sbase + OFF_AX_HI, w, true);
+      for (uint32_t ks = 0; ks < 4; ++ks) {
+        umma_f8(tmem, make_desc_sw128(sbase + OFF_AX_LO + 32 * ks), make_desc_sw128(w + UNIT_PART_BYTES + 32 * ks), ID, 1u);
+        umma_f8(tmem, make_desc_sw128(sbase + OFF_AX_LO + 16384 + 32 * ks), make_desc_sw128(w + UNIT_PART_BYTES + 16384 + 32 * ks), ID, 1u);
+      }
+    } else {
+      issue_part_ts<1, 1, 8, 16384u, ID>(tmem, tmem + TM_HT, tmem + TM_HT, w, true);
+      for (uint32_t ks = 0; ks < 4; ++ks) {
+        umma_f8_ts(tmem, tmem + TM_HT + 64 + 8 * ks, make_desc_sw128(w + UNIT_PART_BYTES + 32 * ks), ID, 1u);
+        umma_f8_ts(tmem, tmem + TM_HT + 96 + 8 * ks, make_desc_sw128(w + UNIT_PART_BYTES + 16384 + 32 * ks), ID, 1u);
+      }
+    }
+    umma_commit(done);
+  }
+  mbar_wait(done, 0);
+  tc_fence_after();
+  for (int j = 0; j < 4; ++j) {
+    float v[32];
+    tmem_ld32(trow + 32 * j, v);
+    tmem_ld_wait();
+    for (int c = 0; c < 32; ++c) D[r * 128 + 32 * j + c] = v[c] * F8_ACC_INV;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
 }  // namespace
 
 // Build the operand images of the three attention layers from the fp32 [K][N] matrices already
@@ -1306,9 +1490,10 @@ int dectc_pack(s3d_model* m, cudaStream_t st) {
     S3D_CUDA(cudaStreamSynchronize(st));
     return S3D_OK;
   };
-  // two images: bf16 hi/lo pairs (S3D_PREC_BF16X3, S3D_PREC_BF16) and fp16 hi/lo pairs (S3D_PREC_FP16X3)
-  for (int fmt = 0; fmt < 2; ++fmt) {
-    const bool f16 = fmt == 1;
+  // three images: bf16 hi/lo pairs (S3D_PREC_BF16X3, S3D_PREC_BF16), fp16 hi/lo pairs (S3D_PREC_FP16X3), and fp16 pairs for
+  // the attention units + fp16 / fp8 / fp8 for the FFN units (S3D_PREC_FP16F8)
+  for (int fmt = 0; fmt < 3; ++fmt) {
+    const bool f16 = fmt >= 1, f8 = fmt == 2;
     for (int l = 0; l < 3; ++l) {
       const DecLayerF32& L = m->dec32.L[l];
       std::vector<float> win, wo, w1, w2;  // each [K][N]: W(n,k) = w[k*N + n]
@@ -1325,11 +1510,15 @@ int dectc_pack(s3d_model* m, cudaStream_t st) {
       pack_unit([&](int n, int k) { return wo[(size_t)k * 128 + n]; }, 128, 128, dst + (size_t)g * UNIT_STRIDE_BYTES, f16);
       ++g;
       auto pack_w1 = [&](int c) {  // hidden units 128c .. +127 as output columns
-        pack_unit([&](int n, int k) { return w1[(size_t)k * 2048 + 128 * c + n]; }, 128, 128, dst + (size_t)g * UNIT_STRIDE_BYTES, f16);
+        auto W = [&](int n, int k) { return w1[(size_t)k * 2048 + 128 * c + n]; };
+        if (f8) pack_unit_f8(W, dst + (size_t)g * UNIT_STRIDE_BYTES);
+        else pack_unit(W, 128, 128, dst + (size_t)g * UNIT_STRIDE_BYTES, f16);
         ++g;
       };
       auto pack_w2 = [&](int c) {  // hidden units 128c .. +127 as the contraction index
-        pack_unit([&](int n, int k) { return w2[(size_t)(128 * c + k) * 128 + n]; }, 128, 128, dst + (size_t)g * UNIT_STRIDE_BYTES, f16);
+        auto W = [&](int n, int k) { return w2[(size_t)(128 * c + k) * 128 + n]; };
+        if (f8) pack_unit_f8(W, dst + (size_t)g * UNIT_STRIDE_BYTES);
+        else pack_unit(W, 128, 128, dst + (size_t)g * UNIT_STRIDE_BYTES, f16);
         ++g;
       };
       // consumption order of the FFN pipeline: W1_0, W1_1, then (W2_c, W1_{c+2}) ...
@@ -1345,7 +1534,8 @@ int dectc_pack(s3d_model* m, cudaStream_t st) {
     m->allocs.push_back(d);
     S3D_CUDA(cudaMemcpyAsync(d, img.data(), total, cudaMemcpyHostToDevice, st));
     S3D_CUDA(cudaStreamSynchronize(st));
-    if (f16) m->dectc.wimg_h = static_cast<__half*>(d);
+    if (f8) m->dectc.wimg_f8 = static_cast<uint8_t*>(d);
+    else if (f16) m->dectc.wimg_h = static_cast<__half*>(d);
     else m->dectc.wimg = static_cast<__nv_bfloat16*>(d);
   }
   m->dectc.wimg_elems = total / 2;
@@ -1377,6 +1567,9 @@ int dectc_pack(s3d_model* m, cudaStream_t st) {
   return S3D_OK;
 }
 
+static int g_tc_dbg = 0;  // s3d_debug_set_decoder_flags: timing experiments (bit 0: skip the weight copies -> garbage results)
+void decoder_tc_set_debug(int flags) { g_tc_dbg = flags; }
+
 bool decoder_tc_supported(const s3d_model* m) { return m && m->K >= 1 && m->K <= 12 && m->dectc.wimg != nullptr; }
 
 int debug_profile(long long* out32, int reset) {
@@ -1404,12 +1597,15 @@ int decoder_tc(const s3d_model* m, const float* planes, int S, const QueryCtx& q
   }
   if (n <= 0) return S3D_OK;
   TcParams p{};
-  p.wimg = reinterpret_cast<const uint8_t*>(precision == S3D_PREC_FP16X3 ? (const void*)m->dectc.wimg_h : (const void*)m->dectc.wimg);
+  p.wimg = reinterpret_cast<const uint8_t*>(precision == S3D_PREC_FP16F8   ? (const void*)m->dectc.wimg_f8
+                                            : precision == S3D_PREC_FP16X3 ? (const void*)m->dectc.wimg_h
+                                                                           : (const void*)m->dectc.wimg);
   p.vecs = m->dectc.vec;
   p.planes = planes;
   p.S = S;
   p.q = q;
   p.n = n;
+  p.dbg = g_tc_dbg;
   p.K = m->K;
   p.n_dev = n_dev;
   p.out_scale = out_scale;
@@ -1447,9 +1643,10 @@ int decoder_tc(const s3d_model* m, const float* planes, int S, const QueryCtx& q
   {  // CTA pairs: clusters of 2, one pair per TPC
     const long long pairs = (p.num_tiles + 1) / 2;
     const unsigned g2 = 2u * (unsigned)((pairs < sms / 2 && !n_dev) ? pairs : sms / 2);
-    if (precision == S3D_PREC_FP16X3) S3D_TRY(launch(decoder_tc_kernel<3, 2, true>, g2, 2));
-    else if (precision == S3D_PREC_BF16X3) S3D_TRY(launch(decoder_tc_kernel<3, 2, false>, g2, 2));
-    else S3D_TRY(launch(decoder_tc_kernel<1, 2, false>, g2, 2));
+    if (precision == S3D_PREC_FP16F8) S3D_TRY(launch(decoder_tc_kernel<3, 2, true, true>, g2, 2));
+    else if (precision == S3D_PREC_FP16X3) S3D_TRY(launch(decoder_tc_kernel<3, 2, true, false>, g2, 2));
+    else if (precision == S3D_PREC_BF16X3) S3D_TRY(launch(decoder_tc_kernel<3, 2, false, false>, g2, 2));
+    else S3D_TRY(launch(decoder_tc_kernel<1, 2, false, false>, g2, 2));
   }
   S3D_LAUNCH_CHECK();
   return S3D_OK;
@@ -1458,7 +1655,8 @@ int decoder_tc(const s3d_model* m, const float* planes, int S, const QueryCtx& q
 // Self-test of the UMMA plumbing (descriptors, swizzle, bulk copy, TMEM load): see include/slice3d_b200.h.
 int umma_selftest(int mode, int passes, const float* a_dev, const float* w_dev, float* d_dev, cudaStream_t st) {
   const bool f16 = passes == 4;  // passes = 4: the three-pass schedule with fp16 hi/lo pairs (S3D_PREC_FP16X3)
-  if ((mode != 0 && mode != 1) || (passes != 1 && passes != 3 && passes != 4) || !a_dev || !w_dev || !d_dev) {
+  const bool f8 = passes == 5;   // passes = 5: fp16 leading term + two fp8 cross terms (S3D_PREC_FP16F8's FFN units)
+  if ((mode != 0 && mode != 1) || (passes != 1 && passes != 3 && passes != 4 && passes != 5) || !a_dev || !w_dev || !d_dev) {
     set_error("selftest: bad argument");
     return S3D_ERR_BAD_ARG;
   }
@@ -1467,11 +1665,15 @@ int umma_selftest(int mode, int passes, const float* a_dev, const float* w_dev, 
   S3D_CUDA(cudaMemcpyAsync(w.data(), w_dev, w.size() * sizeof(float), cudaMemcpyDeviceToHost, st));
   S3D_CUDA(cudaStreamSynchronize(st));
   std::vector<uint8_t> img(UNIT_STRIDE_BYTES);
-  pack_unit([&](int n, int k) { return w[(size_t)n * K + k]; }, N, K, img.data(), f16);
+  if (f8) pack_unit_f8([&](int n, int k) { return w[(size_t)n * K + k]; }, img.data());
+  else pack_unit([&](int n, int k) { return w[(size_t)n * K + k]; }, N, K, img.data(), f16);
   void* d = nullptr;
   S3D_CUDA(cudaMalloc(&d, UNIT_STRIDE_BYTES));
   S3D_CUDA(cudaMemcpyAsync(d, img.data(), UNIT_STRIDE_BYTES, cudaMemcpyHostToDevice, st));
-  if (f16) {
+  if (f8) {
+    cudaFuncSetAttribute(umma_selftest_f8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    umma_selftest_f8_kernel<<<1, 128, SMEM_BYTES, st>>>(a_dev, static_cast<const uint8_t*>(d), mode, d_dev);
+  } else if (f16) {
     cudaFuncSetAttribute(umma_selftest_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     umma_selftest_kernel<3, true><<<1, 128, SMEM_BYTES, st>>>(a_dev, static_cast<const uint8_t*>(d), mode, d_dev);
   } else if (passes == 3) {

@@ -4,6 +4,7 @@
 #pragma once
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
+#include <cuda_fp8.h>
 #include <stdint.h>
 
 namespace s3d {
@@ -300,6 +301,45 @@ __device__ __forceinline__ void umma_ts_pair_lo(uint32_t d_tmem, uint32_t a_tmem
       : "memory");
 }
 
+// kind::f8f6f4 with E4M3 operands (K = 32 per instruction: twice the rate of kind::f16), fp32 accumulate.  The
+// instruction descriptor has the same bit layout as kind::f16's and E4M3 is format code 0 like F16, so make_idesc_f16()
+// serves both; 8-bit K-major SW128 tiles are [rows][128 elements = 128 B], a k-step advances the start address by 32 B.
+__device__ __forceinline__ void umma_f8(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_f8_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_f8_pair_lo(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "mov.b64 da, {%1, %5};\n\t"
+      "mov.b64 db, {%2, %5};\n\t"
+      "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], da, db, %3, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(DESC_HI)
+      : "memory");
+}
+__device__ __forceinline__ void umma_f8_ts_pair_lo(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 db;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "mov.b64 db, {%2, %5};\n\t"
+      "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], [%1], db, %3, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_tmem), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(DESC_HI)
+      : "memory");
+}
+
 // Arrive on an mbarrier once every previously issued MMA of this thread has completed
 // (implies tcgen05.fence::before_thread_sync).
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
@@ -386,6 +426,31 @@ __device__ __forceinline__ void split8_hn(const float* v, uint32_t* h, uint32_t*
     l[i] = *reinterpret_cast<const uint32_t*>(&l2);
   }
 }
+// ---------------------------------------------------------------- fp16 + 2 x fp8 split ("fp16f8")
+// x * w = xh * wh + xl * wh + xh * wl (+ xl * wl, dropped) with xh = fp16(x), xl = x - xh.  The leading term runs on
+// kind::f16; the two cross terms are 2^-11 of it, so 3-4 bits of each factor are enough for them: they run on
+// kind::f8f6f4 (E4M3) at twice the rate.  All three terms accumulate in ONE fp32 accumulator, so they share one power-of
+// -two scale 2^15: the leading term's operands carry 2^7 (activations) and 2^8 (weights), the cross terms 2^11 * 2^4
+// (xl * wh) and 2^0 * 2^15 (xh * wl), which also puts every fp8 factor near 1.  The epilogue multiplies by 2^-15.
+constexpr float F8_XS = 128.f, F8_XLS = 2048.f, F8_ACC_INV = 1.f / 32768.f;
+// 8 floats -> fp16(x * 2^7) x 8 (4 words), e4m3((x - fp16(x)) * 2^11) x 8 (2 words), e4m3(fp16(x)) x 8 (2 words)
+__device__ __forceinline__ void split8_f8(const float* v, uint32_t* h, uint32_t* l8, uint32_t* h8) {
+  uint16_t pl[4], ph[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const __half2 h2 = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+    const float h0 = __low2float(h2), h1 = __high2float(h2);
+    const __half2 hs = __floats2half2_rn(h0 * F8_XS, h1 * F8_XS);  // exact: a power-of-two multiple of an fp16 number
+    h[i] = *reinterpret_cast<const uint32_t*>(&hs);
+    pl[i] = __nv_cvt_float2_to_fp8x2(make_float2((v[2 * i] - h0) * F8_XLS, (v[2 * i + 1] - h1) * F8_XLS), __NV_SATFINITE, __NV_E4M3);
+    ph[i] = __nv_cvt_float2_to_fp8x2(make_float2(h0, h1), __NV_SATFINITE, __NV_E4M3);
+  }
+  l8[0] = pl[0] | (static_cast<uint32_t>(pl[1]) << 16);
+  l8[1] = pl[2] | (static_cast<uint32_t>(pl[3]) << 16);
+  h8[0] = ph[0] | (static_cast<uint32_t>(ph[1]) << 16);
+  h8[1] = ph[2] | (static_cast<uint32_t>(ph[3]) << 16);
+}
+
 // Instruction descriptor, kind::f16 with fp16 operands (both K-major), fp32 accumulate.
 __host__ __device__ constexpr uint32_t make_idesc_f16(int n, int m = 128) {
   return (1u << 4) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);

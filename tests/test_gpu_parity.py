@@ -13,7 +13,7 @@ from tests import helpers
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-4
-TC3 = ["fp16x3", "bf16x3"]  # the two <= 1e-4 tensor-core modes (fp16 / bf16 hi-lo pairs, 3 passes)
+TC3 = ["fp16x3", "fp16f8", "bf16x3"]  # the <= 1e-4 tensor-core modes (fp16 / bf16 hi-lo pairs, 3 passes; fp16 + 2 x fp8 in the FFN)
 CASES = ["cfg0_k4_s128_g64", "k12_s128_g128", "k12_s256_g128_g256"]
 DEV = "cuda:0"
 
@@ -208,6 +208,27 @@ def test_empty_and_ragged_queries():
 
 
 # ------------------------------------------------------------------ tcgen05 decoder
+@pytest.mark.parametrize("mode", [0, 1])
+def test_umma_selftest_fp16_plus_fp8_cross_terms(mode):
+    """The FFN unit of S3D_PREC_FP16F8: x.w = xh.wh (kind::f16) + xl.wh + xh.wl (kind::f8f6f4, E4M3, K = 32), one fp32
+    accumulator at scale 2^15.  Against an exact emulation of the same operand roundings (pins descriptors, 8-bit tile
+    layout and TMEM packing) and against fp64 (the scheme's own error)."""
+    g = torch.Generator().manual_seed(21 + mode)
+    a = torch.randn(128, 128, generator=g) * 1.5
+    w = torch.randn(128, 128, generator=g) * 0.1
+    d = _native.selftest_umma(mode, 5, a.to(DEV), w.to(DEV)).cpu().double()
+    f8 = lambda t: t.clamp(-448, 448).to(torch.float8_e4m3fn).double()
+    ah = a.half().float()
+    wh = w.half().float()
+    emu = ((ah * 128).double() @ (wh * 256).double().t() + f8((a - ah) * 2048) @ f8(wh * 16).t()
+           + f8(ah) @ f8((w - wh) * 32768).t()) / 32768
+    want = a.double() @ w.double().t()
+    e_emu, e_true = float((d - emu).abs().max()), float((d - want).abs().max())
+    print(f"fp16 + 2 x fp8 unit, mode {mode}: vs exact emulation {e_emu:.3e}, vs fp64 {e_true:.3e} (|d| max {float(want.abs().max()):.2f})")
+    assert e_emu < 2e-5, e_emu
+    assert e_true < 5e-4, e_true
+
+
 @pytest.mark.parametrize("mode,passes", [(0, 3), (1, 3), (0, 1), (1, 1), (0, 4), (1, 4)])
 def test_umma_selftest(mode, passes):
     """One UMMA tile vs fp64: validates descriptors / swizzle / bulk copy / TMEM load."""
@@ -450,7 +471,7 @@ def test_decoder_border_and_clamp_cases_match_oracle():
     q = oracle.prepare_queries(pts.unsqueeze(0), None, "test")
     with torch.no_grad():
         want = oracle.decode(sd, [f.cpu() for f in feats], q, T.unsqueeze(0), 12)[0]
-    for prec in ("fp32", "fp16x3", "bf16x3"):
+    for prec in ("fp32", "fp16x3", "fp16f8", "bf16x3"):
         got = nat.decode(planes, 0, pts.to(DEV), T.to(DEV), precision=prec)
         err = helpers.maxabs(got.cpu(), want)
         print(f"border/clamp cases, {prec}: max-abs {err:.3e} over {pts.shape[0]} points")

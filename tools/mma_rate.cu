@@ -11,7 +11,7 @@
 
 using namespace s3d::ptx;
 
-template <int CG, bool TS, int N>
+template <int CG, bool TS, int N, bool F8 = false, int MIX = 0>
 __global__ void __launch_bounds__(128, 1) rate_kernel(int iters, int ks, long long* out) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -43,7 +43,10 @@ __global__ void __launch_bounds__(128, 1) rate_kernel(int iters, int ks, long lo
     for (int it = 0; it < iters; ++it) {
       for (int k = 0; k < ks; ++k) {
         const uint32_t kin = (k & 3) * 32;
-        if (TS) {
+        if (F8 && (MIX == 0 || (MIX == -1 ? (it > 0 || k > 0) : MIX == -2 ? (it < iters / 2) : (k % (2 * MIX)) >= MIX))) {  // kind::f8f6f4, E4M3, K = 32 per instruction (CTA pairs only); MIX: alternate with kind::f16 every MIX MMAs
+          if (TS) umma_f8_ts_pair_lo(tmem, tmem + 256 + 8 * (k & 3), make_desc_lo(b_s) + (kin >> 4), idesc, k ? 1u : 0u);
+          else umma_f8_pair_lo(tmem, make_desc_lo(a_s) + (kin >> 4), make_desc_lo(b_s) + (kin >> 4), idesc, k ? 1u : 0u);
+        } else if (TS) {
           if (CG == 2) umma_bf16_ts_pair(tmem, tmem + 256 + 8 * (k & 7), bd + (kin >> 4), idesc, k ? 1u : 0u);
           else umma_bf16_ts(tmem, tmem + 256 + 8 * (k & 7), bd + (kin >> 4), idesc, k ? 1u : 0u);
         } else {
@@ -69,12 +72,12 @@ __global__ void __launch_bounds__(128, 1) rate_kernel(int iters, int ks, long lo
   }
 }
 
-template <int CG, bool TS, int N>
+template <int CG, bool TS, int N, bool F8 = false, int MIX = 0>
 void run(int grid, int iters, int ks) {
   long long* d;
   cudaMalloc(&d, grid * sizeof(long long));
   cudaMemset(d, 0, grid * sizeof(long long));
-  auto kern = rate_kernel<CG, TS, N>;
+  auto kern = rate_kernel<CG, TS, N, F8, MIX>;
   const int smem = 16384 + 32768 + 64 + 1024;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   cudaLaunchConfig_t cfg{};
@@ -101,8 +104,8 @@ void run(int grid, int iters, int ks) {
   long long mx = 0;
   for (int i = 0; i < grid; i += CG) mx = h[i] > mx ? h[i] : mx;
   const double per = (double)mx / ((double)iters * ks);
-  printf("CG=%d %s N=%3d ks=%2d grid=%3d: %7.1f cycles/MMA  (floor %3d)  -> %5.1f %% of the %d-FLOP/clk/SM pipe\n", CG,
-         TS ? "TS" : "SS", N, ks, grid, per, N / 2, 100.0 * (N / 2) / per, 8192);
+  printf("CG=%d %s %s N=%3d ks=%2d grid=%3d: %7.1f cycles/MMA  (floor %3d)  -> %5.1f %% of the %d-FLOP/clk/SM pipe\n", CG,
+         TS ? "TS" : "SS", F8 ? (MIX ? (MIX == 8 ? "mix 8/8  " : MIX == 16 ? "mix 16/16" : MIX == 64 ? "mix 64/64" : MIX == 256 ? "mix 256  " : MIX == -1 ? "f16 once " : MIX == -2 ? "halves   " : "mix 1024 ") : "f8 K=32 ") : "f16 K=16", N, ks, grid, per, N / 2, 100.0 * (N / 2) / per, F8 ? 16384 : 8192);
   cudaFree(d);
 }
 
@@ -122,6 +125,20 @@ int main(int argc, char** argv) {
     run<2, true, 128>(grid, iters, ks);
     run<2, false, 256>(grid, iters, ks);
     run<2, true, 256>(grid, iters, ks);
+    run<2, false, 128, true>(grid, iters, ks);
+    run<2, true, 128, true>(grid, iters, ks);
+    run<2, false, 256, true>(grid, iters, ks);
+    run<2, true, 256, true>(grid, iters, ks);
   }
+  // alternating kinds (the fp16f8 FFN unit: 8 kind::f16 MMAs, then 8 kind::f8f6f4 MMAs): cost of switching
+  run<2, false, 128, true, 8>(grid, iters, 32);
+  run<2, true, 128, true, 8>(grid, iters, 32);
+  run<2, false, 128, true, 16>(grid, iters, 32);
+  run<2, true, 128, true, 16>(grid, iters, 32);
+  run<2, false, 128, true, 64>(grid, 500, 128);
+  run<2, false, 128, true, 256>(grid, 200, 512);
+  run<2, false, 128, true, 1024>(grid, 50, 2048);
+  run<2, false, 128, true, -1>(grid, iters, 24);   // one kind::f16 MMA first, then only kind::f8f6f4
+  run<2, false, 128, true, -2>(grid, iters, 24);   // first half of the iterations f8, second half f16 (one switch)
   return 0;
 }
