@@ -343,7 +343,7 @@ class NativeModel:
         return out
 
     # ---- decoder ----------------------------------------------------------------
-    def decode(self, planes, b, qry, T, rot=None, flip_in_place=False, out_scale=1.0, precision="fp16x3", out=None):
+    def decode(self, planes, b, qry, T, rot=None, flip_in_place=False, out_scale=1.0, precision="fp16f8", out=None):
         """qry (n,3) of image b -> (n,) = out_scale * sdf_pred.  rot None = test mode (y,z negated)."""
         if not qry.is_cuda or qry.dtype != torch.float32 or not qry.is_contiguous():
             raise NativeError("qry must be a contiguous float32 CUDA tensor")
@@ -361,7 +361,7 @@ class NativeModel:
                                      _stream(self.device)))
         return out
 
-    def decode_batch(self, planes, qry, T, rot=None, flip_in_place=False, out_scale=1.0, precision="fp16x3", out=None):
+    def decode_batch(self, planes, qry, T, rot=None, flip_in_place=False, out_scale=1.0, precision="fp16f8", out=None):
         """All images of an encoder batch in ONE launch: qry (B,n,3), T (B,4,3), rot (B,3,3) or None -> (B,n)."""
         if not qry.is_cuda or qry.dtype != torch.float32 or not qry.is_contiguous() or qry.dim() != 3:
             raise NativeError("qry must be a contiguous float32 CUDA tensor (B,n,3)")
@@ -403,7 +403,7 @@ class NativeModel:
         planes = Planes(blob, B, K, S, None)
         return (planes, taps) if want_taps else planes
 
-    def decode_gt(self, planes, qry, T, rot=None, flip_in_place=False, out_scale=1.0, precision="fp16x3", out=None):
+    def decode_gt(self, planes, qry, T, rot=None, flip_in_place=False, out_scale=1.0, precision="fp16f8", out=None):
         """qry (B,n,3), T (B,4,3), rot (B,3,3) or None -> (B,n): the GT model's per-query path in the library."""
         if not qry.is_cuda or qry.dtype != torch.float32 or not qry.is_contiguous() or qry.dim() != 3:
             raise NativeError("qry must be a contiguous float32 CUDA tensor (B,n,3)")
@@ -422,7 +422,7 @@ class NativeModel:
                                         out.data_ptr(), prec, ws.data_ptr(), ws.numel(), _stream(self.device)))
         return out
 
-    def decode_grid(self, planes, b, axes, first, count, T, out_scale=1.0, precision="fp16x3", out=None):
+    def decode_grid(self, planes, b, axes, first, count, T, out_scale=1.0, precision="fp16f8", out=None):
         """Grid points [first, first+count) of the (nx,ny,nz) grid given by the three per-axis
         coordinate tensors ``axes`` (x slowest, z fastest), test-mode flip applied on the fly."""
         px, py, pz = (_f32c(a, "grid axis") for a in axes)

@@ -440,7 +440,8 @@ __device__ __forceinline__ void split8_f8(const float* v, uint32_t* h, uint32_t*
   for (int i = 0; i < 4; ++i) {
     const __half2 h2 = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
     const float h0 = __low2float(h2), h1 = __high2float(h2);
-    const __half2 hs = __floats2half2_rn(h0 * F8_XS, h1 * F8_XS);  // exact: a power-of-two multiple of an fp16 number
+    // exact (a power-of-two multiple of an fp16 number) below 511.75; saturates beyond instead of overflowing to infinity
+    const __half2 hs = __floats2half2_rn(fminf(fmaxf(h0 * F8_XS, -65504.f), 65504.f), fminf(fmaxf(h1 * F8_XS, -65504.f), 65504.f));
     h[i] = *reinterpret_cast<const uint32_t*>(&hs);
     pl[i] = __nv_cvt_float2_to_fp8x2(make_float2((v[2 * i] - h0) * F8_XLS, (v[2 * i + 1] - h1) * F8_XLS), __NV_SATFINITE, __NV_E4M3);
     ph[i] = __nv_cvt_float2_to_fp8x2(make_float2(h0, h1), __NV_SATFINITE, __NV_E4M3);

@@ -310,7 +310,7 @@ def test_decoder_tc_equals_fp32_path_on_dense_grid():
 
 def test_full_size_dense_grid_256():
     """BASELINE.json's metric configuration end to end: 12 slices 256x256 -> the whole 256^3 grid through
-    Generator3D.generate_grid (the call bench.py's e2e leg times), in the default <= 1e-4 mode (fp16x3).  Checked (a) at the 2071 grid indices the
+    Generator3D.generate_grid (the call bench.py's e2e leg times), in the default <= 1e-4 mode (fp16f8).  Checked (a) at the 2071 grid indices the
     reference golden holds (bit-exact index mapping, values within 1e-4), (b) through size-independent properties:
     every value is finite, a re-run is bit-identical (no atomics / races in the fused kernel), an axis-0 slab
     evaluated on its own equals the same slab of the full volume (what the multi-GPU sharding relies on), and the
@@ -322,12 +322,12 @@ def test_full_size_dense_grid_256():
     with torch.no_grad():
         vol = gen.generate_grid({k: v.cpu() for k, v in feed.items()}, as_numpy=False)
         vol2 = gen.generate_grid({k: v.cpu() for k, v in feed.items()}, as_numpy=False)
-    assert m.precision == "fp16x3"
+    assert m.precision == "fp16f8"
     assert vol.shape == (256, 256, 256)
     flat = vol.reshape(-1)
     err = helpers.maxabs(flat[torch.from_numpy(case["idx_g256"]).to(flat.device)].cpu(), -case["sdf_g256"])
-    print(f"256^3 dense grid, fp16x3: max-abs vs reference at {len(case['idx_g256'])} golden indices {err:.3e}")
-    helpers.record("dense256_fp16x3_max_abs_vs_reference", err)
+    print(f"256^3 dense grid, {m.precision}: max-abs vs reference at {len(case['idx_g256'])} golden indices {err:.3e}")
+    helpers.record(f"dense256_{m.precision}_max_abs_vs_reference", err)
     assert err < TOL
     assert bool(torch.isfinite(flat).all())
     assert torch.equal(vol, vol2)
@@ -369,8 +369,8 @@ def test_tc_decoder_ragged_empty_and_unsupported():
     p4 = m4.encode(f4["img_input"])
     q4 = torch.from_numpy(case4["pts_g64"]).to(DEV)
     # K = 4 (BASELINE configs[0]) on the tensor-core path: 5 live token rows per query, the other 8 dead and masked
-    assert m4.precision == "fp16x3"
-    for prec in ("fp16x3", "bf16x3"):
+    assert m4.precision == "fp16f8"
+    for prec in ("fp16f8", "fp16x3", "bf16x3"):
         got = m4.native().decode(p4, 0, q4, f4["trans_mat_wo_rot_tp"][0], precision=prec)
         err = helpers.maxabs(got.cpu(), case4["sdf_g64"])
         print(f"K=4 model on the tensor-core decoder, {prec}: max-abs vs reference {err:.3e}")

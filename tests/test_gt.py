@@ -49,7 +49,7 @@ def test_gt_native_matches_reference_golden():
     planes, taps = nat.encode_gt(feed["img_slices"].view(12, 3, 128, 128), 1, want_taps=True)
     for i, (cs, ps) in enumerate([(4, 16), (8, 8), (8, 4), (8, 2), (8, 1)]):
         assert helpers.maxabs(taps[i][:, ::cs, ::ps, ::ps].cpu(), g[f"tap{i}"]) < TOL, f"tap {i}"
-    for prec in ("fp32", "fp16x3", "bf16x3"):
+    for prec in ("fp32", "fp16f8", "fp16x3", "bf16x3"):
         m.precision = prec
         feed["qry_norot"] = torch.from_numpy(g["pts_g64"]).unsqueeze(0).to(dev)
         with torch.no_grad():
@@ -60,7 +60,7 @@ def test_gt_native_matches_reference_golden():
         assert err < TOL
         assert torch.equal(feed["qry_norot"][0].cpu(), torch.from_numpy(g["pts_after_g64"]))  # in-place flip (model_gt.py:75)
     # val mode: batch 2, rotations, one launch
-    m.mode, m.precision = "val", "fp16x3"
+    m.mode, m.precision = "val", "fp16f8"
     feed2 = {k: v.to(dev) for k, v in synth.synthetic_inputs(128, 12, int(g["seed"]), batch=2).items()}
     feed2["qry_norot"] = torch.from_numpy(g["val_qry"]).to(dev)
     feed2["obj_rot_mat"] = torch.from_numpy(g["val_rot"]).to(dev)

@@ -1,0 +1,11 @@
+mkdir -p gpurun_out
+timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/r2_u_pytest.log 2>&1; echo "rc=$?" >> gpurun_out/r2_u_pytest.log
+tail -3 gpurun_out/r2_u_pytest.log
+timeout 600 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum,lts__t_sector_hit_rate.pct --clock-control none -k regex:decoder_tc_kernel -c 1 --csv --log-file gpurun_out/r2_u_ncu_dram256_fp16f8.csv python tools/dec_once.py 256 fp16f8 1 > /dev/null 2>&1; tail -4 gpurun_out/r2_u_ncu_dram256_fp16f8.csv | cut -d, -f13-
+python bench.py --steps 3 --warmup 3 > gpurun_out/r2_u_bench.json 2> gpurun_out/r2_u_bench.err; python - <<'PY'
+import json
+d=json.loads([l for l in open('gpurun_out/r2_u_bench.json') if l.startswith('{')][-1])
+print(d['value'], d['e2e']['value'], d['roofline']['frac'], d['parity']['max_abs_vs_golden'], d['dtype'][:8])
+print(d['alt_precision']); print(d['e2e_api']['value'], d['sparse']['noisy']['generate_mesh_ms'], d['sparse']['smooth']['generate_mesh_ms'], d['train']['ms_per_step'])
+PY
+tail -3 gpurun_out/r2_u_bench.err
