@@ -41,7 +41,7 @@ def build(force=False, verbose=False):
         o = os.path.join(OUT_DIR, src.replace(".cu", ".o"))
         objs.append(o)
         if force or _stale(o, [s] + headers):
-            cmd = [_nvcc()] + NVCC_FLAGS + ["-c", s, "-o", o]
+            cmd = [_nvcc()] + NVCC_FLAGS + os.environ.get("S3D_NVCC_EXTRA", "").split() + ["-c", s, "-o", o]
             procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     for src, p in procs:
         out, _ = p.communicate()

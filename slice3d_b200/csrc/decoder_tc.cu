@@ -81,25 +81,44 @@ constexpr uint32_t OFF_BAR = OFF_RED + 5120;  // (last layer: [9][128] fp32 scal
 constexpr uint32_t SMEM_BYTES = OFF_BAR + 512 + 1024;              // + alignment slack
 
 // barrier indices (8 bytes each at OFF_BAR)
-enum { B_AREADY = 0, B_DDONE, B_KDONE, B_QDONE, B_D1READY0, B_D1READY1, B_HREADY, B_HFREE,
+enum { B_AREADY = 0, B_DDONE, B_KDONE, B_QDONE, B_D1READY0, B_D1READY1, B_D1READY2, B_HREADY0, B_HREADY1, B_HREADY2,
        B_TOKFULL0, B_TOKFULL1, B_TOKEMPTY0, B_TOKEMPTY1, B_FULL0, B_EMPTY0 = B_FULL0 + NSLOT,
-       B_PFULL0 = B_EMPTY0 + NSLOT,  // leader CTA only: the peer's half of the slot has landed
-       B_COUNT = B_PFULL0 + NSLOT };
+       B_COUNT = B_EMPTY0 + NSLOT };
 static_assert(8 * B_COUNT + 8 <= 512, "barrier area");
 constexpr uint32_t OFF_TMEMPTR = OFF_BAR + 8 * B_COUNT;
 
 // TMEM columns
 constexpr uint32_t TM_R = 0;      // residual / out-proj / FFN2 accumulator, 128 columns
 constexpr uint32_t TM_S = 128;    // QKV accumulators (384 columns), or during the FFN:
-constexpr uint32_t TM_D1 = 128;   //   128..383  FFN1 chunk accumulators D1 (2 buffers x 128 hidden units)
-constexpr uint32_t TM_HT = 384;   //   384..511  H chunk as the A operand of linear2 (packed bf16, K = 128):
-                                  //             hi 64 | lo 64 columns
+constexpr uint32_t TM_D1 = 128;   //   128..511  three FFN chunk buffers of 128 columns: the accumulator D1 of linear1 (128 hidden
+                                  //             units, fp32), overwritten IN PLACE by the H operand of linear2: the thread that
+                                  //             owns columns 32g .. 32g+31 of a row writes the packed H values of the same hidden
+                                  //             units back into them -- [hi 16 | lo 16] columns, fp16f8: [fp16 16 | e4m3 8 | e4m3 8]
+constexpr int NDBUF = 3;
+constexpr uint32_t TM_HT = 384;   //   (self-test kernels only: a contiguous H operand, hi 64 | lo 64 columns)
 
 // Phase-cycle counters (clock64 deltas summed over CTAs), read through s3d_debug_profile().
 enum { PF_TOKEN = 0, PF_VEC, PF_WAIT_QKV, PF_ATTN, PF_WAIT_OUT, PF_LN1, PF_FFN_WAIT_D1, PF_FFN_MATH, PF_FFN_WAIT_HFREE,
        PF_FFN_STORE, PF_WAIT_FFN, PF_LN2, PF_MMA_WAIT_A, PF_MMA_WAIT_FULL, PF_MMA_WAIT_H, PF_MMA_WAIT_D1FREE, PF_MMA_TOTAL,
        PF_PROD_WAIT_EMPTY, PF_PROD_TOTAL, PF_TILES, PF_COUNT };
 __device__ unsigned long long g_prof[32];
+#ifdef S3D_TRACE  // experiment builds only: event timeline of CTA 0's MMA issuer (role 0) and compute warp 0 (role 1) over
+// FFN chunks 4..11 of one tile, staged in the idle upper KB of the LayerNorm scratch and printed at the end of the launch
+__device__ uint32_t g_trace[256];
+#define TR(role, on, ev, c)                                                                                   \
+  if ((on) && lane == 0 && (c) >= 4 && (c) < 12 && tr_n < 128) {                                              \
+    reinterpret_cast<uint32_t*>(sgen + OFF_RED + 4096)[(role) * 128 + tr_n++] =                               \
+        ((uint32_t)(ev) << 26) | (((uint32_t)(c) & 15u) << 22) | ((uint32_t)clock() & 0x3fffffu);              \
+  }
+#define TR_FLUSH(role, on)                                                                                    \
+  if ((on) && lane == 0) {                                                                                    \
+    for (int i_ = 0; i_ < 128; ++i_)                                                                          \
+      g_trace[(role) * 128 + i_] = i_ < tr_n ? reinterpret_cast<uint32_t*>(sgen + OFF_RED + 4096)[(role) * 128 + i_] : 0u; \
+  }
+#else
+#define TR(role, on, ev, c)
+#define TR_FLUSH(role, on)
+#endif
 
 struct TcParams {
   const uint8_t* wimg;  // [3 layers][36 units][hi 32 KB | lo 32 KB]
@@ -169,8 +188,9 @@ __device__ __forceinline__ void issue_part(uint32_t d_tmem, uint32_t a0, uint32_
   }
 }
 
-// Same with the A operand(s) in tensor memory (8 columns per k-step).
-template <int CG, int NA, int KS, uint32_t B_KB, uint32_t IDESC>
+// Same with the A operand(s) in tensor memory (8 columns per k-step).  INPLACE: the operand sits in the columns of the
+// accumulator it was computed from (see TM_D1): k-step ks (16 values) at column 32 (ks / 2) + 8 (ks % 2).
+template <int CG, int NA, int KS, uint32_t B_KB, uint32_t IDESC, bool INPLACE = false>
 __device__ __forceinline__ void issue_part_ts(uint32_t d_tmem, uint32_t a0_tmem, uint32_t a1_tmem, uint32_t b, bool fresh) {
   if (CG == 2) {
     const uint32_t bl = make_desc_lo(b);
@@ -180,7 +200,8 @@ __device__ __forceinline__ void issue_part_ts(uint32_t d_tmem, uint32_t a0_tmem,
 #pragma unroll
       for (int ks = 0; ks < KS; ++ks) {
         const uint32_t kb = ks >> 2, kin = (ks & 3) * 32;
-        umma_ts_pair_lo(d_tmem, at + 8 * ks, bl + ((kb * B_KB + kin) >> 4), IDESC, (pass == 0 && ks == 0 && fresh) ? 0u : 1u);
+        const uint32_t acol = INPLACE ? 32u * (ks >> 1) + 8u * (ks & 1) : 8u * ks;
+        umma_ts_pair_lo(d_tmem, at + acol, bl + ((kb * B_KB + kin) >> 4), IDESC, (pass == 0 && ks == 0 && fresh) ? 0u : 1u);
       }
     }
   } else {
@@ -239,18 +260,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
     mbar_init(bar(B_DDONE), 1);
     mbar_init(bar(B_KDONE), 1);
     mbar_init(bar(B_QDONE), 1);
-    mbar_init(bar(B_D1READY0), 1);
-    mbar_init(bar(B_D1READY1), 1);
-    mbar_init(bar(B_HREADY), NCW * CG);
-    mbar_init(bar(B_HFREE), 1);
+    for (int b = 0; b < NDBUF; ++b) {
+      mbar_init(bar(B_D1READY0 + b), 1);
+      mbar_init(bar(B_HREADY0 + b), NCW * CG);
+    }
     mbar_init(bar(B_TOKFULL0), NGW);
     mbar_init(bar(B_TOKFULL1), NGW);
     mbar_init(bar(B_TOKEMPTY0), NCW);
     mbar_init(bar(B_TOKEMPTY1), NCW);
     for (int s = 0; s < NSLOT; ++s) {
-      mbar_init(bar(B_FULL0 + s), 1);
+      // leader: the producer's arrive (+ its bytes) and the peer's relay ("my half has landed too") complete ONE barrier
+      mbar_init(bar(B_FULL0 + s), (CG == 2 && leader) ? 2 : 1);
       mbar_init(bar(B_EMPTY0 + s), 1);
-      mbar_init(bar(B_PFULL0 + s), 1);
     }
     fence_barrier_init();
   }
@@ -462,7 +483,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
       for (int g = 0; g < nparts; ++g) {
         mbar_wait(bar(B_FULL0 + slot), (ph_full >> slot) & 1u);
         ph_full ^= 1u << slot;
-        if (lane == 0) mbar_arrive_cluster(mapa_u32(bar(B_PFULL0 + slot), 0));
+        if (lane == 0) mbar_arrive_cluster(mapa_u32(bar(B_FULL0 + slot), 0));
         __syncwarp();
         slot = (slot + 1 == NSLOT) ? 0 : slot + 1;
       }
@@ -478,32 +499,46 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
     }
   } else if (warp == NCW + 1) {
     // ===================================================================== MMA issuer (leader CTA of a pair)
-    // the whole warp runs the control flow (waits are warp-uniform); one elected lane issues
+    // The whole warp runs the control flow (waits are warp-uniform); one elected lane issues -- the form that lets the
+    // compiler keep descriptors in uniform registers (a `lane == 0` region costs ~18 instructions and a waterfall loop per
+    // MMA).  As little as possible sits between two groups of MMAs.  Measured on the B200 (tools/sync_cost.cu,
+    // profiles/r2_sync_cost.log): a tcgen05.mma occupies its issuing thread for ~48 cycles (the pipe needs 64), a
+    // tcgen05.commit for 46, an mbarrier try_wait for 55 even when the phase is complete, elect + syncwarp for 19; a commit
+    // reaches its barrier after ~210 cycles, an arrive wakes a waiter after ~200.  Whatever the issuer does beyond that is a
+    // bubble of the tensor pipe: the first version of this loop (two barriers per ring slot, elect + syncwarp around every
+    // step) spent ~270 cycles per 8-MMA part in such overhead -- hidden with 24 MMAs per weight unit (three-pass modes: at
+    // the pipe's floor), not with 16 (fp16f8: 2.7 instead of 2.05 kcycles per FFN chunk; the FFN loop ran at the same 2.7
+    // kcycles with its MMAs removed).
     {
       uint32_t ph_a = 0, ph_full = 0, ph_hr = 0;  // parity bits (one per barrier / slot)
       int slot = 0;
-      uint32_t w_a = 0, w_full = 0, w_h = 0;  // 32-bit cycle sums (wrap after ~2 s; only read in profiling runs)
+      uint32_t w_a = 0, w_h = 0;  // 32-bit cycle sums (wrap after ~2 s; only read in profiling runs)
+#ifdef S3D_TRACE
+      bool tr_on = false;
+      int tr_n = 0;
+#endif
       const uint32_t t_start = (uint32_t)clock();
       const uint32_t ax_hi = sbase + OFF_AX_HI, ax_lo = sbase + OFF_AX_LO;
       constexpr uint32_t ID128 = F16 ? make_idesc_f16(128, 128 * CG) : make_idesc_bf16(128, 128 * CG);
       constexpr uint32_t BKB = 8192u;  // k-block stride of this CTA's half of a part: [64 n][64 k]
       auto wait_full = [&]() -> uint32_t {
-        const uint32_t t0 = (uint32_t)clock();
-        mbar_wait(bar(B_FULL0 + slot), (ph_full >> slot) & 1u);
-        if (CG == 2) mbar_wait_cluster(bar(B_PFULL0 + slot), (ph_full >> slot) & 1u);
+        wait_lead(B_FULL0 + slot, (ph_full >> slot) & 1u);  // (both halves of the slot: see the barrier's count)
         ph_full ^= 1u << slot;
-        w_full += (uint32_t)clock() - t0;
+        tc_fence_after();
         return sbase + OFF_RING + slot * SLOT_BYTES;
       };
+      auto commit1 = [&](int b) {  // (elected lane)
+        if (CG == 2) umma_commit_pair(bar(b));
+        else umma_commit(bar(b));
+      };
       auto commit = [&](int b) {
-        if (elect_one()) {
-          if (CG == 2) umma_commit_pair(bar(b));
-          else umma_commit(bar(b));
-        }
+        if (elect_one()) commit1(b);
         __syncwarp();
       };
-      auto release = [&]() {
-        commit(B_EMPTY0 + slot);
+      // (the warp reconverges after every elected block: lanes running ahead into the next try_wait would suspend the
+      // warp, the issuing lane with it)
+      auto next_slot = [&]() {
+        __syncwarp();
         slot = (slot + 1 == NSLOT) ? 0 : slot + 1;
       };
       // One weight unit = its hi part (passes A_hi.B_hi [, A_lo.B_hi]) then, for bf16x3, its lo part
@@ -511,16 +546,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
       // D[:, d_col .. +127] (+)= AX . W^T, A = the activation tile in shared memory (K = 128)
       auto unit_ss = [&](uint32_t d_col, bool fresh) {
         uint32_t w = wait_full();
-        tc_fence_after();
-        if (elect_one()) issue_part<CG, (NPASS == 3 ? 2 : 1), 8, 16384u, BKB, ID128>(tmem + d_col, ax_hi, ax_lo, w, fresh);
-        __syncwarp();
-        release();
+        if (elect_one()) {  // the part's MMAs, then the commit that frees its ring slot
+          issue_part<CG, (NPASS == 3 ? 2 : 1), 8, 16384u, BKB, ID128>(tmem + d_col, ax_hi, ax_lo, w, fresh);
+          commit1(B_EMPTY0 + slot);
+        }
+        next_slot();
         if (NPASS == 3) {
           w = wait_full();
-          tc_fence_after();
-          if (elect_one()) issue_part<CG, 1, 8, 16384u, BKB, ID128>(tmem + d_col, ax_hi, ax_hi, w, false);
-          __syncwarp();
-          release();
+          if (elect_one()) {
+            issue_part<CG, 1, 8, 16384u, BKB, ID128>(tmem + d_col, ax_hi, ax_hi, w, false);
+            commit1(B_EMPTY0 + slot);
+          }
+          next_slot();
         }
       };
       auto wait_a = [&]() {
@@ -548,91 +585,111 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
         unit_ss(TM_R, false);
         commit(B_DDONE);
         wait_a();
-        // D1 is double-buffered, H single: the part of a chunk's epilogue that sits between two MMAs of the pipe
-        // is only "h_free -> store H -> h_ready", and it is covered by MMA1 of the chunk after next.
+        // Three chunk buffers in tensor memory; a buffer holds D1 of chunk c, then (in place) the H operand of chunk c.
+        // Issue order: MMA1 of chunks 0, 1, 2; then per chunk c: wait h_ready(c), MMA2(c) [R += H_c . W2_c^T], MMA1(c + 3) into
+        // the buffer MMA2(c) has just read (MMAs of one thread execute in issue order).  There is no "h_free" hand-off, and
+        // between "D1 of chunk c complete" and "MMA2(c) due" the pipe has four units (~4 kcycles) of other work: the
+        // hand-off latencies of this kernel (commit -> barrier -> 32 warps -> arrives -> issuer: ~2.4 kcycles per round trip,
+        // traced with S3D_TRACE) are off the critical path.  The first version (two D1 buffers, one H buffer next to
+        // them, h_free / h_ready per chunk) ran at 2.97 kcycles per chunk in fp16f8 mode against a 2.05-kcycle MMA floor.
         // fp16f8 mode (F8): an FFN unit = part A [fp16(w * 2^8)] for the leading term xh.wh on kind::f16, then part B
         // [e4m3(wh * 2^4) | e4m3(wl * 2^15)] for the two cross terms on kind::f8f6f4 (4 k-steps of 32 each): 16 MMAs per
         // unit instead of 24, the accumulator carries 2^15 (tc_ptx.cuh).
-        auto issue1 = [&](int c) {
+        auto issue1 = [&](int c, int buf) {
+          const uint32_t d = tmem + TM_D1 + 128 * buf;
           if (F8) {
-            const uint32_t d = tmem + TM_D1 + 128 * (c & 1);
             uint32_t w = wait_full();
-            tc_fence_after();
-            if (elect_one()) issue_part<CG, 1, 8, 16384u, BKB, ID128>(d, ax_hi, ax_hi, w, true);
-            __syncwarp();
-            release();
+            TR(0, tr_on, 16, c - 3)
+            if (elect_one()) {
+              issue_part<CG, 1, 8, 16384u, BKB, ID128>(d, ax_hi, ax_hi, w, true);
+              commit1(B_EMPTY0 + slot);
+            }
+            next_slot();
+            TR(0, tr_on, 17, c - 3)
             w = wait_full();
-            tc_fence_after();
+            TR(0, tr_on, 19, c - 3)
             if (elect_one()) {
               const uint32_t al = make_desc_lo(ax_lo), ah = make_desc_lo(ax_lo + 16384u), bl = make_desc_lo(w), bh = make_desc_lo(w + 8192u);
 #pragma unroll
               for (uint32_t ks = 0; ks < 4; ++ks) umma_f8_pair_lo(d, al + 2 * ks, bl + 2 * ks, ID128, 1u);
 #pragma unroll
               for (uint32_t ks = 0; ks < 4; ++ks) umma_f8_pair_lo(d, ah + 2 * ks, bh + 2 * ks, ID128, 1u);
+              commit1(B_EMPTY0 + slot);
+              commit1(B_D1READY0 + buf);
             }
-            __syncwarp();
-            release();
+            next_slot();
+            TR(0, tr_on, 20, c - 3)
           } else {
-            unit_ss(TM_D1 + 128 * (c & 1), true);
+            unit_ss(TM_D1 + 128 * buf, true);
+            commit(B_D1READY0 + buf);
           }
-          commit(B_D1READY0 + (c & 1));
         };
-        auto issue2 = [&](int c) {
-          const uint32_t h_hi = tmem + TM_HT, h_lo = h_hi + 64;
+        auto issue2 = [&](int c, int buf) {
+          (void)c;
+          const uint32_t hb = tmem + TM_D1 + 128 * buf;  // per 32-column block: [hi 16 | lo 16] or [fp16 16 | e4m3 lo 8 | e4m3 hi 8]
           uint32_t w = wait_full();
-          tc_fence_after();
-          if (F8) {  // H in tensor memory: fp16(h * 2^7) 64 columns | e4m3(hl * 2^11) 32 columns | e4m3(hh) 32 columns
-            // (the two e4m3 operands in shared memory instead -- SS mode, H region -- were measured: 169 vs 166 kcycles
-            // per tile pair, no better: profiles/r2_summary.md)
-            if (elect_one()) issue_part_ts<CG, 1, 8, BKB, ID128>(tmem + TM_R, h_hi, h_hi, w, false);
-            __syncwarp();
-            release();
+          TR(0, tr_on, 11, c)
+          if (F8) {
+            if (elect_one()) {
+              issue_part_ts<CG, 1, 8, BKB, ID128, true>(tmem + TM_R, hb, hb, w, false);
+              commit1(B_EMPTY0 + slot);
+            }
+            next_slot();
+            TR(0, tr_on, 12, c)
             w = wait_full();
-            tc_fence_after();
+            TR(0, tr_on, 13, c)
             if (elect_one()) {
               const uint32_t bl = make_desc_lo(w), bh = make_desc_lo(w + 8192u);
 #pragma unroll
-              for (uint32_t ks = 0; ks < 4; ++ks) umma_f8_ts_pair_lo(tmem + TM_R, h_hi + 64 + 8 * ks, bl + 2 * ks, ID128, 1u);
+              for (uint32_t ks = 0; ks < 4; ++ks) umma_f8_ts_pair_lo(tmem + TM_R, hb + 32 * ks + 16, bl + 2 * ks, ID128, 1u);
 #pragma unroll
-              for (uint32_t ks = 0; ks < 4; ++ks) umma_f8_ts_pair_lo(tmem + TM_R, h_hi + 96 + 8 * ks, bh + 2 * ks, ID128, 1u);
+              for (uint32_t ks = 0; ks < 4; ++ks) umma_f8_ts_pair_lo(tmem + TM_R, hb + 32 * ks + 24, bh + 2 * ks, ID128, 1u);
+              commit1(B_EMPTY0 + slot);
             }
-            __syncwarp();
-            release();
+            next_slot();
+            TR(0, tr_on, 14, c)
             return;
           }
-          if (elect_one()) issue_part_ts<CG, (NPASS == 3 ? 2 : 1), 8, BKB, ID128>(tmem + TM_R, h_hi, h_lo, w, false);
-          __syncwarp();
-          release();
+          if (elect_one()) {
+            issue_part_ts<CG, (NPASS == 3 ? 2 : 1), 8, BKB, ID128, true>(tmem + TM_R, hb, hb + 16, w, false);
+            commit1(B_EMPTY0 + slot);
+          }
+          next_slot();
           if (NPASS == 3) {
             w = wait_full();
-            tc_fence_after();
-            if (elect_one()) issue_part_ts<CG, 1, 8, BKB, ID128>(tmem + TM_R, h_hi, h_hi, w, false);
-            __syncwarp();
-            release();
+            if (elect_one()) {
+              issue_part_ts<CG, 1, 8, BKB, ID128, true>(tmem + TM_R, hb, hb, w, false);
+              commit1(B_EMPTY0 + slot);
+            }
+            next_slot();
           }
         };
-        // one call site per unit kind (the unrolled issue sequences are large: instruction-cache footprint):
-        // c = -2, -1 only issue MMA1 of chunks 0, 1; then MMA2(c), MMA1(c + 2)
+        int buf = 0;  // buffer of chunk c (c >= 0) = c % 3 = buffer of chunk c + 3
 #pragma unroll 1
-        for (int c = -2; c < NCHUNK; ++c) {
+        for (int c = -NDBUF; c < NCHUNK; ++c) {
           if (c >= 0) {
-            // h_ready(c): the compute warps have drained D1[c&1] and written the H operand of chunk c
+            // h_ready(c): the compute warps have written the H operand of chunk c over its D1
             const uint32_t t0 = (uint32_t)clock();
-            wait_lead(B_HREADY, ph_hr);
-            ph_hr ^= 1u;
+            wait_lead(B_HREADY0 + buf, (ph_hr >> buf) & 1u);
+            ph_hr ^= 1u << buf;
             w_h += (uint32_t)clock() - t0;
+            TR(0, tr_on, 10, c)
             tc_fence_after();
-            issue2(c);
-            if (c + 1 < NCHUNK) commit(B_HFREE);  // H may be rewritten once MMA2 of chunk c has completed
+            issue2(c, buf);
           }
-          if (c + 2 < NCHUNK) issue1(c + 2);
+          if (c + NDBUF < NCHUNK) issue1(c + NDBUF, buf);
+          buf = (buf + 1 == NDBUF) ? 0 : buf + 1;
         }
         commit(B_DDONE);
+        TR_FLUSH(0, tr_on)
       };
       int pending = 0;
       for (long long base = base_first; base < n_tiles; base += gridDim.x) {
 #pragma unroll 1
         for (int layer = 0; layer < 3; ++layer) {  // (one call site for each of the two issue sequences)
+#ifdef S3D_TRACE
+          tr_on = blockIdx.x == 0 && base == base_first + 6 * (long long)gridDim.x && layer == 0;
+#endif
           mma_qkv();
           bool ffn = true;
           if (layer == 2) {  // last layer: only token 0 of every query is consumed downstream -> batched tail pass
@@ -645,7 +702,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
       }
       if (lane == 0) {
         atomicAdd(&g_prof[PF_MMA_WAIT_A], (unsigned long long)w_a);
-        atomicAdd(&g_prof[PF_MMA_WAIT_FULL], (unsigned long long)w_full);
         atomicAdd(&g_prof[PF_MMA_WAIT_H], (unsigned long long)w_h);
         atomicAdd(&g_prof[PF_MMA_TOTAL], (unsigned long long)((uint32_t)clock() - t_start));
       }
@@ -662,9 +718,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
     uint8_t* ax_lo = sgen + OFF_AX_LO;
     const float* vec = reinterpret_cast<const float*>(sgen + OFF_VEC);
     float* red0 = reinterpret_cast<float*>(sgen + OFF_RED);
-    uint32_t ph_d = 0, ph_d1r = 0, ph_hf = 0, ph_kq = 0;
+    uint32_t ph_d = 0, ph_d1r = 0, ph_kq = 0;
     const int qi = r / NTOK, tk = r - qi * NTOK;
     uint32_t pf[16];
+#ifdef S3D_TRACE
+    int tr_tile = 0, tr_n = 0;
+#define TRC ((int)blockIdx.x == ((p.dbg >> 16) & 1) && warp == ((p.dbg >> 8) & 15) && tr_tile == 7 && layer == 0)
+#endif
 #pragma unroll
     for (int i = 0; i < 16; ++i) pf[i] = 0;
     uint32_t tprev = (uint32_t)clock();
@@ -779,8 +839,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
     };
     auto vecB_store = [&](const float4* v2) {
       float4* dst = reinterpret_cast<float4*>(sgen + OFF_VEC) + V_PART_B / 4;
-      dst[tid] = v2[0];
-      if (tid + NCT < (VEC_FLOATS - V_PART_B) / 4) dst[tid + NCT] = v2[1];
+      // fp16f8: b1 is staged as 128 b1 (the linear1 epilogue produces 128 h, see split8_f8_h)
+      const float s0 = (F8 && tid >= (V_B1 - V_PART_B) / 4) ? F8_XS : 1.f, s1 = F8 ? F8_XS : 1.f;
+      dst[tid] = make_float4(v2[0].x * s0, v2[0].y * s0, v2[0].z * s0, v2[0].w * s0);
+      if (tid + NCT < (VEC_FLOATS - V_PART_B) / 4) dst[tid + NCT] = make_float4(v2[1].x * s1, v2[1].y * s1, v2[1].z * s1, v2[1].w * s1);
     };
     auto vecA_next = [&](int layer) {  // b_in of the layer after `layer`
       if (tid < V_PART_B / 4) {
@@ -1083,52 +1145,54 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
         lap(PF_LN1)
         // -------------------------------------------------------------- FFN hidden chunks (32 columns per thread)
         {
+          int buf = 0;  // chunk buffer c % 3
 #pragma unroll 1
           for (int c = 0; c < NCHUNK; ++c) {
-            const int bsel = c & 1;
-            mbar_wait(bar(B_D1READY0 + bsel), (ph_d1r >> bsel) & 1u);
-            ph_d1r ^= 1u << bsel;
+            mbar_wait(bar(B_D1READY0 + buf), (ph_d1r >> buf) & 1u);
+            ph_d1r ^= 1u << buf;
             tc_fence_after();
+            TR(1, TRC, 30, c)
             lap(PF_FFN_WAIT_D1)
+            const uint32_t tb = trow + TM_D1 + 128 * buf + 32 * g;  // my 32 columns of the chunk buffer
             float d[32];
-            tmem_ld32(trow + TM_D1 + 128 * bsel + 32 * g, d);
+            tmem_ld32(tb, d);
             tmem_ld_wait();
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               const float4 b4 = *reinterpret_cast<const float4*>(vec + V_B1 + c * 128 + 32 * g + 4 * j);
-              const float ds = F8 ? F8_ACC_INV : 1.f;
+              const float ds = F8 ? F8_ACC_INV * F8_XS : 1.f;  // (fp16f8: 128 h; the staged b1 carries the 2^7 too)
               d[4 * j] = fmaxf(fmaf(d[4 * j], ds, b4.x), 0.f);
               d[4 * j + 1] = fmaxf(fmaf(d[4 * j + 1], ds, b4.y), 0.f);
               d[4 * j + 2] = fmaxf(fmaf(d[4 * j + 2], ds, b4.z), 0.f);
               d[4 * j + 3] = fmaxf(fmaf(d[4 * j + 3], ds, b4.w), 0.f);
             }
             lap(PF_FFN_MATH)
-            {  // H chunk -> A operand of linear2 in tensor memory (16 packed columns per thread, hi and lo)
+            TR(1, TRC, 31, c)
+            {  // H chunk -> A operand of linear2, written over the D1 values it was computed from (my own 32 columns:
+              // nobody else reads or writes them until MMA2 of this chunk)
               uint32_t hh[16], hl[16];  // (fp16f8: hl[0..7] = e4m3 lo parts, hl[8..15] = e4m3 hi parts)
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
-                if (F8) split8_f8(d + 8 * j, hh + 4 * j, hl + 2 * j, hl + 8 + 2 * j);
+                if (F8) split8_f8_h(d + 8 * j, hh + 4 * j, hl + 2 * j, hl + 8 + 2 * j);
                 else split8x<NPASS == 3, F16>(d + 8 * j, hh + 4 * j, hl + 4 * j);
               }
-              if (c > 0) {  // MMA2 of the previous chunk has finished reading H
-                mbar_wait(bar(B_HFREE), ph_hf);
-                ph_hf ^= 1u;
-                tc_fence_after();
-              }
-              lap(PF_FFN_WAIT_HFREE)
-              tmem_st16(trow + TM_HT + 16 * g, hh);
+              tmem_st16(tb, hh);
               if (F8) {
-                tmem_st8(trow + TM_HT + 64 + 8 * g, hl);
-                tmem_st8(trow + TM_HT + 96 + 8 * g, hl + 8);
+                tmem_st8(tb + 16, hl);
+                tmem_st8(tb + 24, hl + 8);
               } else if (NPASS == 3) {
-                tmem_st16(trow + TM_HT + 64 + 16 * g, hl);
+                tmem_st16(tb + 16, hl);
               }
               tmem_st_wait();
             }
             tc_fence_before();  // orders this thread's D1 load / H store before the MMAs that follow the arrive
-            arrive_lead(B_HREADY);
+            TR(1, TRC, 33, c)
+            arrive_lead(B_HREADY0 + buf);
+            TR(1, TRC, 34, c)
             lap(PF_FFN_STORE)
+            buf = (buf + 1 == NDBUF) ? 0 : buf + 1;
           }
+          TR_FLUSH(1, TRC)
         }
         // -------------------------------------------------------------- residual + LayerNorm 2
         mbar_wait(bar(B_DDONE), ph_d);
@@ -1195,6 +1259,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
         publish(v, p.b_o0);
       }
       ++tile_it;
+#ifdef S3D_TRACE
+      ++tr_tile;
+#endif
       lap(PF_TOKEN)
 
 #pragma unroll 1
@@ -1259,6 +1326,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const TcParams 
     }
 #undef lap
   }
+#ifdef S3D_TRACE
+  __syncthreads();
+  if (blockIdx.x == 1) {  // (the peer's trace flush may still be in flight: crude delay)
+    for (int i = 0; i < 2000; ++i) asm volatile("nanosleep.u32 100;");
+  }
+  if (blockIdx.x == 1 && threadIdx.x == 0) {
+    for (int i = 0; i < 256; ++i)
+      if (g_trace[i]) printf("TR %d %u %u %u\n", i >> 7, g_trace[i] >> 26, (g_trace[i] >> 22) & 15u, g_trace[i] & 0x3fffffu);
+    for (int i = 0; i < 256; ++i) g_trace[i] = 0;
+  }
+#endif
   tc_fence_before();
   if (CG == 2) cluster_sync_all();  // neither CTA frees tensor memory (or exits) while the pair's MMAs may touch it
   else __syncthreads();
@@ -1521,12 +1599,11 @@ int dectc_pack(s3d_model* m, cudaStream_t st) {
         else pack_unit(W, 128, 128, dst + (size_t)g * UNIT_STRIDE_BYTES, f16);
         ++g;
       };
-      // consumption order of the FFN pipeline: W1_0, W1_1, then (W2_c, W1_{c+2}) ...
-      pack_w1(0);
-      pack_w1(1);
+      // consumption order of the FFN pipeline: W1_0 .. W1_2, then (W2_c, W1_{c+3}) ...
+      for (int c = 0; c < NDBUF; ++c) pack_w1(c);
       for (int c = 0; c < NCHUNK; ++c) {
         pack_w2(c);
-        if (c + 2 < NCHUNK) pack_w1(c + 2);
+        if (c + NDBUF < NCHUNK) pack_w1(c + NDBUF);
       }
     }
     void* d = nullptr;

@@ -46,6 +46,22 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
 }
+// Pure polling (test_wait never suspends the thread): for the one or two waits whose wake-up latency is on the critical path.
+__device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_spin(uint32_t bar, uint32_t parity) {
+  while (!mbar_test_wait(bar, parity)) {
+  }
+}
 
 // ---------------------------------------------------------------- cluster (CTA pair) helpers
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -445,6 +461,30 @@ __device__ __forceinline__ void split8_f8(const float* v, uint32_t* h, uint32_t*
     h[i] = *reinterpret_cast<const uint32_t*>(&hs);
     pl[i] = __nv_cvt_float2_to_fp8x2(make_float2((v[2 * i] - h0) * F8_XLS, (v[2 * i + 1] - h1) * F8_XLS), __NV_SATFINITE, __NV_E4M3);
     ph[i] = __nv_cvt_float2_to_fp8x2(make_float2(h0, h1), __NV_SATFINITE, __NV_E4M3);
+  }
+  l8[0] = pl[0] | (static_cast<uint32_t>(pl[1]) << 16);
+  l8[1] = pl[2] | (static_cast<uint32_t>(pl[3]) << 16);
+  h8[0] = ph[0] | (static_cast<uint32_t>(ph[1]) << 16);
+  h8[1] = ph[2] | (static_cast<uint32_t>(ph[3]) << 16);
+}
+
+// The same split for the H chunks of the FFN, which arrive as D = 128 h >= 0 (the epilogue of linear1 folds the 2^7 into its
+// scale and bias): fp16 operand = fp16(D) (saturating: h above 511.75 clamps), residual (D - fp16(D)) * 2^4 = (h - hh) 2^11,
+// e4m3(hh) from the fp16 pair scaled back by 2^-7 (exact).  7 instructions per value instead of 11 (the compute warps'
+// issue slots bound the FFN loop once the MMA hand-offs are off the critical path).
+__device__ __forceinline__ void split8_f8_h(const float* D, uint32_t* h, uint32_t* l8, uint32_t* h8) {
+  uint16_t pl[4], ph[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    uint32_t h2;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(h2) : "f"(D[2 * i + 1]), "f"(D[2 * i]));
+    h[i] = h2;
+    const __half2 hv = *reinterpret_cast<const __half2*>(&h2);
+    const float h0 = __low2float(hv), h1 = __high2float(hv);
+    pl[i] = __nv_cvt_float2_to_fp8x2(make_float2((D[2 * i] - h0) * 16.f, (D[2 * i + 1] - h1) * 16.f), __NV_SATFINITE, __NV_E4M3);
+    const __half2 hh = __hmul2(hv, __float2half2_rn(0.0078125f));
+    const uint32_t hhb = *reinterpret_cast<const uint32_t*>(&hh);
+    asm("cvt.rn.satfinite.e4m3x2.f16x2 %0, %1;" : "=h"(ph[i]) : "r"(hhb));
   }
   l8[0] = pl[0] | (static_cast<uint32_t>(pl[1]) << 16);
   l8[1] = pl[2] | (static_cast<uint32_t>(pl[3]) << 16);

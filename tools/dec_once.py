@@ -17,6 +17,9 @@ m.load_state_dict(synth.synthetic_state_dict(m.state_dict(), 0))
 m = m.to(dev).eval()
 feed = synth.synthetic_inputs(256, 12, 0)
 nat = m.native()
+if os.environ.get("DEC_BENCH_DBG"):
+    from slice3d_b200 import _native as _n
+    _n.lib().s3d_debug_set_decoder_flags(int(os.environ["DEC_BENCH_DBG"]))
 planes = nat.encode(feed["img_input"].to(dev))
 ax = torch.linspace(-0.5, 0.5, nx).to(dev)
 T = feed["trans_mat_wo_rot_tp"][0].to(dev)
