@@ -27,7 +27,7 @@ FLOP_PER_QUERY = 32.82e6  # minimal exact algorithm (con
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE decoder launch from ncu captures of the same configuration
 # (profiles/r2_summary.md; round 1 measured 85.5 GB before the locality order of the grid walk); keyed by
 # (grid, precision, queries in the launch).  Not measured -> null.
-DECODER_DRAM_BYTES = {(256, "fp16x3", 256 ** 3): 4.956e9 + 2.926e9, (256, "fp16f8", 256 ** 3): 9.010e9 + 6.758e9}
+DECODER_DRAM_BYTES = {(256, "fp16x3", 256 ** 3): 4.956e9 + 2.926e9, (256, "fp16f8", 256 ** 3): 12.016e9 + 9.573e9}
 METRIC = "occupancy_queries_per_sec"
 UNIT = "queries/s"
 
