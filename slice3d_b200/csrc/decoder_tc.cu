@@ -1,4 +1,4 @@
-// Fused tensor-core decoder for sm_100a (S3D_PREC_BF16X3 / S3D_PREC_BF16).
+// Fused tensor-core decoder for sm_100a (S3D_PREC_FP16F8 / FP16X3 / BF16X3 / BF16).
 //
 // One persistent CTA per SM processes tiles of 9 queries = 117 token rows (+11 pad rows) = one
 // 128-row UMMA tile, start to finish inside the SM:
@@ -15,6 +15,8 @@
 // as 16 KB parts through a 5-slot ring with bulk async copies (TMA engine) completing on mbarriers.
 // The residual stream never leaves TMEM: the accumulator of out-proj / FFN2 is pre-loaded with
 // x + bias, so the MMA result is already residual + bias + contraction and LayerNorm runs in place.
+// The FFN's hidden chunks live in three 128-column TMEM buffers: linear1's accumulator, overwritten in place by
+// the packed H operand of linear2 (see TM_D1 and the MMA issuer).
 // Only token 0 of a query feeds fc_out, so in the last layer only those rows attend and the rest of
 // that layer (out-proj, FFN, LayerNorms, head) runs as one "tail pass" per 14 tiles over 126 queries.
 //
