@@ -29,7 +29,7 @@ from .unet import UNet
 #   "bf16x3"  bf16 hi/lo three passes                                                                      ~3.5e-5
 #   "fp32"    CUDA-core validation path                                                                    ~4e-6, slow
 #   ("bf16": single pass, 1.8e-2 -- outside the contract, for comparison only)
-DEFAULT_PRECISION = "fp16f8"
+DEFAULT_PRECISION = "auto"  # fp16f8 when a probe against the fp32 path confirms it on the loaded checkpoint, else fp16x3
 
 
 def default_precision(n_slices):

@@ -322,12 +322,14 @@ def test_full_size_dense_grid_256():
     with torch.no_grad():
         vol = gen.generate_grid({k: v.cpu() for k, v in feed.items()}, as_numpy=False)
         vol2 = gen.generate_grid({k: v.cpu() for k, v in feed.items()}, as_numpy=False)
-    assert m.precision == "fp16f8"
+    # the package default: "auto", which selects fp16f8 for this checkpoint (a probe against the fp32 path, _native.py)
+    assert m.precision == "auto" and m.native().auto_info["selected"] == "fp16f8"
+    sel = m.native().auto_info["selected"]
     assert vol.shape == (256, 256, 256)
     flat = vol.reshape(-1)
     err = helpers.maxabs(flat[torch.from_numpy(case["idx_g256"]).to(flat.device)].cpu(), -case["sdf_g256"])
-    print(f"256^3 dense grid, {m.precision}: max-abs vs reference at {len(case['idx_g256'])} golden indices {err:.3e}")
-    helpers.record(f"dense256_{m.precision}_max_abs_vs_reference", err)
+    print(f"256^3 dense grid, {sel}: max-abs vs reference at {len(case['idx_g256'])} golden indices {err:.3e}")
+    helpers.record(f"dense256_{sel}_max_abs_vs_reference", err)
     assert err < TOL
     assert bool(torch.isfinite(flat).all())
     assert torch.equal(vol, vol2)
@@ -369,7 +371,7 @@ def test_tc_decoder_ragged_empty_and_unsupported():
     p4 = m4.encode(f4["img_input"])
     q4 = torch.from_numpy(case4["pts_g64"]).to(DEV)
     # K = 4 (BASELINE configs[0]) on the tensor-core path: 5 live token rows per query, the other 8 dead and masked
-    assert m4.precision == "fp16f8"
+    assert m4.precision == "auto"
     for prec in ("fp16f8", "fp16x3", "bf16x3"):
         got = m4.native().decode(p4, 0, q4, f4["trans_mat_wo_rot_tp"][0], precision=prec)
         err = helpers.maxabs(got.cpu(), case4["sdf_g64"])
@@ -475,4 +477,64 @@ def test_decoder_border_and_clamp_cases_match_oracle():
         got = nat.decode(planes, 0, pts.to(DEV), T.to(DEV), precision=prec)
         err = helpers.maxabs(got.cpu(), want)
         print(f"border/clamp cases, {prec}: max-abs {err:.3e} over {pts.shape[0]} points")
+        assert err < TOL
+
+
+@pytest.mark.parametrize("variant", ["synthetic", "ln_gain_x2", "ffn_x1p5", "attn_sharp_x3", "all"])
+def test_decoder_error_margin_under_weight_scale_stress(variant):
+    """How much of the 1e-4 budget each mode uses when the transformer's weights are less benign than the synthetic
+    checkpoint: LayerNorm gains doubled, FFN weights x 1.5 (hidden activations x 1.5), in_proj's query rows x 3 (sharper
+    softmax), all of them together.  The reference for each variant is the CPU oracle evaluated in FLOAT64 on the same
+    feature planes and the same perturbed weights, so the fp32 CUDA path's own rounding shows up too; errors are reported
+    next to the spread of sdf_pred, because the bar is absolute.  Asserted: every <= 1e-4 mode on the unperturbed
+    checkpoint, fp16x3 under every single-factor stress; the rest is recorded (gpurun_out/parity_figures.json ->
+    profiles/): it tells a user with large LayerNorm gains to select precision='fp16x3'."""
+    case = helpers.load_case("k12_s128_g128")
+    m, sd = helpers.case_weights(case)
+    sd = {k: v.clone() for k, v in sd.items()}
+    for k in sd:
+        if "att_decoder" not in k:
+            continue
+        if variant in ("ln_gain_x2", "all") and (k.endswith("norm1.weight") or k.endswith("norm2.weight")):
+            sd[k] *= 2.0
+        if variant in ("ffn_x1p5", "all") and (k.endswith("linear1.weight") or k.endswith("linear2.weight")):
+            sd[k] *= 1.5
+        if variant in ("attn_sharp_x3", "all") and k.endswith("in_proj_weight"):
+            sd[k][:128] *= 3.0
+    m.load_state_dict(sd, strict=True)
+    m = m.to(DEV).eval()
+    feed = _feed(case)
+    nat = m.native()
+    planes, feats = nat.encode(feed["img_input"], want_feats=True)
+    pts = synth.make_3d_grid((-0.5,) * 3, (0.5,) * 3, (17, 17, 17))
+    T = feed["trans_mat_wo_rot_tp"][0]
+    q = oracle.prepare_queries(pts.unsqueeze(0), None, "test")
+    sd64 = {k: (v.double() if v.is_floating_point() else v) for k, v in sd.items()}
+    with torch.no_grad():
+        want = oracle.decode(sd64, [f.cpu().double() for f in feats], q.double(), T.cpu().double().unsqueeze(0), 12)[0]
+    spread = float(want.std())
+    helpers.record(f"stress_{variant}_sdf_std", spread)
+    for prec in ["fp32"] + TC3:
+        got = nat.decode(planes, 0, pts.to(DEV), T, precision=prec)
+        err = helpers.maxabs(got.cpu(), want)
+        print(f"stress {variant}: {prec} max-abs {err:.3e} vs float64 (sdf std {spread:.3f})")
+        helpers.record(f"stress_{variant}_{prec}_max_abs_vs_float64", err)
+        assert np.isfinite(err)
+        if variant == "synthetic" or (prec in ("fp32", "fp16x3") and variant != "all"):
+            assert err < TOL
+    # precision="auto" (the default): fp16f8 only where a probe against the fp32 path on these planes confirms it
+    import warnings
+    with warnings.catch_warnings(record=True) as caught:
+        warnings.simplefilter("always")
+        got = nat.decode(planes, 0, pts.to(DEV), T, precision="auto")
+    err = helpers.maxabs(got.cpu(), want)
+    info = nat.auto_info
+    print(f"stress {variant}: auto -> {info['selected']} (probe {info['fp16f8_max_abs_vs_fp32']:.3e}), max-abs {err:.3e}")
+    helpers.record(f"stress_{variant}_auto_probe_fp16f8_vs_fp32", info["fp16f8_max_abs_vs_fp32"])
+    helpers.record(f"stress_{variant}_auto_max_abs_vs_float64", err)
+    if variant == "synthetic":
+        assert info["selected"] == "fp16f8" and not caught
+    if variant in ("ln_gain_x2", "all"):
+        assert info["selected"] == "fp16x3" and any("fp16x3" in str(w.message) for w in caught)
+    if variant != "all":
         assert err < TOL
