@@ -15,7 +15,7 @@
 //                   which IS the convolution's zero padding -- landing as [128 pixels][64 ch] K-major tiles in the
 //                   128-byte-swizzle layout UMMA reads; plus one bulk copy of the pre-swizzled weight tile
 //                   ([BN][64] hi | lo).  NST-stage ring, mbarrier complete_tx.
-//   MMA warp        per k-block 4 k-steps x 3 passes (lo.hi + hi.lo + hi.hi) into one of two TMEM accumulators;
+//   MMA warp        per k-block 4 k-steps x 3 passes (lo.hi + hi.lo + hi.hi) into the next of the 512 / BN TMEM accumulators;
 //                   tcgen05.commit frees the stage and hands the accumulator to the epilogue warps.
 //   8 epilogue warps  drain every k-block's accumulator into fp32 registers (round-to-nearest running sum, see the
 //                   note at the kernel), then (+ slice-independent addend) * scale + shift, ReLU -> fp32 NHWC
@@ -76,15 +76,26 @@ struct CtSmem {
   static constexpr uint32_t B_PART = BN * 128;                    // [BN][64] fp16
   static constexpr uint32_t STAGE = 2 * CT_A_PART + 2 * B_PART;   // A hi | A lo | B hi | B lo
   static constexpr uint32_t OFF_BAR = NST * STAGE;
-  static constexpr uint32_t OFF_TMEMPTR = OFF_BAR + 8 * (2 * NST + 4);
+  static constexpr int NACC = 512 / BN;                           // accumulator buffers: all of tensor memory
+  static constexpr uint32_t OFF_TMEMPTR = OFF_BAR + 8 * (2 * NST + 2 * NACC);
   static constexpr uint32_t BYTES = OFF_TMEMPTR + 16 + 1024;      // + alignment slack
 };
 
 // Accumulation: the tensor core adds every MMA's products into the fp32 TMEM accumulator with truncation, a
 // bias of ~2^-24 of the accumulator per instruction; over the 864 instructions of a K = 4608 contraction that
 // was measured as ~1e-4 relative error after the 13-convolution trunk.  So a TMEM accumulator only ever holds ONE
-// k-block (12 instructions); the epilogue warps drain it (double-buffered) and keep the running sum in registers
-// with round-to-nearest fp32 adds.
+// k-block (12 instructions); the epilogue warps drain it and keep the running sum in registers with round-to-nearest
+// fp32 adds.  (Measured in round 2: chaining 2 / 3 k-blocks per drain costs 1.0e-4 / 1.6e-4 on the feature planes instead
+// of 4.7e-5, for 4-5 % of the encoder's time.)  The accumulators rotate through ALL of tensor memory (512 / BN buffers):
+// with two, the hand-over "commit -> 8 epilogue warps drain -> 8 arrives -> MMA warp" (~1 kcycle round trip, see
+// tools/sync_cost.cu) sat between every second k-block and the next; with 4-8 in flight it is hidden (encoder 2.20 -> 1.97 ms).
+// What is left is the MMA warp's own issue time: a Cout = 64 layer issues N = 64 MMAs at ~55 cycles each (their floor is
+// 32) plus ~350 cycles of waits / commits per k-block -- the two 64 -> 64 convolutions of the last Up stage run 10.3 kcycles
+// per 128-pixel tile against 3.5 of tensor-pipe time.  L2 -> shared-memory traffic is NOT the limit: a variant that kept
+// the nine weight tiles resident and loaded three 130-pixel halo rows per tile (100 KB instead of 432 KB per tile; tap
+// operands = descriptors whose start address is shifted by dx x 128 bytes, which works with the descriptor's base-offset
+// field left at ZERO -- the swizzle follows the absolute shared-memory address; setting the field as the PTX text
+// suggests gives wrong results) was bit-identical and exactly as fast (2.11 vs 2.12 ms), so it was not kept.
 template <int BN, int NST>
 __global__ void __launch_bounds__(CT_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo, const ConvTcParams p) {
@@ -96,21 +107,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   auto full = [&](int s) { return sbase + L::OFF_BAR + 8u * s; };
   auto empty = [&](int s) { return sbase + L::OFF_BAR + 8u * (NST + s); };
+  constexpr uint32_t NACC = L::NACC;
   auto acc_full = [&](int b) { return sbase + L::OFF_BAR + 8u * (2 * NST + b); };
-  auto acc_empty = [&](int b) { return sbase + L::OFF_BAR + 8u * (2 * NST + 2 + b); };
+  auto acc_empty = [&](int b) { return sbase + L::OFF_BAR + 8u * (2 * NST + NACC + b); };
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < NST; ++s) {
       mbar_init(full(s), 1);
       mbar_init(empty(s), 1);
     }
-    for (int b = 0; b < 2; ++b) {
+    for (int b = 0; b < (int)NACC; ++b) {
       mbar_init(acc_full(b), 1);
       mbar_init(acc_empty(b), CT_EPI_WARPS);
     }
     fence_barrier_init();
   }
-  if (warp == 0) tmem_alloc(sbase + L::OFF_TMEMPTR, 2 * BN);
+  if (warp == 0) tmem_alloc(sbase + L::OFF_TMEMPTR, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -167,8 +179,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
 #pragma unroll 1
       for (int kb = 0; kb < p.nkb; ++kb, ++g) {
         const uint32_t s = g % NST, it = g / NST;
-        const uint32_t buf = g & 1;
-        mbar_wait(acc_empty(buf), ((g >> 1) & 1) ^ 1u);  // the epilogue has drained this accumulator
+        const uint32_t buf = g % NACC;
+        mbar_wait(acc_empty(buf), ((g / NACC) & 1) ^ 1u);  // the epilogue has drained this accumulator
         mbar_wait(full(s), it & 1);
         tc_fence_after();
         if (elect_one()) {
@@ -215,8 +227,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
     for (int c = 0; c < NC; ++c) acc[c] = 0.f;
 #pragma unroll 1
     for (int kb = 0; kb < p.nkb; ++kb, ++g) {
-      const uint32_t buf = g & 1;
-      mbar_wait(acc_full(buf), (g >> 1) & 1);
+      const uint32_t buf = g % NACC;
+      mbar_wait(acc_full(buf), (g / NACC) & 1);
       tc_fence_after();
 #pragma unroll
       for (int j = 0; j < NC / 32; ++j) {
@@ -294,7 +306,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem, 2 * BN);
+  if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
