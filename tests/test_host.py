@@ -222,3 +222,43 @@ def test_load_pretrained_vgg_maps_torchvision_keys():
         warnings.simplefilter("always")
         fresh(feed)
     assert any("pretrained" in str(x.message) for x in w)
+
+
+def test_auto_precision_selection_policy():
+    """precision='auto' (the package default): fp16f8 only when the probe against the fp32 path stays within AUTO_TOL,
+    otherwise fp16x3 with a warning; resolved once per packed-weight handle; explicit modes pass through untouched.  (The
+    probe itself needs a GPU: tests/test_gpu_parity.py::test_decoder_error_margin_under_weight_scale_stress.)"""
+    import warnings
+
+    def handle():
+        nm = object.__new__(_native.NativeModel)  # no CUDA handle: only the selection logic is exercised
+        nm._auto, nm.auto_info, nm._h = None, None, None
+        return nm
+
+    calls = []
+
+    def probe(err):
+        def run(prec):
+            calls.append(prec)
+            return torch.zeros(64) if prec == "fp32" else torch.full((64,), err)
+        return run
+
+    nm = handle()
+    assert nm.resolve_precision("fp16x3") == "fp16x3" and nm.resolve_precision("fp32", probe(1.0)) == "fp32" and not calls
+    with pytest.raises(_native.NativeError):
+        nm.resolve_precision("auto")
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        assert nm.resolve_precision("auto", probe(0.5 * _native.AUTO_TOL)) == "fp16f8" and not w
+    assert calls == ["fp32", "fp16f8"] and nm.auto_info["selected"] == "fp16f8"
+    assert nm.resolve_precision("auto", probe(1.0)) == "fp16f8" and len(calls) == 2  # resolved once per handle
+    nm = handle()
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        assert nm.resolve_precision("auto", probe(2.0 * _native.AUTO_TOL)) == "fp16x3"
+    assert any("fp16x3" in str(x.message) for x in w) and nm.auto_info["fp16f8_max_abs_vs_fp32"] > _native.AUTO_TOL
+    nm = handle()
+    with warnings.catch_warnings(record=True):
+        warnings.simplefilter("always")
+        assert nm.resolve_precision("auto", probe(float("nan"))) == "fp16x3"  # a NaN probe never selects the fast mode
+    assert Slices3DRegModel(64, 12, "test").precision == "auto"
