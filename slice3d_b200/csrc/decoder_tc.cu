@@ -97,7 +97,7 @@ constexpr uint32_t TM_D1 = 128;   //   128..511  three FFN chunk buffers of 128 
                                   //             owns columns 32g .. 32g+31 of a row writes the packed H values of the same hidden
                                   //             units back into them -- [hi 16 | lo 16] columns, fp16f8: [fp16 16 | e4m3 8 | e4m3 8]
 constexpr int NDBUF = 3;
-constexpr uint32_t TM_HT = 384;   //   (self-test kernels only: a contiguous H operand, hi 64 | lo 64 columns)
+constexpr uint32_t TM_HT = 384;   //   (self-test kernels: one chunk buffer in the same in-place layout)
 
 // Phase-cycle counters (clock64 deltas summed over CTAs), read through s3d_debug_profile().
 enum { PF_TOKEN = 0, PF_VEC, PF_WAIT_QKV, PF_ATTN, PF_WAIT_OUT, PF_LN1, PF_FFN_WAIT_D1, PF_FFN_MATH, PF_FFN_WAIT_HFREE,
@@ -214,7 +214,8 @@ __device__ __forceinline__ void issue_part_ts(uint32_t d_tmem, uint32_t a0_tmem,
 #pragma unroll
       for (int ks = 0; ks < KS; ++ks) {
         const uint32_t kb = ks >> 2, kin = (ks & 3) * 32;
-        umma_bf16_ts(d_tmem, at + 8 * ks, bd + ((kb * B_KB + kin) >> 4), IDESC, (pass == 0 && ks == 0 && fresh) ? 0u : 1u);
+        const uint32_t acol = INPLACE ? 32u * (ks >> 1) + 8u * (ks & 1) : 8u * ks;
+        umma_bf16_ts(d_tmem, at + acol, bd + ((kb * B_KB + kin) >> 4), IDESC, (pass == 0 && ks == 0 && fresh) ? 0u : 1u);
       }
     }
   }
@@ -1383,14 +1384,14 @@ __global__ void __launch_bounds__(128, 1) umma_selftest_kernel(const float* __re
       store_chunk<NPASS, F16>(sgen + OFF_AX_HI + (kc >> 3) * 16384, sgen + OFF_AX_LO + (kc >> 3) * 16384, r, kc & 7, v);
     }
     fence_proxy_async_smem();
-  } else {  // packed bf16 pairs, column = k / 2: hi at columns TM_HT.., lo at TM_HT + 64..
+  } else {  // the decoder's in-place H layout (TM_D1): per 32 k values one 32-column block [hi 16 | lo 16]
     for (int j = 0; j < 4; ++j) {
       float v[32];
       for (int i = 0; i < 32; ++i) v[i] = A[r * 128 + 32 * j + i];
       uint32_t h[16], l[16];
       for (int c = 0; c < 4; ++c) split8x<NPASS == 3, F16>(v + 8 * c, h + 4 * c, l + 4 * c);
-      tmem_st16(trow + TM_HT + 16 * j, h);
-      if (NPASS == 3) tmem_st16(trow + TM_HT + 64 + 16 * j, l);
+      tmem_st16(trow + TM_HT + 32 * j, h);
+      if (NPASS == 3) tmem_st16(trow + TM_HT + 32 * j + 16, l);
     }
     tmem_st_wait();
     tc_fence_before();
@@ -1405,8 +1406,8 @@ __global__ void __launch_bounds__(128, 1) umma_selftest_kernel(const float* __re
       issue_part<1, (NPASS == 3 ? 2 : 1), 8, 16384u, 16384u, ID>(tmem, sbase + OFF_AX_HI, sbase + OFF_AX_LO, w, true);
       if (NPASS == 3) issue_part<1, 1, 8, 16384u, 16384u, ID>(tmem, sbase + OFF_AX_HI, sbase + OFF_AX_HI, w + UNIT_PART_BYTES, false);
     } else {
-      issue_part_ts<1, (NPASS == 3 ? 2 : 1), 8, 16384u, ID>(tmem, tmem + TM_HT, tmem + TM_HT + 64, w, true);
-      if (NPASS == 3) issue_part_ts<1, 1, 8, 16384u, ID>(tmem, tmem + TM_HT, tmem + TM_HT, w + UNIT_PART_BYTES, false);
+      issue_part_ts<1, (NPASS == 3 ? 2 : 1), 8, 16384u, ID, true>(tmem, tmem + TM_HT, tmem + TM_HT + 16, w, true);
+      if (NPASS == 3) issue_part_ts<1, 1, 8, 16384u, ID, true>(tmem, tmem + TM_HT, tmem + TM_HT, w + UNIT_PART_BYTES, false);
     }
     umma_commit(done);
   }
@@ -1501,7 +1502,12 @@ __global__ void __launch_bounds__(128, 1) umma_selftest_f8_kernel(const float* _
     float v[32];
     for (int i = 0; i < 32; ++i) v[i] = A[r * 128 + 32 * j + i];
     uint32_t h[16], l8[8], h8[8];
-    for (int c = 0; c < 4; ++c) split8_f8(v + 8 * c, h + 4 * c, l8 + 2 * c, h8 + 2 * c);
+    if (mode == 0) {
+      for (int c = 0; c < 4; ++c) split8_f8(v + 8 * c, h + 4 * c, l8 + 2 * c, h8 + 2 * c);
+    } else {  // linear2's path: the H split from 128 h, as the linear1 epilogue does it
+      for (int i = 0; i < 32; ++i) v[i] *= F8_XS;
+      for (int c = 0; c < 4; ++c) split8_f8_h(v + 8 * c, h + 4 * c, l8 + 2 * c, h8 + 2 * c);
+    }
     if (mode == 0) {
       for (int c = 0; c < 4; ++c)
         *reinterpret_cast<uint4*>(sgen + OFF_AX_HI + (j >> 1) * 16384 + sw128_chunk_off(r, (j & 1) * 4 + c)) =
@@ -1513,9 +1519,9 @@ __global__ void __launch_bounds__(128, 1) umma_selftest_f8_kernel(const float* _
             make_uint4(h8[4 * c], h8[4 * c + 1], h8[4 * c + 2], h8[4 * c + 3]);
       }
     } else {
-      tmem_st16(trow + TM_HT + 16 * j, h);
-      tmem_st8(trow + TM_HT + 64 + 8 * j, l8);
-      tmem_st8(trow + TM_HT + 96 + 8 * j, h8);
+      tmem_st16(trow + TM_HT + 32 * j, h);  // the decoder's in-place layout: [fp16 16 | e4m3 lo 8 | e4m3 hi 8] per block
+      tmem_st8(trow + TM_HT + 32 * j + 16, l8);
+      tmem_st8(trow + TM_HT + 32 * j + 24, h8);
     }
   }
   if (mode == 0) fence_proxy_async_smem();
@@ -1536,10 +1542,10 @@ __global__ void __launch_bounds__(128, 1) umma_selftest_f8_kernel(const float* _
         umma_f8(tmem, make_desc_sw128(sbase + OFF_AX_LO + 16384 + 32 * ks), make_desc_sw128(w + UNIT_PART_BYTES + 16384 + 32 * ks), ID, 1u);
       }
     } else {
-      issue_part_ts<1, 1, 8, 16384u, ID>(tmem, tmem + TM_HT, tmem + TM_HT, w, true);
+      issue_part_ts<1, 1, 8, 16384u, ID, true>(tmem, tmem + TM_HT, tmem + TM_HT, w, true);
       for (uint32_t ks = 0; ks < 4; ++ks) {
-        umma_f8_ts(tmem, tmem + TM_HT + 64 + 8 * ks, make_desc_sw128(w + UNIT_PART_BYTES + 32 * ks), ID, 1u);
-        umma_f8_ts(tmem, tmem + TM_HT + 96 + 8 * ks, make_desc_sw128(w + UNIT_PART_BYTES + 16384 + 32 * ks), ID, 1u);
+        umma_f8_ts(tmem, tmem + TM_HT + 32 * ks + 16, make_desc_sw128(w + UNIT_PART_BYTES + 32 * ks), ID, 1u);
+        umma_f8_ts(tmem, tmem + TM_HT + 32 * ks + 24, make_desc_sw128(w + UNIT_PART_BYTES + 16384 + 32 * ks), ID, 1u);
       }
     }
     umma_commit(done);

@@ -46,23 +46,6 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
 }
-// Pure polling (test_wait never suspends the thread): for the one or two waits whose wake-up latency is on the critical path.
-__device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait_spin(uint32_t bar, uint32_t parity) {
-  while (!mbar_test_wait(bar, parity)) {
-  }
-}
-
 // ---------------------------------------------------------------- cluster (CTA pair) helpers
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
