@@ -162,9 +162,19 @@ size_t encoder_workspace_bytes(int B, int K, int S);
 
 // conv_tc.cu
 int convtc_pack(s3d_model* m, const ConvW& cw, int src_cin, int ci0, int cin, ConvTC& out, cudaStream_t st);
+// Split-K scratch of the tensor-core convolutions: partial tiles + per-tile arrival counters.  The owner zeroes the
+// counters before the first launch that uses them; the kernel leaves them zero.
+struct SplitK {
+  float* part = nullptr;
+  size_t part_bytes = 0;
+  unsigned* cnt = nullptr;
+  int n_cnt = 0;
+};
+constexpr size_t SPLITK_PART_BYTES = 16u << 20;
+constexpr int SPLITK_COUNTERS = 1024;
 int conv_tc(const ConvTC& w, const __half* in_hi, const __half* in_lo, int NI, int H, int W, const float* add,
             int add_div, int relu, float* out_f32, int ldf, __half* out_hi, __half* out_lo, int lds, cudaStream_t st,
-            int shuffle_c = 0);
+            int shuffle_c = 0, const SplitK* sk = nullptr);
 int enctc_pack(s3d_model* m, cudaStream_t st);
 
 // mcubes.cu
@@ -246,7 +256,7 @@ size_t gt_decoder_workspace_bytes(int64_t n, int precision);
 int gt_decoder_fwd(const s3d_model* m, const void* planes, int S, QueryCtx q, int64_t n, float out_scale, float* out,
                    int precision, void* ws, size_t ws_bytes, cudaStream_t st);
 int trunk_tc(const s3d_model* m, const float* img, int B, int S, float* x0, float* ta, float* tb, float* const* x,
-             float* const* xs, cudaStream_t st);
+             float* const* xs, cudaStream_t st, const SplitK* sk = nullptr);
 
 // decoder_simt.cu
 size_t decoder_simt_workspace_bytes(int64_t n);

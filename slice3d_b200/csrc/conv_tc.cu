@@ -38,6 +38,7 @@ using namespace ptx;
 constexpr int CT_EPI_WARPS = 8;
 constexpr int CT_THREADS = 64 + 32 * CT_EPI_WARPS;
 constexpr uint32_t CT_A_PART = 16384;  // [128 pixels][64 ch] fp16
+constexpr int CT_MAX_KSPLIT = 4;       // split-K factor: the last item of a tile reads every partial tile through ONE SM
 
 struct ConvTcParams {
   int H, W, NI;
@@ -62,6 +63,13 @@ struct ConvTcParams {
   __half* out_hi;  // split NHWC, row pitch lds >= Cout; channels [Cout, lds) are written as zero (or null)
   __half* out_lo;
   int lds;
+  // split-K (deep contractions over few pixels: the 16^2 / 32^2 trunk layers fill 8-32 of the 148 SMs otherwise): work
+  // item = (tile, split) with the split fastest; every item writes its fp32 partial tile to `part`, the item that arrives
+  // LAST at the tile's counter sums the partials in split order (so the result does not depend on who was last) and runs
+  // the epilogue.  The counters are zero before the launch and are left zero.
+  int ksplit;
+  float* part;    // [tiles][ksplit][128 rows][BN]
+  unsigned* cnt;  // [tiles]
 };
 
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, int c2, int c3, uint32_t bar) {
@@ -96,7 +104,7 @@ struct CtSmem {
 // operands = descriptors whose start address is shifted by dx x 128 bytes, which works with the descriptor's base-offset
 // field left at ZERO -- the swizzle follows the absolute shared-memory address; setting the field as the PTX text
 // suggests gives wrong results) was bit-identical and exactly as fast (2.11 vs 2.12 ms), so it was not kept.
-template <int BN, int NST>
+template <int BN, int NST, bool SPLIT>
 __global__ void __launch_bounds__(CT_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo, const ConvTcParams p) {
   using L = CtSmem<BN, NST>;
@@ -133,8 +141,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
   // tile (affine, stores) the producer and the MMA warp are already in the next one.
   const int tiles_img = p.tiles_x * p.tiles_y;
   const int n_tiles = p.n_tiles;
-  const int total_tiles = tiles_img * p.NI * n_tiles;
-  auto decode = [&](int t, int& img, int& x0, int& y0, int& n_tile) {
+  const int ksplit = SPLIT ? p.ksplit : 1;  // (compile-time 1 in the unsplit instantiation: its code is the round-1 kernel's)
+  const int total_tiles = tiles_img * p.NI * n_tiles * ksplit;  // work items
+  auto kb_range = [&](int item, int& kb0, int& kb1) {
+    const int sp = item % ksplit;
+    kb0 = (int)((long long)sp * p.nkb / ksplit);
+    kb1 = (int)((long long)(sp + 1) * p.nkb / ksplit);
+  };
+  auto decode = [&](int item, int& img, int& x0, int& y0, int& n_tile) {
+    const int t = item / ksplit;
     n_tile = t % n_tiles;
     const int mt = t / n_tiles;
     img = mt / tiles_img;
@@ -151,8 +166,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
       int img, x0, y0, n_tile;
       decode(t, img, x0, y0, n_tile);
       const uint8_t* wsrc = p.wimg + (size_t)n_tile * p.nkb * (2 * L::B_PART);
+      int kb0, kb1;
+      kb_range(t, kb0, kb1);
 #pragma unroll 1
-      for (int kb = 0; kb < p.nkb; ++kb, ++g) {
+      for (int kb = kb0; kb < kb1; ++kb, ++g) {
         const uint32_t s = g % NST, it = g / NST;
         mbar_wait(empty(s), (it & 1) ^ 1u);  // "empty"-type: the first pass over the ring does not block
         if (lane == 0) {
@@ -173,11 +190,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
     }
   } else if (warp == 1) {
     // ===================================================================== MMA issuer
+    // (Round 2 experiment, not kept: TWO issuer warps taking the k-blocks alternately -- every k-block has its own
+    // accumulator, so they need no order -- made the big layers 4-7 % SLOWER: 243 vs 230 us for the 64 -> 64 layers.)
     constexpr uint32_t IDESC = make_idesc_f16(BN, 128);
     uint32_t g = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      int kb0, kb1;
+      kb_range(t, kb0, kb1);
 #pragma unroll 1
-      for (int kb = 0; kb < p.nkb; ++kb, ++g) {
+      for (int kb = kb0; kb < kb1; ++kb, ++g) {
         const uint32_t s = g % NST, it = g / NST;
         const uint32_t buf = g % NACC;
         mbar_wait(acc_empty(buf), ((g / NACC) & 1) ^ 1u);  // the epilogue has drained this accumulator
@@ -225,8 +246,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
     float acc[NC];
 #pragma unroll
     for (int c = 0; c < NC; ++c) acc[c] = 0.f;
+    int kb0, kb1;
+    kb_range(t, kb0, kb1);
 #pragma unroll 1
-    for (int kb = 0; kb < p.nkb; ++kb, ++g) {
+    for (int kb = kb0; kb < kb1; ++kb, ++g) {
       const uint32_t buf = g % NACC;
       mbar_wait(acc_full(buf), (g / NACC) & 1);
       tc_fence_after();
@@ -242,7 +265,54 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
       __syncwarp();
       if (lane == 0) mbar_arrive(acc_empty(buf));
     }
-    if (valid) {
+    bool finish = true;
+    if (SPLIT) {
+      const int tile = t / ksplit, sp = t - tile * ksplit;
+      // partial tile of item (tile, sp): [column half ch][16-byte chunk c][row] -- a warp's 32 rows are contiguous
+      auto part_ptr = [&](int sp_) {
+        return reinterpret_cast<float4*>(p.part) + (((size_t)tile * ksplit + sp_) * 2 + ch) * (size_t)(NC / 4) * 128 + row;
+      };
+      float4* mine = part_ptr(sp);
+#pragma unroll
+      for (int c = 0; c < NC / 4; ++c) __stcg(mine + c * 128, make_float4(acc[4 * c], acc[4 * c + 1], acc[4 * c + 2], acc[4 * c + 3]));
+      __threadfence();
+      named_bar_sync(1, 32 * CT_EPI_WARPS);  // all partial rows of this item are written
+      uint32_t* flag = reinterpret_cast<uint32_t*>(sgen + L::OFF_TMEMPTR + 8);
+      if (warp == 2 && lane == 0) {
+        const unsigned old = atomicAdd(p.cnt + tile, 1u);
+        const bool last = old == (unsigned)(ksplit - 1);
+        if (last) p.cnt[tile] = 0;  // every item of the tile has arrived: leave the counter ready for the next launch
+        __threadfence();
+        *flag = last ? 1u : 0u;
+      }
+      named_bar_sync(1, 32 * CT_EPI_WARPS);
+      finish = *reinterpret_cast<volatile uint32_t*>(flag) != 0u;
+      named_bar_sync(1, 32 * CT_EPI_WARPS);  // (the flag is rewritten by the next item)
+      if (finish) {
+        // sum in split order whoever arrived last (ksplit <= CT_MAX_KSPLIT; absent splits add an exact zero); four
+        // chunks x four splits of loads in flight per thread
+#pragma unroll
+        for (int c0 = 0; c0 < NC / 4; c0 += 4) {
+          float4 v4[CT_MAX_KSPLIT][4];
+#pragma unroll
+          for (int s2 = 0; s2 < CT_MAX_KSPLIT; ++s2) {
+            const float4* src = part_ptr(s2 < ksplit ? s2 : 0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) v4[s2][j] = s2 < ksplit ? __ldcg(src + (c0 + j) * 128) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float4 a = v4[0][j];
+#pragma unroll
+            for (int s2 = 1; s2 < CT_MAX_KSPLIT; ++s2) {
+              a.x += v4[s2][j].x; a.y += v4[s2][j].y; a.z += v4[s2][j].z; a.w += v4[s2][j].w;
+            }
+            acc[4 * (c0 + j)] = a.x; acc[4 * (c0 + j) + 1] = a.y; acc[4 * (c0 + j) + 2] = a.z; acc[4 * (c0 + j) + 3] = a.w;
+          }
+        }
+      }
+    }
+    if (valid && finish) {
 #pragma unroll
       for (int j = 0; j < NC / 32; ++j) {
         float* v = acc + 32 * j;
@@ -346,6 +416,34 @@ int make_tmap(CUtensorMap* tm, const __half* base, int NI, int H, int W, int C, 
   return S3D_OK;
 }
 
+// Split-K factor of one launch.  Cost model in units of one k-block (~0.75 us): waves x k-blocks per item, + 3 per wave
+// for the pipeline fill / drain of an item, + the last item's reduction (2 + ks: it pulls ks x 64 KB through one SM --
+// a first version that split 18 ways made the 16^2 layers SLOWER, 60 vs 54 us).  Split only when the model promises
+// < 0.7 x the unsplit cost and the scratch holds the partial tiles.
+int choose_ksplit(long long tiles, int nkb, int sms, size_t tile_bytes, const SplitK* sk) {
+#ifdef CT_NO_SPLITK  // (A / B builds)
+  return 1;
+#endif
+  if (!sk || !sk->part || !sk->cnt || tiles > sk->n_cnt || tiles >= sms || nkb < 8) return 1;
+  auto cost = [&](int ks) {
+    const long long waves = (tiles * ks + sms - 1) / sms;
+    const int per = (nkb + ks - 1) / ks;
+    return (double)waves * (per + 3) + (ks > 1 ? 2.0 + ks : 0.0);
+  };
+  int best = 1;
+  double best_cost = cost(1);
+  const double base = best_cost;
+  for (int ks = 2; ks <= nkb / 2 && ks <= CT_MAX_KSPLIT; ++ks) {
+    if ((size_t)tiles * ks * tile_bytes > sk->part_bytes) break;
+    const double c = cost(ks);
+    if (c < best_cost) {
+      best_cost = c;
+      best = ks;
+    }
+  }
+  return best_cost < 0.7 * base ? best : 1;
+}
+
 inline uint16_t f16_bits_h(float x) { return __half_as_ushort(__float2half_rn(x)); }
 inline float f16_val_h(uint16_t b) { return __half2float(__ushort_as_half(b)); }
 
@@ -418,7 +516,7 @@ int convtc_pack(s3d_model* m, const ConvW& cw, int src_cin, int ci0, int cin, Co
 // in: split NHWC [NI][H][W][w.cinp] (hi, lo).  Outputs: fp32 NHWC (pitch ldf) and / or split NHWC (pitch lds).
 int conv_tc(const ConvTC& w, const __half* in_hi, const __half* in_lo, int NI, int H, int W, const float* add,
             int add_div, int relu, float* out_f32, int ldf, __half* out_hi, __half* out_lo, int lds,
-            cudaStream_t st, int shuffle_c) {
+            cudaStream_t st, int shuffle_c, const SplitK* sk) {
   if (NI <= 0) return S3D_OK;
   int BW = 1, lg = 0;
   while (BW * 2 <= W && BW < 128) {
@@ -454,18 +552,25 @@ int conv_tc(const ConvTC& w, const __half* in_hi, const __half* in_lo, int NI, i
     S3D_CUDA(cudaGetDevice(&dev));
     S3D_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   }
-  const long long total = (long long)p.tiles_x * p.tiles_y * NI * w.n_tiles;
+  const long long tiles = (long long)p.tiles_x * p.tiles_y * NI * w.n_tiles;
+  p.ksplit = choose_ksplit(tiles, p.nkb, sms, (size_t)128 * w.bn * sizeof(float), sk);
+  if (p.ksplit > 1) {
+    p.part = sk->part;
+    p.cnt = sk->cnt;
+  }
+  const long long total = tiles * p.ksplit;
   dim3 grid((unsigned)(total < sms ? total : sms));
+  auto launch = [&](auto kern, size_t smem) -> int {
+    S3D_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, CT_THREADS, smem, st>>>(tm_hi, tm_lo, p);
+    return S3D_OK;
+  };
   if (w.bn == 128) {
-    using L = CtSmem<128, 3>;
-    auto kern = conv_tc_kernel<128, 3>;
-    S3D_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::BYTES));
-    kern<<<grid, CT_THREADS, L::BYTES, st>>>(tm_hi, tm_lo, p);
+    if (p.ksplit > 1) S3D_TRY(launch(conv_tc_kernel<128, 3, true>, CtSmem<128, 3>::BYTES));
+    else S3D_TRY(launch(conv_tc_kernel<128, 3, false>, CtSmem<128, 3>::BYTES));
   } else {
-    using L = CtSmem<64, 4>;
-    auto kern = conv_tc_kernel<64, 4>;
-    S3D_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::BYTES));
-    kern<<<grid, CT_THREADS, L::BYTES, st>>>(tm_hi, tm_lo, p);
+    if (p.ksplit > 1) S3D_TRY(launch(conv_tc_kernel<64, 4, true>, CtSmem<64, 4>::BYTES));
+    else S3D_TRY(launch(conv_tc_kernel<64, 4, false>, CtSmem<64, 4>::BYTES));
   }
   S3D_LAUNCH_CHECK();
   return S3D_OK;

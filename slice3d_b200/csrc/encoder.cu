@@ -161,6 +161,7 @@ struct Bump {
 struct EncBufs {
   float *x0, *ta, *tb, *x[6], *base5, *skip[5], *pskip[5], *feat[5], *u, *d;
   float *xs[6], *fs[5];  // split copies of the taps / feature planes (inputs of tensor-core GEMMs)
+  SplitK sk;             // split-K scratch of the small-image convolutions (conv_tc.cu)
 };
 
 // A split-fp16 activation tensor carved from `elems` floats of workspace: hi then lo, `elems` bf16 each.
@@ -191,6 +192,10 @@ void carve(Bump& bp, EncBufs& e, int B, int K, int S) {
   for (int s = 0; s < 5; ++s) e.feat[s] = bp.take((size_t)B * K * plane_res(S, s) * plane_res(S, s) * kPlaneC[s]);
   e.u = bp.take((size_t)B * K * S2 * 64);  // (split tensors with the channel pitch padded to 64 at the last stage)
   e.d = bp.take((size_t)B * K * S2 * 64);
+  e.sk.part = bp.take(SPLITK_PART_BYTES / sizeof(float));
+  e.sk.part_bytes = SPLITK_PART_BYTES;
+  e.sk.cnt = reinterpret_cast<unsigned*>(bp.take(SPLITK_COUNTERS));
+  e.sk.n_cnt = SPLITK_COUNTERS;
 }
 
 int conv(const ConvW& w, const float* src0, int c0, int bcast0, const float* src1, int c1, int NI, int H, int W,
@@ -214,7 +219,7 @@ inline unsigned blocks_for(long long n, int t) { return (unsigned)((n + t - 1) /
 // VGG16-BN trunk on B images on the tensor cores (unet_custom.py:42-48 / vgg16bn_feats.py:44-52): taps x[1..5] = the
 // pre-BatchNorm outputs of the last convolution of each block, fp32 NHWC, and their split-fp16 copies xs[1..5].
 int trunk_tc(const s3d_model* m, const float* img, int B, int S, float* x0, float* ta, float* tb, float* const* x,
-             float* const* xs, cudaStream_t st) {
+             float* const* xs, cudaStream_t st, const SplitK* sk) {
   const size_t S2 = (size_t)S * S;
   k_nchw3_to_nhwc4<<<blocks_for((long long)B * S * S, 256), 256, 0, st>>>(img, x0, B, S * S);
   S3D_LAUNCH_CHECK();
@@ -247,10 +252,10 @@ int trunk_tc(const s3d_model* m, const float* img, int B, int S, float* x0, floa
       const bool last = (j == n_conv[b] - 1);
       if (last) {
         Split xo = xs_of(b + 2);
-        S3D_TRY(conv_tc(w, cur.hi, cur.lo, B, H, H, nullptr, 1, 0, x[b + 2], w.cout, xo.hi, xo.lo, w.cout, st));
+        S3D_TRY(conv_tc(w, cur.hi, cur.lo, B, H, H, nullptr, 1, 0, x[b + 2], w.cout, xo.hi, xo.lo, w.cout, st, 0, sk));
       } else {
         Split nxt = split_of(nxt_base, (size_t)B * H * H * w.cout);
-        S3D_TRY(conv_tc(w, cur.hi, cur.lo, B, H, H, nullptr, 1, 1, nullptr, 0, nxt.hi, nxt.lo, w.cout, st));
+        S3D_TRY(conv_tc(w, cur.hi, cur.lo, B, H, H, nullptr, 1, 1, nullptr, 0, nxt.hi, nxt.lo, w.cout, st, 0, sk));
         cur = nxt;
         float* t = cur_base;
         cur_base = nxt_base;
@@ -275,7 +280,7 @@ int trunk_and_up_tc(const s3d_model* m, const float* img, int B, int S, EncBufs&
   const size_t S2 = (size_t)S * S;
   const int xc[6] = {0, 64, 128, 256, 512, 512};
   auto xs_of = [&](int i) { return split_of(e.xs[i], B * (S2 >> (2 * (i - 1))) * xc[i]); };
-  S3D_TRY(trunk_tc(m, img, B, S, e.x0, e.ta, e.tb, e.x, e.xs, st));
+  S3D_TRY(trunk_tc(m, img, B, S, e.x0, e.ta, e.tb, e.x, e.xs, st, &e.sk));
   // latent = trans_c(cat[x5 tiled, slice embedding]) (unet_custom.py:52-57) -> feat[0]
   const int R0 = S / 16;
   auto fs_of = [&](int s) {
@@ -284,7 +289,7 @@ int trunk_and_up_tc(const s3d_model* m, const float* img, int B, int S, EncBufs&
   };
   {
     Split x5 = xs_of(5);
-    S3D_TRY(conv_tc(m->ttrans_c, x5.hi, x5.lo, B, R0, R0, nullptr, 1, 0, e.base5, 512, nullptr, nullptr, 0, st));
+    S3D_TRY(conv_tc(m->ttrans_c, x5.hi, x5.lo, B, R0, R0, nullptr, 1, 0, e.base5, 512, nullptr, nullptr, 0, st, 0, &e.sk));
     long long tot = (long long)B * K * R0 * R0 * (512 / 4);
     Split f0 = fs_of(0);
     k_add_slice_bias<<<blocks_for(tot, 256), 256, 0, st>>>(e.base5, m->trans_c_e, e.feat[0], B, K, R0 * R0, 512, f0.hi, f0.lo);
@@ -298,14 +303,14 @@ int trunk_and_up_tc(const s3d_model* m, const float* img, int B, int S, EncBufs&
     Split sk = split_of(e.skip[n], (size_t)B * R * R * CP);
     Split xin = xs_of(5 - n), fin = fs_of(n - 1), fout = fs_of(n);
     // skip adapter on the un-tiled tap, then the skip half of DoubleConv's first convolution (raw sums)
-    S3D_TRY(conv_tc(m->ttrans_up[n - 1], xin.hi, xin.lo, B, R, R, nullptr, 1, 0, nullptr, 0, sk.hi, sk.lo, CP, st));
-    S3D_TRY(conv_tc(m->tdc1s[n - 1], sk.hi, sk.lo, B, R, R, nullptr, 1, 0, e.pskip[n], C, nullptr, nullptr, 0, st));
+    S3D_TRY(conv_tc(m->ttrans_up[n - 1], xin.hi, xin.lo, B, R, R, nullptr, 1, 0, nullptr, 0, sk.hi, sk.lo, CP, st, 0, &e.sk));
+    S3D_TRY(conv_tc(m->tdc1s[n - 1], sk.hi, sk.lo, B, R, R, nullptr, 1, 0, e.pskip[n], C, nullptr, nullptr, 0, st, 0, &e.sk));
     // ConvTranspose2d 2x2 s2: 1x1 GEMM with N = 4*C + pixel shuffle
     if (CP != C) S3D_CUDA(cudaMemsetAsync(e.u, 0, elems * 4, st));  // zero channel padding of `up`
     S3D_TRY(conv_tc(m->tup_t[n - 1], fin.hi, fin.lo, B * K, Rp, Rp, nullptr, 1, 0, nullptr, 0, su.hi, su.lo, CP, st, C));
     // DoubleConv: per-slice half of the first convolution (+ skip half, BN, ReLU), then the second convolution
-    S3D_TRY(conv_tc(m->tdc1[n - 1], su.hi, su.lo, B * K, R, R, e.pskip[n], K, 1, nullptr, 0, sd.hi, sd.lo, CP, st));
-    S3D_TRY(conv_tc(m->tdc2[n - 1], sd.hi, sd.lo, B * K, R, R, nullptr, 1, 1, e.feat[n], C, fout.hi, fout.lo, CP, st));
+    S3D_TRY(conv_tc(m->tdc1[n - 1], su.hi, su.lo, B * K, R, R, e.pskip[n], K, 1, nullptr, 0, sd.hi, sd.lo, CP, st, 0, &e.sk));
+    S3D_TRY(conv_tc(m->tdc2[n - 1], sd.hi, sd.lo, B * K, R, R, nullptr, 1, 1, e.feat[n], C, fout.hi, fout.lo, CP, st, 0, &e.sk));
   }
   return S3D_OK;
 }
@@ -408,6 +413,7 @@ int encoder_fwd(const s3d_model* m, const float* img, int B, int S, void* planes
   carve(bp, e, B, K, S);
 
   if (!m->enc_simt) {
+    S3D_CUDA(cudaMemsetAsync(e.sk.cnt, 0, SPLITK_COUNTERS * sizeof(unsigned), st));
     S3D_TRY(trunk_and_up_tc(m, img, B, S, e, st));
   } else {
     // ---- VGG16-BN trunk on the input view (unet_custom.py:42-48); taps x1..x5 are the
@@ -524,7 +530,8 @@ int gt_encoder_fwd(const s3d_model* m, const float* img_slices, int B, int S, vo
   Bump bp{static_cast<char*>(ws), 0, ws_bytes};
   EncBufs e;
   carve(bp, e, N, 1, S);
-  S3D_TRY(trunk_tc(m, img_slices, N, S, e.x0, e.ta, e.tb, e.x, e.xs, st));
+  S3D_CUDA(cudaMemsetAsync(e.sk.cnt, 0, SPLITK_COUNTERS * sizeof(unsigned), st));
+  S3D_TRY(trunk_tc(m, img_slices, N, S, e.x0, e.ta, e.tb, e.x, e.xs, st, &e.sk));
   const int xc[6] = {0, 64, 128, 256, 512, 512};
   const size_t per_img = s3d_planes_bytes(1, K, S) / sizeof(float);
   float* pl = static_cast<float*>(planes);

@@ -70,6 +70,23 @@ def test_encoder_odd_sizes_match_oracle(S, K, B):
         c0 += c
 
 
+def test_encoder_split_k_layers_are_run_to_run_identical():
+    """The 16^2 .. 64^2 trunk convolutions run split-K (conv_tc.cu): partial tiles in global scratch, summed in split order
+    by whichever item arrives last -- the planes must not depend on the arrival order: five calls, identical bits; and the
+    workspace counters are left ready (a second call on the same workspace is the same again)."""
+    case = helpers.load_case("k12_s256_g128_g256")
+    m, _ = _model(case)
+    img = _feed(case)["img_input"]
+    nat = m.native()
+    first, feats0 = nat.encode(img, want_feats=True)
+    ref_blob, ref_rec = first.blob.clone(), first.slices_rec.clone()
+    for _ in range(4):
+        planes, feats = nat.encode(img, want_feats=True)
+        assert torch.equal(planes.blob, ref_blob)
+        assert torch.equal(planes.slices_rec, ref_rec)
+        assert all(torch.equal(a, b) for a, b in zip(feats, feats0))
+
+
 def test_projected_planes_are_fc_s_of_feature_planes():
     """The hoisted fc_s projection: plane_s = fc_s[:, scale s columns] . feature plane s."""
     case = helpers.load_case("k12_s128_g128")
