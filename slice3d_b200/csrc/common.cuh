@@ -246,7 +246,10 @@ struct QueryCtx {
   long long per_img;
   size_t plane_stride;
 };
-constexpr int GRID_BX = 16, GRID_BY = 16;
+#ifndef S3D_GRID_B
+#define S3D_GRID_B 16  // (overridable for locality experiments: profiles/r2_summary.md)
+#endif
+constexpr int GRID_BX = S3D_GRID_B, GRID_BY = S3D_GRID_B;
 
 // gt.cu (Slices3DGTModel)
 size_t gt_encoder_workspace_bytes(int N, int S);
