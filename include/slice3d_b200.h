@@ -100,6 +100,9 @@ int s3d_model_n_slices(const s3d_model* m);
  *   feats_nchw_dev  optional (may be NULL, entries may be NULL): the five raw feature
  *                   planes (B*K, C_s, H_s, W_s) fp32 NCHW, C = 512,256,128,64,32.
  *   slices_rec_dev  optional: (B*K,3,S,S) fp32 NCHW, tanh output.
+ *   workspace_dev   s3d_encoder_workspace_bytes(B,K,S) bytes, uninitialised, owned by the caller for the duration of
+ *                   the call (activations + 16 MB of split-K partial tiles and their counters); two calls that may
+ *                   overlap on different streams need two workspaces.
  */
 size_t s3d_planes_bytes(int32_t B, int32_t K, int32_t S);
 size_t s3d_encoder_workspace_bytes(int32_t B, int32_t K, int32_t S);
