@@ -50,6 +50,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the BASELINE configs[4] training leg")
     ap.add_argument("--no-extra", action="store_true", help="skip the e2e_api / sparse / parity blocks")
+    ap.add_argument("--slab-unit", default="auto", choices=["auto", "plane", "row"],
+                    help="granularity of the multi-GPU slabs (Generator3D.slab_unit)")
     ap.add_argument("--cpu-sample", type=int, default=60000, help="queries in the bounded CPU sample (decoder-only leg)")
     return ap.parse_args()
 
@@ -237,6 +239,7 @@ def run_native(args):
     model = model.to(dev).eval()
     feed = synth.synthetic_inputs(S, K, 0)
     gen = Generator3D(model, upsampling_steps=0, resolution0=nx, pred_type="sdf")
+    gen.slab_unit = args.slab_unit
     nat = model.native()
     img_d = feed["img_input"].to(dev)
     T_d = feed["trans_mat_wo_rot_tp"].to(dev)
@@ -297,7 +300,7 @@ def run_native(args):
         launches = _native.launch_count() - l0
         ms = max_over_ranks(s0.elapsed_time(s1))
         dec_ms = sum(a.elapsed_time(b) for a, b, _ in dec_ev) / len(dec_ev)
-        count = int(sum(p for _, _, p in dec_ev) / len(dec_ev)) * nx * nx  # queries of this rank's launch (mean over steps)
+        count = int(round(sum(p for _, _, p in dec_ev) / len(dec_ev) * nx * nx))  # queries of this rank's launches (mean over steps)
         dec_ms_max = max_over_ranks(dec_ms)  # slowest rank's decoder launch (power-capped clocks differ per GPU)
         per_rank = None
         if world > 1:
@@ -305,7 +308,7 @@ def run_native(args):
             allr = torch.empty(world, 2, dtype=torch.float64, device=dev)
             dist.all_gather_into_tensor(allr, mine)
             allr = allr.cpu()
-            per_rank = {"decoder_ms": [round(float(x), 3) for x in allr[:, 0]], "slab_planes": [int(x) for x in allr[:, 1]],
+            per_rank = {"decoder_ms": [round(float(x), 3) for x in allr[:, 0]], "slab_planes": [round(float(x), 4) for x in allr[:, 1]],
                         "decoder_ms_min_mean_max": [float(allr[:, 0].min()), float(allr[:, 0].mean()), float(allr[:, 0].max())]}
         clocks = sampler.stop() if rank == 0 else None
 
@@ -341,7 +344,8 @@ def run_native(args):
         "data": "synthetic",
         "config": bench_config(S, nx),
         "variant": {"step": "plane encoder + decoder over the grid" + (" + slab all-gather" if world > 1 else ""),
-                    "precision": prec, "precision_selection": nat.auto_info, "parallelism": f"axis-0 slabs x{world}" if world > 1 else "single GPU"},
+                    "precision": prec, "precision_selection": nat.auto_info, "parallelism": f"axis-0 slabs x{world}" if world > 1 else "single GPU",
+                    "slab_unit": ("row" if gen._slab_units(nx, world) == nx * nx else "plane") if world > 1 else None},
         "e2e": {"value": nx ** 3 * args.steps / (e2e_ms / 1e3), "unit": UNIT,
                 "h2d_bytes_per_step": int(feed["img_input"].numel() * 4 + feed["trans_mat_wo_rot_tp"].numel() * 4),
                 "d2h_bytes_per_step": int(nx ** 3 * 4), "ms_per_step": e2e_ms / args.steps},

@@ -55,13 +55,35 @@ def proportional_bounds(nx, rates):
     return b
 
 
-def all_gather_slabs(vol_flat, nx, group=None, bounds=None):
-    """In place: every rank has filled its own slab of ``vol_flat`` (nx^3 values, flat; slab r = planes
-    [bounds[r], bounds[r+1]), equal slabs by default); afterwards every rank holds the whole volume."""
+def split_at_planes(q0, q1, plane):
+    """A contiguous query range [q0, q1) of the flat volume as at most three launch segments (first, count, whole):
+    the rows before the first whole axis-0 plane, the whole planes, the rows after them.  Whole planes are decoded in the
+    locality order of the library (csrc/common.cuh:grid_point); partial planes in flat order.  Values do not depend on
+    the segmentation (every query is computed independently)."""
+    if q1 <= q0:
+        return []
+    a = -(-q0 // plane) * plane  # first plane boundary >= q0
+    b = (q1 // plane) * plane    # last plane boundary <= q1
+    if a >= b:  # no whole plane inside the range: one launch in flat order
+        return [(q0, q1 - q0, False)]
+    segs = []
+    if a > q0:
+        segs.append((q0, a - q0, False))
+    segs.append((a, b - a, True))
+    if q1 > b:
+        segs.append((b, q1 - b, False))
+    return segs
+
+
+def all_gather_slabs(vol_flat, nx, group=None, bounds=None, units=None):
+    """In place: every rank has filled its own slab of ``vol_flat`` (nx^3 values, flat; slab r = units
+    [bounds[r], bounds[r+1]) of ``units`` equal parts of the volume -- axis-0 planes by default (units = nx), rows when
+    units = nx * nx; equal plane slabs by default); afterwards every rank holds the whole volume."""
     rank, world = rank_world(group)
     if world == 1:
         return vol_flat
-    plane = vol_flat.numel() // nx
+    units = nx if units is None else int(units)
+    plane = vol_flat.numel() // units
     b = list(bounds) if bounds is not None else slab_bounds(nx, world)
     if all(b[r + 1] - b[r] == b[1] - b[0] for r in range(world)):
         lo, hi = b[rank], b[rank + 1]

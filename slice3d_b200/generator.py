@@ -58,6 +58,10 @@ class Generator3D(object):
         self.device_rounds = True
         self.sparse_capacity = None
         self.balance_slabs = True   # multi-GPU dense grid: slab widths follow the ranks' measured decoder rates
+        # granularity of those slabs: "plane" (axis-0 planes), "row" (rows of nz queries: a slab may start / end inside a
+        # plane, decoded as up to three launches), or "auto" = rows once a plane is more than ~1.5 % of a rank's share
+        # (fewer than 64 planes per rank: one plane of 32 is 3 %, the ranks' rates differ by ~1 %)
+        self.slab_unit = "auto"
         self._last_dec = None
         if vol_info is not None:
             self.input_vol, _, _ = vol_info
@@ -137,20 +141,31 @@ class Generator3D(object):
         ax = box_size * torch.linspace(-0.5, 0.5, nx)
         return ax.to(device)
 
+    def _slab_units(self, nx, world):
+        """Number of equal parts the volume is cut into for the slab boundaries: nx (planes) or nx * nx (rows)."""
+        unit = self.slab_unit
+        if unit == "auto":
+            unit = "row" if (world > 1 and nx // world < 64) else "plane"
+        if unit not in ("plane", "row"):
+            raise ValueError(f"slab_unit must be 'plane', 'row' or 'auto', not {self.slab_unit!r}")
+        return nx * nx if unit == "row" else nx
+
     def _slab_plan(self, nx, rank, world, group, dev):
-        """Axis-0 slab boundaries of this call.  With ``balance_slabs`` the widths follow the ranks' measured decoder
-        rates of the previous call at the same size (GPUs of one box differ by a few per cent under the power cap;
-        the step ends when the slowest rank does): one tiny all-gather of (planes, milliseconds) per call."""
+        """Slab boundaries of this call, in units of 1 / ``_slab_units`` of the volume (axis-0 planes or rows).  With
+        ``balance_slabs`` the widths follow the ranks' measured decoder rates of the previous call at the same size
+        (GPUs of one box differ by a few per cent under the power cap; the step ends when the slowest rank does): one
+        tiny all-gather of (planes, milliseconds) per call."""
+        units = self._slab_units(nx, world)
         prev = self._last_dec
         if not (self.balance_slabs and world > 1 and prev is not None and prev[3:] == (nx, world)):
-            return s3d_dist.slab_bounds(nx, world)
+            return [b * (units // nx) for b in s3d_dist.slab_bounds(nx, world)], units
         e0, e1, planes = prev[:3]
         e1.synchronize()
         mine = torch.tensor([float(planes), max(e0.elapsed_time(e1), 1e-3)], dtype=torch.float64, device=dev)
         allr = torch.empty(world, 2, dtype=torch.float64, device=dev)
         torch.distributed.all_gather_into_tensor(allr, mine, group=group)
         allr = allr.cpu()
-        return s3d_dist.proportional_bounds(nx, [float(p / t) for p, t in allr.tolist()])
+        return s3d_dist.proportional_bounds(units, [float(p / t) for p, t in allr.tolist()]), units
 
     def generate_grid(self, data, resolution=None, precision=None, group=None, as_numpy=True, out_host=None,
                       host_rank=None):
@@ -182,19 +197,21 @@ class Generator3D(object):
         planes = model.encode(img)
         ax = self.grid_axes(nx, dev)
         rank, world = s3d_dist.rank_world(group)
-        bounds = self._slab_plan(nx, rank, world, group, dev)
+        bounds, units = self._slab_plan(nx, rank, world, group, dev)
+        per_unit = nx ** 3 // units  # queries per boundary unit (a plane or a row)
         lo, hi = bounds[rank], bounds[rank + 1]
         vol = torch.empty(nx * nx * nx, dtype=torch.float32, device=dev)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        if hi > lo:
-            first, count = lo * nx * nx, (hi - lo) * nx * nx
+        # whole planes in one launch (locality order); with row-granular slabs the rows before / after them in two more
+        for first, count, _whole in s3d_dist.split_at_planes(lo * per_unit, hi * per_unit, nx * nx):
             nat.decode_grid(planes, 0, (ax, ax, ax), first, count, T[0], out_scale=-1.0, precision=precision,
                             out=vol[first:first + count])
         e1.record()
-        self._last_dec = (e0, e1, hi - lo, nx, world)
+        # (e0, e1, this rank's share in PLANES -- fractional with row-granular slabs --, nx, world)
+        self._last_dec = (e0, e1, (hi - lo) * per_unit / float(nx * nx), nx, world)
         if world > 1:
-            s3d_dist.all_gather_slabs(vol, nx, group, bounds)
+            s3d_dist.all_gather_slabs(vol, nx, group, bounds, units=units)
         vol = vol.view(nx, nx, nx)
         if host_rank is not None and rank != host_rank:
             return None

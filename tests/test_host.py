@@ -124,6 +124,16 @@ r = dist.get_rank()
 vol[b[r] * 6:b[r + 1] * 6] = full[b[r] * 6:b[r + 1] * 6]
 sd.all_gather_slabs(vol, 8, bounds=b)
 ok = ok and torch.equal(vol, full)
+# row-granular slabs (Generator3D.slab_unit = "row"): boundaries in rows of nz values, a slab ends inside a plane
+nx = 6
+full = torch.arange(nx ** 3, dtype=torch.float32)
+for rates in ([1.0, 1.3], [2.0, 1.0], [1.0, 1.0]):
+    b = sd.proportional_bounds(nx * nx, rates)
+    vol = torch.full_like(full, -1.0)
+    for first, count, whole in sd.split_at_planes(b[r] * nx, b[r + 1] * nx, nx * nx):
+        vol[first:first + count] = full[first:first + count]
+    sd.all_gather_slabs(vol, nx, bounds=b, units=nx * nx)
+    ok = ok and torch.equal(vol, full)
 dist.destroy_process_group()
 sys.exit(0 if ok else 3)
 """
@@ -135,6 +145,53 @@ def test_proportional_bounds():
     assert b[0] == 0 and b[-1] == 256 and b[8] - b[7] == 31 and all(b[i + 1] - b[i] in (32, 33) for i in range(7))
     assert s3d_dist.proportional_bounds(3, [1, 100, 1]) == [0, 1, 2, 3]  # every rank keeps a plane
     assert s3d_dist.proportional_bounds(2, [1, 1, 1]) == s3d_dist.slab_bounds(2, 3)  # fewer planes than ranks
+
+
+@pytest.mark.parametrize("plane", [1, 4, 36, 65536])
+def test_split_at_planes_covers_the_range_once(plane):
+    """Row-granular slabs: a rank's query range becomes <= 3 launch segments -- rows before the first whole plane, whole
+    planes (marked: decoded in locality order), rows after -- that tile the range exactly, in order."""
+    import random
+    rnd = random.Random(plane)
+    total = plane * 9
+    cases = [(0, total), (0, 0), (5 % total, 5 % total), (plane, 2 * plane), (1 % total, total)]
+    cases += [tuple(sorted((rnd.randrange(total + 1), rnd.randrange(total + 1)))) for _ in range(200)]
+    for q0, q1 in cases:
+        segs = s3d_dist.split_at_planes(q0, q1, plane)
+        assert len(segs) <= 3
+        pos = q0
+        for first, count, whole in segs:
+            assert first == pos and count > 0
+            assert whole == (first % plane == 0 and count % plane == 0)
+            pos += count
+        assert pos == max(q0, q1) if q1 > q0 else segs == []
+        if q1 > q0:
+            assert sum(w for _, _, w in segs) <= 1  # one launch of whole planes at most
+            inner = (q1 // plane) - (-(-q0 // plane))  # whole planes inside the range
+            assert sum(c for _, c, w in segs if w) == max(inner, 0) * plane
+
+
+def test_generator_slab_units_and_row_plan():
+    from slice3d_b200 import Generator3D
+    g = Generator3D(model=None, upsampling_steps=0, resolution0=256)
+    assert g._slab_units(256, 1) == 256 and g._slab_units(256, 2) == 256  # 128 planes per rank: planes are fine enough
+    assert g._slab_units(256, 4) == 256                                   # 64 planes per rank
+    assert g._slab_units(256, 8) == 256 * 256                             # 32 planes per rank: one plane is 3 % -> rows
+    g.slab_unit = "row"
+    assert g._slab_units(256, 2) == 256 * 256
+    g.slab_unit = "plane"
+    assert g._slab_units(256, 8) == 256
+    g.slab_unit = "bogus"
+    with pytest.raises(ValueError):
+        g._slab_units(256, 8)
+    # rates 1 % apart at 8 ranks: plane slabs can only answer with 31 / 32 / 33 planes (3 % steps), row slabs follow them
+    rates = [1.0, 1.01, 0.99, 1.0, 1.005, 0.995, 1.0, 1.0]
+    rows = s3d_dist.proportional_bounds(256 * 256, rates)
+    t_rows = max((rows[i + 1] - rows[i]) / rates[i] for i in range(8))
+    planes = s3d_dist.proportional_bounds(256, rates)
+    t_planes = max((planes[i + 1] - planes[i]) * 256 / rates[i] for i in range(8))
+    ideal = 256 * 256 / sum(rates)
+    assert t_rows / ideal < 1.0002 and t_planes / ideal > 1.005
 
 
 def test_slab_all_gather_world2_gloo(tmp_path):
