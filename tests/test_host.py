@@ -194,6 +194,49 @@ def test_generator_slab_units_and_row_plan():
     assert t_rows / ideal < 1.0002 and t_planes / ideal > 1.005
 
 
+def test_slab_plan_averages_the_last_four_calls(monkeypatch):
+    """Generator3D._slab_plan: this rank's rate is planes / ms summed over its last four launches at the same size (a
+    single call scatters by ~0.4 %); a new size starts a new history.  Events and the all-gather are faked (world 2, the
+    other rank always reports 128 planes in 640 ms per call)."""
+    import torch.distributed as dist
+    from slice3d_b200 import Generator3D
+
+    class Ev:
+        def __init__(self, t):
+            self.t = t
+
+        def synchronize(self):
+            pass
+
+        def elapsed_time(self, other):
+            return other.t - self.t
+
+    g = Generator3D(model=None, upsampling_steps=0, resolution0=256)
+    g.slab_unit = "row"
+
+    def fake_all_gather(out, inp, group=None):
+        n = len(g._rate_hist)
+        out[0] = inp
+        out[1] = torch.tensor([128.0 * n, 640.0 * n], dtype=torch.float64)
+
+    monkeypatch.setattr(dist, "all_gather_into_tensor", fake_all_gather)
+    b, units = g._slab_plan(256, 0, 2, None, "cpu")
+    assert units == 65536 and b == [0, 32768, 65536]  # no history: equal plane-aligned slabs, in rows
+    g._last_dec = (Ev(0.0), Ev(630.0), 128.0, 256, 2)  # this rank was 1.6 % faster than the other
+    b, _ = g._slab_plan(256, 0, 2, None, "cpu")
+    assert b[1] == 33026  # round(65536 * (128/630) / (128/630 + 128/640))
+    g._last_dec = (Ev(0.0), Ev(650.0), 128.0, 256, 2)  # ... then 1.6 % slower: the two calls average out
+    b, _ = g._slab_plan(256, 0, 2, None, "cpu")
+    assert b[1] == 32768 and len(g._rate_hist) == 2
+    for _ in range(5):
+        g._last_dec = (Ev(0.0), Ev(640.0), 128.0, 256, 2)
+        b, _ = g._slab_plan(256, 0, 2, None, "cpu")
+    assert len(g._rate_hist) == 4 and b[1] == 32768
+    g._last_dec = (Ev(0.0), Ev(100.0), 64.0, 128, 2)  # another grid size: the history starts again
+    b, units = g._slab_plan(128, 0, 2, None, "cpu")
+    assert units == 128 * 128 and len(g._rate_hist) == 1 and b[0] == 0 and b[-1] == units
+
+
 def test_slab_all_gather_world2_gloo(tmp_path):
     script = tmp_path / "w.py"
     script.write_text(_WORKER)
