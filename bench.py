@@ -359,23 +359,36 @@ def run_native(args):
                      "peak_source": how + " sustained bf16"},
         "clocks": clocks,
     }
+    # The blocks below are reported beside the headline figures; none of them holds a collective at world == 1 (and the
+    # parity block never does), so a failure there is recorded in its block ({"error": ...}, traceback on stderr) instead
+    # of costing the measured line above.  The multi-rank train leg is left unguarded: its ranks must fail together.
     if not args.no_extra:
         with torch.no_grad():
-            line["parity"] = parity_block(dev, prec)
+            line["parity"] = _guarded(parity_block, dev, prec)
             if world == 1:
-                line["alt_precision"] = alt_precision_block(nat, img_d, T_d, gen, nx, dev, prec, sustained)
-                line["e2e_api"] = e2e_api_block(model, gen, feed, nx, dev, args.steps)
-                line["sparse"] = sparse_block(dev, prec)
-                line["configs1_128"] = small_grid_block(nat, img_d, T_d, gen, dev, prec)
-                line["inputs"] = inputs_block(dev)
+                line["alt_precision"] = _guarded(alt_precision_block, nat, img_d, T_d, gen, nx, dev, prec, sustained)
+                line["e2e_api"] = _guarded(e2e_api_block, model, gen, feed, nx, dev, args.steps)
+                line["sparse"] = _guarded(sparse_block, dev, prec)
+                line["configs1_128"] = _guarded(small_grid_block, nat, img_d, T_d, gen, dev, prec)
+                line["inputs"] = _guarded(inputs_block, dev)
     if not args.no_train:
-        line["train"] = train_leg(dev, world, rank, args.steps, args.warmup, max_over_ranks, barrier)
+        train = _guarded if world == 1 else (lambda f, *a: f(*a))
+        line["train"] = train(train_leg, dev, world, rank, args.steps, args.warmup, max_over_ranks, barrier)
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline(S, nx, args.cpu_sample)
+            line["cpu_baseline"] = _guarded(cpu_baseline, S, nx, args.cpu_sample)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def _guarded(fn, *a):
+    try:
+        return fn(*a)
+    except Exception as e:  # noqa: BLE001 -- reported in the line, never silently dropped
+        import traceback
+        traceback.print_exc(file=sys.stderr)
+        return {"error": f"{type(e).__name__}: {e}"[:400]}
 
 
 def parity_block(dev, prec):
@@ -409,8 +422,11 @@ def alt_precision_block(nat, img_d, T_d, gen, nx, dev, prec, peak):
     ax = gen.grid_axes(nx, dev)
     vol = torch.empty(nx ** 3, dtype=torch.float32, device=dev)
     planes = nat.encode(img_d)
-    for p in ("fp16x3", "bf16x3", "fp16f8"):
+    # "bf16" = configs[2] as literally worded (single bf16 pass): reported with its error, OUTSIDE the 1e-4 contract
+    for p in ("fp16x3", "bf16x3", "fp16f8", "bf16"):
         if p == prec:
+            continue
+        if p == "bf16" and p not in _native_precisions():
             continue
         nat.decode_grid(planes, 0, (ax, ax, ax), 0, nx ** 3, T_d[0], out_scale=-1.0, precision=p, out=vol)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -422,7 +438,14 @@ def alt_precision_block(nat, img_d, T_d, gen, nx, dev, prec, peak):
         out[p] = {"decoder_ms": ms, "value": nx ** 3 / (ms / 1e3), "unit": UNIT,
                   "roofline_frac": FLOP_PER_QUERY * nx ** 3 / (ms / 1e3) / 1e12 / peak,
                   "max_abs_vs_golden": parity_block(dev, p)["max_abs_vs_golden"]}
+        if p == "bf16":
+            out[p]["note"] = "single bf16 pass: outside the 1e-4 contract, reported for BASELINE configs[2]'s wording only"
     return out
+
+
+def _native_precisions():
+    from slice3d_b200 import _native
+    return _native.available_precisions()
 
 
 def e2e_api_block(model, gen, feed, nx, dev, steps):
