@@ -1,5 +1,6 @@
 """Training-loop pieces of the reference's ``train.py`` for ``Slices3DRegModel`` (reference: reg_slices/train.py:21-53,
-70-93, 131-136), plus the one-process-per-GPU wrapper BASELINE configs[4] asks for.
+70-93, 131-136) and of ``train_gt.py`` for ``Slices3DGTModel`` (reg_slices/train_gt.py:21-71: ``*_gt``), plus the
+one-process-per-GPU wrapper BASELINE configs[4] asks for.
 
 ``train_step`` keeps the reference's signature and return values (the three loss terms and the sign accuracy as Python
 floats).  With CUDA tensors the decoder's forward and backward run in the CUDA library (``slice3d_b200.train_ops``);
@@ -63,6 +64,46 @@ def val_step(model, val_loader, pred_type="sdf", device=None):
         avg_acc += cal_acc(x, batch, pred_type).item()
         ni += 1
     return avg_loss_pred / max(ni, 1), avg_acc / max(ni, 1), loss_img
+
+
+# ---------------------------------------------------------------------- Slices3DGTModel (reference: reg_slices/train_gt.py)
+def cal_loss_pred_gt(x, gt, pred_type="sdf"):
+    """train_gt.py:29-36: the GT-slices model has no image head, so the loss is the prediction term alone."""
+    if pred_type == "occ":
+        return F.binary_cross_entropy_with_logits(x["occ_pred"], gt["occ"])
+    return F.l1_loss(x["sdf_pred"], gt["sdf"])
+
+
+def train_step_gt(batch, model, opt, args=None, device=None):
+    """train_gt.py:38-50 for ``Slices3DGTModel``: returns (loss_pred, acc) as Python floats."""
+    pred_type = getattr(args, "pred_type", "sdf")
+    device = device or next(model.parameters()).device
+    for key in batch:
+        batch[key] = batch[key].to(device, non_blocking=True)
+    opt.zero_grad()
+    x = model(batch)
+    loss_pred = cal_loss_pred_gt(x, batch, pred_type)
+    loss_pred.backward()
+    opt.step()
+    with torch.no_grad():
+        acc = cal_acc(x, batch, pred_type)
+    return loss_pred.item(), acc.item()
+
+
+@torch.no_grad()
+def val_step_gt(model, val_loader, pred_type="sdf", device=None):
+    """train_gt.py:53-71: average prediction loss and sign accuracy over the loader (an empty loader gives zeros where
+    the reference divides by zero)."""
+    device = device or next(model.parameters()).device
+    avg_loss_pred, avg_acc, ni = 0.0, 0.0, 0
+    for batch in val_loader:
+        for key in batch:
+            batch[key] = batch[key].to(device, non_blocking=True)
+        x = model(batch)
+        avg_loss_pred += cal_loss_pred_gt(x, batch, pred_type).item()
+        avg_acc += cal_acc(x, batch, pred_type).item()
+        ni += 1
+    return avg_loss_pred / max(ni, 1), avg_acc / max(ni, 1)
 
 
 def wrap_ddp(model, device=None):

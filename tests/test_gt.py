@@ -82,3 +82,45 @@ def test_gt_native_matches_reference_golden():
         a = m({**feed, "qry_norot": big.clone()})["sdf_pred"][0]
         b = m({**feed, "qry_norot": big[:, 32700:32900].clone().contiguous()})["sdf_pred"][0]
     assert helpers.maxabs(a[32700:32900].cpu(), b.cpu()) < 1e-6
+
+
+def test_gt_train_step_cpu_matches_reference_gradients():
+    """Training of Slices3DGTModel (reference reg_slices/train_gt.py:21-50) against a golden produced by the UNMODIFIED
+    reference module in train mode (oracle/make_golden_train_gt.py; dropout p = 0 on both sides): the loss, the sign
+    accuracy, sdf_pred, the autograd gradients of tensors spanning the graph from fc_out back to the first trunk
+    convolution, the set of parameters that never get a gradient, and -- through ``train_step_gt`` itself -- the loss
+    after one Adam step and the BatchNorm running statistics the two train-mode forwards leave behind."""
+    from slice3d_b200 import train_step_gt, val_step_gt
+    case = helpers.load_case("gt_train_grads_b2_s128")
+    S, K, seed, B = int(case["img_size"]), int(case["n_slices"]), int(case["seed"]), int(case["batch"])
+    torch.manual_seed(0)
+    m = Slices3DGTModel(S, K, "train")
+    m.load_state_dict(synth.synthetic_state_dict(m.state_dict(), seed), strict=True)
+    m = synth.set_dropout(m.train(), 0.0)
+    feed = synth.synthetic_train_batch(S, K, batch=B, n_qry=256, seed=seed)
+
+    opt = torch.optim.Adam(m.parameters(), lr=float(case["lr"]))  # train_gt.py:115
+    # (train_step zeroes the gradients BEFORE the forward, so they can be read after the step)
+    loss, acc = train_step_gt({k: v.clone() for k, v in feed.items()}, m, opt)
+    assert abs(loss - float(case["loss"])) <= 2e-5 * abs(float(case["loss"])) + 1e-6, (loss, float(case["loss"]))
+    assert abs(acc - float(case["acc"])) < 1e-6, (acc, float(case["acc"]))
+    named = dict(m.named_parameters())
+    rels = {}
+    for key in [k[5:] for k in case if k.startswith("grad:")]:
+        g = named[key].grad.detach().reshape(-1)[::int(case["stride:" + key])].double().numpy()
+        ref = case["grad:" + key].astype(np.float64)
+        rels[key] = float(np.linalg.norm(g - ref) / max(np.linalg.norm(ref), 1e-30))
+    print("GT train gradients, |g - ref| / |ref|: " + ", ".join(f"{k} {v:.1e}" for k, v in rels.items()))
+    assert max(rels.values()) < 2e-4, rels
+    unused = sorted(k for k, p in named.items() if p.requires_grad and p.grad is None)
+    assert unused == sorted(str(x) for x in case["unused"])
+    # second call: the loss after the first Adam step (what the reference's loop prints next)
+    loss2, _ = train_step_gt({k: v.clone() for k, v in feed.items()}, m, opt)
+    ref2 = float(case["loss_after_step"])
+    assert abs(loss2 - ref2) <= 1e-3 * abs(ref2), (loss2, ref2)
+    rm = m.state_dict()["img_encoder.conv1_2.1.running_mean"].numpy()
+    assert np.allclose(rm, case["running_mean_conv1_2_1"], rtol=1e-4, atol=1e-6)
+    # val_step_gt over a one-batch "loader": the same loss function, eval-mode arithmetic on grad-free tensors is the
+    # native path (CUDA only), so the CPU check runs the loader through the train-mode module
+    lv, av = val_step_gt(m, [{k: v.clone() for k, v in feed.items()}])
+    assert np.isfinite(lv) and 0.0 <= av <= 1.0
