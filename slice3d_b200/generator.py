@@ -17,11 +17,13 @@
   ceil(n / 3000) model calls; the resulting (R+1)^3 volume equals the reference's.
 
 * ``extract_mesh(value_grid)`` is reconstruct.py:175-243 without the dead branches: pad with -1e6, marching cubes
-  (``slice3d_b200.mcubes``: same vertex array as libmcubes bit for bit, same oriented polygons, its own fan
-  triangulation), undo the padding / cell-centre shift, normalise to the unit box.  Returns a minimal ``Mesh``
-  (vertices, faces, ``export``) in place of the trimesh object.
+  (``slice3d_b200.mcubes``: the vertex AND face arrays of libmcubes bit for bit), undo the padding / cell-centre
+  shift, normalise to the unit box.  Returns a minimal ``Mesh`` (vertices, faces, ``export``) in place of the trimesh
+  object; ``stats_dict`` gets the reference's ``time (eval points)`` / ``time (marching cubes)`` keys (host wall clock
+  around calls that end in a device-to-host read) plus ``n_vertices`` / ``n_faces``.
 """
 import math
+import time
 
 import numpy as np
 import torch
@@ -109,8 +111,11 @@ class Generator3D(object):
         return (mesh, stats_dict) if return_stats else mesh
 
     def generate_from_latent(self, c=None, stats_dict=None):
+        stats_dict = stats_dict if stats_dict is not None else {}
+        t0 = time.time()
         value_grid = self.generate_grid(c) if self.upsampling_steps == 0 else self.generate_sparse_grid(c)
-        return self.extract_mesh(value_grid, c, stats_dict=stats_dict if stats_dict is not None else {})
+        stats_dict["time (eval points)"] = time.time() - t0  # reconstruct.py:170 (the grid is on the host here)
+        return self.extract_mesh(value_grid, c, stats_dict=stats_dict)
 
     def extract_mesh(self, occ_hat, c=None, stats_dict=None):
         """reconstruct.py:175-243.  ``occ_hat``: (nx,ny,nz) value grid (numpy or tensor; evaluated in float64 like the
@@ -125,8 +130,13 @@ class Generator3D(object):
         n_x, n_y, n_z = vol.shape
         box_size = 1 + self.padding
         threshold = self.threshold_logit()
+        t0 = time.time()
         padded = torch.nn.functional.pad(vol, (1, 1, 1, 1, 1, 1), value=-1e6)  # make sure that the mesh is watertight
         vertices, triangles = marching_cubes(padded, threshold)
+        if stats_dict is not None:
+            if vertices.is_cuda:
+                torch.cuda.current_stream(vertices.device).synchronize()
+            stats_dict["time (marching cubes)"] = time.time() - t0  # reconstruct.py:188-193
         vertices = vertices - 0.5  # libmcubes' cell-centre shift (reconstruct.py:193-194)
         vertices = vertices - 1    # undo padding
         vertices = vertices / torch.tensor([n_x - 1, n_y - 1, n_z - 1], dtype=torch.float64, device=vertices.device)

@@ -99,6 +99,7 @@ def test_extract_mesh_transform_and_export(tmp_path):
     mesh = gen.extract_mesh(vol, stats_dict=stats)
     assert np.array_equal(mesh.vertices, gold["vertices"]) and np.array_equal(mesh.faces, gold["triangles"])
     assert stats["n_vertices"] == len(mesh.vertices)
+    assert stats["time (marching cubes)"] >= 0.0  # the reference's stats key (reconstruct.py:193)
     # closed surface: every undirected edge is shared by exactly two faces, with opposite directions
     d = {}
     for t in mesh.faces:
@@ -108,6 +109,12 @@ def test_extract_mesh_transform_and_export(tmp_path):
     for ext in ("obj", "off", "ply"):
         p = mesh.export(os.path.join(tmp_path, "m." + ext))
         assert os.path.getsize(p) > 1000
+    # generate_mesh's plumbing (reconstruct.py:104-173) with the value grid supplied: same mesh, the reference's stats keys
+    gen.generate_grid = lambda data: np.asarray(vol)
+    mesh2, stats2 = gen.generate_mesh({})
+    assert np.array_equal(mesh2.vertices, mesh.vertices) and np.array_equal(mesh2.faces, mesh.faces)
+    assert {"time (eval points)", "time (marching cubes)", "n_vertices", "n_faces"} <= set(stats2)
+    assert gen.generate_mesh({}, return_stats=False).faces.shape == mesh.faces.shape
     with pytest.raises(NotImplementedError):
         Generator3D(None, with_normals=True, pred_type="sdf").extract_mesh(vol)
 
