@@ -12,8 +12,11 @@ Two arithmetic paths:
   instead of once per 3000-point chunk as ``Generator3D.eval_points`` makes the reference do
   (reference: reg_slices/reconstruct.py:82-93); the values are identical.  There is no CPU or
   PyTorch fallback for this path: without a CUDA device or the built library it raises.
-* **training** (``model.train()`` or grad enabled): autograd arithmetic written with torch ops
-  (batch-statistics BatchNorm, dropout), used by ``train_step`` (reference: reg_slices/train.py:41-53).
+* **training** (``model.train()`` or grad enabled; ``train_step``, reference: reg_slices/train.py:41-53): with CUDA
+  tensors the per-query half (projection, grid_sample, fc_s / fc_p, transformer with dropout, fc_out) and the VGG19
+  perceptual loss run forward AND backward in the CUDA library (``slice3d_b200.train_ops``); the U-Net (convolutions,
+  batch-statistics BatchNorm) runs through torch autograd.  CPU tensors take an all-torch restatement that the CPU tests
+  pin to the reference bit for bit.
 """
 import torch
 import torch.nn as nn
@@ -115,7 +118,7 @@ class Slices3DRegModel(NativeHandleMixin, nn.Module):
         self.vggptlossfunc = VGGPerceptualLoss()
         self.n_slices = n_slices
         # --- not part of the reference API ---
-        self.precision = precision or default_precision(n_slices)  # decoder arithmetic: fp32 | fp16x3 | bf16x3 | bf16
+        self.precision = precision or default_precision(n_slices)  # decoder arithmetic: auto | fp16f8 | fp16x3 | bf16x3 | fp32 | bf16
         self.test_time_vgg_loss = True  # the reference evaluates (and discards) it at test time too
         self._pretrained_loaded = False  # set by load_pretrained_vgg / load_state_dict
         self._warned_init = False
