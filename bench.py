@@ -46,7 +46,7 @@ def parse():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--grid", type=int, default=256)
     ap.add_argument("--img", type=int, default=256)
-    ap.add_argument("--precision", default=None, help="fp32 | bf16x3 | bf16 (default: best <=1e-4 mode built)")
+    ap.add_argument("--precision", default=None, help="auto | fp16f8 | fp16x3 | bf16x3 | fp32 | bf16 (default: the package's own, 'auto': the fastest mode a probe confirms within 1e-4)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the BASELINE configs[4] training leg")
     ap.add_argument("--no-extra", action="store_true", help="skip the e2e_api / sparse / parity blocks")
