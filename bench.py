@@ -423,11 +423,7 @@ def alt_precision_block(nat, img_d, T_d, gen, nx, dev, prec, peak):
     vol = torch.empty(nx ** 3, dtype=torch.float32, device=dev)
     planes = nat.encode(img_d)
     # "bf16" = configs[2] as literally worded (single bf16 pass): reported with its error, OUTSIDE the 1e-4 contract
-    for p in ("fp16x3", "bf16x3", "fp16f8", "bf16"):
-        if p == prec:
-            continue
-        if p == "bf16" and p not in _native_precisions():
-            continue
+    def one(p):
         nat.decode_grid(planes, 0, (ax, ax, ax), 0, nx ** 3, T_d[0], out_scale=-1.0, precision=p, out=vol)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -435,11 +431,17 @@ def alt_precision_block(nat, img_d, T_d, gen, nx, dev, prec, peak):
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)
-        out[p] = {"decoder_ms": ms, "value": nx ** 3 / (ms / 1e3), "unit": UNIT,
-                  "roofline_frac": FLOP_PER_QUERY * nx ** 3 / (ms / 1e3) / 1e12 / peak,
-                  "max_abs_vs_golden": parity_block(dev, p)["max_abs_vs_golden"]}
+        r = {"decoder_ms": ms, "value": nx ** 3 / (ms / 1e3), "unit": UNIT,
+             "roofline_frac": FLOP_PER_QUERY * nx ** 3 / (ms / 1e3) / 1e12 / peak,
+             "max_abs_vs_golden": parity_block(dev, p)["max_abs_vs_golden"]}
         if p == "bf16":
-            out[p]["note"] = "single bf16 pass: outside the 1e-4 contract, reported for BASELINE configs[2]'s wording only"
+            r["note"] = "single bf16 pass: outside the 1e-4 contract, reported for BASELINE configs[2]'s wording only"
+        return r
+
+    for p in ("fp16x3", "bf16x3", "fp16f8", "bf16"):
+        if p == prec or p not in _native_precisions():
+            continue
+        out[p] = _guarded(one, p)  # a mode that fails is recorded as such; the others are still reported
     return out
 
 
