@@ -10,9 +10,10 @@ from .generator import Generator3D  # noqa: F401
 from .mcubes import Mesh, marching_cubes  # noqa: F401
 from .mise import MISE  # noqa: F401
 from . import inputs  # noqa: F401
+from .datasets import Slice3DDataset  # noqa: F401
 from .synth import make_3d_grid  # noqa: F401
 from .train import (cal_acc, cal_loss_pred, cal_loss_pred_gt, train_step, train_step_gt, val_step, val_step_gt,  # noqa: F401
                     wrap_ddp)
 
 __all__ = ["Slices3DRegModel", "Slices3DGTModel", "Generator3D", "MISE", "Mesh", "marching_cubes", "make_3d_grid", "train_step", "val_step",
-           "cal_loss_pred", "cal_acc", "wrap_ddp", "train_step_gt", "val_step_gt", "cal_loss_pred_gt"]
+           "cal_loss_pred", "cal_acc", "wrap_ddp", "train_step_gt", "val_step_gt", "cal_loss_pred_gt", "Slice3DDataset"]

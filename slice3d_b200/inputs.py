@@ -180,7 +180,9 @@ def prepare_queries(sdf_npy, scale, offset, n_qry, split="train", rng=None):
     val = (sdf_npy[:, 3] - 0.003) * scale
     occ = (val <= 0).astype(np.float32)
     if split == "train":
-        perm = (rng.permutation(len(pt)) if rng is not None else np.random.permutation(len(pt)))[:n_qry]
+        # the reference re-seeds numpy's global generator from the OS before every draw (``np.random.seed()``), so that
+        # forked DataLoader workers do not repeat each other's permutations: a fresh generator does the same
+        perm = (rng if rng is not None else np.random.default_rng()).permutation(len(pt))[:n_qry]
     else:
         perm = np.random.RandomState(1234).permutation(len(pt))[:n_qry]
     return torch.tensor(pt[perm]).float(), torch.tensor(occ[perm]).float(), torch.tensor(val[perm]).float()
