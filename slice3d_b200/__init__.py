@@ -12,8 +12,9 @@ from .mise import MISE  # noqa: F401
 from . import inputs  # noqa: F401
 from .datasets import Slice3DDataset  # noqa: F401
 from .synth import make_3d_grid  # noqa: F401
-from .train import (cal_acc, cal_loss_pred, cal_loss_pred_gt, train_step, train_step_gt, val_step, val_step_gt,  # noqa: F401
-                    wrap_ddp)
+from .train import (cal_acc, cal_loss_pred, cal_loss_pred_gt, fit, latest_checkpoint, save_checkpoint,  # noqa: F401
+                    train_step, train_step_gt, val_step, val_step_gt, wrap_ddp)
 
 __all__ = ["Slices3DRegModel", "Slices3DGTModel", "Generator3D", "MISE", "Mesh", "marching_cubes", "make_3d_grid", "train_step", "val_step",
-           "cal_loss_pred", "cal_acc", "wrap_ddp", "train_step_gt", "val_step_gt", "cal_loss_pred_gt", "Slice3DDataset"]
+           "cal_loss_pred", "cal_acc", "wrap_ddp", "train_step_gt", "val_step_gt", "cal_loss_pred_gt", "Slice3DDataset", "fit", "save_checkpoint",
+           "latest_checkpoint"]

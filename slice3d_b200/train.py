@@ -106,6 +106,69 @@ def val_step_gt(model, val_loader, pred_type="sdf", device=None):
     return avg_loss_pred / max(ni, 1), avg_acc / max(ni, 1)
 
 
+# ---------------------------------------------------------------------- the epoch loop, checkpoints, resume
+def latest_checkpoint(dir_ckpt):
+    """train.py:138-140: the most recently created file of the checkpoint directory (None when there is none)."""
+    import glob
+    import os
+    names = [n for n in glob.glob(os.path.join(dir_ckpt, "*")) if n.endswith(".ckpt")]
+    return max(names, key=os.path.getctime) if names else None
+
+
+def save_checkpoint(dir_ckpt, model, opt, n_epoch, n_iter, val_metrics):
+    """train.py:166-169 / train_gt.py: ``{'model', 'opt', 'n_epoch', 'n_iter'}`` of the UNWRAPPED module under the
+    reference's file name ``<epoch>_<iter>_<metric:.4>_..._.ckpt`` (the validation figures, four significant digits)."""
+    import os
+    os.makedirs(dir_ckpt, exist_ok=True)
+    inner = model.module if hasattr(model, "module") else model
+    name = "_".join([str(n_epoch), str(n_iter)] + [f"{float(v):.4}" for v in val_metrics]) + ".ckpt"
+    path = os.path.join(dir_ckpt, name)
+    torch.save({"model": inner.state_dict(), "opt": opt.state_dict(), "n_epoch": n_epoch, "n_iter": n_iter}, path)
+    return path
+
+
+def fit(args, model, opt, train_loader, val_loader, dir_ckpt, step_fn=None, val_fn=None, log=print, is_main=None):
+    """The epoch loop of train.py:136-183 (and train_gt.py's, with ``step_fn=train_step_gt, val_fn=val_step_gt``):
+    optional resume from the latest checkpoint (``args.resume``), ``train_step`` per batch with a log line every
+    ``args.freq_log`` iterations, validation + checkpoint every ``args.freq_ckpt`` epochs, learning rate times
+    ``args.weight_decay`` every ``args.freq_decay`` epochs (the reference's naming: it is an lr decay factor).
+    Under torch.distributed only rank 0 writes checkpoints (``is_main``); every rank resumes from the same file.
+    Returns (n_epoch, n_iter)."""
+    step_fn = step_fn or train_step
+    val_fn = val_fn or val_step
+    if is_main is None:
+        is_main = not (torch.distributed.is_available() and torch.distributed.is_initialized()) or \
+            torch.distributed.get_rank() == 0
+    inner = model.module if hasattr(model, "module") else model
+    n_epoch = n_iter = 0
+    if getattr(args, "resume", False):
+        path = latest_checkpoint(dir_ckpt)
+        if path is None:
+            raise FileNotFoundError(f"--resume: no checkpoint in {dir_ckpt}")
+        ckpt = torch.load(path, map_location=next(inner.parameters()).device)
+        inner.load_state_dict(ckpt["model"])
+        opt.load_state_dict(ckpt["opt"])
+        n_epoch, n_iter = ckpt["n_epoch"] + 1, ckpt["n_iter"]
+    for _ in range(n_epoch, args.n_epochs):
+        model.train()
+        for batch in train_loader:
+            out = step_fn(batch, model, opt, args)
+            if n_iter % args.freq_log == 0:
+                log("[train] epoch:", n_epoch, ", iter:", n_iter, " losses / acc:", out)
+            n_iter += 1
+        if n_epoch % args.freq_ckpt == 0:
+            model.eval()
+            metrics = val_fn(model, val_loader, getattr(args, "pred_type", "sdf"))
+            log("[val] epoch:", n_epoch, ", iter:", n_iter, " metrics:", metrics)
+            if is_main:
+                save_checkpoint(dir_ckpt, model, opt, n_epoch, n_iter, [m for m in metrics if m is not None])
+        if n_epoch > 0 and n_epoch % args.freq_decay == 0:
+            for g in opt.param_groups:
+                g["lr"] = g["lr"] * args.weight_decay
+        n_epoch += 1
+    return n_epoch, n_iter
+
+
 def wrap_ddp(model, device=None):
     """One process per GPU (torchrun): DistributedDataParallel in place of train.py:131-132's DataParallel."""
     from torch.nn.parallel import DistributedDataParallel as DDP

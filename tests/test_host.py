@@ -362,3 +362,61 @@ def test_auto_precision_selection_policy():
         warnings.simplefilter("always")
         assert nm.resolve_precision("auto", probe(float("nan"))) == "fp16x3"  # a NaN probe never selects the fast mode
     assert Slices3DRegModel(64, 12, "test").precision == "auto"
+
+
+def test_fit_loop_checkpoints_resume_and_lr_decay(tmp_path):
+    """The epoch loop of train.py:136-183: checkpoint dict and file name, resume from the latest file, lr decay schedule."""
+    import time
+    from types import SimpleNamespace
+    from slice3d_b200 import train as T
+
+    def make():
+        torch.manual_seed(0)
+        m = torch.nn.Linear(3, 1)
+        return m, torch.optim.Adam(m.parameters(), lr=1e-2)
+
+    def step(batch, model, opt, args):
+        opt.zero_grad()
+        loss = (model(batch["x"]) - batch["y"]).abs().mean()
+        loss.backward()
+        opt.step()
+        return loss.item(), 0.5
+
+    def val(model, loader, pred_type):
+        time.sleep(0.02)  # distinct creation times for latest_checkpoint
+        return 0.123456, 0.98765, torch.tensor(0.4567891)
+
+    g = torch.Generator().manual_seed(1)
+    loader = [{"x": torch.randn(4, 3, generator=g), "y": torch.randn(4, 1, generator=g)} for _ in range(5)]
+    args = SimpleNamespace(n_epochs=5, freq_log=2, freq_ckpt=2, freq_decay=2, weight_decay=0.5, resume=False, pred_type="sdf")
+    d = str(tmp_path / "ckpt")
+    logs = []
+    m, opt = make()
+    assert T.fit(args, m, opt, loader, loader, d, step, val, log=lambda *a: logs.append(a)) == (5, 25)
+    # validation + checkpoint at epochs 0, 2, 4; the reference's file name (train.py:169)
+    assert sorted(os.listdir(d)) == ["0_5_0.1235_0.9877_0.4568.ckpt", "2_15_0.1235_0.9877_0.4568.ckpt",
+                                     "4_25_0.1235_0.9877_0.4568.ckpt"]
+    ck = torch.load(T.latest_checkpoint(d))
+    assert set(ck) == {"model", "opt", "n_epoch", "n_iter"} and (ck["n_epoch"], ck["n_iter"]) == (4, 25)
+    assert all(torch.equal(ck["model"][k], v) for k, v in m.state_dict().items())
+    # lr halves after epochs 2 and 4 (n_epoch > 0 and n_epoch % freq_decay == 0); the checkpoint of epoch 4 was written before
+    assert opt.param_groups[0]["lr"] == pytest.approx(1e-2 * 0.25)
+    assert ck["opt"]["param_groups"][0]["lr"] == pytest.approx(1e-2 * 0.5)
+    assert sum(1 for l in logs if l[0] == "[train] epoch:") == 13 and sum(1 for l in logs if l[0] == "[val] epoch:") == 3
+    # resume: weights, Adam state and counters continue from the latest file (epoch 5 onwards)
+    m2, opt2 = make()
+    args2 = SimpleNamespace(**{**vars(args), "resume": True, "n_epochs": 7})
+    assert T.fit(args2, m2, opt2, loader, loader, d, step, val, log=lambda *a: None) == (7, 35)
+    assert "6_35_0.1235_0.9877_0.4568.ckpt" in os.listdir(d)
+    m3, opt3 = make()  # the same 7 epochs without interruption
+    d3 = str(tmp_path / "ckpt3")
+    T.fit(SimpleNamespace(**{**vars(args), "n_epochs": 7}), m3, opt3, loader, loader, d3, step, val, log=lambda *a: None)
+    # (the resumed run restarts from the epoch-4 optimizer state: lr 0.5e-2 at epoch 5, as the reference's resume does,
+    #  while the uninterrupted run had already decayed to 0.25e-2 -- the reference's own resume semantics, kept)
+    assert opt2.param_groups[0]["lr"] == pytest.approx(1e-2 * 0.5 * 0.5) and opt3.param_groups[0]["lr"] == pytest.approx(1e-2 * 0.125)
+    with pytest.raises(FileNotFoundError):
+        T.fit(args2, m2, opt2, loader, loader, str(tmp_path / "none"), step, val)
+    # a DDP / DataParallel wrapper is unwrapped for the checkpoint
+    wrapped = SimpleNamespace(module=m)
+    p = T.save_checkpoint(str(tmp_path / "w"), wrapped, opt, 1, 2, [0.5])
+    assert os.path.basename(p) == "1_2_0.5.ckpt" and set(torch.load(p)["model"]) == set(m.state_dict())
