@@ -88,3 +88,20 @@ def test_device_preprocessing_batch_of_samples():
     assert torch.equal(got, want)
     with pytest.raises(Exception):
         inputs.preprocess_rgba(torch.from_numpy(rgba), 128, True)  # host tensor: no silent CPU path
+
+
+def test_factored_projection_equals_full_camera_projection():
+    """The reference's own check (reg_slices/test_projection.py:8-20, 99-112, printed side by side there): projecting a point
+    with the full matrix K.RT.rot.W2O equals rotating it by ``obj_rot_mat`` and applying ``trans_mat_wo_rot_tp`` -- the
+    factorisation Slices3DRegModel.forward relies on (models.py:57-60, 28-36)."""
+    rng = np.random.RandomState(11)
+    for _ in range(20):
+        az, el, dist = rng.rand() * 2 * np.pi, (rng.rand() - 0.5) * 1.2, 1.0 + rng.rand()
+        rot, T = inputs.camera_matrices(az, el, dist)
+        K, RT = inputs.blender_proj(az, el, dist, img_w=1, img_h=1)
+        full = np.transpose(np.linalg.multi_dot([K, RT, inputs.rotate_matrix(-np.pi / 2), np.eye(4)]))  # (4,3)
+        pts = rng.rand(50, 3) - 0.5
+        a = np.concatenate([pts, np.ones((50, 1))], 1) @ full
+        b = np.concatenate([pts @ rot.double().numpy(), np.ones((50, 1))], 1) @ T.double().numpy()
+        assert np.allclose(a, b, rtol=0, atol=2e-6), np.abs(a - b).max()
+        assert np.all(a[:, 2] > 0.3)  # in front of the camera: the perspective divide of project_coord is safe
