@@ -420,3 +420,34 @@ def test_fit_loop_checkpoints_resume_and_lr_decay(tmp_path):
     wrapped = SimpleNamespace(module=m)
     p = T.save_checkpoint(str(tmp_path / "w"), wrapped, opt, 1, 2, [0.5])
     assert os.path.basename(p) == "1_2_0.5.ckpt" and set(torch.load(p)["model"]) == set(m.state_dict())
+
+
+def test_abi_size_queries_and_argument_errors_need_no_gpu():
+    """Host-only entry points of include/slice3d_b200.h: the size queries a caller allocates from, and the argument checks
+    that run before any CUDA call (negative S3D_ERR_* + a message from s3d_last_error, nothing thrown, nothing touched)."""
+    L = _native.lib()
+    # projected planes: per image (K, R_s, R_s, 128) fp32 for R_s = S/16 * 2^s, s = 0..4 (DESIGN.md section 3)
+    for B, K, S in [(1, 12, 256), (2, 4, 128), (3, 1, 64)]:
+        assert L.s3d_planes_bytes(B, K, S) == B * K * 128 * 4 * sum((S // 16 * 2 ** s) ** 2 for s in range(5))
+    assert L.s3d_planes_bytes(1, 12, 256) == 536346624
+    # workspaces: positive, non-decreasing in the problem size, the decoder's bounded by its persistent grid
+    assert 0 < L.s3d_encoder_workspace_bytes(1, 12, 128) < L.s3d_encoder_workspace_bytes(1, 12, 256) \
+        <= L.s3d_encoder_workspace_bytes(2, 12, 256)
+    for prec in _native.PRECISIONS.values():
+        a, b = L.s3d_decoder_workspace_bytes(3000, prec), L.s3d_decoder_workspace_bytes(256 ** 3, prec)
+        assert 0 < a <= b < (1 << 33)
+    assert L.s3d_decoder_workspace_bytes(256 ** 3, _native.PREC_FP16F8) == L.s3d_decoder_workspace_bytes(128 ** 3, _native.PREC_FP16F8)
+    assert L.s3d_sparse_scratch_bytes(32, 3, 1 << 20) > 12 * (1 << 20)  # at least the compacted points of one round
+    assert L.s3d_mise_scratch_ints(32, 3) >= (32 * 8 + 1) ** 3 // 8
+    assert L.s3d_scan_scratch_bytes(10 ** 6) > 0 and L.s3d_vgg_loss_workspace_bytes(12, 128) > 0
+    assert L.s3d_preprocess_workspace_bytes(13, 137, 128) >= 13 * 137 * 128 * 3  # the 8-bit intermediate of the two passes
+    # argument errors
+    h = ctypes.c_void_p()
+    assert L.s3d_model_create(ctypes.byref(h), None, 0, 12, 0, None) == -1 and not h.value  # S3D_ERR_BAD_ARG
+    assert b"model_create" in L.s3d_last_error()
+    assert L.s3d_decoder_fwd(None, None, 256, None, 10, None, None, 0, 1.0, None, 3, None, 0, None) < 0
+    assert b"decoder" in L.s3d_last_error()
+    assert L.s3d_encoder_fwd(None, None, 1, 256, None, None, None, None, 0, None) < 0
+    assert b"encoder" in L.s3d_last_error()
+    assert L.s3d_model_n_slices(None) == 0
+    L.s3d_model_destroy(None)  # destroying nothing is a no-op
