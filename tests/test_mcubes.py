@@ -110,7 +110,7 @@ def test_extract_mesh_transform_and_export(tmp_path):
         p = mesh.export(os.path.join(tmp_path, "m." + ext))
         assert os.path.getsize(p) > 1000
     # generate_mesh's plumbing (reconstruct.py:104-173) with the value grid supplied: same mesh, the reference's stats keys
-    gen.generate_grid = lambda data: np.asarray(vol)
+    gen.generate_grid = lambda data, as_numpy=True: np.asarray(vol)
     mesh2, stats2 = gen.generate_mesh({})
     assert np.array_equal(mesh2.vertices, mesh.vertices) and np.array_equal(mesh2.faces, mesh.faces)
     assert {"time (eval points)", "time (marching cubes)", "n_vertices", "n_faces"} <= set(stats2)
