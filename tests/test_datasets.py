@@ -8,8 +8,10 @@ import numpy as np
 import pytest
 import torch
 
-from slice3d_b200.datasets import Slice3DDataset
-from tests import dataset_files, helpers
+pytest.importorskip("PIL.Image")  # the files are written and decoded with Pillow
+
+from slice3d_b200.datasets import Slice3DDataset  # noqa: E402
+from tests import dataset_files, helpers  # noqa: E402
 
 KEYS = {"img_input", "qry_norot", "obj_rot_mat", "trans_mat_wo_rot_tp", "occ", "sdf", "img_slices"}
 
